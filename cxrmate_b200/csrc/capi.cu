@@ -1,0 +1,186 @@
+// extern "C" boundary (include/cxrm.h): exception -> status translation only.
+#include <cstring>
+#include <string>
+
+#include "engine.cuh"
+
+using namespace cxrm;
+
+struct cxrm_engine {
+  EngineBase* impl = nullptr;
+};
+
+static thread_local std::string g_create_error;
+
+#define CXRM_GUARD(e, body)                                   \
+  if (!(e) || !(e)->impl) return CXRM_ERR_INVALID;            \
+  try {                                                       \
+    body;                                                     \
+    return CXRM_OK;                                           \
+  } catch (const std::exception& ex) {                        \
+    (e)->impl->last_error = ex.what();                        \
+    const std::string m = ex.what();                          \
+    if (m.find("weight") != std::string::npos) return CXRM_ERR_WEIGHT; \
+    if (m.find("cuda") != std::string::npos || m.find("CUDA") != std::string::npos) return CXRM_ERR_CUDA; \
+    return CXRM_ERR_INVALID;                                  \
+  } catch (...) {                                             \
+    (e)->impl->last_error = "unknown exception";              \
+    return CXRM_ERR_INTERNAL;                                 \
+  }
+
+extern "C" {
+
+void cxrm_default_config(cxrm_config* c) {
+  std::memset(c, 0, sizeof(*c));
+  c->dtype = CXRM_BF16;
+  c->image_h = c->image_w = 384;
+  c->max_studies = 32;
+  c->max_images = 5;
+  c->max_prompt = 256;
+  c->max_new_tokens = 255;
+  c->vocab = 30000;
+  c->cvt_depth[0] = 1; c->cvt_depth[1] = 4; c->cvt_depth[2] = 16;
+  c->dec_layers = 6;
+  c->rwd_layers = 12;
+  c->rwd_vocab = 30522;
+  c->rwd_max_len = 512;
+  c->rwd_max_seqs = 96;
+  c->enc_chunk = 32;
+  c->use_tensor_cores = 1;
+  c->use_cuda_graph = 1;
+}
+
+int cxrm_create(const cxrm_config* cfg, int device, cxrm_engine** out) {
+  if (!cfg || !out) return CXRM_ERR_INVALID;
+  *out = nullptr;
+  try {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0)
+      throw std::runtime_error("no CUDA device: the engine has no CPU fallback");
+    cxrm_engine* e = new cxrm_engine();
+    e->impl = make_engine(*cfg, device);
+    *out = e;
+    return CXRM_OK;
+  } catch (const std::exception& ex) {
+    g_create_error = ex.what();
+    return CXRM_ERR_CUDA;
+  }
+}
+
+void cxrm_destroy(cxrm_engine* e) {
+  if (!e) return;
+  delete e->impl;
+  delete e;
+}
+
+const char* cxrm_last_error(const cxrm_engine* e) {
+  if (!e || !e->impl) return g_create_error.c_str();
+  return e->impl->last_error.c_str();
+}
+
+size_t cxrm_workspace_bytes(const cxrm_engine* e) { return (e && e->impl) ? e->impl->workspace_bytes() : 0; }
+uint64_t cxrm_launch_count(const cxrm_engine* e) { (void)e; return g_launch_count; }
+
+int cxrm_load_weight(cxrm_engine* e, const char* name, const float* data, const int64_t* shape, int ndim,
+                     int on_device) {
+  CXRM_GUARD(e, e->impl->load_weight(name, data, shape, ndim, on_device != 0));
+}
+int cxrm_finalize_weights(cxrm_engine* e) { CXRM_GUARD(e, e->impl->finalize_weights()); }
+
+int cxrm_encode(cxrm_engine* e, const float* pixels, int B, int N, void* memory_out, uint8_t* mask_out, void* stream) {
+  CXRM_GUARD(e, e->impl->encode(pixels, B, N, memory_out, mask_out, static_cast<cudaStream_t>(stream)));
+}
+int cxrm_prefill_cross_kv(cxrm_engine* e, const void* memory, const uint8_t* mask, int B, int S, void* stream) {
+  CXRM_GUARD(e, e->impl->prefill_cross_kv(memory, mask, B, S, static_cast<cudaStream_t>(stream)));
+}
+int cxrm_rollout(cxrm_engine* e, const cxrm_rollout_args* a, void* stream) {
+  if (!a) return CXRM_ERR_INVALID;
+  CXRM_GUARD(e, e->impl->rollout(*a, static_cast<cudaStream_t>(stream)));
+}
+int cxrm_decoder_forward(cxrm_engine* e, const int32_t* ids, const int32_t* tt, const int32_t* pos,
+                         const uint8_t* key_mask, int R, int L, int B, int last_only, float* logits_out, void* stream) {
+  CXRM_GUARD(e, e->impl->decoder_forward(ids, tt, pos, key_mask, R, L, B, last_only != 0, logits_out,
+                                         static_cast<cudaStream_t>(stream)));
+}
+int cxrm_reward_embed(cxrm_engine* e, const int32_t* ids, const int32_t* lens, int n, int L, float* emb_out,
+                      void* stream) {
+  CXRM_GUARD(e, e->impl->reward_embed(ids, lens, n, L, emb_out, static_cast<cudaStream_t>(stream)));
+}
+int cxrm_cosine(cxrm_engine* e, const float* a, const float* b, int n, int dim, float* out, void* stream) {
+  CXRM_GUARD(e, cosine_rows(a, b, out, n, dim, static_cast<cudaStream_t>(stream)));
+}
+int cxrm_reward(cxrm_engine* e, const int32_t* pred_ids, const int32_t* pred_lens, int L_pred,
+                const int32_t* label_ids, const int32_t* label_lens, int L_label, int n, float* reward_out,
+                void* stream) {
+  CXRM_GUARD(e, {
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    float* emb = nullptr;
+    CXRM_CUDA_CHECK(cudaMallocAsync(&emb, static_cast<size_t>(2) * n * 128 * sizeof(float), s));
+    e->impl->reward_embed(pred_ids, pred_lens, n, L_pred, emb, s);
+    e->impl->reward_embed(label_ids, label_lens, n, L_label, emb + static_cast<size_t>(n) * 128, s);
+    cosine_rows(emb, emb + static_cast<size_t>(n) * 128, reward_out, n, 128, s);
+    CXRM_CUDA_CHECK(cudaFreeAsync(emb, s));
+  });
+}
+int cxrm_set_id_map(cxrm_engine* e, const int32_t* id_map_host, int n, int cls_id, int sep_id, int bos_id,
+                    int sep_dec_id) {
+  CXRM_GUARD(e, e->impl->set_id_map(id_map_host, n, cls_id, sep_id, bos_id, sep_dec_id));
+}
+int cxrm_scst_step_host(cxrm_engine* e, const float* pixels, int B, int N, const int32_t* prompt_ids, int P,
+                        const cxrm_rollout_args* tmpl, const int32_t* label_ids, const int32_t* label_lens,
+                        int L_label, int32_t* sequences, float* logprobs, float* reward, float* baseline,
+                        float* advantage, int32_t* steps_out, void* stream) {
+  if (!tmpl) return CXRM_ERR_INVALID;
+  CXRM_GUARD(e, e->impl->scst_step_host(pixels, B, N, prompt_ids, P, *tmpl, label_ids, label_lens, L_label, sequences,
+                                        logprobs, reward, baseline, advantage, steps_out,
+                                        static_cast<cudaStream_t>(stream)));
+}
+
+int cxrm_test_gemm(int impl, int dtype, const void* A, const void* W, void* C, int M, int N, int K, const float* bias,
+                   int act, const void* residual, int out_f32, void* stream) {
+  try {
+    GemmArgs g;
+    g.A = A; g.lda = K; g.W = W; g.ldw = K; g.C = C; g.ldc = N; g.M = M; g.N = N; g.K = K;
+    g.bias = bias; g.act = act; g.residual = residual; g.ldr = N; g.out_f32 = out_f32; g.skip_flag = nullptr;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (impl == 1) {
+      if (dtype != CXRM_BF16 || gemm_tcgen05_supported(g) != 0) return CXRM_ERR_INVALID;
+      gemm_tcgen05(g, s);
+    } else if (dtype == CXRM_F32) {
+      gemm_simt<float>(g, s);
+    } else {
+      gemm_simt<bf16>(g, s);
+    }
+    return CXRM_OK;
+  } catch (const std::exception& ex) {
+    g_create_error = ex.what();
+    return CXRM_ERR_CUDA;
+  }
+}
+
+int cxrm_test_attention(int dtype, const void* q, const void* k, const void* v, void* o, int batch, int heads, int Lq,
+                        int Lk, const uint8_t* key_mask, int causal, float scale, void* stream) {
+  try {
+    AttnArgs a{};
+    const long long C = static_cast<long long>(heads) * 64;
+    a.q = q; a.k = k; a.v = v; a.o = o;
+    a.q_bs = Lq * C; a.q_hs = 64; a.q_ts = C;
+    a.k_bs = Lk * C; a.k_hs = 64; a.k_ts = C;
+    a.v_bs = Lk * C; a.v_hs = 64; a.v_ts = C;
+    a.o_bs = Lq * C; a.o_hs = 64; a.o_ts = C;
+    a.batch = batch; a.heads = heads; a.Lq = Lq; a.Lk = Lk;
+    a.key_mask = key_mask; a.key_mask_ld = Lk; a.key_mask_per_q_batch = 1;
+    a.causal = causal; a.q_pos_offset = Lk - Lq; a.scale = scale;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dtype == CXRM_F32)
+      attention_simt<float>(a, s);
+    else
+      attention_simt<bf16>(a, s);
+    return CXRM_OK;
+  } catch (const std::exception& ex) {
+    g_create_error = ex.what();
+    return CXRM_ERR_CUDA;
+  }
+}
+
+}  // extern "C"

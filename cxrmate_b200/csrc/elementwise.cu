@@ -1,0 +1,505 @@
+// Bandwidth-bound kernels of the path: LayerNorm, embedding gather + LayerNorm,
+// im2col for the CvT convolutional token embeddings, the depth-wise
+// convolutional q/k/v projections with folded BatchNorm, row gathers/scatters
+// and the weight-packing helpers.  All math in fp32; storage type T.
+#include "kernels.h"
+
+namespace cxrm {
+
+namespace {
+
+constexpr int kMaxPerLane = 24;  // supports C <= 768
+
+// ---- LayerNorm: one warp per row -------------------------------------------
+// Two-pass (mean, then centred variance) in registers, like
+// torch.nn.functional.layer_norm (HF modeling_cvt.py:112,366; modeling_bert.py:62,292,348,479).
+template <typename T>
+__global__ void layernorm_kernel(const T* __restrict__ x, int ldx, T* __restrict__ y, int ldy,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta, long long rows, int C,
+                                 float eps) {
+  const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) / kWarp;
+  const int lane = threadIdx.x % kWarp;
+  if (row >= rows) return;
+  const T* xr = x + row * ldx;
+  float v[kMaxPerLane];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxPerLane; ++i) {
+    const int c = lane + i * kWarp;
+    v[i] = (c < C) ? to_f(xr[c]) : 0.f;
+    s += v[i];
+  }
+  const float mean = warp_sum(s) / C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxPerLane; ++i) {
+    const int c = lane + i * kWarp;
+    const float d = (c < C) ? v[i] - mean : 0.f;
+    q += d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(q) / C + eps);
+  T* yr = y + row * ldy;
+#pragma unroll
+  for (int i = 0; i < kMaxPerLane; ++i) {
+    const int c = lane + i * kWarp;
+    if (c < C) yr[c] = from_f<T>((v[i] - mean) * rstd * gamma[c] + beta[c]);
+  }
+}
+
+template <typename T>
+__global__ void embed_ln_kernel(const int* __restrict__ ids, const int* __restrict__ types, const int* __restrict__ pos,
+                                const T* __restrict__ word, const T* __restrict__ type_emb,
+                                const T* __restrict__ pos_emb, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, T* __restrict__ out, long long rows, int C, float eps) {
+  const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) / kWarp;
+  const int lane = threadIdx.x % kWarp;
+  if (row >= rows) return;
+  const T* w = word + static_cast<long long>(ids[row]) * C;
+  const T* t = type_emb + static_cast<long long>(types ? types[row] : 0) * C;
+  const T* p = pos_emb + static_cast<long long>(pos[row]) * C;
+  float v[kMaxPerLane];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxPerLane; ++i) {
+    const int c = lane + i * kWarp;
+    // (word + type) + position in fp32, same association order as BertEmbeddings.forward
+    float e = 0.f;
+    if (c < C) e = (to_f(w[c]) + to_f(t[c])) + to_f(p[c]);
+    v[i] = e;
+    s += e;
+  }
+  const float mean = warp_sum(s) / C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxPerLane; ++i) {
+    const int c = lane + i * kWarp;
+    const float d = (c < C) ? v[i] - mean : 0.f;
+    q += d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(q) / C + eps);
+  T* yr = out + row * C;
+#pragma unroll
+  for (int i = 0; i < kMaxPerLane; ++i) {
+    const int c = lane + i * kWarp;
+    if (c < C) yr[c] = from_f<T>((v[i] - mean) * rstd * gamma[c] + beta[c]);
+  }
+}
+
+// ---- im2col ------------------------------------------------------------------
+template <typename T>
+__global__ void im2col_pixels_kernel(const float* __restrict__ pixels, const int* __restrict__ img_idx,
+                                     T* __restrict__ out, int n_img, int H, int W, int Ho, int Wo, int ksz, int stride,
+                                     int pad, int Kpad) {
+  const long long total = static_cast<long long>(n_img) * Ho * Wo * Kpad;
+  const int K = 3 * ksz * ksz;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int kk = static_cast<int>(i % Kpad);
+    const long long r = i / Kpad;
+    const int ox = static_cast<int>(r % Wo);
+    const int oy = static_cast<int>((r / Wo) % Ho);
+    const int n = static_cast<int>(r / (static_cast<long long>(Wo) * Ho));
+    float v = 0.f;
+    if (kk < K) {
+      const int kx = kk % ksz, ky = (kk / ksz) % ksz, c = kk / (ksz * ksz);
+      const int iy = oy * stride - pad + ky, ix = ox * stride - pad + kx;
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+        const long long src = img_idx ? img_idx[n] : n;
+        v = pixels[((src * 3 + c) * H + iy) * static_cast<long long>(W) + ix];
+      }
+    }
+    out[i] = from_f<T>(v);
+  }
+}
+
+// one thread per 16-byte channel vector
+template <typename T>
+__global__ void im2col_tokens_kernel(const T* __restrict__ in, T* __restrict__ out, int n_img, int H, int W, int C,
+                                     int Ho, int Wo, int ksz, int stride, int pad) {
+  constexpr int V = Vec16<T>::N;
+  const int cv = C / V;
+  const long long total = static_cast<long long>(n_img) * Ho * Wo * ksz * ksz * cv;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % cv) * V;
+    long long r = i / cv;
+    const int tap = static_cast<int>(r % (ksz * ksz));
+    r /= (ksz * ksz);
+    const int ox = static_cast<int>(r % Wo);
+    const int oy = static_cast<int>((r / Wo) % Ho);
+    const int n = static_cast<int>(r / (static_cast<long long>(Wo) * Ho));
+    const int ky = tap / ksz, kx = tap % ksz;
+    const int iy = oy * stride - pad + ky, ix = ox * stride - pad + kx;
+    Vec16<T> v;
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+      v.load(in + ((static_cast<long long>(n) * H + iy) * W + ix) * C + c);
+    } else {
+      float z[V];
+#pragma unroll
+      for (int j = 0; j < V; ++j) z[j] = 0.f;
+      v.pack(z);
+    }
+    v.store(out + i * V);
+  }
+}
+
+// ---- depth-wise 3x3 + BN(eval) ------------------------------------------------
+// HF modeling_cvt.py:124-141 (Conv2d groups=C, bias=False -> BatchNorm2d).
+// BatchNorm in eval mode is the affine map y*scale + shift with
+// scale = gamma / sqrt(var + eps), shift = beta - mean * scale.
+template <typename T, int NOUT>
+__global__ void dwconv_bn_kernel(const T* __restrict__ y, T* __restrict__ o0, T* __restrict__ o1,
+                                 const float* __restrict__ w, const float* __restrict__ scale,
+                                 const float* __restrict__ shift, int n_img, int H, int W, int C, int cls, int stride,
+                                 int Ho, int Wo, int which0) {
+  constexpr int V = Vec16<T>::N;
+  const int cv = C / V;
+  const long long total = static_cast<long long>(n_img) * Ho * Wo * cv;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = static_cast<int>(i % cv) * V;
+  long long r = i / cv;
+  const int ox = static_cast<int>(r % Wo);
+  const int oy = static_cast<int>((r / Wo) % Ho);
+  const int n = static_cast<int>(r / (static_cast<long long>(Wo) * Ho));
+  const T* img = y + (static_cast<long long>(n) * (cls + H * W) + cls) * C;
+  float acc[NOUT][V];
+#pragma unroll
+  for (int t = 0; t < NOUT; ++t)
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc[t][j] = 0.f;
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int iy = oy * stride - 1 + ky;
+    if (iy < 0 || iy >= H) continue;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int ix = ox * stride - 1 + kx;
+      if (ix < 0 || ix >= W) continue;
+      Vec16<T> xv;
+      xv.load(img + (static_cast<long long>(iy) * W + ix) * C + c);
+      float xf[V];
+      xv.unpack(xf);
+#pragma unroll
+      for (int t = 0; t < NOUT; ++t) {
+        const float* wt = w + (static_cast<long long>(which0 + t) * 9 + ky * 3 + kx) * C + c;
+#pragma unroll
+        for (int j = 0; j < V; ++j) acc[t][j] = fmaf(xf[j], wt[j], acc[t][j]);
+      }
+    }
+  }
+  const long long orow = static_cast<long long>(n) * (cls + Ho * Wo) + cls + static_cast<long long>(oy) * Wo + ox;
+#pragma unroll
+  for (int t = 0; t < NOUT; ++t) {
+    const float* sc = scale + static_cast<long long>(which0 + t) * C + c;
+    const float* sh = shift + static_cast<long long>(which0 + t) * C + c;
+    float of[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) of[j] = fmaf(acc[t][j], sc[j], sh[j]);
+    Vec16<T> ov;
+    ov.pack(of);
+    ov.store((t == 0 ? o0 : o1) + orow * C + c);
+  }
+}
+
+// copy the cls row of y into row 0 of q, k, v
+template <typename T>
+__global__ void copy_cls_kernel(const T* __restrict__ y, T* __restrict__ q, T* __restrict__ k, T* __restrict__ v,
+                                int n_img, int HWq, int HWk, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_img * C) return;
+  const int n = i / C, c = i % C;
+  const T val = y[static_cast<long long>(n) * (1 + HWq) * C + c];
+  q[static_cast<long long>(n) * (1 + HWq) * C + c] = val;
+  k[static_cast<long long>(n) * (1 + HWk) * C + c] = val;
+  v[static_cast<long long>(n) * (1 + HWk) * C + c] = val;
+}
+
+template <typename T>
+__global__ void cat_cls_kernel(const T* __restrict__ tokens, const float* __restrict__ cls_token, T* __restrict__ out,
+                               int n_img, int HW, int C) {
+  const long long total = static_cast<long long>(n_img) * (1 + HW) * C;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const long long r = i / C;
+    const int t = static_cast<int>(r % (1 + HW));
+    const long long n = r / (1 + HW);
+    out[i] = (t == 0) ? from_f<T>(cls_token[c]) : tokens[(n * HW + (t - 1)) * C + c];
+  }
+}
+
+template <typename T>
+__global__ void drop_cls_kernel(const T* __restrict__ in, T* __restrict__ out, int n_img, int HW, int C) {
+  const long long total = static_cast<long long>(n_img) * HW * C;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const long long r = i / C;
+    const int t = static_cast<int>(r % HW);
+    const long long n = r / HW;
+    out[i] = in[(n * (1 + HW) + 1 + t) * C + c];
+  }
+}
+
+template <typename T, bool SCATTER>
+__global__ void move_rows_kernel(const T* __restrict__ src, const int* __restrict__ idx, T* __restrict__ dst,
+                                 long long n_rows, int C) {
+  constexpr int V = Vec16<T>::N;
+  const int cv = C / V;
+  const long long total = n_rows * cv;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % cv) * V;
+    const long long r = i / cv;
+    const int j = idx[r];
+    Vec16<T> v;
+    if (SCATTER) {
+      if (j < 0) continue;
+      v.load(src + r * C + c);
+      v.store(dst + static_cast<long long>(j) * C + c);
+    } else {
+      if (j >= 0) {
+        v.load(src + static_cast<long long>(j) * C + c);
+      } else {
+        float z[V];
+#pragma unroll
+        for (int q = 0; q < V; ++q) z[q] = 0.f;
+        v.pack(z);
+      }
+      v.store(dst + r * C + c);
+    }
+  }
+}
+
+template <typename TS, typename TD>
+__global__ void cast_copy_kernel(const TS* __restrict__ src, TD* __restrict__ dst, long long n) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    dst[i] = from_f<TD>(to_f(src[i]));
+}
+
+__global__ void bn_fold_kernel(const float* gamma, const float* beta, const float* mean, const float* var, float eps,
+                               float* scale, float* shift, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float s = gamma[c] / sqrtf(var[c] + eps);
+  scale[c] = s;
+  shift[c] = beta[c] - mean[c] * s;
+}
+
+__global__ void lora_merge_kernel(float* W, const float* A, const float* B, int n_out, int n_in, int r, float s) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(n_out) * n_in) return;
+  const int o = static_cast<int>(i / n_in), c = static_cast<int>(i % n_in);
+  float d = 0.f;
+  for (int j = 0; j < r; ++j) d = fmaf(B[o * r + j], A[j * n_in + c], d);
+  W[i] += s * d;
+}
+
+template <typename T>
+__global__ void pack_matrix_kernel(const float* src, T* dst, int rows, int cols_src, int cols_dst) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(rows) * cols_dst) return;
+  const int r = static_cast<int>(i / cols_dst), c = static_cast<int>(i % cols_dst);
+  dst[i] = from_f<T>(c < cols_src ? src[static_cast<long long>(r) * cols_src + c] : 0.f);
+}
+
+template <typename T>
+__global__ void pack_conv_khwc_kernel(const float* src, T* dst, int Cout, int Cin, int ksz) {
+  const long long total = static_cast<long long>(Cout) * Cin * ksz * ksz;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  // dst index = ((o*ksz + ky)*ksz + kx)*Cin + c
+  const int c = static_cast<int>(i % Cin);
+  long long r = i / Cin;
+  const int kx = static_cast<int>(r % ksz);
+  r /= ksz;
+  const int ky = static_cast<int>(r % ksz);
+  const int o = static_cast<int>(r / ksz);
+  dst[i] = from_f<T>(src[((static_cast<long long>(o) * Cin + c) * ksz + ky) * ksz + kx]);
+}
+
+__global__ void pack_dw_kernel(const float* src, float* dst, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 9 * C) return;
+  const int tap = i / C, c = i % C;
+  dst[i] = src[c * 9 + tap];
+}
+
+inline unsigned grid_for(long long total, int block, long long cap = 148LL * 32) {
+  long long g = ceil_div_ll(total, block);
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<unsigned>(g);
+}
+
+}  // namespace
+
+template <typename T>
+void layernorm(const T* x, int ldx, T* y, int ldy, const float* gamma, const float* beta, long long rows, int C,
+               float eps, cudaStream_t stream) {
+  if (rows <= 0) return;
+  CXRM_CHECK(C <= kMaxPerLane * kWarp, "layernorm supports C <= 768");
+  const int block = 256;
+  const long long grid = ceil_div_ll(rows * kWarp, block);
+  layernorm_kernel<T><<<static_cast<unsigned>(grid), block, 0, stream>>>(x, ldx, y, ldy, gamma, beta, rows, C, eps);
+  check_launch("layernorm");
+}
+
+template <typename T>
+void embed_ln(const int* ids, const int* types, const int* pos, const T* word, const T* type_emb, const T* pos_emb,
+              const float* gamma, const float* beta, T* out, long long rows, int C, float eps, cudaStream_t stream) {
+  if (rows <= 0) return;
+  CXRM_CHECK(C <= kMaxPerLane * kWarp, "embed_ln supports C <= 768");
+  const int block = 256;
+  const long long grid = ceil_div_ll(rows * kWarp, block);
+  embed_ln_kernel<T><<<static_cast<unsigned>(grid), block, 0, stream>>>(ids, types, pos, word, type_emb, pos_emb, gamma,
+                                                                        beta, out, rows, C, eps);
+  check_launch("embed_ln");
+}
+
+template <typename T>
+void im2col_pixels(const float* pixels, const int* img_idx, T* out, int n_img, int H, int W, int ksz, int stride,
+                   int pad, int Kpad, cudaStream_t stream) {
+  const int Ho = (H + 2 * pad - ksz) / stride + 1, Wo = (W + 2 * pad - ksz) / stride + 1;
+  const long long total = static_cast<long long>(n_img) * Ho * Wo * Kpad;
+  if (total <= 0) return;
+  im2col_pixels_kernel<T><<<grid_for(total, 256), 256, 0, stream>>>(pixels, img_idx, out, n_img, H, W, Ho, Wo, ksz,
+                                                                    stride, pad, Kpad);
+  check_launch("im2col_pixels");
+}
+
+template <typename T>
+void im2col_tokens(const T* in, T* out, int n_img, int H, int W, int C, int ksz, int stride, int pad,
+                   cudaStream_t stream) {
+  const int Ho = (H + 2 * pad - ksz) / stride + 1, Wo = (W + 2 * pad - ksz) / stride + 1;
+  CXRM_CHECK(C % Vec16<T>::N == 0, "im2col_tokens needs C multiple of the vector width");
+  const long long total = static_cast<long long>(n_img) * Ho * Wo * ksz * ksz * (C / Vec16<T>::N);
+  if (total <= 0) return;
+  im2col_tokens_kernel<T><<<grid_for(total, 256), 256, 0, stream>>>(in, out, n_img, H, W, C, Ho, Wo, ksz, stride, pad);
+  check_launch("im2col_tokens");
+}
+
+template <typename T>
+void dwconv_bn_qkv(const T* y, T* q, T* k, T* v, const float* w, const float* scale, const float* shift, int n_img,
+                   int H, int W, int C, int cls, cudaStream_t stream) {
+  if (n_img <= 0) return;
+  constexpr int V = Vec16<T>::N;
+  CXRM_CHECK(C % V == 0, "dwconv needs C multiple of the vector width");
+  const int Hk = (H + 2 - 3) / 2 + 1, Wk = (W + 2 - 3) / 2 + 1;
+  {
+    const long long total = static_cast<long long>(n_img) * H * W * (C / V);
+    dwconv_bn_kernel<T, 1><<<static_cast<unsigned>(ceil_div_ll(total, 256)), 256, 0, stream>>>(
+        y, q, nullptr, w, scale, shift, n_img, H, W, C, cls, 1, H, W, 0);
+    check_launch("dwconv_q");
+  }
+  {
+    const long long total = static_cast<long long>(n_img) * Hk * Wk * (C / V);
+    dwconv_bn_kernel<T, 2><<<static_cast<unsigned>(ceil_div_ll(total, 256)), 256, 0, stream>>>(
+        y, k, v, w, scale, shift, n_img, H, W, C, cls, 2, Hk, Wk, 1);
+    check_launch("dwconv_kv");
+  }
+  if (cls) {
+    copy_cls_kernel<T><<<ceil_div(n_img * C, 256), 256, 0, stream>>>(y, q, k, v, n_img, H * W, Hk * Wk, C);
+    check_launch("copy_cls");
+  }
+}
+
+template <typename T>
+void cat_cls(const T* tokens, const float* cls_token, T* out, int n_img, int HW, int C, cudaStream_t stream) {
+  const long long total = static_cast<long long>(n_img) * (1 + HW) * C;
+  if (total <= 0) return;
+  cat_cls_kernel<T><<<grid_for(total, 256), 256, 0, stream>>>(tokens, cls_token, out, n_img, HW, C);
+  check_launch("cat_cls");
+}
+
+template <typename T>
+void drop_cls(const T* in, T* out, int n_img, int HW, int C, cudaStream_t stream) {
+  const long long total = static_cast<long long>(n_img) * HW * C;
+  if (total <= 0) return;
+  drop_cls_kernel<T><<<grid_for(total, 256), 256, 0, stream>>>(in, out, n_img, HW, C);
+  check_launch("drop_cls");
+}
+
+template <typename T>
+void gather_rows(const T* src, const int* idx, T* dst, long long n_rows, int C, cudaStream_t stream) {
+  if (n_rows <= 0) return;
+  CXRM_CHECK(C % Vec16<T>::N == 0, "gather_rows needs C multiple of the vector width");
+  move_rows_kernel<T, false><<<grid_for(n_rows * (C / Vec16<T>::N), 256), 256, 0, stream>>>(src, idx, dst, n_rows, C);
+  check_launch("gather_rows");
+}
+
+template <typename T>
+void scatter_rows(const T* src, const int* idx, T* dst, long long n_rows, int C, cudaStream_t stream) {
+  if (n_rows <= 0) return;
+  CXRM_CHECK(C % Vec16<T>::N == 0, "scatter_rows needs C multiple of the vector width");
+  move_rows_kernel<T, true><<<grid_for(n_rows * (C / Vec16<T>::N), 256), 256, 0, stream>>>(src, idx, dst, n_rows, C);
+  check_launch("scatter_rows");
+}
+
+template <typename TS, typename TD>
+void cast_copy(const TS* src, TD* dst, long long n, cudaStream_t stream) {
+  if (n <= 0) return;
+  cast_copy_kernel<TS, TD><<<grid_for(n, 256), 256, 0, stream>>>(src, dst, n);
+  check_launch("cast_copy");
+}
+
+void fill_zero(void* p, size_t bytes, cudaStream_t stream) { CXRM_CUDA_CHECK(cudaMemsetAsync(p, 0, bytes, stream)); }
+
+void bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, float eps, float* scale,
+             float* shift, int C, cudaStream_t stream) {
+  bn_fold_kernel<<<ceil_div(C, 128), 128, 0, stream>>>(gamma, beta, mean, var, eps, scale, shift, C);
+  check_launch("bn_fold");
+}
+
+void lora_merge(float* W, const float* A, const float* B, int n_out, int n_in, int r, float s, cudaStream_t stream) {
+  const long long total = static_cast<long long>(n_out) * n_in;
+  lora_merge_kernel<<<static_cast<unsigned>(ceil_div_ll(total, 256)), 256, 0, stream>>>(W, A, B, n_out, n_in, r, s);
+  check_launch("lora_merge");
+}
+
+template <typename T>
+void pack_matrix(const float* src, T* dst, int rows, int cols_src, int cols_dst, cudaStream_t stream) {
+  const long long total = static_cast<long long>(rows) * cols_dst;
+  if (total <= 0) return;
+  pack_matrix_kernel<T><<<static_cast<unsigned>(ceil_div_ll(total, 256)), 256, 0, stream>>>(src, dst, rows, cols_src,
+                                                                                          cols_dst);
+  check_launch("pack_matrix");
+}
+
+template <typename T>
+void pack_conv_khwc(const float* src, T* dst, int Cout, int Cin, int ksz, cudaStream_t stream) {
+  const long long total = static_cast<long long>(Cout) * Cin * ksz * ksz;
+  pack_conv_khwc_kernel<T><<<static_cast<unsigned>(ceil_div_ll(total, 256)), 256, 0, stream>>>(src, dst, Cout, Cin, ksz);
+  check_launch("pack_conv_khwc");
+}
+
+void pack_dw(const float* src, float* dst, int C, cudaStream_t stream) {
+  pack_dw_kernel<<<ceil_div(9 * C, 256), 256, 0, stream>>>(src, dst, C);
+  check_launch("pack_dw");
+}
+
+#define INST(T)                                                                                                      \
+  template void layernorm<T>(const T*, int, T*, int, const float*, const float*, long long, int, float, cudaStream_t); \
+  template void embed_ln<T>(const int*, const int*, const int*, const T*, const T*, const T*, const float*,           \
+                            const float*, T*, long long, int, float, cudaStream_t);                                   \
+  template void im2col_pixels<T>(const float*, const int*, T*, int, int, int, int, int, int, int, cudaStream_t);      \
+  template void im2col_tokens<T>(const T*, T*, int, int, int, int, int, int, int, cudaStream_t);                      \
+  template void dwconv_bn_qkv<T>(const T*, T*, T*, T*, const float*, const float*, const float*, int, int, int, int,  \
+                                 int, cudaStream_t);                                                                  \
+  template void cat_cls<T>(const T*, const float*, T*, int, int, int, cudaStream_t);                                  \
+  template void drop_cls<T>(const T*, T*, int, int, int, cudaStream_t);                                               \
+  template void gather_rows<T>(const T*, const int*, T*, long long, int, cudaStream_t);                               \
+  template void scatter_rows<T>(const T*, const int*, T*, long long, int, cudaStream_t);                              \
+  template void pack_matrix<T>(const float*, T*, int, int, int, cudaStream_t);                                        \
+  template void pack_conv_khwc<T>(const float*, T*, int, int, int, cudaStream_t);
+INST(float)
+INST(bf16)
+#undef INST
+template void cast_copy<float, float>(const float*, float*, long long, cudaStream_t);
+template void cast_copy<float, bf16>(const float*, bf16*, long long, cudaStream_t);
+template void cast_copy<bf16, float>(const bf16*, float*, long long, cudaStream_t);
+template void cast_copy<bf16, bf16>(const bf16*, bf16*, long long, cudaStream_t);
+
+}  // namespace cxrm

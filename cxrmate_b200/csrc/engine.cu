@@ -1,0 +1,988 @@
+// Engine implementation: weight packing, CvT-21 encoder, cross-K/V prefill,
+// KV-cached rollout (prefill + decode steps), teacher-forced forward, CXR-BERT
+// reward, and the host-buffer SCST step.  Templated on the storage type
+// (float = fp32 validation mode, bf16 = tensor-core mode).
+#include "engine.cuh"
+
+#include <algorithm>
+#include <cstring>
+
+namespace cxrm {
+
+unsigned long long g_launch_count = 0;
+
+// ---- Arena --------------------------------------------------------------------
+void Arena::init(size_t bytes) {
+  release();
+  CXRM_CUDA_CHECK(cudaMalloc(&base_, bytes));
+  cap_ = bytes;
+  off_ = 0;
+}
+void Arena::release() {
+  if (base_) cudaFree(base_);
+  base_ = nullptr;
+  cap_ = off_ = 0;
+}
+void* Arena::alloc(size_t bytes) {
+  const size_t a = (off_ + 255) & ~static_cast<size_t>(255);
+  if (a + bytes > cap_)
+    throw std::runtime_error("engine scratch arena exhausted: need " + std::to_string(a + bytes) + " of " +
+                             std::to_string(cap_) + " bytes (raise the cxrm_config maxima)");
+  off_ = a + bytes;
+  return base_ + a;
+}
+
+namespace {
+
+constexpr int DH = 768, DFF = 3072, NHEAD = 12;
+constexpr int CVT_C[3] = {64, 192, 384};
+constexpr int CVT_HEADS[3] = {1, 3, 6};
+constexpr int CVT_K[3] = {7, 3, 3};
+constexpr int CVT_S[3] = {4, 2, 2};
+constexpr int CVT_P[3] = {2, 1, 1};
+constexpr float LN_EPS_CVT = 1e-5f, BN_EPS = 1e-5f, LN_EPS_BERT = 1e-12f;
+constexpr float LORA_SCALE = 32.0f / 8.0f;   // lora_alpha / r (modelling_longitudinal.py:165-166)
+
+// ---- small device helpers local to the engine ------------------------------------
+__global__ void valid_images_kernel(const float* pixels, uint8_t* valid, int n, long long img_stride) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) valid[i] = pixels[i * img_stride] != 0.0f ? 1 : 0;   // pixel_values[:, :, 0, 0, 0] != 0.0
+}
+__global__ void expand_mask_kernel(const uint8_t* valid, uint8_t* mask, int n_img, int T) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < static_cast<long long>(n_img) * T) mask[i] = valid[i / T];
+}
+// per study: number of visible encoder tokens
+__global__ void count_mask_kernel(const uint8_t* mask, int* len, int B, int S) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  int c = 0;
+  if (mask)
+    for (int j = 0; j < S; ++j) c += mask[static_cast<long long>(b) * S + j] ? 1 : 0;
+  else
+    c = S;
+  len[b] = c;
+}
+// compact row list: idx[off[b] + k] = b*S + (k-th visible token of study b)
+__global__ void compact_rows_kernel(const uint8_t* mask, const int* off, int* idx, int B, int S) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  int k = off[b];
+  for (int j = 0; j < S; ++j)
+    if (!mask || mask[static_cast<long long>(b) * S + j]) idx[k++] = b * S + j;
+}
+__global__ void iota_pos_kernel(int* pos, int n, int L) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < static_cast<long long>(n) * L) pos[i] = static_cast<int>(i % L);
+}
+
+// Device-side id bridge standing in for split_and_decode_sections + re-tokenisation
+// (reference modelling_longitudinal.py:413-457, tools/rewards/cxrbert.py:33-40).
+__global__ void bridge_ids_kernel(const int* __restrict__ seq, int ld_seq, int L, int R, int bos, int sep, int eos,
+                                  int n_special_vocab, const int* __restrict__ id_map, int cls_id, int sep_id,
+                                  int* __restrict__ out_ids, int* __restrict__ out_len, int Lout) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  const int* row = seq + static_cast<long long>(r) * ld_seq;
+  const int specials[3] = {bos, sep, eos};
+  int lo[3], hi[3];
+  int prev = 0;
+  for (int j = 0; j < 3; ++j) {
+    if (prev >= L) {
+      lo[j] = hi[j] = 0;
+      continue;
+    }
+    int col = 0;
+    for (int c = 0; c < L; ++c)
+      if (row[c] == specials[j]) {
+        col = c;
+        break;
+      }
+    if (col == 0) col = L;
+    lo[j] = prev;
+    hi[j] = col;
+    prev = col;
+  }
+  int* out = out_ids + static_cast<long long>(r) * Lout;
+  int n = 0;
+  out[n++] = cls_id;
+  for (int j = 1; j < 3; ++j)
+    for (int c = lo[j]; c < hi[j]; ++c) {
+      const int id = row[c];
+      if (id < n_special_vocab) continue;     // skip_special_tokens=True
+      if (n < Lout - 1) out[n++] = id_map[id];
+    }
+  out[n++] = sep_id;
+  out_len[r] = n;
+  for (int c = n; c < Lout; ++c) out[c] = 0;
+}
+__global__ void advantage_kernel(const float* r, const float* b, float* adv, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) adv[i] = r[i] - b[i];
+}
+
+template <typename T>
+class Engine : public EngineBase {
+ public:
+  Engine(const cxrm_config& c, int dev) : cfg(c), device(dev) { setup(); }
+  ~Engine() override {
+    for (void* p : owned) cudaFree(p);
+    for (auto& kv : raw) cudaFree(kv.second.data);
+    arena.release();
+    if (graph_exec) cudaGraphExecDestroy(graph_exec);
+    if (side_stream) cudaStreamDestroy(side_stream);
+  }
+
+  // =========================================================================== weights
+  void load_weight(const std::string& name, const float* data, const int64_t* shape, int ndim,
+                   bool on_device) override {
+    RawTensor t;
+    t.shape.assign(shape, shape + ndim);
+    const long long n = std::max<long long>(t.numel(), 1);
+    auto it = raw.find(name);
+    if (it != raw.end()) {
+      cudaFree(it->second.data);
+      raw.erase(it);
+    }
+    CXRM_CUDA_CHECK(cudaMalloc(&t.data, n * sizeof(float)));
+    CXRM_CUDA_CHECK(cudaMemcpy(t.data, data, n * sizeof(float), on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+    raw[name] = t;
+    finalized = false;
+  }
+
+  const RawTensor& need(const std::string& name, std::initializer_list<int64_t> shape) {
+    auto it = raw.find(name);
+    if (it == raw.end()) throw std::runtime_error("missing weight: " + name);
+    std::vector<int64_t> want(shape);
+    if (it->second.shape != want) {
+      std::string got;
+      for (auto s : it->second.shape) got += std::to_string(s) + ",";
+      throw std::runtime_error("weight " + name + " has shape [" + got + "]");
+    }
+    return it->second;
+  }
+  bool has(const std::string& name) const { return raw.count(name) != 0; }
+
+  template <typename U> U* dalloc(long long n) {
+    void* p = nullptr;
+    CXRM_CUDA_CHECK(cudaMalloc(&p, std::max<long long>(n, 1) * sizeof(U)));
+    owned.push_back(p);
+    persistent_bytes += n * sizeof(U);
+    return static_cast<U*>(p);
+  }
+  float* vecf(const std::string& name, int n) {
+    const RawTensor& t = need(name, {n});
+    float* d = dalloc<float>(n);
+    CXRM_CUDA_CHECK(cudaMemcpyAsync(d, t.data, n * sizeof(float), cudaMemcpyDeviceToDevice, 0));
+    return d;
+  }
+  struct Lin { T* w = nullptr; float* b = nullptr; int n_out = 0, n_in = 0; };
+  struct LNp { float* g = nullptr; float* b = nullptr; };
+  LNp lnp(const std::string& prefix, int n) { return LNp{vecf(prefix + ".weight", n), vecf(prefix + ".bias", n)}; }
+  Lin lin(const std::string& prefix, int n_out, int n_in, bool bias = true) {
+    Lin L;
+    L.n_out = n_out;
+    L.n_in = n_in;
+    const RawTensor& w = need(prefix + ".weight", {n_out, n_in});
+    L.w = dalloc<T>(static_cast<long long>(n_out) * n_in);
+    pack_matrix<T>(w.data, L.w, n_out, n_in, n_in, 0);
+    if (bias) L.b = vecf(prefix + ".bias", n_out);
+    return L;
+  }
+  // rows of several [n_i, n_in] matrices stacked into one [sum n_i, n_in]; optional LoRA merge on each part
+  Lin lin_cat(const std::vector<std::string>& prefixes, int n_each, int n_in) {
+    Lin L;
+    L.n_out = n_each * static_cast<int>(prefixes.size());
+    L.n_in = n_in;
+    L.w = dalloc<T>(static_cast<long long>(L.n_out) * n_in);
+    L.b = dalloc<float>(L.n_out);
+    float* tmp = nullptr;
+    CXRM_CUDA_CHECK(cudaMalloc(&tmp, static_cast<size_t>(n_each) * n_in * sizeof(float)));
+    for (size_t i = 0; i < prefixes.size(); ++i) {
+      const std::string& p = prefixes[i];
+      const RawTensor& w = need(p + ".weight", {n_each, n_in});
+      const RawTensor& b = need(p + ".bias", {n_each});
+      CXRM_CUDA_CHECK(cudaMemcpyAsync(tmp, w.data, static_cast<size_t>(n_each) * n_in * sizeof(float), cudaMemcpyDeviceToDevice, 0));
+      if (has(p + ".lora_A.weight")) {
+        const RawTensor& A = raw.at(p + ".lora_A.weight");
+        const RawTensor& Bm = raw.at(p + ".lora_B.weight");
+        CXRM_CHECK(A.shape.size() == 2 && A.shape[1] == n_in && Bm.shape.size() == 2 && Bm.shape[0] == n_each &&
+                       Bm.shape[1] == A.shape[0], "LoRA shapes");
+        lora_merge(tmp, A.data, Bm.data, n_each, n_in, static_cast<int>(A.shape[0]), LORA_SCALE, 0);
+      }
+      pack_matrix<T>(tmp, L.w + static_cast<long long>(i) * n_each * n_in, n_each, n_in, n_in, 0);
+      CXRM_CUDA_CHECK(cudaMemcpyAsync(L.b + i * n_each, b.data, n_each * sizeof(float), cudaMemcpyDeviceToDevice, 0));
+    }
+    CXRM_CUDA_CHECK(cudaStreamSynchronize(0));
+    cudaFree(tmp);
+    return L;
+  }
+
+  struct CvtLayerW { LNp ln1, ln2; float* dw; float* bn_scale; float* bn_shift; Lin q, k, v, o, fc1, fc2; };
+  struct CvtStageW { Lin emb; LNp emb_ln; std::vector<CvtLayerW> layers; };
+  struct BertLayerW { Lin qkv, o; LNp ln1; Lin cq, ckv, co; LNp ln2; Lin fc1, fc2; LNp ln3; };
+  struct BertW { T* word = nullptr; T* pos = nullptr; T* type = nullptr; LNp emb_ln; std::vector<BertLayerW> layers; int vocab = 0; };
+
+  T* table(const std::string& name, int rows, int cols) {
+    const RawTensor& w = need(name, {rows, cols});
+    T* d = dalloc<T>(static_cast<long long>(rows) * cols);
+    pack_matrix<T>(w.data, d, rows, cols, cols, 0);
+    return d;
+  }
+
+  void load_bert(BertW& bw, const std::string& pre, int layers, int vocab, bool cross) {
+    bw.vocab = vocab;
+    bw.word = table(pre + "embeddings.word_embeddings.weight", vocab, DH);
+    bw.pos = table(pre + "embeddings.position_embeddings.weight", 512, DH);
+    bw.type = table(pre + "embeddings.token_type_embeddings.weight", 2, DH);
+    bw.emb_ln = lnp(pre + "embeddings.LayerNorm", DH);
+    bw.layers.resize(layers);
+    for (int l = 0; l < layers; ++l) {
+      const std::string p = pre + "encoder.layer." + std::to_string(l) + ".";
+      BertLayerW& w = bw.layers[l];
+      w.qkv = lin_cat({p + "attention.self.query", p + "attention.self.key", p + "attention.self.value"}, DH, DH);
+      w.o = lin(p + "attention.output.dense", DH, DH);
+      w.ln1 = lnp(p + "attention.output.LayerNorm", DH);
+      if (cross) {
+        w.cq = lin(p + "crossattention.self.query", DH, DH);
+        w.ckv = lin_cat({p + "crossattention.self.key", p + "crossattention.self.value"}, DH, DH);
+        w.co = lin(p + "crossattention.output.dense", DH, DH);
+        w.ln2 = lnp(p + "crossattention.output.LayerNorm", DH);
+      }
+      w.fc1 = lin(p + "intermediate.dense", DFF, DH);
+      w.fc2 = lin(p + "output.dense", DH, DFF);
+      w.ln3 = lnp(p + "output.LayerNorm", DH);
+    }
+  }
+
+  void finalize_weights() override {
+    CXRM_CUDA_CHECK(cudaSetDevice(device));
+    // ---- encoder ----
+    int cin = 3;
+    for (int s = 0; s < 3; ++s) {
+      const int C = CVT_C[s], k = CVT_K[s];
+      const std::string p = "encoder.cvt.encoder.stages." + std::to_string(s) + ".";
+      CvtStageW& st = stages[s];
+      const RawTensor& w = need(p + "embedding.convolution_embeddings.projection.weight", {C, cin, k, k});
+      const int K = cin * k * k;
+      const int Kpad = (K + 7) / 8 * 8;
+      st.emb.n_out = C;
+      st.emb.n_in = Kpad;
+      st.emb.w = dalloc<T>(static_cast<long long>(C) * Kpad);
+      if (s == 0) {
+        pack_matrix<T>(w.data, st.emb.w, C, K, Kpad, 0);          // K order (cin, ky, kx), zero padded
+      } else {
+        pack_conv_khwc<T>(w.data, st.emb.w, C, cin, k, 0);        // K order (ky, kx, cin)
+      }
+      st.emb.b = vecf(p + "embedding.convolution_embeddings.projection.bias", C);
+      st.emb_ln = lnp(p + "embedding.convolution_embeddings.normalization", C);
+      st.layers.resize(cfg.cvt_depth[s]);
+      for (int i = 0; i < cfg.cvt_depth[s]; ++i) {
+        const std::string q = p + "layers." + std::to_string(i) + ".";
+        CvtLayerW& L = st.layers[i];
+        L.ln1 = lnp(q + "layernorm_before", C);
+        L.ln2 = lnp(q + "layernorm_after", C);
+        L.dw = dalloc<float>(3LL * 9 * C);
+        L.bn_scale = dalloc<float>(3LL * C);
+        L.bn_shift = dalloc<float>(3LL * C);
+        const char* names[3] = {"query", "key", "value"};
+        for (int j = 0; j < 3; ++j) {
+          const std::string cp = q + "attention.attention.convolution_projection_" + names[j] + ".convolution_projection.";
+          pack_dw(need(cp + "convolution.weight", {C, 1, 3, 3}).data, L.dw + static_cast<long long>(j) * 9 * C, C, 0);
+          bn_fold(need(cp + "normalization.weight", {C}).data, need(cp + "normalization.bias", {C}).data,
+                  need(cp + "normalization.running_mean", {C}).data, need(cp + "normalization.running_var", {C}).data,
+                  BN_EPS, L.bn_scale + j * C, L.bn_shift + j * C, C, 0);
+        }
+        L.q = lin(q + "attention.attention.projection_query", C, C);
+        L.k = lin(q + "attention.attention.projection_key", C, C);
+        L.v = lin(q + "attention.attention.projection_value", C, C);
+        L.o = lin(q + "attention.output.dense", C, C);
+        L.fc1 = lin(q + "intermediate.dense", 4 * C, C);
+        L.fc2 = lin(q + "output.dense", C, 4 * C);
+      }
+      cin = C;
+    }
+    {
+      const RawTensor& c = need("encoder.cvt.encoder.stages.2.cls_token", {1, 1, CVT_C[2]});
+      cls_token = dalloc<float>(CVT_C[2]);
+      CXRM_CUDA_CHECK(cudaMemcpyAsync(cls_token, c.data, CVT_C[2] * sizeof(float), cudaMemcpyDeviceToDevice, 0));
+    }
+    head_ln = lnp("encoder.projection_head.layer_norm", CVT_C[2]);
+    head_proj = lin("encoder.projection_head.projection", DH, CVT_C[2], /*bias=*/false);
+    // ---- decoder ----
+    load_bert(dec, "decoder.bert.", cfg.dec_layers, cfg.vocab, true);
+    dec_head_t = lin("decoder.cls.predictions.transform.dense", DH, DH);
+    dec_head_ln = lnp("decoder.cls.predictions.transform.LayerNorm", DH);
+    dec_vocab_bias = vecf("decoder.cls.predictions.bias", cfg.vocab);
+    dec_lm.w = dec.word;            // tied LM head (SURVEY.md finding 3)
+    dec_lm.b = dec_vocab_bias;
+    dec_lm.n_out = cfg.vocab;
+    dec_lm.n_in = DH;
+    // ---- reward model ----
+    if (cfg.rwd_layers > 0 && has("reward.bert.embeddings.word_embeddings.weight")) {
+      load_bert(rwd, "reward.bert.", cfg.rwd_layers, cfg.rwd_vocab, false);
+      rp1 = lin("reward.cls_projection_head.dense_to_hidden", 128, DH);
+      rp_ln = lnp("reward.cls_projection_head.LayerNorm", 128);
+      rp2 = lin("reward.cls_projection_head.dense_to_output", 128, 128);
+      have_reward = true;
+    }
+    CXRM_CUDA_CHECK(cudaDeviceSynchronize());
+    for (auto& kv : raw) cudaFree(kv.second.data);
+    raw.clear();
+    finalized = true;
+  }
+
+  // =========================================================================== set-up
+  void setup() {
+    CXRM_CUDA_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CXRM_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    CXRM_CHECK(prop.major == 10, "this engine is built for sm_100a (B200) only; found sm_" +
+                                     std::to_string(prop.major) + std::to_string(prop.minor));
+    CXRM_CHECK(cfg.image_h % 16 == 0 && cfg.image_w % 16 == 0, "image size must be a multiple of 16");
+    CXRM_CHECK(cfg.max_prompt + cfg.max_new_tokens <= 512, "prompt + new tokens must fit 512 positions");
+    if (cfg.enc_chunk <= 0) cfg.enc_chunk = 32;
+    T2 = (cfg.image_h / 16) * (cfg.image_w / 16);
+    Smax = cfg.max_images * T2;
+    Rmax = 2 * cfg.max_studies;
+    Lmax = cfg.max_prompt + cfg.max_new_tokens;
+    const long long B = cfg.max_studies;
+    // persistent buffers
+    memory = dalloc<T>(B * Smax * DH);
+    mem_mask = dalloc<uint8_t>(B * Smax);
+    mem_compact = dalloc<T>(B * Smax * DH);
+    compact_idx = dalloc<int>(B * Smax);
+    kv_off = dalloc<int>(B);
+    kv_len = dalloc<int>(B);
+    cross_kv = dalloc<T>(static_cast<long long>(cfg.dec_layers) * B * Smax * 2 * DH);
+    self_k = dalloc<T>(static_cast<long long>(cfg.dec_layers) * Rmax * Lmax * DH);
+    self_v = dalloc<T>(static_cast<long long>(cfg.dec_layers) * Rmax * Lmax * DH);
+    logits = dalloc<float>(static_cast<long long>(Rmax) * cfg.vocab);
+    valid_img = dalloc<uint8_t>(B * cfg.max_images);
+    img_idx = dalloc<int>(B * cfg.max_images);
+    // rollout state
+    st.cur_token = dalloc<int>(Rmax);
+    st.cur_len = dalloc<int>(Rmax);
+    st.cur_type = dalloc<int>(Rmax);
+    st.cur_pos = dalloc<int>(Rmax);
+    st.n_valid = dalloc<int>(Rmax);
+    st.seen = dalloc<unsigned>(Rmax);
+    st.finished = dalloc<uint8_t>(Rmax);
+    st.key_valid = dalloc<uint8_t>(static_cast<long long>(Rmax) * Lmax);
+    st.seq = dalloc<int>(static_cast<long long>(Rmax) * Lmax);
+    st.logprob = dalloc<float>(static_cast<long long>(Rmax) * cfg.max_new_tokens);
+    st.margin = dalloc<float>(static_cast<long long>(Rmax) * cfg.max_new_tokens);
+    st.topk_idx = dalloc<int>(static_cast<long long>(Rmax) * cfg.max_new_tokens * kTopKCap);
+    st.topk_val = dalloc<float>(static_cast<long long>(Rmax) * cfg.max_new_tokens * kTopKCap);
+    st.topk_cnt = dalloc<int>(static_cast<long long>(Rmax) * cfg.max_new_tokens);
+    st.step = dalloc<int>(1);
+    st.done = dalloc<int>(1);
+    st.arrive = dalloc<unsigned>(1);
+    pre_ids = dalloc<int>(static_cast<long long>(Rmax) * cfg.max_prompt);
+    pre_types = dalloc<int>(static_cast<long long>(Rmax) * cfg.max_prompt);
+    pre_pos = dalloc<int>(static_cast<long long>(Rmax) * cfg.max_prompt);
+    prompt_dev = dalloc<int>(B * cfg.max_prompt);
+    cross_nsplit = 1;
+    cross_ws = dalloc<float>(static_cast<long long>(decode_cross_ws_bytes(Rmax, 64) / sizeof(float)));
+
+    // scratch arena: max over the phases
+    const long long e = sizeof(T);
+    const long long H0 = cfg.image_h / 4, W0 = cfg.image_w / 4;
+    const long long tok0 = H0 * W0;
+    const long long nimg = cfg.enc_chunk;
+    const long long big = nimg * tok0 * 64 + nimg * 384 * 2;            // mirrors encode_chunk()
+    const long long enc_elems = 5 * big + 4 * (big / 4 + nimg * 384) + std::max<long long>(nimg * tok0 * 152, 4 * big);
+    const long long enc_bytes = enc_elems * e + (1 << 20);
+    const long long dec_tok = static_cast<long long>(Rmax) * std::max(cfg.max_prompt, 1);
+    const long long per_tok = (4LL * DH + 3 * DH + DFF) * e + 64;
+    const long long dec_bytes = (dec_tok + 4LL * Rmax) * per_tok + (1 << 20);
+    const long long rwd_tok = static_cast<long long>(std::max(cfg.rwd_max_seqs, 1)) * cfg.rwd_max_len;
+    const long long rwd_bytes = cfg.rwd_layers > 0 ? rwd_tok * (per_tok + 16) + (1 << 22) : 0;
+    arena.init(static_cast<size_t>(std::max({enc_bytes, dec_bytes, rwd_bytes})) + (8 << 20));
+    CXRM_CUDA_CHECK(cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking));
+    CXRM_CUDA_CHECK(cudaEventCreateWithFlags(&ev_a, cudaEventDisableTiming));
+    CXRM_CUDA_CHECK(cudaEventCreateWithFlags(&ev_b, cudaEventDisableTiming));
+    std::memset(&graph_key, 0, sizeof(graph_key));
+  }
+  size_t workspace_bytes() const override { return arena.capacity() + static_cast<size_t>(persistent_bytes); }
+
+  // =========================================================================== GEMM dispatch
+  void gemm(const T* A, int lda, const Lin& L, void* C, int ldc, long long M, int act, const T* residual, int ldr,
+            bool out_f32, const int* skip, cudaStream_t s) {
+    GemmArgs g;
+    g.A = A; g.lda = lda; g.W = L.w; g.ldw = L.n_in; g.C = C; g.ldc = ldc;
+    g.M = static_cast<int>(M); g.N = L.n_out; g.K = L.n_in;
+    g.bias = L.b; g.act = act; g.residual = residual; g.ldr = ldr; g.out_f32 = out_f32 ? 1 : 0; g.skip_flag = skip;
+    dispatch_gemm(g, s);
+  }
+  void dispatch_gemm(const GemmArgs& g, cudaStream_t s);
+
+  // =========================================================================== encoder
+  // n images (indices img_idx_dev into `pixels`) -> proj [n*T2, 768] in the arena
+  T* encode_chunk(const float* pixels, const int* idx_dev, int n, cudaStream_t s) {
+    arena.reset();
+    int H = cfg.image_h, W = cfg.image_w;
+    const long long tok0 = static_cast<long long>(H / 4) * (W / 4);
+    const long long nt = static_cast<long long>(n) * tok0;   // largest token count (stage 1)
+    // buffers sized for stage 1 (tokens*C is largest there: tok0*64 >= tok0/4*192 >= (tok0/16+1)*384 holds for tok0 >= 16)
+    const long long big = nt * 64 + static_cast<long long>(n) * 384 * 2;
+    T* x = arena.get<T>(big);
+    T* x2 = arena.get<T>(big);
+    T* y = arena.get<T>(big);
+    T* q = arena.get<T>(big);
+    T* qp = arena.get<T>(big);
+    T* k = arena.get<T>(big / 4 + n * 384);
+    T* v = arena.get<T>(big / 4 + n * 384);
+    T* kp = arena.get<T>(big / 4 + n * 384);
+    T* vp = arena.get<T>(big / 4 + n * 384);
+    const long long hid_elems = std::max<long long>(nt * 152, 4 * big);
+    T* hid = arena.get<T>(hid_elems);   // im2col buffer and MLP hidden share storage
+    T* prev = nullptr;                  // previous stage's tokens [n, Hp*Wp, Cp]
+    int Hp = 0, Wp = 0;
+    for (int s_ = 0; s_ < 3; ++s_) {
+      const CvtStageW& sw = stages[s_];
+      const int C = CVT_C[s_], ks = CVT_K[s_], sd = CVT_S[s_], pd = CVT_P[s_];
+      int Ho, Wo;
+      if (s_ == 0) {
+        Ho = (H + 2 * pd - ks) / sd + 1;
+        Wo = (W + 2 * pd - ks) / sd + 1;
+        im2col_pixels<T>(pixels, idx_dev, hid, n, H, W, ks, sd, pd, sw.emb.n_in, s);
+      } else {
+        Ho = (Hp + 2 * pd - ks) / sd + 1;
+        Wo = (Wp + 2 * pd - ks) / sd + 1;
+        im2col_tokens<T>(prev, hid, n, Hp, Wp, CVT_C[s_ - 1], ks, sd, pd, s);
+      }
+      const long long rows = static_cast<long long>(n) * Ho * Wo;
+      const int cls = (s_ == 2) ? 1 : 0;
+      T* emb_out = cls ? x2 : x;
+      gemm(hid, sw.emb.n_in, sw.emb, emb_out, C, rows, ACT_NONE, nullptr, 0, false, nullptr, s);
+      layernorm<T>(emb_out, C, emb_out, C, sw.emb_ln.g, sw.emb_ln.b, rows, C, LN_EPS_CVT, s);
+      if (cls) cat_cls<T>(x2, cls_token, x, n, Ho * Wo, C, s);
+      const int Tq = cls + Ho * Wo;
+      const int Hk = (Ho + 2 - 3) / 2 + 1, Wk = (Wo + 2 - 3) / 2 + 1;
+      const int Tk = cls + Hk * Wk;
+      const long long rq = static_cast<long long>(n) * Tq, rk = static_cast<long long>(n) * Tk;
+      for (const CvtLayerW& L : sw.layers) {
+        layernorm<T>(x, C, y, C, L.ln1.g, L.ln1.b, rq, C, LN_EPS_CVT, s);
+        dwconv_bn_qkv<T>(y, q, k, v, L.dw, L.bn_scale, L.bn_shift, n, Ho, Wo, C, cls, s);
+        gemm(q, C, L.q, qp, C, rq, ACT_NONE, nullptr, 0, false, nullptr, s);
+        gemm(k, C, L.k, kp, C, rk, ACT_NONE, nullptr, 0, false, nullptr, s);
+        gemm(v, C, L.v, vp, C, rk, ACT_NONE, nullptr, 0, false, nullptr, s);
+        AttnArgs a{};
+        a.q = qp; a.k = kp; a.v = vp; a.o = q;     // context reuses the q buffer
+        a.q_bs = static_cast<long long>(Tq) * C; a.q_hs = 64; a.q_ts = C;
+        a.k_bs = static_cast<long long>(Tk) * C; a.k_hs = 64; a.k_ts = C;
+        a.v_bs = a.k_bs; a.v_hs = 64; a.v_ts = C;
+        a.o_bs = a.q_bs; a.o_hs = 64; a.o_ts = C;
+        a.batch = n; a.heads = CVT_HEADS[s_]; a.Lq = Tq; a.Lk = Tk;
+        a.scale = 1.0f / sqrtf(static_cast<float>(C));   // embed_dim ** -0.5 (modeling_cvt.py:183)
+        attention(a, s);
+        gemm(q, C, L.o, x2, C, rq, ACT_NONE, x, C, false, nullptr, s);          // + residual
+        layernorm<T>(x2, C, y, C, L.ln2.g, L.ln2.b, rq, C, LN_EPS_CVT, s);
+        gemm(y, C, L.fc1, hid, 4 * C, rq, ACT_GELU, nullptr, 0, false, nullptr, s);
+        gemm(hid, 4 * C, L.fc2, x, C, rq, ACT_NONE, x2, C, false, nullptr, s);  // + residual
+      }
+      if (cls) {
+        drop_cls<T>(x, x2, n, Ho * Wo, C, s);
+        std::swap(x, x2);
+      }
+      // x now holds [n, Ho*Wo, C]; it becomes `prev`; continue in the other buffer
+      prev = x;
+      std::swap(x, x2);
+      Hp = Ho;
+      Wp = Wo;
+    }
+    // projection head: LN(eps 1e-12) -> Linear 384 -> 768 without bias (modelling_longitudinal.py:40-43)
+    const long long rows = static_cast<long long>(n) * T2;
+    layernorm<T>(prev, CVT_C[2], y, CVT_C[2], head_ln.g, head_ln.b, rows, CVT_C[2], LN_EPS_BERT, s);
+    T* proj = qp;
+    gemm(y, CVT_C[2], head_proj, proj, DH, rows, ACT_NONE, nullptr, 0, false, nullptr, s);
+    return proj;
+  }
+
+  void encode(const float* pixels, int B, int N, void* memory_out, uint8_t* mask_out, cudaStream_t s) override {
+    CXRM_CHECK(finalized, "weights not finalized");
+    CXRM_CHECK(B >= 1 && B <= cfg.max_studies && N >= 1 && N <= cfg.max_images, "B/N exceed the configured maxima");
+    const int n_all = B * N;
+    const long long img_stride = 3LL * cfg.image_h * cfg.image_w;
+    valid_images_kernel<<<ceil_div(n_all, 128), 128, 0, s>>>(pixels, valid_img, n_all, img_stride);
+    check_launch("valid_images");
+    std::vector<uint8_t> valid(n_all);
+    CXRM_CUDA_CHECK(cudaMemcpyAsync(valid.data(), valid_img, n_all, cudaMemcpyDeviceToHost, s));
+    CXRM_CUDA_CHECK(cudaStreamSynchronize(s));
+    std::vector<int> idx;
+    for (int i = 0; i < n_all; ++i)
+      if (valid[i]) idx.push_back(i);
+    enc_B = B;
+    enc_S = N * T2;
+    fill_zero(memory, static_cast<size_t>(B) * enc_S * DH * sizeof(T), s);
+    expand_mask_kernel<<<static_cast<unsigned>(ceil_div_ll(static_cast<long long>(n_all) * T2, 256)), 256, 0, s>>>(
+        valid_img, mem_mask, n_all, T2);
+    check_launch("expand_mask");
+    if (!idx.empty()) {
+      CXRM_CUDA_CHECK(cudaMemcpyAsync(img_idx, idx.data(), idx.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+      for (size_t c0 = 0; c0 < idx.size(); c0 += cfg.enc_chunk) {
+        const int n = static_cast<int>(std::min<size_t>(cfg.enc_chunk, idx.size() - c0));
+        T* proj = encode_chunk(pixels, img_idx + c0, n, s);
+        for (int i = 0; i < n; ++i) {
+          const long long dst_img = idx[c0 + i];   // = b*N + slot, i.e. row block dst_img*T2 of memory [B, N*T2, 768]
+          CXRM_CUDA_CHECK(cudaMemcpyAsync(memory + dst_img * T2 * DH, proj + static_cast<long long>(i) * T2 * DH,
+                                          static_cast<size_t>(T2) * DH * sizeof(T), cudaMemcpyDeviceToDevice, s));
+        }
+      }
+    }
+    if (memory_out)
+      CXRM_CUDA_CHECK(cudaMemcpyAsync(memory_out, memory, static_cast<size_t>(B) * enc_S * DH * sizeof(T), cudaMemcpyDeviceToDevice, s));
+    if (mask_out)
+      CXRM_CUDA_CHECK(cudaMemcpyAsync(mask_out, mem_mask, static_cast<size_t>(B) * enc_S, cudaMemcpyDeviceToDevice, s));
+  }
+
+  // =========================================================================== cross K/V
+  void prefill_cross_kv(const void* mem_in, const uint8_t* mask_in, int B, int S, cudaStream_t s) override {
+    CXRM_CHECK(finalized, "weights not finalized");
+    const T* mem = static_cast<const T*>(mem_in);
+    const uint8_t* mask = mask_in;
+    if (!mem) {
+      CXRM_CHECK(enc_B > 0, "cxrm_prefill_cross_kv(NULL) needs a preceding cxrm_encode");
+      mem = memory;
+      mask = mem_mask;
+      B = enc_B;
+      S = enc_S;
+    }
+    CXRM_CHECK(B >= 1 && B <= cfg.max_studies && S >= 1 && S <= Smax, "B/S exceed the configured maxima");
+    count_mask_kernel<<<ceil_div(B, 64), 64, 0, s>>>(mask, kv_len, B, S);
+    check_launch("count_mask");
+    std::vector<int> len(B), off(B);
+    CXRM_CUDA_CHECK(cudaMemcpyAsync(len.data(), kv_len, B * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CXRM_CUDA_CHECK(cudaStreamSynchronize(s));
+    int total = 0, mx = 0;
+    for (int b = 0; b < B; ++b) {
+      off[b] = total;
+      total += len[b];
+      mx = std::max(mx, len[b]);
+      CXRM_CHECK(len[b] > 0, "a study has no visible encoder token");
+    }
+    kv_total = total;
+    kv_maxlen = mx;
+    kv_B = B;
+    CXRM_CUDA_CHECK(cudaMemcpyAsync(kv_off, off.data(), B * sizeof(int), cudaMemcpyHostToDevice, s));
+    compact_rows_kernel<<<ceil_div(B, 64), 64, 0, s>>>(mask, kv_off, compact_idx, B, S);
+    check_launch("compact_rows");
+    gather_rows<T>(mem, compact_idx, mem_compact, total, DH, s);
+    for (int l = 0; l < cfg.dec_layers; ++l) {
+      T* kvl = cross_kv + static_cast<long long>(l) * cross_layer_stride();
+      gemm(mem_compact, DH, dec.layers[l].ckv, kvl, 2 * DH, total, ACT_NONE, nullptr, 0, false, nullptr, s);
+    }
+    // split the per-study key range when there are too few (study, head) blocks to fill the GPU
+    const int blocks = B * NHEAD;
+    cross_nsplit = 1;
+    while (blocks * cross_nsplit < 2 * 148 && cross_nsplit < 16 && Smax / (cross_nsplit * 2) >= 64) cross_nsplit *= 2;
+    graph_valid = false;
+  }
+  long long cross_layer_stride() const { return static_cast<long long>(cfg.max_studies) * Smax * 2 * DH; }
+
+  // =========================================================================== attention dispatch
+  void attention(const AttnArgs& a, cudaStream_t s) { attention_simt<T>(a, s); }
+
+  // =========================================================================== decoder trunk
+  // tokens M = R*qlen already embedded in x [M,768]; returns the buffer holding the output hidden states
+  struct DecBufs { T* x; T* x1; T* qkv; T* ctx; T* hid; };
+  DecBufs dec_bufs(long long M) {
+    DecBufs b;
+    b.x = arena.get<T>(M * DH);
+    b.x1 = arena.get<T>(M * DH);
+    b.qkv = arena.get<T>(M * 3 * DH);
+    b.ctx = arena.get<T>(M * DH);
+    b.hid = arena.get<T>(M * DFF);
+    return b;
+  }
+
+  // full-sequence pass (prefill / teacher forcing): R rows of q tokens, causal + key_mask [R, ld_mask]
+  T* decoder_full(DecBufs& b, int R, int q, int B, const uint8_t* key_mask, int ld_mask, bool store_cache,
+                  cudaStream_t s) {
+    const long long M = static_cast<long long>(R) * q;
+    for (int l = 0; l < cfg.dec_layers; ++l) {
+      const BertLayerW& w = dec.layers[l];
+      gemm(b.x, DH, w.qkv, b.qkv, 3 * DH, M, ACT_NONE, nullptr, 0, false, nullptr, s);
+      if (store_cache)
+        prefill_store_kv<T>(b.qkv, self_k + l * self_layer_stride(), self_v + l * self_layer_stride(), R, q, Lmax, s);
+      AttnArgs a{};
+      a.q = b.qkv; a.k = b.qkv + DH; a.v = b.qkv + 2 * DH; a.o = b.ctx;
+      a.q_bs = static_cast<long long>(q) * 3 * DH; a.q_hs = 64; a.q_ts = 3 * DH;
+      a.k_bs = a.q_bs; a.k_hs = 64; a.k_ts = 3 * DH;
+      a.v_bs = a.q_bs; a.v_hs = 64; a.v_ts = 3 * DH;
+      a.o_bs = static_cast<long long>(q) * DH; a.o_hs = 64; a.o_ts = DH;
+      a.batch = R; a.heads = NHEAD; a.Lq = q; a.Lk = q;
+      a.key_mask = key_mask; a.key_mask_ld = ld_mask; a.key_mask_per_q_batch = 1;
+      a.causal = 1; a.q_pos_offset = 0;
+      a.scale = 0.125f;
+      attention(a, s);
+      gemm(b.ctx, DH, w.o, b.x1, DH, M, ACT_NONE, b.x, DH, false, nullptr, s);
+      layernorm<T>(b.x1, DH, b.x1, DH, w.ln1.g, w.ln1.b, M, DH, LN_EPS_BERT, s);
+      // cross-attention over the ragged encoder K/V cache
+      gemm(b.x1, DH, w.cq, b.qkv, DH, M, ACT_NONE, nullptr, 0, false, nullptr, s);
+      const T* kvl = cross_kv + static_cast<long long>(l) * cross_layer_stride();
+      AttnArgs c{};
+      c.q = b.qkv; c.k = kvl; c.v = kvl + DH; c.o = b.ctx;
+      c.q_bs = static_cast<long long>(q) * DH; c.q_hs = 64; c.q_ts = DH;
+      c.k_bs = 0; c.k_hs = 64; c.k_ts = 2 * DH;
+      c.v_bs = 0; c.v_hs = 64; c.v_ts = 2 * DH;
+      c.o_bs = c.q_bs; c.o_hs = 64; c.o_ts = DH;
+      c.batch = R; c.heads = NHEAD; c.Lq = q; c.Lk = kv_maxlen;
+      c.Lk_per_batch = kv_len; c.kv_offset = kv_off; c.kv_batch_mod = B;
+      c.scale = 0.125f;
+      attention(c, s);
+      gemm(b.ctx, DH, w.co, b.x, DH, M, ACT_NONE, b.x1, DH, false, nullptr, s);
+      layernorm<T>(b.x, DH, b.x, DH, w.ln2.g, w.ln2.b, M, DH, LN_EPS_BERT, s);
+      gemm(b.x, DH, w.fc1, b.hid, DFF, M, ACT_GELU, nullptr, 0, false, nullptr, s);
+      gemm(b.hid, DFF, w.fc2, b.x1, DH, M, ACT_NONE, b.x, DH, false, nullptr, s);
+      layernorm<T>(b.x1, DH, b.x, DH, w.ln3.g, w.ln3.b, M, DH, LN_EPS_BERT, s);
+    }
+    return b.x;
+  }
+  long long self_layer_stride() const { return static_cast<long long>(Rmax) * Lmax * DH; }
+
+  // LM head on `rows` hidden rows -> fp32 logits (dense -> GELU -> LN -> tied decoder + bias)
+  void lm_head(const T* hidden, long long rows, T* tmp, float* out, int ld_out, const int* skip, cudaStream_t s) {
+    gemm(hidden, DH, dec_head_t, tmp, DH, rows, ACT_GELU, nullptr, 0, false, skip, s);
+    layernorm<T>(tmp, DH, tmp, DH, dec_head_ln.g, dec_head_ln.b, rows, DH, LN_EPS_BERT, s);
+    gemm(tmp, DH, dec_lm, out, ld_out, rows, ACT_NONE, nullptr, 0, true, skip, s);
+  }
+
+  // one decode step for R rows (all inputs come from the device-side rollout state)
+  void decode_step(DecBufs& b, T* head_tmp, const RolloutParams& rp, const float* noise, cudaStream_t s) {
+    const int R = rp.R, B = rp.B;
+    const int* skip = st.done;
+    embed_ln<T>(st.cur_token, st.cur_type, st.cur_pos, dec.word, dec.type, dec.pos, dec.emb_ln.g, dec.emb_ln.b, b.x, R,
+                DH, LN_EPS_BERT, s);
+    for (int l = 0; l < cfg.dec_layers; ++l) {
+      const BertLayerW& w = dec.layers[l];
+      gemm(b.x, DH, w.qkv, b.qkv, 3 * DH, R, ACT_NONE, nullptr, 0, false, skip, s);
+      decode_self_attention<T>(b.qkv, self_k + l * self_layer_stride(), self_v + l * self_layer_stride(), b.ctx, st, R,
+                               Lmax, s);
+      gemm(b.ctx, DH, w.o, b.x1, DH, R, ACT_NONE, b.x, DH, false, skip, s);
+      layernorm<T>(b.x1, DH, b.x1, DH, w.ln1.g, w.ln1.b, R, DH, LN_EPS_BERT, s);
+      gemm(b.x1, DH, w.cq, b.qkv, DH, R, ACT_NONE, nullptr, 0, false, skip, s);
+      const T* kvl = cross_kv + static_cast<long long>(l) * cross_layer_stride();
+      // smem sized for the configured maximum so that the captured graph does not depend on the batch's image counts
+      decode_cross_attention<T>(b.qkv, kvl, kvl + DH, 2 * DH, b.ctx, kv_off, kv_len, st, R, B, Smax, cross_nsplit,
+                                cross_ws, s);
+      gemm(b.ctx, DH, w.co, b.x, DH, R, ACT_NONE, b.x1, DH, false, skip, s);
+      layernorm<T>(b.x, DH, b.x, DH, w.ln2.g, w.ln2.b, R, DH, LN_EPS_BERT, s);
+      gemm(b.x, DH, w.fc1, b.hid, DFF, R, ACT_GELU, nullptr, 0, false, skip, s);
+      gemm(b.hid, DFF, w.fc2, b.x1, DH, R, ACT_NONE, b.x, DH, false, skip, s);
+      layernorm<T>(b.x1, DH, b.x, DH, w.ln3.g, w.ln3.b, R, DH, LN_EPS_BERT, s);
+    }
+    lm_head(b.x, R, head_tmp, logits, cfg.vocab, skip, s);
+    sample_step(st, rp, logits, cfg.vocab, noise, s);
+  }
+
+  void rollout(const cxrm_rollout_args& a, cudaStream_t s_user) override {
+    CXRM_CHECK(finalized, "weights not finalized");
+    // stream capture is illegal on the legacy default stream: hop to the engine's own stream
+    cudaStream_t s = s_user;
+    const bool hop = cfg.use_cuda_graph && (s_user == nullptr || s_user == cudaStreamLegacy);
+    if (hop) {
+      s = side_stream;
+      CXRM_CUDA_CHECK(cudaEventRecord(ev_a, s_user));
+      CXRM_CUDA_CHECK(cudaStreamWaitEvent(s, ev_a, 0));
+    }
+    CXRM_CHECK(a.mode >= 1 && a.mode <= 3, "mode");
+    CXRM_CHECK(kv_B == a.B && kv_total > 0, "cxrm_rollout needs cxrm_prefill_cross_kv for the same B");
+    const int nm = a.mode == CXRM_BOTH ? 2 : 1;
+    const int R = a.B * nm, P = a.P, Tn = a.max_new_tokens;
+    CXRM_CHECK(R <= Rmax && P >= 1 && P <= cfg.max_prompt && Tn >= 1 && Tn <= cfg.max_new_tokens, "rollout shape");
+    CXRM_CHECK(a.n_special_sample <= kMaxSpecial && a.n_special_greedy <= kMaxSpecial, "too many special tokens");
+    RolloutParams rp{};
+    rp.R = R; rp.B = a.B; rp.P = P; rp.Lmax = Lmax; rp.Tmax = Tn; rp.V = cfg.vocab;
+    auto set_blk = [&](int blk, bool greedy) {
+      rp.mode_of_block[blk] = greedy ? 1 : 0;
+      rp.n_special[blk] = greedy ? a.n_special_greedy : a.n_special_sample;
+      for (int i = 0; i < rp.n_special[blk]; ++i) rp.special_ids[blk][i] = greedy ? a.special_greedy[i] : a.special_sample[i];
+      for (int i = 0; i <= rp.n_special[blk]; ++i) rp.sections[blk][i] = greedy ? a.sections_greedy[i] : a.sections_sample[i];
+    };
+    if (a.mode == CXRM_BOTH) {
+      set_blk(0, false);
+      set_blk(1, true);
+    } else {
+      set_blk(0, a.mode == CXRM_GREEDY);
+    }
+    rp.mask_token_id = a.mask_token_id; rp.eos = a.eos_token_id; rp.pad = a.pad_token_id;
+    rp.top_k = a.top_k; rp.temperature = a.temperature; rp.seed = a.seed;
+    // the kernels index logprob/topk buffers with Tmax = Tn
+    rollout_init(st, rp, a.prompt_ids, pre_ids, pre_types, pre_pos, s);
+
+    arena.reset();
+    const long long M = static_cast<long long>(R) * P;
+    DecBufs db = dec_bufs(R);     // first: keeps the decode-step pointers (and the captured graph) independent of P
+    T* last = arena.get<T>(static_cast<long long>(R) * DH);
+    T* head_tmp = arena.get<T>(static_cast<long long>(R) * DH);
+    DecBufs pb = dec_bufs(M);
+    embed_ln<T>(pre_ids, pre_types, pre_pos, dec.word, dec.type, dec.pos, dec.emb_ln.g, dec.emb_ln.b, pb.x, M, DH,
+                LN_EPS_BERT, s);
+    T* hid = decoder_full(pb, R, P, a.B, st.key_valid, Lmax, /*store_cache=*/true, s);
+    take_last_token<T>(hid, last, R, P, DH, s);
+    lm_head(last, R, head_tmp, logits, cfg.vocab, nullptr, s);
+    sample_step(st, rp, logits, cfg.vocab, a.exp_noise, s);
+
+    if (Tn > 1) {
+      if (cfg.use_cuda_graph) {
+        run_decode_graph(db, head_tmp, rp, a.exp_noise, Tn - 1, s);
+      } else {
+        for (int t = 1; t < Tn; ++t) decode_step(db, head_tmp, rp, a.exp_noise, s);
+      }
+    }
+    // outputs
+    const int Lout = P + Tn;
+    CXRM_CUDA_CHECK(cudaMemcpy2DAsync(a.sequences, Lout * sizeof(int), st.seq, Lmax * sizeof(int), Lout * sizeof(int), R,
+                                      cudaMemcpyDeviceToDevice, s));
+    const size_t rt = static_cast<size_t>(R) * Tn;
+    if (a.logprobs) CXRM_CUDA_CHECK(cudaMemcpyAsync(a.logprobs, st.logprob, rt * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    if (a.margins) CXRM_CUDA_CHECK(cudaMemcpyAsync(a.margins, st.margin, rt * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    if (a.topk_idx) CXRM_CUDA_CHECK(cudaMemcpyAsync(a.topk_idx, st.topk_idx, rt * kTopKCap * sizeof(int), cudaMemcpyDeviceToDevice, s));
+    if (a.topk_val) CXRM_CUDA_CHECK(cudaMemcpyAsync(a.topk_val, st.topk_val, rt * kTopKCap * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    if (a.topk_cnt) CXRM_CUDA_CHECK(cudaMemcpyAsync(a.topk_cnt, st.topk_cnt, rt * sizeof(int), cudaMemcpyDeviceToDevice, s));
+    if (a.last_logits)
+      CXRM_CUDA_CHECK(cudaMemcpyAsync(a.last_logits, logits, static_cast<size_t>(R) * cfg.vocab * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    if (hop) {
+      CXRM_CUDA_CHECK(cudaEventRecord(ev_b, s));
+      CXRM_CUDA_CHECK(cudaStreamWaitEvent(s_user, ev_b, 0));
+    }
+    if (a.steps_out) {
+      int steps = 0;
+      CXRM_CUDA_CHECK(cudaMemcpyAsync(&steps, st.step, sizeof(int), cudaMemcpyDeviceToHost, s));
+      CXRM_CUDA_CHECK(cudaStreamSynchronize(s));
+      *a.steps_out = steps;
+    }
+  }
+
+  // The decode step reads everything that changes from device memory, so one captured
+  // graph serves every step of every rollout with the same (R, B, buffers, parameters).
+  void run_decode_graph(DecBufs& db, T* head_tmp, const RolloutParams& rp, const float* noise, int n_steps,
+                        cudaStream_t s) {
+    GraphKey key;
+    std::memset(&key, 0, sizeof(key));
+    key.R = rp.R; key.B = rp.B; key.P = rp.P; key.Tmax = rp.Tmax; key.top_k = rp.top_k;
+    key.temperature = rp.temperature; key.seed = rp.seed; key.noise = noise; key.buf = db.x;
+    key.nsplit = cross_nsplit;
+    key.mask_id = rp.mask_token_id; key.eos = rp.eos; key.pad = rp.pad;
+    std::memcpy(key.special, rp.special_ids, sizeof(key.special));
+    std::memcpy(key.sections, rp.sections, sizeof(key.sections));
+    std::memcpy(key.nspecial, rp.n_special, sizeof(key.nspecial));
+    std::memcpy(key.modes, rp.mode_of_block, sizeof(key.modes));
+    if (!graph_exec || !graph_valid || std::memcmp(&key, &graph_key, sizeof(GraphKey)) != 0) {
+      if (graph_exec) {
+        cudaGraphExecDestroy(graph_exec);
+        graph_exec = nullptr;
+      }
+      // one eager step first: sets the kernels' function attributes outside the capture
+      decode_step(db, head_tmp, rp, noise, s);
+      --n_steps;
+      cudaGraph_t graph = nullptr;
+      const unsigned long long before = g_launch_count;
+      CXRM_CUDA_CHECK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+      try {
+        decode_step(db, head_tmp, rp, noise, s);
+      } catch (...) {
+        cudaStreamEndCapture(s, &graph);
+        if (graph) cudaGraphDestroy(graph);
+        throw;
+      }
+      CXRM_CUDA_CHECK(cudaStreamEndCapture(s, &graph));
+      graph_nodes = g_launch_count - before;
+      g_launch_count = before;
+      CXRM_CUDA_CHECK(cudaGraphInstantiate(&graph_exec, graph, 0));
+      cudaGraphDestroy(graph);
+      std::memcpy(&graph_key, &key, sizeof(GraphKey));
+      graph_valid = true;
+    }
+    for (int t = 0; t < n_steps; ++t) CXRM_CUDA_CHECK(cudaGraphLaunch(graph_exec, s));
+    g_launch_count += graph_nodes * static_cast<unsigned long long>(n_steps);
+  }
+
+  // =========================================================================== teacher-forced forward
+  void decoder_forward(const int* ids, const int* tt, const int* pos, const uint8_t* key_mask, int R, int L, int B,
+                       bool last_only, float* logits_out, cudaStream_t s) override {
+    CXRM_CHECK(finalized, "weights not finalized");
+    CXRM_CHECK(kv_B == B && kv_total > 0, "cxrm_decoder_forward needs cxrm_prefill_cross_kv for the same B");
+    CXRM_CHECK(R >= 1 && R % B == 0 && L >= 1 && L <= 512, "decoder_forward shape");
+    arena.reset();
+    const long long M = static_cast<long long>(R) * L;
+    DecBufs b = dec_bufs(M);
+    embed_ln<T>(ids, tt, pos, dec.word, dec.type, dec.pos, dec.emb_ln.g, dec.emb_ln.b, b.x, M, DH, LN_EPS_BERT, s);
+    T* hid = decoder_full(b, R, L, B, key_mask, L, /*store_cache=*/false, s);
+    if (last_only) {
+      T* last = b.ctx;
+      take_last_token<T>(hid, last, R, L, DH, s);
+      lm_head(last, R, b.x1, logits_out, cfg.vocab, nullptr, s);
+    } else {
+      lm_head(hid, M, b.x1, logits_out, cfg.vocab, nullptr, s);
+    }
+  }
+
+  // =========================================================================== reward model
+  void reward_embed(const int* ids, const int* lens, int n, int L, float* emb_out, cudaStream_t s) override {
+    CXRM_CHECK(finalized && have_reward, "reward model weights not loaded");
+    CXRM_CHECK(n >= 1 && L >= 1 && L <= cfg.rwd_max_len && static_cast<long long>(n) * L <=
+                   static_cast<long long>(std::max(cfg.rwd_max_seqs, 1)) * cfg.rwd_max_len, "reward batch too large");
+    arena.reset();
+    const long long M = static_cast<long long>(n) * L;
+    DecBufs b = dec_bufs(M);
+    int* pos = arena.get<int>(M);
+    iota_pos_kernel<<<static_cast<unsigned>(ceil_div_ll(M, 256)), 256, 0, s>>>(pos, n, L);
+    check_launch("iota_pos");
+    embed_ln<T>(ids, nullptr, pos, rwd.word, rwd.type, rwd.pos, rwd.emb_ln.g, rwd.emb_ln.b, b.x, M, DH, LN_EPS_BERT, s);
+    for (int l = 0; l < cfg.rwd_layers; ++l) {
+      const BertLayerW& w = rwd.layers[l];
+      gemm(b.x, DH, w.qkv, b.qkv, 3 * DH, M, ACT_NONE, nullptr, 0, false, nullptr, s);
+      AttnArgs a{};
+      a.q = b.qkv; a.k = b.qkv + DH; a.v = b.qkv + 2 * DH; a.o = b.ctx;
+      a.q_bs = static_cast<long long>(L) * 3 * DH; a.q_hs = 64; a.q_ts = 3 * DH;
+      a.k_bs = a.q_bs; a.k_hs = 64; a.k_ts = 3 * DH;
+      a.v_bs = a.q_bs; a.v_hs = 64; a.v_ts = 3 * DH;
+      a.o_bs = static_cast<long long>(L) * DH; a.o_hs = 64; a.o_ts = DH;
+      a.batch = n; a.heads = NHEAD; a.Lq = L; a.Lk = L;
+      a.Lk_per_batch = lens;      // attention_mask from padding='longest' == (j < len)
+      a.scale = 0.125f;
+      attention(a, s);
+      gemm(b.ctx, DH, w.o, b.x1, DH, M, ACT_NONE, b.x, DH, false, nullptr, s);
+      layernorm<T>(b.x1, DH, b.x1, DH, w.ln1.g, w.ln1.b, M, DH, LN_EPS_BERT, s);
+      gemm(b.x1, DH, w.fc1, b.hid, DFF, M, ACT_GELU, nullptr, 0, false, nullptr, s);
+      gemm(b.hid, DFF, w.fc2, b.x, DH, M, ACT_NONE, b.x1, DH, false, nullptr, s);
+      layernorm<T>(b.x, DH, b.x, DH, w.ln3.g, w.ln3.b, M, DH, LN_EPS_BERT, s);
+    }
+    // [CLS] rows (token 0 of every sequence: row stride L*768) -> 768 -> 128 GELU -> LN -> 128
+    T* h1 = b.ctx;
+    T* h2 = b.x1;
+    gemm(b.x, L * DH, rp1, h1, 128, n, ACT_GELU, nullptr, 0, false, nullptr, s);
+    layernorm<T>(h1, 128, h1, 128, rp_ln.g, rp_ln.b, n, 128, LN_EPS_BERT, s);
+    gemm(h1, 128, rp2, emb_out, 128, n, ACT_NONE, nullptr, 0, true, nullptr, s);
+    (void)h2;
+  }
+
+  // =========================================================================== host-buffer SCST step
+  void set_id_map(const int* id_map_host, int n, int cls_id, int sep_id, int bos_id, int sep_dec_id) override {
+    CXRM_CHECK(n == cfg.vocab, "id map must cover the decoder vocabulary");
+    if (!id_map) id_map = dalloc<int>(n);
+    CXRM_CUDA_CHECK(cudaMemcpy(id_map, id_map_host, n * sizeof(int), cudaMemcpyHostToDevice));
+    bridge_cls = cls_id;
+    bridge_sep = sep_id;
+    bridge_bos = bos_id;
+    bridge_sep_dec = sep_dec_id;
+  }
+
+  void scst_step_host(const float* pixels, int B, int N, const int* prompt_ids, int P, const cxrm_rollout_args& tmpl,
+                      const int* label_ids, const int* label_lens, int L_label, int* sequences, float* logprobs,
+                      float* reward, float* baseline, float* advantage, int* steps_out, cudaStream_t s) override {
+    CXRM_CHECK(finalized && have_reward && id_map, "scst_step_host needs all weights and cxrm_set_id_map");
+    CXRM_CHECK(B <= cfg.max_studies && N <= cfg.max_images && P <= cfg.max_prompt, "scst_step_host shape");
+    CXRM_CHECK(3 * B <= cfg.rwd_max_seqs && L_label <= cfg.rwd_max_len, "reward batch exceeds rwd_max_seqs");
+    const int Tn = tmpl.max_new_tokens, R = 2 * B, Lseq = P + Tn, Lr = cfg.rwd_max_len;
+    if (!h_pixels) {
+      h_pixels = dalloc<float>(static_cast<long long>(cfg.max_studies) * cfg.max_images * 3 * cfg.image_h * cfg.image_w);
+      h_seq = dalloc<int>(static_cast<long long>(Rmax) * Lmax);
+      h_lp = dalloc<float>(static_cast<long long>(Rmax) * cfg.max_new_tokens);
+      h_rids = dalloc<int>(3LL * cfg.max_studies * Lr);
+      h_rlens = dalloc<int>(3LL * cfg.max_studies);
+      h_emb = dalloc<float>(3LL * cfg.max_studies * 128);
+      h_out = dalloc<float>(3LL * cfg.max_studies);
+      h_labels = dalloc<int>(static_cast<long long>(cfg.max_studies) * Lr);
+    }
+    const size_t px = static_cast<size_t>(B) * N * 3 * cfg.image_h * cfg.image_w * sizeof(float);
+    CXRM_CUDA_CHECK(cudaMemcpyAsync(h_pixels, pixels, px, cudaMemcpyHostToDevice, s));
+    CXRM_CUDA_CHECK(cudaMemcpyAsync(prompt_dev, prompt_ids, static_cast<size_t>(B) * P * sizeof(int), cudaMemcpyHostToDevice, s));
+    encode(h_pixels, B, N, nullptr, nullptr, s);
+    prefill_cross_kv(nullptr, nullptr, 0, 0, s);
+    cxrm_rollout_args a = tmpl;
+    a.mode = CXRM_BOTH; a.B = B; a.P = P; a.prompt_ids = prompt_dev;
+    a.sequences = h_seq; a.logprobs = h_lp;
+    a.margins = nullptr; a.topk_idx = nullptr; a.topk_val = nullptr; a.topk_cnt = nullptr; a.last_logits = nullptr;
+    a.steps_out = nullptr;
+    rollout(a, s);
+    // text bridge: sample rows [0,B), greedy rows [B,2B) -> reward ids rows [0,2B); labels -> rows [2B,3B)
+    bridge_ids_kernel<<<ceil_div(R, 64), 64, 0, s>>>(h_seq, Lseq, Lseq, R, bridge_bos, bridge_sep_dec, a.eos_token_id,
+                                                      12, id_map, bridge_cls, bridge_sep, h_rids, h_rlens, Lr);
+    check_launch("bridge_ids");
+    // labels are already reward-model ids, padded to L_label: copy into the [*, Lr] layout
+    CXRM_CUDA_CHECK(cudaMemsetAsync(h_rids + static_cast<long long>(R) * Lr, 0, static_cast<size_t>(B) * Lr * sizeof(int), s));
+    CXRM_CUDA_CHECK(cudaMemcpy2DAsync(h_rids + static_cast<long long>(R) * Lr, Lr * sizeof(int), label_ids,
+                                      L_label * sizeof(int), L_label * sizeof(int), B, cudaMemcpyHostToDevice, s));
+    CXRM_CUDA_CHECK(cudaMemcpyAsync(h_rlens + R, label_lens, B * sizeof(int), cudaMemcpyHostToDevice, s));
+    reward_embed(h_rids, h_rlens, 3 * B, Lr, h_emb, s);
+    cosine_rows(h_emb, h_emb + static_cast<long long>(R) * 128, h_out, B, 128, s);                               // sample vs label
+    cosine_rows(h_emb + static_cast<long long>(B) * 128, h_emb + static_cast<long long>(R) * 128, h_out + B, B, 128, s);  // greedy vs label
+    advantage_kernel<<<ceil_div(B, 64), 64, 0, s>>>(h_out, h_out + B, h_out + 2 * B, B);
+    check_launch("advantage");
+    CXRM_CUDA_CHECK(cudaMemcpyAsync(sequences, h_seq, static_cast<size_t>(R) * Lseq * sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (logprobs) CXRM_CUDA_CHECK(cudaMemcpyAsync(logprobs, h_lp, static_cast<size_t>(R) * Tn * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CXRM_CUDA_CHECK(cudaMemcpyAsync(reward, h_out, B * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CXRM_CUDA_CHECK(cudaMemcpyAsync(baseline, h_out + B, B * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CXRM_CUDA_CHECK(cudaMemcpyAsync(advantage, h_out + 2 * B, B * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (steps_out) CXRM_CUDA_CHECK(cudaMemcpyAsync(steps_out, st.step, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CXRM_CUDA_CHECK(cudaStreamSynchronize(s));
+  }
+
+ private:
+  cxrm_config cfg;
+  int device;
+  std::map<std::string, RawTensor> raw;
+  std::vector<void*> owned;
+  long long persistent_bytes = 0;
+  bool finalized = false, have_reward = false;
+  Arena arena;
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+  // weights
+  CvtStageW stages[3];
+  float* cls_token = nullptr;
+  LNp head_ln;
+  Lin head_proj;
+  BertW dec, rwd;
+  Lin dec_head_t, dec_lm, rp1, rp2;
+  LNp dec_head_ln, rp_ln;
+  float* dec_vocab_bias = nullptr;
+  // geometry
+  int T2 = 0, Smax = 0, Rmax = 0, Lmax = 0;
+  // persistent activations / caches
+  T* memory = nullptr; uint8_t* mem_mask = nullptr; T* mem_compact = nullptr; int* compact_idx = nullptr;
+  int* kv_off = nullptr; int* kv_len = nullptr; T* cross_kv = nullptr; T* self_k = nullptr; T* self_v = nullptr;
+  float* logits = nullptr; uint8_t* valid_img = nullptr; int* img_idx = nullptr;
+  int enc_B = 0, enc_S = 0, kv_B = 0, kv_total = 0, kv_maxlen = 0, cross_nsplit = 1;
+  float* cross_ws = nullptr;
+  RolloutState st{};
+  int* pre_ids = nullptr; int* pre_types = nullptr; int* pre_pos = nullptr; int* prompt_dev = nullptr;
+  // host-step staging
+  float* h_pixels = nullptr; int* h_seq = nullptr; float* h_lp = nullptr; int* h_rids = nullptr; int* h_rlens = nullptr;
+  float* h_emb = nullptr; float* h_out = nullptr; int* h_labels = nullptr;
+  int* id_map = nullptr; int bridge_cls = 0, bridge_sep = 0, bridge_bos = 1, bridge_sep_dec = 3;
+  // CUDA graph of one decode step
+  struct GraphKey {
+    int R, B, P, Tmax, top_k; float temperature; unsigned long long seed; const float* noise; const void* buf;
+    int kv_total, kv_maxlen, nsplit, mask_id, eos, pad;
+    int special[2][kMaxSpecial]; int sections[2][kMaxSpecial + 1]; int nspecial[2]; int modes[2];
+  };
+  GraphKey graph_key;
+  cudaGraphExec_t graph_exec = nullptr;
+  bool graph_valid = false;
+  unsigned long long graph_nodes = 0;
+};
+
+template <>
+void Engine<float>::dispatch_gemm(const GemmArgs& g, cudaStream_t s) { gemm_simt<float>(g, s); }
+template <>
+void Engine<bf16>::dispatch_gemm(const GemmArgs& g, cudaStream_t s) {
+  if (cfg.use_tensor_cores && gemm_tcgen05_supported(g) == 0)
+    gemm_tcgen05(g, s);
+  else
+    gemm_simt<bf16>(g, s);
+}
+
+}  // namespace
+
+EngineBase* make_engine(const cxrm_config& cfg, int device) {
+  if (cfg.dtype == CXRM_F32) return new Engine<float>(cfg, device);
+  if (cfg.dtype == CXRM_BF16) return new Engine<bf16>(cfg, device);
+  throw std::runtime_error("unknown dtype");
+}
+
+}  // namespace cxrm

@@ -1,0 +1,63 @@
+// Engine: owns weights, caches and scratch; sequences the kernels of the path.
+#pragma once
+
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/cxrm.h"
+#include "kernels.h"
+
+namespace cxrm {
+
+struct RawTensor {
+  float* data = nullptr;          // device fp32 staging copy
+  std::vector<int64_t> shape;
+  long long numel() const {
+    long long n = 1;
+    for (auto s : shape) n *= s;
+    return n;
+  }
+};
+
+// bump allocator over one device arena; reset between phases
+class Arena {
+ public:
+  void init(size_t bytes);
+  void release();
+  void reset() { off_ = 0; }
+  void* alloc(size_t bytes);
+  template <typename U> U* get(long long n) { return static_cast<U*>(alloc(static_cast<size_t>(n) * sizeof(U))); }
+  size_t capacity() const { return cap_; }
+
+ private:
+  char* base_ = nullptr;
+  size_t cap_ = 0, off_ = 0;
+};
+
+class EngineBase {
+ public:
+  virtual ~EngineBase() {}
+  virtual void load_weight(const std::string& name, const float* data, const int64_t* shape, int ndim,
+                           bool on_device) = 0;
+  virtual void finalize_weights() = 0;
+  virtual void encode(const float* pixels, int B, int N, void* memory_out, uint8_t* mask_out, cudaStream_t s) = 0;
+  virtual void prefill_cross_kv(const void* memory, const uint8_t* mask, int B, int S, cudaStream_t s) = 0;
+  virtual void rollout(const cxrm_rollout_args& a, cudaStream_t s) = 0;
+  virtual void decoder_forward(const int* ids, const int* tt, const int* pos, const uint8_t* key_mask, int R, int L,
+                               int B, bool last_only, float* logits_out, cudaStream_t s) = 0;
+  virtual void reward_embed(const int* ids, const int* lens, int n, int L, float* emb_out, cudaStream_t s) = 0;
+  virtual void set_id_map(const int* id_map_host, int n, int cls_id, int sep_id, int bos_id, int sep_dec_id) = 0;
+  virtual void scst_step_host(const float* pixels, int B, int N, const int* prompt_ids, int P,
+                              const cxrm_rollout_args& tmpl, const int* label_ids, const int* label_lens, int L_label,
+                              int* sequences, float* logprobs, float* reward, float* baseline, float* advantage,
+                              int* steps_out, cudaStream_t s) = 0;
+  virtual size_t workspace_bytes() const = 0;
+  std::string last_error;
+  unsigned long long launches = 0;
+};
+
+EngineBase* make_engine(const cxrm_config& cfg, int device);
+
+}  // namespace cxrm

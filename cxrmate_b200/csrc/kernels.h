@@ -1,0 +1,190 @@
+// Host-side launchers of every CUDA kernel on the SCST rollout path.
+// All launchers are asynchronous on `stream`; pointers are device pointers.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace cxrm {
+
+enum Act : int { ACT_NONE = 0, ACT_GELU = 1 };
+
+// C[M,N] = epi(A[M,K] . W[N,K]^T): + bias[N] (fp32, nullable) -> act -> + residual[M,N] (T, nullable);
+// stored as T, or as fp32 when out_f32.  K % 8 == 0, lda/ldw % 8 == 0.
+struct GemmArgs {
+  const void* A; int lda;
+  const void* W; int ldw;
+  void* C; int ldc;
+  int M, N, K;
+  const float* bias;
+  int act;
+  const void* residual; int ldr;
+  int out_f32;
+  const int* skip_flag;   // nullable device flag: kernel returns immediately when *skip_flag != 0
+};
+
+// strict-fp32 FMA path (validation mode; also the bf16-storage SIMT debug path)
+template <typename T> void gemm_simt(const GemmArgs& g, cudaStream_t stream);
+// tcgen05 / TMEM / TMA path (bf16 operands, fp32 accumulate)
+void gemm_tcgen05(const GemmArgs& g, cudaStream_t stream);
+// returns 0 when the tcgen05 path can take this shape
+int gemm_tcgen05_supported(const GemmArgs& g);
+
+// ---- elementwise / normalisation (elementwise.cu) -------------------------
+template <typename T>
+void layernorm(const T* x, int ldx, T* y, int ldy, const float* gamma, const float* beta, long long rows, int C,
+               float eps, cudaStream_t stream);
+
+// pixels [*,3,H,W] fp32 NCHW; img_idx[n] selects the source image of output image n (nullable = identity).
+// out [n_img*Ho*Wo, Kpad], K index = (cin*kh + ky)*kw + kx, zero padded to Kpad.
+template <typename T>
+void im2col_pixels(const float* pixels, const int* img_idx, T* out, int n_img, int H, int W, int ksz, int stride,
+                   int pad, int Kpad, cudaStream_t stream);
+// tokens [n_img, H*W, C] (token-major == NHWC); out [n_img*Ho*Wo, ksz*ksz*C], K index = (ky*ksz + kx)*C + c.
+template <typename T>
+void im2col_tokens(const T* in, T* out, int n_img, int H, int W, int C, int ksz, int stride, int pad,
+                   cudaStream_t stream);
+// depth-wise 3x3 (pad 1) + folded BatchNorm for the CvT q/k/v convolutional projections.
+// y [n_img, cls+H*W, C]; q [n_img, cls+H*W, C] (stride 1); k,v [n_img, cls+Hk*Wk, C] (stride 2).
+// w [3][9][C] fp32 (q,k,v; tap-major), scale/shift [3][C] fp32.  cls rows are copied through.
+template <typename T>
+void dwconv_bn_qkv(const T* y, T* q, T* k, T* v, const float* w, const float* scale, const float* shift, int n_img,
+                   int H, int W, int C, int cls, cudaStream_t stream);
+// x[n_img, 1+HW, C] <- cat(cls_token[C], tokens[n_img, HW, C])
+template <typename T>
+void cat_cls(const T* tokens, const float* cls_token, T* out, int n_img, int HW, int C, cudaStream_t stream);
+// out[n_img, HW, C] <- in[n_img, 1+HW, C][:, 1:]
+template <typename T>
+void drop_cls(const T* in, T* out, int n_img, int HW, int C, cudaStream_t stream);
+// dst rows <- src rows gathered: dst[i, :] = src[idx[i], :] (idx < 0 -> zeros)
+template <typename T>
+void gather_rows(const T* src, const int* idx, T* dst, long long n_rows, int C, cudaStream_t stream);
+// dst[idx[i], :] = src[i, :]
+template <typename T>
+void scatter_rows(const T* src, const int* idx, T* dst, long long n_rows, int C, cudaStream_t stream);
+template <typename TS, typename TD>
+void cast_copy(const TS* src, TD* dst, long long n, cudaStream_t stream);
+void fill_zero(void* p, size_t bytes, cudaStream_t stream);
+// BERT embeddings: (word[id] + type[tt]) + pos[p] -> LayerNorm.  One row per token.
+template <typename T>
+void embed_ln(const int* ids, const int* types, const int* pos, const T* word, const T* type_emb, const T* pos_emb,
+              const float* gamma, const float* beta, T* out, long long rows, int C, float eps, cudaStream_t stream);
+// weight preparation
+void bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, float eps, float* scale,
+             float* shift, int C, cudaStream_t stream);
+// W[out,in] += s * B[out,r] . A[r,in]
+void lora_merge(float* W, const float* A, const float* B, int n_out, int n_in, int r, float s, cudaStream_t stream);
+// dst[rows, cols_dst] (T) <- src[rows, cols_src] fp32 with zero padding of the extra columns
+template <typename T>
+void pack_matrix(const float* src, T* dst, int rows, int cols_src, int cols_dst, cudaStream_t stream);
+// conv weight [Cout, Cin, k, k] fp32 -> [Cout, k, k, Cin] T
+template <typename T>
+void pack_conv_khwc(const float* src, T* dst, int Cout, int Cin, int ksz, cudaStream_t stream);
+// dw weight [C,1,3,3] fp32 -> [9][C] fp32
+void pack_dw(const float* src, float* dst, int C, cudaStream_t stream);
+
+// ---- attention (attention.cu) ----------------------------------------------
+struct AttnArgs {
+  const void* q; const void* k; const void* v; void* o;
+  long long q_bs, q_hs, q_ts;    // batch / head / token strides (elements); head dim is 64, unit stride
+  long long k_bs, k_hs, k_ts;
+  long long v_bs, v_hs, v_ts;
+  long long o_bs, o_hs, o_ts;
+  int batch, heads, Lq, Lk;
+  const int* Lk_per_batch;       // nullable: per kv-batch key count (<= Lk)
+  const uint8_t* key_mask;       // nullable: [kv_batch or batch][key_mask_ld], 1 = visible
+  int key_mask_ld;
+  int key_mask_per_q_batch;      // 1: key_mask indexed by q batch; 0: by kv batch
+  int causal;                    // key j visible to query i iff j <= i + q_pos_offset
+  int q_pos_offset;
+  int kv_batch_mod;              // > 0: kv batch = q batch % kv_batch_mod
+  const int* kv_offset;          // nullable: per kv-batch token offset added to the key index (ragged caches)
+  float scale;
+};
+template <typename T> void attention_simt(const AttnArgs& a, cudaStream_t stream);
+
+}  // namespace cxrm
+
+// ---- decode-step kernels and rollout state (decode.cu) -----------------------
+namespace cxrm {
+
+constexpr int kMaxSpecial = 8;
+constexpr int kTopKCap = 64;     // slots per (row, step) for the surviving (index, score) pairs
+
+// Per-row rollout state, all device memory owned by the engine.
+struct RolloutState {
+  int* cur_token;        // [R] token fed at the next decoder step
+  int* cur_len;          // [R] cache slot of that token (= tokens already cached)
+  int* cur_type;         // [R] its token-type id
+  int* cur_pos;          // [R] its position id
+  int* n_valid;          // [R] number of non-masked tokens so far (incl. the fed one)
+  unsigned* seen;        // [R] bit i set: special_ids[i] occurred before the fed token
+  uint8_t* finished;     // [R]
+  uint8_t* key_valid;    // [R, Lmax] self-attention key validity (ids != mask_token_id)
+  int* seq;              // [R, Lmax] prompt + generated ids
+  float* logprob;        // [R, Tmax] log-prob of the emitted token under the (top-k-masked) distribution
+  float* margin;         // [R, Tmax] decision margin (tie diagnosis)
+  int* topk_idx;         // [R, Tmax, kTopKCap]
+  float* topk_val;       // [R, Tmax, kTopKCap]
+  int* topk_cnt;         // [R, Tmax] number of survivors (may exceed kTopKCap on ties)
+  int* step;             // scalar: decode steps executed so far
+  int* done;             // scalar: 1 once every row is finished or the budget is spent
+  unsigned* arrive;      // scalar: block-arrival counter of the sampling kernel
+};
+
+struct RolloutParams {
+  int R, B;              // rows (= B * n_modes), studies
+  int P;                 // prompt length (columns)
+  int Lmax;              // row stride of seq / key_valid
+  int Tmax;              // max new tokens
+  int V;
+  int n_special[2];      // per mode (0 = sample rows [0,B), 1 = greedy rows [B,2B) when both run)
+  int special_ids[2][kMaxSpecial];
+  int sections[2][kMaxSpecial + 1];
+  int mode_of_block[2];  // mode (0 sample / 1 greedy) of row block 0 and 1
+  int mask_token_id;     // -1: none (all keys valid)
+  int eos, pad;
+  int top_k;
+  float temperature;
+  unsigned long long seed;
+};
+
+// state from the prompt (reference modelling_longitudinal.py:274-282): types (full rule), positions,
+// key validity, `seen` bitmask; copies the prompt into seq; also emits the [R,P] prefill inputs.
+void rollout_init(const RolloutState& st, const RolloutParams& p, const int* prompt_ids, int* pre_ids, int* pre_types,
+                  int* pre_pos, cudaStream_t stream);
+
+// logits [R,V] fp32 (row stride ldl) -> next token per row (greedy argmax or top-k multinomial),
+// log-prob, survivors, and the state for the next decoder step.  exp_noise: nullable [Tmax, B, V].
+void sample_step(const RolloutState& st, const RolloutParams& p, const float* logits, int ldl, const float* exp_noise,
+                 cudaStream_t stream);
+
+// one-token self-attention over the row's KV cache; appends the new K/V first.
+// qkv [R, 3*768] (q | k | v); kcache/vcache [R, Lmax, 768] of this layer; ctx [R,768].
+template <typename T>
+void decode_self_attention(const T* qkv, T* kcache, T* vcache, T* ctx, const RolloutState& st, int R, int Lmax,
+                           cudaStream_t stream);
+
+// one-token cross-attention of the rows of each study over that study's encoder K/V.
+// q [R,768]; kc/vc [total_tokens, 768] with row stride ld, of this layer; study b owns tokens
+// [kv_off[b], kv_off[b]+kv_len[b]).  rows of study b: b, b+B, ... (R/B rows).  ws: fp32 workspace for split partials.
+template <typename T>
+void decode_cross_attention(const T* q, const T* kc, const T* vc, int ld, T* ctx, const int* kv_off, const int* kv_len,
+                            const RolloutState& st, int R, int B, int max_len, int nsplit, float* ws,
+                            cudaStream_t stream);
+size_t decode_cross_ws_bytes(int R, int nsplit);
+
+// qkv [R*P, 3*768] -> kcache/vcache [R, Lmax, 768] columns [0,P)
+template <typename T>
+void prefill_store_kv(const T* qkv, T* kcache, T* vcache, int R, int P, int Lmax, cudaStream_t stream);
+
+// copy rows [r, P-1] of x [R*P, C] into out [R, C]
+template <typename T>
+void take_last_token(const T* x, T* out, int R, int P, int C, cudaStream_t stream);
+
+// cosine similarity of rows: out[i] = <a_i, b_i> / (max(|a_i|, eps) * max(|b_i|, eps))  (torch eps 1e-8)
+void cosine_rows(const float* a, const float* b, float* out, int n, int C, cudaStream_t stream);
+
+}  // namespace cxrm

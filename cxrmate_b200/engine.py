@@ -1,0 +1,293 @@
+"""Thin torch-tensor wrapper over the C ABI: tensors in, tensors out, raw
+pointers across the boundary.  PyTorch is only the allocator / stream owner."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import torch
+
+from . import lib as _lib
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+@dataclass
+class RolloutOutput:
+    sequences: torch.Tensor       # [R, P+T] int64 (PAD filled); R = B, or 2B for mode 'both' (sample rows first)
+    steps: int                    # executed decode steps (== len(scores) of HF generate)
+    logprobs: torch.Tensor        # [R, T] fp32
+    margins: torch.Tensor         # [R, T] fp32 decision margins
+    topk_idx: torch.Tensor        # [R, T, 64] int32
+    topk_val: torch.Tensor        # [R, T, 64] fp32
+    topk_cnt: torch.Tensor        # [R, T] int32
+    last_logits: torch.Tensor     # [R, V] fp32
+
+
+class Engine:
+    """One engine per process / GPU."""
+
+    def __init__(self, *, dtype: str = "bf16", device: int = 0, image_size: int = 384, max_studies: int = 32,
+                 max_images: int = 5, max_prompt: int = 256, max_new_tokens: int = 255, vocab: int = 30000,
+                 cvt_depth: Sequence[int] = (1, 4, 16), dec_layers: int = 6, rwd_layers: int = 12,
+                 rwd_vocab: int = 30522, rwd_max_len: int = 512, rwd_max_seqs: Optional[int] = None,
+                 enc_chunk: int = 32, use_tensor_cores: bool = True, use_cuda_graph: bool = True):
+        if not torch.cuda.is_available():
+            raise RuntimeError("cxrmate_b200.Engine needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.lib = _lib.load()
+        cfg = _lib.default_config()
+        cfg.dtype = {"fp32": _lib.CXRM_F32, "bf16": _lib.CXRM_BF16}[dtype]
+        cfg.image_h = cfg.image_w = image_size
+        cfg.max_studies, cfg.max_images = max_studies, max_images
+        cfg.max_prompt, cfg.max_new_tokens, cfg.vocab = max_prompt, max_new_tokens, vocab
+        for i in range(3):
+            cfg.cvt_depth[i] = cvt_depth[i]
+        cfg.dec_layers, cfg.rwd_layers, cfg.rwd_vocab, cfg.rwd_max_len = dec_layers, rwd_layers, rwd_vocab, rwd_max_len
+        cfg.rwd_max_seqs = rwd_max_seqs if rwd_max_seqs is not None else 3 * max_studies
+        cfg.enc_chunk = enc_chunk
+        cfg.use_tensor_cores = int(use_tensor_cores)
+        cfg.use_cuda_graph = int(use_cuda_graph)
+        self.cfg = cfg
+        self.dtype = dtype
+        self.torch_dtype = torch.float32 if dtype == "fp32" else torch.bfloat16
+        self.device = torch.device("cuda", device)
+        self.tokens_per_image = (image_size // 16) ** 2
+        h = C.c_void_p()
+        rc = self.lib.cxrm_create(C.byref(cfg), device, C.byref(h))
+        if rc != 0:
+            raise RuntimeError(f"cxrm_create failed ({rc}): {self.lib.cxrm_last_error(None).decode()}")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.cxrm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise RuntimeError(f"{what} failed ({rc}): {self.lib.cxrm_last_error(self.h).decode()}")
+
+    # ------------------------------------------------------------------ weights
+    def load_state_dict(self, sd, prefix: str = ""):
+        """sd: mapping name -> fp32 tensor (CPU or CUDA) in the reference's naming."""
+        for name, t in sd.items():
+            if not torch.is_floating_point(t):
+                continue                       # num_batches_tracked
+            t = t.detach().to(torch.float32).contiguous()
+            shape = (C.c_int64 * max(t.dim(), 1))(*t.shape)
+            rc = self.lib.cxrm_load_weight(self.h, (prefix + name).encode(), C.c_void_p(t.data_ptr()), shape, t.dim(),
+                                           int(t.is_cuda))
+            self._check(rc, f"cxrm_load_weight({name})")
+
+    def finalize(self):
+        self._check(self.lib.cxrm_finalize_weights(self.h), "cxrm_finalize_weights")
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.cxrm_launch_count(self.h))
+
+    @property
+    def workspace_bytes(self) -> int:
+        return int(self.lib.cxrm_workspace_bytes(self.h))
+
+    # ------------------------------------------------------------------ encoder
+    def encode(self, pixels: torch.Tensor):
+        """pixels [B,N,3,H,W] fp32 cuda -> (memory [B,N*T,768] engine dtype, mask [B,N*T] bool)."""
+        assert pixels.is_cuda and pixels.dtype == torch.float32 and pixels.dim() == 5
+        pixels = pixels.contiguous()
+        B, N = pixels.shape[:2]
+        S = N * self.tokens_per_image
+        mem = torch.empty(B, S, 768, dtype=self.torch_dtype, device=pixels.device)
+        mask = torch.empty(B, S, dtype=torch.uint8, device=pixels.device)
+        self._check(self.lib.cxrm_encode(self.h, _ptr(pixels), B, N, _ptr(mem), _ptr(mask), _stream()), "cxrm_encode")
+        return mem, mask.bool()
+
+    def prefill_cross_kv(self, memory: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None):
+        if memory is None:
+            self._check(self.lib.cxrm_prefill_cross_kv(self.h, None, None, 0, 0, _stream()), "cxrm_prefill_cross_kv")
+            return
+        memory = memory.to(self.torch_dtype).contiguous()
+        B, S = memory.shape[:2]
+        m8 = None if mask is None else mask.to(torch.uint8).contiguous()
+        self._check(self.lib.cxrm_prefill_cross_kv(self.h, _ptr(memory), _ptr(m8), B, S, _stream()),
+                    "cxrm_prefill_cross_kv")
+
+    # ------------------------------------------------------------------ rollout
+    def rollout(self, prompt_ids: torch.Tensor, *, mode: str, max_new_tokens: int, eos_token_id: int,
+                pad_token_id: int, mask_token_id: Optional[int], special_sample=(), sections_sample=(0,),
+                special_greedy=(), sections_greedy=(0,), top_k: int = 50, temperature: float = 1.0,
+                exp_noise: Optional[torch.Tensor] = None, seed: int = 0) -> RolloutOutput:
+        dev = prompt_ids.device
+        B, P = prompt_ids.shape
+        p32 = prompt_ids.to(torch.int32).contiguous()
+        m = {"greedy": _lib.CXRM_GREEDY, "sample": _lib.CXRM_SAMPLE, "both": _lib.CXRM_BOTH}[mode]
+        R = B * (2 if mode == "both" else 1)
+        T, V = max_new_tokens, self.cfg.vocab
+        out = RolloutOutput(
+            sequences=torch.empty(R, P + T, dtype=torch.int32, device=dev), steps=0,
+            logprobs=torch.empty(R, T, dtype=torch.float32, device=dev),
+            margins=torch.empty(R, T, dtype=torch.float32, device=dev),
+            topk_idx=torch.zeros(R, T, _lib.TOPK_CAP, dtype=torch.int32, device=dev),
+            topk_val=torch.zeros(R, T, _lib.TOPK_CAP, dtype=torch.float32, device=dev),
+            topk_cnt=torch.zeros(R, T, dtype=torch.int32, device=dev),
+            last_logits=torch.empty(R, V, dtype=torch.float32, device=dev))
+        a = _lib.CxrmRolloutArgs()
+        a.mode, a.B, a.P = m, B, P
+        a.prompt_ids = p32.data_ptr()
+        a.mask_token_id = -1 if mask_token_id is None else int(mask_token_id)
+        assert len(sections_sample) == len(special_sample) + 1 and len(sections_greedy) == len(special_greedy) + 1
+        a.n_special_sample = len(special_sample)
+        a.n_special_greedy = len(special_greedy)
+        for i, v in enumerate(special_sample):
+            a.special_sample[i] = int(v)
+        for i, v in enumerate(sections_sample):
+            a.sections_sample[i] = int(v)
+        for i, v in enumerate(special_greedy):
+            a.special_greedy[i] = int(v)
+        for i, v in enumerate(sections_greedy):
+            a.sections_greedy[i] = int(v)
+        a.max_new_tokens, a.eos_token_id, a.pad_token_id = T, int(eos_token_id), int(pad_token_id)
+        a.top_k, a.temperature, a.seed = int(top_k), float(temperature), int(seed)
+        if exp_noise is not None:
+            assert exp_noise.shape == (T, B, V) and exp_noise.dtype == torch.float32 and exp_noise.is_cuda
+            exp_noise = exp_noise.contiguous()
+            a.exp_noise = exp_noise.data_ptr()
+        a.sequences = out.sequences.data_ptr()
+        a.logprobs = out.logprobs.data_ptr()
+        a.margins = out.margins.data_ptr()
+        a.topk_idx = out.topk_idx.data_ptr()
+        a.topk_val = out.topk_val.data_ptr()
+        a.topk_cnt = out.topk_cnt.data_ptr()
+        a.last_logits = out.last_logits.data_ptr()
+        steps = C.c_int32(0)
+        a.steps_out = C.addressof(steps)
+        self._check(self.lib.cxrm_rollout(self.h, C.byref(a), _stream()), "cxrm_rollout")
+        out.steps = int(steps.value)
+        out.sequences = out.sequences.to(torch.int64)
+        return out
+
+    # ------------------------------------------------------------------ teacher-forced forward
+    def decoder_forward(self, ids, token_type_ids, position_ids, key_mask, n_studies: int, last_only: bool = False):
+        R, L = ids.shape
+        dev = ids.device
+        i32 = lambda t: t.to(torch.int32).contiguous()
+        ids32, tt32, pos32 = i32(ids), i32(token_type_ids), i32(position_ids)
+        km = key_mask.to(torch.uint8).contiguous()
+        shape = (R, self.cfg.vocab) if last_only else (R, L, self.cfg.vocab)
+        logits = torch.empty(shape, dtype=torch.float32, device=dev)
+        self._check(self.lib.cxrm_decoder_forward(self.h, _ptr(ids32), _ptr(tt32), _ptr(pos32), _ptr(km), R, L,
+                                                  n_studies, int(last_only), _ptr(logits), _stream()),
+                    "cxrm_decoder_forward")
+        return logits
+
+    # ------------------------------------------------------------------ reward
+    def reward_embed(self, ids: torch.Tensor, lens: torch.Tensor) -> torch.Tensor:
+        n, L = ids.shape
+        ids32, lens32 = ids.to(torch.int32).contiguous(), lens.to(torch.int32).contiguous()
+        emb = torch.empty(n, 128, dtype=torch.float32, device=ids.device)
+        self._check(self.lib.cxrm_reward_embed(self.h, _ptr(ids32), _ptr(lens32), n, L, _ptr(emb), _stream()),
+                    "cxrm_reward_embed")
+        return emb
+
+    def cosine(self, a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+        a, b = a.contiguous().float(), b.contiguous().float()
+        out = torch.empty(a.shape[0], dtype=torch.float32, device=a.device)
+        self._check(self.lib.cxrm_cosine(self.h, _ptr(a), _ptr(b), a.shape[0], a.shape[1], _ptr(out), _stream()),
+                    "cxrm_cosine")
+        return out
+
+    def reward(self, pred_ids, pred_lens, label_ids, label_lens) -> torch.Tensor:
+        n = pred_ids.shape[0]
+        p32, pl = pred_ids.to(torch.int32).contiguous(), pred_lens.to(torch.int32).contiguous()
+        l32, ll = label_ids.to(torch.int32).contiguous(), label_lens.to(torch.int32).contiguous()
+        out = torch.empty(n, dtype=torch.float32, device=pred_ids.device)
+        self._check(self.lib.cxrm_reward(self.h, _ptr(p32), _ptr(pl), p32.shape[1], _ptr(l32), _ptr(ll), l32.shape[1],
+                                         n, _ptr(out), _stream()), "cxrm_reward")
+        return out
+
+    # ------------------------------------------------------------------ host-buffer SCST step
+    def set_id_map(self, id_map: torch.Tensor, cls_id: int, sep_id: int, bos_id: int, sep_dec_id: int):
+        m = id_map.to(torch.int32).cpu().contiguous()
+        self._check(self.lib.cxrm_set_id_map(self.h, _ptr(m), m.numel(), cls_id, sep_id, bos_id, sep_dec_id),
+                    "cxrm_set_id_map")
+
+    def scst_step_host(self, pixels: torch.Tensor, prompt_ids: torch.Tensor, label_ids: torch.Tensor,
+                       label_lens: torch.Tensor, *, max_new_tokens: int, eos_token_id: int, pad_token_id: int,
+                       mask_token_id: int, special_sample, sections_sample, special_greedy, sections_greedy,
+                       top_k: int = 50, temperature: float = 1.0, seed: int = 0, out=None):
+        """All inputs and outputs are HOST tensors (pinned for speed)."""
+        assert not pixels.is_cuda and pixels.dtype == torch.float32
+        B, N = pixels.shape[:2]
+        P = prompt_ids.shape[1]
+        T = max_new_tokens
+        p32 = prompt_ids.to(torch.int32).contiguous()
+        l32, ll = label_ids.to(torch.int32).contiguous(), label_lens.to(torch.int32).contiguous()
+        if out is None:
+            pin = dict(pin_memory=True)
+            out = dict(sequences=torch.empty(2 * B, P + T, dtype=torch.int32, **pin),
+                       logprobs=torch.empty(2 * B, T, dtype=torch.float32, **pin),
+                       reward=torch.empty(B, dtype=torch.float32, **pin),
+                       baseline=torch.empty(B, dtype=torch.float32, **pin),
+                       advantage=torch.empty(B, dtype=torch.float32, **pin),
+                       steps=torch.zeros(1, dtype=torch.int32, **pin))
+        a = _lib.CxrmRolloutArgs()
+        a.mask_token_id = int(mask_token_id)
+        a.n_special_sample, a.n_special_greedy = len(special_sample), len(special_greedy)
+        for i, v in enumerate(special_sample):
+            a.special_sample[i] = int(v)
+        for i, v in enumerate(sections_sample):
+            a.sections_sample[i] = int(v)
+        for i, v in enumerate(special_greedy):
+            a.special_greedy[i] = int(v)
+        for i, v in enumerate(sections_greedy):
+            a.sections_greedy[i] = int(v)
+        a.max_new_tokens, a.eos_token_id, a.pad_token_id = T, int(eos_token_id), int(pad_token_id)
+        a.top_k, a.temperature, a.seed = int(top_k), float(temperature), int(seed)
+        rc = self.lib.cxrm_scst_step_host(
+            self.h, _ptr(pixels), B, N, _ptr(p32), P, C.byref(a), _ptr(l32), _ptr(ll), l32.shape[1],
+            _ptr(out["sequences"]), _ptr(out["logprobs"]), _ptr(out["reward"]), _ptr(out["baseline"]),
+            _ptr(out["advantage"]), _ptr(out["steps"]), _stream())
+        self._check(rc, "cxrm_scst_step_host")
+        return out
+
+
+# ---------------------------------------------------------------------- kernel-level test hooks
+def gemm_hook(impl: str, A, W, bias=None, act: int = 0, residual=None, out_f32: bool = False):
+    lib = _lib.load()
+    M, K = A.shape
+    N = W.shape[0]
+    dt = _lib.CXRM_F32 if A.dtype == torch.float32 else _lib.CXRM_BF16
+    out = torch.empty(M, N, dtype=torch.float32 if (out_f32 or dt == _lib.CXRM_F32) else torch.bfloat16, device=A.device)
+    rc = lib.cxrm_test_gemm(1 if impl == "tcgen05" else 0, dt, _ptr(A), _ptr(W), _ptr(out), M, N, K, _ptr(bias), act,
+                            _ptr(residual), int(out_f32), _stream())
+    if rc != 0:
+        raise RuntimeError(f"cxrm_test_gemm failed ({rc}): {lib.cxrm_last_error(None).decode()}")
+    return out
+
+
+def attention_hook(q, k, v, key_mask=None, causal: bool = False, scale: float = 0.125):
+    """q [b, Lq, h*64], k/v [b, Lk, h*64] -> o like q."""
+    lib = _lib.load()
+    b, Lq, Cdim = q.shape
+    Lk = k.shape[1]
+    dt = _lib.CXRM_F32 if q.dtype == torch.float32 else _lib.CXRM_BF16
+    o = torch.empty_like(q)
+    km = None if key_mask is None else key_mask.to(torch.uint8).contiguous()
+    rc = lib.cxrm_test_attention(dt, _ptr(q), _ptr(k), _ptr(v), _ptr(o), b, Cdim // 64, Lq, Lk, _ptr(km), int(causal),
+                                 float(scale), _stream())
+    if rc != 0:
+        raise RuntimeError(f"cxrm_test_attention failed ({rc}): {lib.cxrm_last_error(None).decode()}")
+    return o
