@@ -132,8 +132,26 @@ int cxrm_scst_step_host(cxrm_engine* e, const float* pixels, int B, int N, const
                         float* advantage, int32_t* steps_out, void* stream) {
   if (!tmpl) return CXRM_ERR_INVALID;
   CXRM_GUARD(e, e->impl->scst_step_host(pixels, B, N, prompt_ids, P, *tmpl, label_ids, label_lens, L_label, sequences,
-                                        logprobs, reward, baseline, advantage, steps_out,
+                                        logprobs, reward, baseline, advantage, steps_out, /*on_device=*/false,
                                         static_cast<cudaStream_t>(stream)));
+}
+int cxrm_scst_step_device(cxrm_engine* e, const float* pixels, int B, int N, const int32_t* prompt_ids, int P,
+                          const cxrm_rollout_args* tmpl, const int32_t* label_ids, const int32_t* label_lens,
+                          int L_label, int32_t* sequences, float* logprobs, float* reward, float* baseline,
+                          float* advantage, int32_t* steps_out, void* stream) {
+  if (!tmpl) return CXRM_ERR_INVALID;
+  CXRM_GUARD(e, e->impl->scst_step_host(pixels, B, N, prompt_ids, P, *tmpl, label_ids, label_lens, L_label, sequences,
+                                        logprobs, reward, baseline, advantage, steps_out, /*on_device=*/true,
+                                        static_cast<cudaStream_t>(stream)));
+}
+int cxrm_set_profile(cxrm_engine* e, int on) { CXRM_GUARD(e, e->impl->set_profile(on != 0)); }
+int cxrm_profile_report(cxrm_engine* e, char* buf, size_t len) {
+  CXRM_GUARD(e, {
+    const std::string r = e->impl->profile_report();
+    if (!buf || len == 0) throw std::runtime_error("buffer");
+    std::strncpy(buf, r.c_str(), len - 1);
+    buf[len - 1] = 0;
+  });
 }
 
 int cxrm_test_gemm(int impl, int dtype, const void* A, const void* W, void* C, int M, int N, int K, const float* bias,

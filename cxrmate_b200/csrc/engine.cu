@@ -406,20 +406,69 @@ class Engine : public EngineBase {
   }
   size_t workspace_bytes() const override { return arena.capacity() + static_cast<size_t>(persistent_bytes); }
 
+  // =========================================================================== per-kernel-class profiler
+  // When enabled (cxrm_set_profile), every kernel launch of the engine is bracketed by a CUDA event pair on
+  // the launching stream and attributed to a class tag; graphs are bypassed so that each launch is visible.
+  struct ProfRec { std::string tag; cudaEvent_t a, b; };
+  template <class F> void PF(const char* tag, cudaStream_t s, F&& f) {
+    if (!profiling) {
+      f();
+      return;
+    }
+    ProfRec r;
+    r.tag = std::string(phase) + "." + tag;
+    if (ev_pool.size() >= 2) {
+      r.a = ev_pool.back(); ev_pool.pop_back();
+      r.b = ev_pool.back(); ev_pool.pop_back();
+    } else {
+      CXRM_CUDA_CHECK(cudaEventCreate(&r.a));
+      CXRM_CUDA_CHECK(cudaEventCreate(&r.b));
+    }
+    CXRM_CUDA_CHECK(cudaEventRecord(r.a, s));
+    f();
+    CXRM_CUDA_CHECK(cudaEventRecord(r.b, s));
+    prof_recs.push_back(r);
+  }
+  void set_profile(bool on) override { profiling = on; }
+  std::string profile_report() override {
+    CXRM_CUDA_CHECK(cudaDeviceSynchronize());
+    std::map<std::string, std::pair<double, long long>> agg;
+    for (auto& r : prof_recs) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, r.a, r.b);
+      auto& e = agg[r.tag];
+      e.first += ms;
+      e.second += 1;
+      ev_pool.push_back(r.a);
+      ev_pool.push_back(r.b);
+    }
+    prof_recs.clear();
+    std::string out = "{";
+    bool first = true;
+    for (auto& kv : agg) {
+      if (!first) out += ", ";
+      first = false;
+      out += "\"" + kv.first + "\": {\"ms\": " + std::to_string(kv.second.first) + ", \"n\": " +
+             std::to_string(kv.second.second) + "}";
+    }
+    return out + "}";
+  }
+
   // =========================================================================== GEMM dispatch
   void gemm(const T* A, int lda, const Lin& L, void* C, int ldc, long long M, int act, const T* residual, int ldr,
-            bool out_f32, const int* skip, cudaStream_t s) {
+            bool out_f32, const int* skip, cudaStream_t s, const char* tag = "gemm") {
     GemmArgs g;
     g.A = A; g.lda = lda; g.W = L.w; g.ldw = L.n_in; g.C = C; g.ldc = ldc;
     g.M = static_cast<int>(M); g.N = L.n_out; g.K = L.n_in;
     g.bias = L.b; g.act = act; g.residual = residual; g.ldr = ldr; g.out_f32 = out_f32 ? 1 : 0; g.skip_flag = skip;
-    dispatch_gemm(g, s);
+    PF(tag, s, [&] { dispatch_gemm(g, s); });
   }
   void dispatch_gemm(const GemmArgs& g, cudaStream_t s);
 
   // =========================================================================== encoder
   // n images (indices img_idx_dev into `pixels`) -> proj [n*T2, 768] in the arena
   T* encode_chunk(const float* pixels, const int* idx_dev, int n, cudaStream_t s) {
+    phase = "enc";
     arena.reset();
     int H = cfg.image_h, W = cfg.image_w;
     const long long tok0 = static_cast<long long>(H / 4) * (W / 4);
@@ -446,25 +495,25 @@ class Engine : public EngineBase {
       if (s_ == 0) {
         Ho = (H + 2 * pd - ks) / sd + 1;
         Wo = (W + 2 * pd - ks) / sd + 1;
-        im2col_pixels<T>(pixels, idx_dev, hid, n, H, W, ks, sd, pd, sw.emb.n_in, s);
+        PF("im2col", s, [&] { im2col_pixels<T>(pixels, idx_dev, hid, n, H, W, ks, sd, pd, sw.emb.n_in, s); });
       } else {
         Ho = (Hp + 2 * pd - ks) / sd + 1;
         Wo = (Wp + 2 * pd - ks) / sd + 1;
-        im2col_tokens<T>(prev, hid, n, Hp, Wp, CVT_C[s_ - 1], ks, sd, pd, s);
+        PF("im2col", s, [&] { im2col_tokens<T>(prev, hid, n, Hp, Wp, CVT_C[s_ - 1], ks, sd, pd, s); });
       }
       const long long rows = static_cast<long long>(n) * Ho * Wo;
       const int cls = (s_ == 2) ? 1 : 0;
       T* emb_out = cls ? x2 : x;
       gemm(hid, sw.emb.n_in, sw.emb, emb_out, C, rows, ACT_NONE, nullptr, 0, false, nullptr, s);
-      layernorm<T>(emb_out, C, emb_out, C, sw.emb_ln.g, sw.emb_ln.b, rows, C, LN_EPS_CVT, s);
-      if (cls) cat_cls<T>(x2, cls_token, x, n, Ho * Wo, C, s);
+      PF("layernorm", s, [&] { layernorm<T>(emb_out, C, emb_out, C, sw.emb_ln.g, sw.emb_ln.b, rows, C, LN_EPS_CVT, s); });
+      if (cls) PF("cls", s, [&] { cat_cls<T>(x2, cls_token, x, n, Ho * Wo, C, s); });
       const int Tq = cls + Ho * Wo;
       const int Hk = (Ho + 2 - 3) / 2 + 1, Wk = (Wo + 2 - 3) / 2 + 1;
       const int Tk = cls + Hk * Wk;
       const long long rq = static_cast<long long>(n) * Tq, rk = static_cast<long long>(n) * Tk;
       for (const CvtLayerW& L : sw.layers) {
-        layernorm<T>(x, C, y, C, L.ln1.g, L.ln1.b, rq, C, LN_EPS_CVT, s);
-        dwconv_bn_qkv<T>(y, q, k, v, L.dw, L.bn_scale, L.bn_shift, n, Ho, Wo, C, cls, s);
+        PF("layernorm", s, [&] { layernorm<T>(x, C, y, C, L.ln1.g, L.ln1.b, rq, C, LN_EPS_CVT, s); });
+        PF("dwconv", s, [&] { dwconv_bn_qkv<T>(y, q, k, v, L.dw, L.bn_scale, L.bn_shift, n, Ho, Wo, C, cls, s); });
         gemm(q, C, L.q, qp, C, rq, ACT_NONE, nullptr, 0, false, nullptr, s);
         gemm(k, C, L.k, kp, C, rk, ACT_NONE, nullptr, 0, false, nullptr, s);
         gemm(v, C, L.v, vp, C, rk, ACT_NONE, nullptr, 0, false, nullptr, s);
@@ -476,14 +525,14 @@ class Engine : public EngineBase {
         a.o_bs = a.q_bs; a.o_hs = 64; a.o_ts = C;
         a.batch = n; a.heads = CVT_HEADS[s_]; a.Lq = Tq; a.Lk = Tk;
         a.scale = 1.0f / sqrtf(static_cast<float>(C));   // embed_dim ** -0.5 (modeling_cvt.py:183)
-        attention(a, s);
+        PF("attn", s, [&] { attention(a, s); });
         gemm(q, C, L.o, x2, C, rq, ACT_NONE, x, C, false, nullptr, s);          // + residual
-        layernorm<T>(x2, C, y, C, L.ln2.g, L.ln2.b, rq, C, LN_EPS_CVT, s);
+        PF("layernorm", s, [&] { layernorm<T>(x2, C, y, C, L.ln2.g, L.ln2.b, rq, C, LN_EPS_CVT, s); });
         gemm(y, C, L.fc1, hid, 4 * C, rq, ACT_GELU, nullptr, 0, false, nullptr, s);
         gemm(hid, 4 * C, L.fc2, x, C, rq, ACT_NONE, x2, C, false, nullptr, s);  // + residual
       }
       if (cls) {
-        drop_cls<T>(x, x2, n, Ho * Wo, C, s);
+        PF("cls", s, [&] { drop_cls<T>(x, x2, n, Ho * Wo, C, s); });
         std::swap(x, x2);
       }
       // x now holds [n, Ho*Wo, C]; it becomes `prev`; continue in the other buffer
@@ -494,7 +543,7 @@ class Engine : public EngineBase {
     }
     // projection head: LN(eps 1e-12) -> Linear 384 -> 768 without bias (modelling_longitudinal.py:40-43)
     const long long rows = static_cast<long long>(n) * T2;
-    layernorm<T>(prev, CVT_C[2], y, CVT_C[2], head_ln.g, head_ln.b, rows, CVT_C[2], LN_EPS_BERT, s);
+    PF("layernorm", s, [&] { layernorm<T>(prev, CVT_C[2], y, CVT_C[2], head_ln.g, head_ln.b, rows, CVT_C[2], LN_EPS_BERT, s); });
     T* proj = qp;
     gemm(y, CVT_C[2], head_proj, proj, DH, rows, ACT_NONE, nullptr, 0, false, nullptr, s);
     return proj;
@@ -550,6 +599,7 @@ class Engine : public EngineBase {
       S = enc_S;
     }
     CXRM_CHECK(B >= 1 && B <= cfg.max_studies && S >= 1 && S <= Smax, "B/S exceed the configured maxima");
+    phase = "xkv";
     count_mask_kernel<<<ceil_div(B, 64), 64, 0, s>>>(mask, kv_len, B, S);
     check_launch("count_mask");
     std::vector<int> len(B), off(B);
@@ -568,7 +618,7 @@ class Engine : public EngineBase {
     CXRM_CUDA_CHECK(cudaMemcpyAsync(kv_off, off.data(), B * sizeof(int), cudaMemcpyHostToDevice, s));
     compact_rows_kernel<<<ceil_div(B, 64), 64, 0, s>>>(mask, kv_off, compact_idx, B, S);
     check_launch("compact_rows");
-    gather_rows<T>(mem, compact_idx, mem_compact, total, DH, s);
+    PF("gather", s, [&] { gather_rows<T>(mem, compact_idx, mem_compact, total, DH, s); });
     for (int l = 0; l < cfg.dec_layers; ++l) {
       T* kvl = cross_kv + static_cast<long long>(l) * cross_layer_stride();
       gemm(mem_compact, DH, dec.layers[l].ckv, kvl, 2 * DH, total, ACT_NONE, nullptr, 0, false, nullptr, s);
@@ -605,7 +655,7 @@ class Engine : public EngineBase {
       const BertLayerW& w = dec.layers[l];
       gemm(b.x, DH, w.qkv, b.qkv, 3 * DH, M, ACT_NONE, nullptr, 0, false, nullptr, s);
       if (store_cache)
-        prefill_store_kv<T>(b.qkv, self_k + l * self_layer_stride(), self_v + l * self_layer_stride(), R, q, Lmax, s);
+        PF("store_kv", s, [&] { prefill_store_kv<T>(b.qkv, self_k + l * self_layer_stride(), self_v + l * self_layer_stride(), R, q, Lmax, s); });
       AttnArgs a{};
       a.q = b.qkv; a.k = b.qkv + DH; a.v = b.qkv + 2 * DH; a.o = b.ctx;
       a.q_bs = static_cast<long long>(q) * 3 * DH; a.q_hs = 64; a.q_ts = 3 * DH;
@@ -616,9 +666,9 @@ class Engine : public EngineBase {
       a.key_mask = key_mask; a.key_mask_ld = ld_mask; a.key_mask_per_q_batch = 1;
       a.causal = 1; a.q_pos_offset = 0;
       a.scale = 0.125f;
-      attention(a, s);
+      PF("attn", s, [&] { attention(a, s); });
       gemm(b.ctx, DH, w.o, b.x1, DH, M, ACT_NONE, b.x, DH, false, nullptr, s);
-      layernorm<T>(b.x1, DH, b.x1, DH, w.ln1.g, w.ln1.b, M, DH, LN_EPS_BERT, s);
+      PF("layernorm", s, [&] { layernorm<T>(b.x1, DH, b.x1, DH, w.ln1.g, w.ln1.b, M, DH, LN_EPS_BERT, s); });
       // cross-attention over the ragged encoder K/V cache
       gemm(b.x1, DH, w.cq, b.qkv, DH, M, ACT_NONE, nullptr, 0, false, nullptr, s);
       const T* kvl = cross_kv + static_cast<long long>(l) * cross_layer_stride();
@@ -631,12 +681,12 @@ class Engine : public EngineBase {
       c.batch = R; c.heads = NHEAD; c.Lq = q; c.Lk = kv_maxlen;
       c.Lk_per_batch = kv_len; c.kv_offset = kv_off; c.kv_batch_mod = B;
       c.scale = 0.125f;
-      attention(c, s);
+      PF("attn", s, [&] { attention(c, s); });
       gemm(b.ctx, DH, w.co, b.x, DH, M, ACT_NONE, b.x1, DH, false, nullptr, s);
-      layernorm<T>(b.x, DH, b.x, DH, w.ln2.g, w.ln2.b, M, DH, LN_EPS_BERT, s);
+      PF("layernorm", s, [&] { layernorm<T>(b.x, DH, b.x, DH, w.ln2.g, w.ln2.b, M, DH, LN_EPS_BERT, s); });
       gemm(b.x, DH, w.fc1, b.hid, DFF, M, ACT_GELU, nullptr, 0, false, nullptr, s);
       gemm(b.hid, DFF, w.fc2, b.x1, DH, M, ACT_NONE, b.x, DH, false, nullptr, s);
-      layernorm<T>(b.x1, DH, b.x, DH, w.ln3.g, w.ln3.b, M, DH, LN_EPS_BERT, s);
+      PF("layernorm", s, [&] { layernorm<T>(b.x1, DH, b.x, DH, w.ln3.g, w.ln3.b, M, DH, LN_EPS_BERT, s); });
     }
     return b.x;
   }
@@ -645,36 +695,37 @@ class Engine : public EngineBase {
   // LM head on `rows` hidden rows -> fp32 logits (dense -> GELU -> LN -> tied decoder + bias)
   void lm_head(const T* hidden, long long rows, T* tmp, float* out, int ld_out, const int* skip, cudaStream_t s) {
     gemm(hidden, DH, dec_head_t, tmp, DH, rows, ACT_GELU, nullptr, 0, false, skip, s);
-    layernorm<T>(tmp, DH, tmp, DH, dec_head_ln.g, dec_head_ln.b, rows, DH, LN_EPS_BERT, s);
+    PF("layernorm", s, [&] { layernorm<T>(tmp, DH, tmp, DH, dec_head_ln.g, dec_head_ln.b, rows, DH, LN_EPS_BERT, s); });
     gemm(tmp, DH, dec_lm, out, ld_out, rows, ACT_NONE, nullptr, 0, true, skip, s);
   }
 
   // one decode step for R rows (all inputs come from the device-side rollout state)
   void decode_step(DecBufs& b, T* head_tmp, const RolloutParams& rp, const float* noise, cudaStream_t s) {
+    phase = "decode";
     const int R = rp.R, B = rp.B;
     const int* skip = st.done;
-    embed_ln<T>(st.cur_token, st.cur_type, st.cur_pos, dec.word, dec.type, dec.pos, dec.emb_ln.g, dec.emb_ln.b, b.x, R,
-                DH, LN_EPS_BERT, s);
+    PF("embed_ln", s, [&] { embed_ln<T>(st.cur_token, st.cur_type, st.cur_pos, dec.word, dec.type, dec.pos, dec.emb_ln.g, dec.emb_ln.b, b.x, R,
+                DH, LN_EPS_BERT, s); });
     for (int l = 0; l < cfg.dec_layers; ++l) {
       const BertLayerW& w = dec.layers[l];
       gemm(b.x, DH, w.qkv, b.qkv, 3 * DH, R, ACT_NONE, nullptr, 0, false, skip, s);
-      decode_self_attention<T>(b.qkv, self_k + l * self_layer_stride(), self_v + l * self_layer_stride(), b.ctx, st, R,
-                               Lmax, s);
+      PF("self_attn", s, [&] { decode_self_attention<T>(b.qkv, self_k + l * self_layer_stride(), self_v + l * self_layer_stride(), b.ctx, st, R,
+                               Lmax, s); });
       gemm(b.ctx, DH, w.o, b.x1, DH, R, ACT_NONE, b.x, DH, false, skip, s);
-      layernorm<T>(b.x1, DH, b.x1, DH, w.ln1.g, w.ln1.b, R, DH, LN_EPS_BERT, s);
+      PF("layernorm", s, [&] { layernorm<T>(b.x1, DH, b.x1, DH, w.ln1.g, w.ln1.b, R, DH, LN_EPS_BERT, s); });
       gemm(b.x1, DH, w.cq, b.qkv, DH, R, ACT_NONE, nullptr, 0, false, skip, s);
       const T* kvl = cross_kv + static_cast<long long>(l) * cross_layer_stride();
       // smem sized for the configured maximum so that the captured graph does not depend on the batch's image counts
-      decode_cross_attention<T>(b.qkv, kvl, kvl + DH, 2 * DH, b.ctx, kv_off, kv_len, st, R, B, Smax, cross_nsplit,
-                                cross_ws, s);
+      PF("cross_attn", s, [&] { decode_cross_attention<T>(b.qkv, kvl, kvl + DH, 2 * DH, b.ctx, kv_off, kv_len, st, R, B, Smax, cross_nsplit,
+                                cross_ws, s); });
       gemm(b.ctx, DH, w.co, b.x, DH, R, ACT_NONE, b.x1, DH, false, skip, s);
-      layernorm<T>(b.x, DH, b.x, DH, w.ln2.g, w.ln2.b, R, DH, LN_EPS_BERT, s);
+      PF("layernorm", s, [&] { layernorm<T>(b.x, DH, b.x, DH, w.ln2.g, w.ln2.b, R, DH, LN_EPS_BERT, s); });
       gemm(b.x, DH, w.fc1, b.hid, DFF, R, ACT_GELU, nullptr, 0, false, skip, s);
       gemm(b.hid, DFF, w.fc2, b.x1, DH, R, ACT_NONE, b.x, DH, false, skip, s);
-      layernorm<T>(b.x1, DH, b.x, DH, w.ln3.g, w.ln3.b, R, DH, LN_EPS_BERT, s);
+      PF("layernorm", s, [&] { layernorm<T>(b.x1, DH, b.x, DH, w.ln3.g, w.ln3.b, R, DH, LN_EPS_BERT, s); });
     }
     lm_head(b.x, R, head_tmp, logits, cfg.vocab, skip, s);
-    sample_step(st, rp, logits, cfg.vocab, noise, s);
+    PF("sample", s, [&] { sample_step(st, rp, logits, cfg.vocab, noise, s); });
   }
 
   void rollout(const cxrm_rollout_args& a, cudaStream_t s_user) override {
@@ -710,7 +761,7 @@ class Engine : public EngineBase {
     rp.mask_token_id = a.mask_token_id; rp.eos = a.eos_token_id; rp.pad = a.pad_token_id;
     rp.top_k = a.top_k; rp.temperature = a.temperature; rp.seed = a.seed;
     // the kernels index logprob/topk buffers with Tmax = Tn
-    rollout_init(st, rp, a.prompt_ids, pre_ids, pre_types, pre_pos, s);
+    PF("init", s, [&] { rollout_init(st, rp, a.prompt_ids, pre_ids, pre_types, pre_pos, s); });
 
     arena.reset();
     const long long M = static_cast<long long>(R) * P;
@@ -718,15 +769,15 @@ class Engine : public EngineBase {
     T* last = arena.get<T>(static_cast<long long>(R) * DH);
     T* head_tmp = arena.get<T>(static_cast<long long>(R) * DH);
     DecBufs pb = dec_bufs(M);
-    embed_ln<T>(pre_ids, pre_types, pre_pos, dec.word, dec.type, dec.pos, dec.emb_ln.g, dec.emb_ln.b, pb.x, M, DH,
-                LN_EPS_BERT, s);
+    PF("embed_ln", s, [&] { embed_ln<T>(pre_ids, pre_types, pre_pos, dec.word, dec.type, dec.pos, dec.emb_ln.g, dec.emb_ln.b, pb.x, M, DH,
+                LN_EPS_BERT, s); });
     T* hid = decoder_full(pb, R, P, a.B, st.key_valid, Lmax, /*store_cache=*/true, s);
-    take_last_token<T>(hid, last, R, P, DH, s);
+    PF("take_last", s, [&] { take_last_token<T>(hid, last, R, P, DH, s); });
     lm_head(last, R, head_tmp, logits, cfg.vocab, nullptr, s);
-    sample_step(st, rp, logits, cfg.vocab, a.exp_noise, s);
+    PF("sample", s, [&] { sample_step(st, rp, logits, cfg.vocab, a.exp_noise, s); });
 
     if (Tn > 1) {
-      if (cfg.use_cuda_graph) {
+      if (cfg.use_cuda_graph && !profiling) {
         run_decode_graph(db, head_tmp, rp, a.exp_noise, Tn - 1, s);
       } else {
         for (int t = 1; t < Tn; ++t) decode_step(db, head_tmp, rp, a.exp_noise, s);
@@ -806,14 +857,15 @@ class Engine : public EngineBase {
     CXRM_CHECK(finalized, "weights not finalized");
     CXRM_CHECK(kv_B == B && kv_total > 0, "cxrm_decoder_forward needs cxrm_prefill_cross_kv for the same B");
     CXRM_CHECK(R >= 1 && R % B == 0 && L >= 1 && L <= 512, "decoder_forward shape");
+    phase = "fwd";
     arena.reset();
     const long long M = static_cast<long long>(R) * L;
     DecBufs b = dec_bufs(M);
-    embed_ln<T>(ids, tt, pos, dec.word, dec.type, dec.pos, dec.emb_ln.g, dec.emb_ln.b, b.x, M, DH, LN_EPS_BERT, s);
+    PF("embed_ln", s, [&] { embed_ln<T>(ids, tt, pos, dec.word, dec.type, dec.pos, dec.emb_ln.g, dec.emb_ln.b, b.x, M, DH, LN_EPS_BERT, s); });
     T* hid = decoder_full(b, R, L, B, key_mask, L, /*store_cache=*/false, s);
     if (last_only) {
       T* last = b.ctx;
-      take_last_token<T>(hid, last, R, L, DH, s);
+      PF("take_last", s, [&] { take_last_token<T>(hid, last, R, L, DH, s); });
       lm_head(last, R, b.x1, logits_out, cfg.vocab, nullptr, s);
     } else {
       lm_head(hid, M, b.x1, logits_out, cfg.vocab, nullptr, s);
@@ -825,13 +877,14 @@ class Engine : public EngineBase {
     CXRM_CHECK(finalized && have_reward, "reward model weights not loaded");
     CXRM_CHECK(n >= 1 && L >= 1 && L <= cfg.rwd_max_len && static_cast<long long>(n) * L <=
                    static_cast<long long>(std::max(cfg.rwd_max_seqs, 1)) * cfg.rwd_max_len, "reward batch too large");
+    phase = "rwd";
     arena.reset();
     const long long M = static_cast<long long>(n) * L;
     DecBufs b = dec_bufs(M);
     int* pos = arena.get<int>(M);
     iota_pos_kernel<<<static_cast<unsigned>(ceil_div_ll(M, 256)), 256, 0, s>>>(pos, n, L);
     check_launch("iota_pos");
-    embed_ln<T>(ids, nullptr, pos, rwd.word, rwd.type, rwd.pos, rwd.emb_ln.g, rwd.emb_ln.b, b.x, M, DH, LN_EPS_BERT, s);
+    PF("embed_ln", s, [&] { embed_ln<T>(ids, nullptr, pos, rwd.word, rwd.type, rwd.pos, rwd.emb_ln.g, rwd.emb_ln.b, b.x, M, DH, LN_EPS_BERT, s); });
     for (int l = 0; l < cfg.rwd_layers; ++l) {
       const BertLayerW& w = rwd.layers[l];
       gemm(b.x, DH, w.qkv, b.qkv, 3 * DH, M, ACT_NONE, nullptr, 0, false, nullptr, s);
@@ -844,18 +897,18 @@ class Engine : public EngineBase {
       a.batch = n; a.heads = NHEAD; a.Lq = L; a.Lk = L;
       a.Lk_per_batch = lens;      // attention_mask from padding='longest' == (j < len)
       a.scale = 0.125f;
-      attention(a, s);
+      PF("attn", s, [&] { attention(a, s); });
       gemm(b.ctx, DH, w.o, b.x1, DH, M, ACT_NONE, b.x, DH, false, nullptr, s);
-      layernorm<T>(b.x1, DH, b.x1, DH, w.ln1.g, w.ln1.b, M, DH, LN_EPS_BERT, s);
+      PF("layernorm", s, [&] { layernorm<T>(b.x1, DH, b.x1, DH, w.ln1.g, w.ln1.b, M, DH, LN_EPS_BERT, s); });
       gemm(b.x1, DH, w.fc1, b.hid, DFF, M, ACT_GELU, nullptr, 0, false, nullptr, s);
       gemm(b.hid, DFF, w.fc2, b.x, DH, M, ACT_NONE, b.x1, DH, false, nullptr, s);
-      layernorm<T>(b.x, DH, b.x, DH, w.ln3.g, w.ln3.b, M, DH, LN_EPS_BERT, s);
+      PF("layernorm", s, [&] { layernorm<T>(b.x, DH, b.x, DH, w.ln3.g, w.ln3.b, M, DH, LN_EPS_BERT, s); });
     }
     // [CLS] rows (token 0 of every sequence: row stride L*768) -> 768 -> 128 GELU -> LN -> 128
     T* h1 = b.ctx;
     T* h2 = b.x1;
     gemm(b.x, L * DH, rp1, h1, 128, n, ACT_GELU, nullptr, 0, false, nullptr, s);
-    layernorm<T>(h1, 128, h1, 128, rp_ln.g, rp_ln.b, n, 128, LN_EPS_BERT, s);
+    PF("layernorm", s, [&] { layernorm<T>(h1, 128, h1, 128, rp_ln.g, rp_ln.b, n, 128, LN_EPS_BERT, s); });
     gemm(h1, 128, rp2, emb_out, 128, n, ACT_NONE, nullptr, 0, true, nullptr, s);
     (void)h2;
   }
@@ -873,25 +926,33 @@ class Engine : public EngineBase {
 
   void scst_step_host(const float* pixels, int B, int N, const int* prompt_ids, int P, const cxrm_rollout_args& tmpl,
                       const int* label_ids, const int* label_lens, int L_label, int* sequences, float* logprobs,
-                      float* reward, float* baseline, float* advantage, int* steps_out, cudaStream_t s) override {
+                      float* reward, float* baseline, float* advantage, int* steps_out, bool on_device,
+                      cudaStream_t s) override {
     CXRM_CHECK(finalized && have_reward && id_map, "scst_step_host needs all weights and cxrm_set_id_map");
     CXRM_CHECK(B <= cfg.max_studies && N <= cfg.max_images && P <= cfg.max_prompt, "scst_step_host shape");
     CXRM_CHECK(3 * B <= cfg.rwd_max_seqs && L_label <= cfg.rwd_max_len, "reward batch exceeds rwd_max_seqs");
-    const int Tn = tmpl.max_new_tokens, R = 2 * B, Lseq = P + Tn, Lr = cfg.rwd_max_len;
+    const int Tn = tmpl.max_new_tokens, R = 2 * B, Lseq = P + Tn;
+    // longest possible reward input: [CLS] + generated words + [SEP], or the longest label
+    const int Lr = std::min(cfg.rwd_max_len, std::max(Tn + 2, L_label));
     if (!h_pixels) {
       h_pixels = dalloc<float>(static_cast<long long>(cfg.max_studies) * cfg.max_images * 3 * cfg.image_h * cfg.image_w);
       h_seq = dalloc<int>(static_cast<long long>(Rmax) * Lmax);
       h_lp = dalloc<float>(static_cast<long long>(Rmax) * cfg.max_new_tokens);
-      h_rids = dalloc<int>(3LL * cfg.max_studies * Lr);
+      h_rids = dalloc<int>(3LL * cfg.max_studies * cfg.rwd_max_len);
       h_rlens = dalloc<int>(3LL * cfg.max_studies);
       h_emb = dalloc<float>(3LL * cfg.max_studies * 128);
       h_out = dalloc<float>(3LL * cfg.max_studies);
-      h_labels = dalloc<int>(static_cast<long long>(cfg.max_studies) * Lr);
+      h_labels = dalloc<int>(static_cast<long long>(cfg.max_studies) * cfg.rwd_max_len);
     }
     const size_t px = static_cast<size_t>(B) * N * 3 * cfg.image_h * cfg.image_w * sizeof(float);
-    CXRM_CUDA_CHECK(cudaMemcpyAsync(h_pixels, pixels, px, cudaMemcpyHostToDevice, s));
-    CXRM_CUDA_CHECK(cudaMemcpyAsync(prompt_dev, prompt_ids, static_cast<size_t>(B) * P * sizeof(int), cudaMemcpyHostToDevice, s));
-    encode(h_pixels, B, N, nullptr, nullptr, s);
+    const float* px_dev = pixels;
+    if (!on_device) {
+      CXRM_CUDA_CHECK(cudaMemcpyAsync(h_pixels, pixels, px, cudaMemcpyHostToDevice, s));
+      px_dev = h_pixels;
+    }
+    // cudaMemcpyDefault: the direction is inferred from the (unified) addresses, host or device
+    CXRM_CUDA_CHECK(cudaMemcpyAsync(prompt_dev, prompt_ids, static_cast<size_t>(B) * P * sizeof(int), cudaMemcpyDefault, s));
+    encode(px_dev, B, N, nullptr, nullptr, s);
     prefill_cross_kv(nullptr, nullptr, 0, 0, s);
     cxrm_rollout_args a = tmpl;
     a.mode = CXRM_BOTH; a.B = B; a.P = P; a.prompt_ids = prompt_dev;
@@ -906,19 +967,19 @@ class Engine : public EngineBase {
     // labels are already reward-model ids, padded to L_label: copy into the [*, Lr] layout
     CXRM_CUDA_CHECK(cudaMemsetAsync(h_rids + static_cast<long long>(R) * Lr, 0, static_cast<size_t>(B) * Lr * sizeof(int), s));
     CXRM_CUDA_CHECK(cudaMemcpy2DAsync(h_rids + static_cast<long long>(R) * Lr, Lr * sizeof(int), label_ids,
-                                      L_label * sizeof(int), L_label * sizeof(int), B, cudaMemcpyHostToDevice, s));
-    CXRM_CUDA_CHECK(cudaMemcpyAsync(h_rlens + R, label_lens, B * sizeof(int), cudaMemcpyHostToDevice, s));
+                                      L_label * sizeof(int), L_label * sizeof(int), B, cudaMemcpyDefault, s));
+    CXRM_CUDA_CHECK(cudaMemcpyAsync(h_rlens + R, label_lens, B * sizeof(int), cudaMemcpyDefault, s));
     reward_embed(h_rids, h_rlens, 3 * B, Lr, h_emb, s);
     cosine_rows(h_emb, h_emb + static_cast<long long>(R) * 128, h_out, B, 128, s);                               // sample vs label
     cosine_rows(h_emb + static_cast<long long>(B) * 128, h_emb + static_cast<long long>(R) * 128, h_out + B, B, 128, s);  // greedy vs label
     advantage_kernel<<<ceil_div(B, 64), 64, 0, s>>>(h_out, h_out + B, h_out + 2 * B, B);
     check_launch("advantage");
-    CXRM_CUDA_CHECK(cudaMemcpyAsync(sequences, h_seq, static_cast<size_t>(R) * Lseq * sizeof(int), cudaMemcpyDeviceToHost, s));
-    if (logprobs) CXRM_CUDA_CHECK(cudaMemcpyAsync(logprobs, h_lp, static_cast<size_t>(R) * Tn * sizeof(float), cudaMemcpyDeviceToHost, s));
-    CXRM_CUDA_CHECK(cudaMemcpyAsync(reward, h_out, B * sizeof(float), cudaMemcpyDeviceToHost, s));
-    CXRM_CUDA_CHECK(cudaMemcpyAsync(baseline, h_out + B, B * sizeof(float), cudaMemcpyDeviceToHost, s));
-    CXRM_CUDA_CHECK(cudaMemcpyAsync(advantage, h_out + 2 * B, B * sizeof(float), cudaMemcpyDeviceToHost, s));
-    if (steps_out) CXRM_CUDA_CHECK(cudaMemcpyAsync(steps_out, st.step, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CXRM_CUDA_CHECK(cudaMemcpyAsync(sequences, h_seq, static_cast<size_t>(R) * Lseq * sizeof(int), cudaMemcpyDefault, s));
+    if (logprobs) CXRM_CUDA_CHECK(cudaMemcpyAsync(logprobs, h_lp, static_cast<size_t>(R) * Tn * sizeof(float), cudaMemcpyDefault, s));
+    CXRM_CUDA_CHECK(cudaMemcpyAsync(reward, h_out, B * sizeof(float), cudaMemcpyDefault, s));
+    CXRM_CUDA_CHECK(cudaMemcpyAsync(baseline, h_out + B, B * sizeof(float), cudaMemcpyDefault, s));
+    CXRM_CUDA_CHECK(cudaMemcpyAsync(advantage, h_out + 2 * B, B * sizeof(float), cudaMemcpyDefault, s));
+    if (steps_out) CXRM_CUDA_CHECK(cudaMemcpyAsync(steps_out, st.step, sizeof(int), cudaMemcpyDefault, s));
     CXRM_CUDA_CHECK(cudaStreamSynchronize(s));
   }
 
@@ -932,6 +993,10 @@ class Engine : public EngineBase {
   Arena arena;
   cudaStream_t side_stream = nullptr;
   cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+  bool profiling = false;
+  const char* phase = "misc";
+  std::vector<ProfRec> prof_recs;
+  std::vector<cudaEvent_t> ev_pool;
   // weights
   CvtStageW stages[3];
   float* cls_token = nullptr;

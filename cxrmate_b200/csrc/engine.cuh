@@ -52,8 +52,10 @@ class EngineBase {
   virtual void scst_step_host(const float* pixels, int B, int N, const int* prompt_ids, int P,
                               const cxrm_rollout_args& tmpl, const int* label_ids, const int* label_lens, int L_label,
                               int* sequences, float* logprobs, float* reward, float* baseline, float* advantage,
-                              int* steps_out, cudaStream_t s) = 0;
+                              int* steps_out, bool on_device, cudaStream_t s) = 0;
   virtual size_t workspace_bytes() const = 0;
+  virtual void set_profile(bool on) = 0;
+  virtual std::string profile_report() = 0;
   std::string last_error;
   unsigned long long launches = 0;
 };

@@ -224,19 +224,32 @@ class Engine:
         self._check(self.lib.cxrm_set_id_map(self.h, _ptr(m), m.numel(), cls_id, sep_id, bos_id, sep_dec_id),
                     "cxrm_set_id_map")
 
-    def scst_step_host(self, pixels: torch.Tensor, prompt_ids: torch.Tensor, label_ids: torch.Tensor,
-                       label_lens: torch.Tensor, *, max_new_tokens: int, eos_token_id: int, pad_token_id: int,
-                       mask_token_id: int, special_sample, sections_sample, special_greedy, sections_greedy,
-                       top_k: int = 50, temperature: float = 1.0, seed: int = 0, out=None):
-        """All inputs and outputs are HOST tensors (pinned for speed)."""
-        assert not pixels.is_cuda and pixels.dtype == torch.float32
+    def set_profile(self, on: bool):
+        self._check(self.lib.cxrm_set_profile(self.h, int(on)), "cxrm_set_profile")
+
+    def profile_report(self) -> dict:
+        import json
+        buf = C.create_string_buffer(1 << 16)
+        self._check(self.lib.cxrm_profile_report(self.h, buf, len(buf)), "cxrm_profile_report")
+        return json.loads(buf.value.decode())
+
+    def scst_step(self, pixels: torch.Tensor, prompt_ids: torch.Tensor, label_ids: torch.Tensor,
+                  label_lens: torch.Tensor, *, max_new_tokens: int, eos_token_id: int, pad_token_id: int,
+                  mask_token_id: int, special_sample, sections_sample, special_greedy, sections_greedy,
+                  top_k: int = 50, temperature: float = 1.0, seed: int = 0, out=None):
+        """Whole SCST rollout step.  Either every tensor is a HOST tensor (pinned for speed; the timed end-to-end
+        call: H2D inside, D2H inside, synchronous) or every tensor is a CUDA tensor (device-resident variant).
+        prompt_ids / label_ids / label_lens must be int32."""
+        on_dev = pixels.is_cuda
+        assert pixels.dtype == torch.float32 and pixels.is_contiguous()
         B, N = pixels.shape[:2]
         P = prompt_ids.shape[1]
         T = max_new_tokens
         p32 = prompt_ids.to(torch.int32).contiguous()
         l32, ll = label_ids.to(torch.int32).contiguous(), label_lens.to(torch.int32).contiguous()
+        assert p32.is_cuda == on_dev and l32.is_cuda == on_dev and ll.is_cuda == on_dev
         if out is None:
-            pin = dict(pin_memory=True)
+            pin = dict(device=pixels.device) if on_dev else dict(pin_memory=True)
             out = dict(sequences=torch.empty(2 * B, P + T, dtype=torch.int32, **pin),
                        logprobs=torch.empty(2 * B, T, dtype=torch.float32, **pin),
                        reward=torch.empty(B, dtype=torch.float32, **pin),
@@ -256,11 +269,12 @@ class Engine:
             a.sections_greedy[i] = int(v)
         a.max_new_tokens, a.eos_token_id, a.pad_token_id = T, int(eos_token_id), int(pad_token_id)
         a.top_k, a.temperature, a.seed = int(top_k), float(temperature), int(seed)
-        rc = self.lib.cxrm_scst_step_host(
+        fn = self.lib.cxrm_scst_step_device if on_dev else self.lib.cxrm_scst_step_host
+        rc = fn(
             self.h, _ptr(pixels), B, N, _ptr(p32), P, C.byref(a), _ptr(l32), _ptr(ll), l32.shape[1],
             _ptr(out["sequences"]), _ptr(out["logprobs"]), _ptr(out["reward"]), _ptr(out["baseline"]),
             _ptr(out["advantage"]), _ptr(out["steps"]), _stream())
-        self._check(rc, "cxrm_scst_step_host")
+        self._check(rc, "cxrm_scst_step")
         return out
 
 

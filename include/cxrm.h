@@ -217,6 +217,20 @@ CXRM_API int cxrm_scst_step_host(cxrm_engine* e, const float* pixels, int B, int
                         const int32_t* label_lens, int L_label, int32_t* sequences, float* logprobs, float* reward,
                         float* baseline, float* advantage, int32_t* steps_out, void* stream);
 
+/* Same step with every input and output buffer already resident in device memory (bench.py's `value`). */
+CXRM_API int cxrm_scst_step_device(cxrm_engine* e, const float* pixels, int B, int N, const int32_t* prompt_ids, int P,
+                          const cxrm_rollout_args* rollout_template, const int32_t* label_ids,
+                          const int32_t* label_lens, int L_label, int32_t* sequences, float* logprobs, float* reward,
+                          float* baseline, float* advantage, int32_t* steps_out, void* stream);
+
+/*
+ * Per-kernel-class timing: while enabled every kernel launch is bracketed by a CUDA event pair on its stream
+ * (CUDA-graph replay is bypassed so each launch is visible).  cxrm_profile_report synchronises, writes a JSON
+ * object {"<phase>.<kernel class>": {"ms": total, "n": launches}, ...} into buf and clears the records.
+ */
+CXRM_API int cxrm_set_profile(cxrm_engine* e, int on);
+CXRM_API int cxrm_profile_report(cxrm_engine* e, char* buf, size_t len);
+
 /* Standalone GEMM entry used by the kernel tests: C = A[M,K] . W[N,K]^T (+bias, act, +residual).
  * impl: 0 = SIMT fp32-FMA, 1 = tcgen05.  dtype: cxrm_dtype of A/W/C/residual. */
 CXRM_API int cxrm_test_gemm(int impl, int dtype, const void* A, const void* W, void* C, int M, int N, int K,

@@ -38,7 +38,8 @@ def test_gemm(impl, dtype, M, N, K):
         torch.cuda.synchronize()
         ref = _ref_gemm(A, W, bias if use_bias else None, act, res if use_res else None)
         err = (out.float() - ref).abs().max().item()
-        tol = 2e-4 if dtype == torch.float32 else (2e-3 if out_f32 else 3e-2)
+        # bf16 stores: half an ulp of the largest output (2^-8 relative) on top of the accumulation error
+        tol = 2e-4 if dtype == torch.float32 else (2e-3 if out_f32 else 2e-3 + ref.abs().max().item() * 2 ** -8)
         assert err < tol, f"{impl} {dtype} {M}x{N}x{K} bias={use_bias} act={act} res={use_res} f32={out_f32}: max err {err}"
 
 
