@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-profile", action="store_true", help="skip the per-kernel-class event profile (no roofline)")
     ap.add_argument("--profile-out", default="")
     ap.add_argument("--cpu-tokens", type=int, default=12, help="decode steps of the bounded CPU sample")
     return ap.parse_args()
@@ -279,7 +280,7 @@ def run_b200(a):
 
         # ---- per-kernel-class profile of one more step (event pairs around every launch, no graph) ------
         roofline, breakdown = None, None
-        if rank == 0:
+        if rank == 0 and not a.no_profile:
             eng.set_profile(True)
             eng.scst_step(px_d, prompt_d, lab_d, lab_len_d, seed=999, **kw)
             rep = eng.profile_report()

@@ -159,7 +159,7 @@ int cxrm_test_gemm(int impl, int dtype, const void* A, const void* W, void* C, i
   try {
     GemmArgs g;
     g.A = A; g.lda = K; g.W = W; g.ldw = K; g.C = C; g.ldc = N; g.M = M; g.N = N; g.K = K;
-    g.bias = bias; g.act = act; g.residual = residual; g.ldr = N; g.out_f32 = out_f32; g.skip_flag = nullptr;
+    g.bias = bias; g.act = act; g.residual = residual; g.ldr = N; g.out_f32 = out_f32; g.skip_flag = nullptr; g.c_head_stride = 0;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (impl == 1) {
       if (dtype != CXRM_BF16 || gemm_tcgen05_supported(g) != 0) return CXRM_ERR_INVALID;

@@ -29,6 +29,7 @@ __global__ void rollout_init_kernel(RolloutState st, RolloutParams p, const int*
     *st.step = 0;
     *st.done = 0;
     *st.arrive = 0;
+    *st.seed = p.seed;
   }
   if (r >= p.R) return;
   const int blk = r / p.B, study = r % p.B;
@@ -268,7 +269,7 @@ __global__ void __launch_bounds__(SNT) sample_step_kernel(RolloutState st, Rollo
         if (k < thr_key) continue;
         const float s = key2f(k);
         const float prob = expf(s - smax) / esum;
-        const float q = qrow ? qrow[i] : philox_exp(p.seed, stream_id, static_cast<unsigned>(i));
+        const float q = qrow ? qrow[i] : philox_exp(*st.seed, stream_id, static_cast<unsigned>(i));
         win = better(win, ValIdx{prob / q, i});
         const int slot = atomicAdd(&sh_cnt, 1);
         if (slot < kTopKCap) {
@@ -284,7 +285,7 @@ __global__ void __launch_bounds__(SNT) sample_step_kernel(RolloutState st, Rollo
         const unsigned k = keys[i];
         if (k < thr_key || i == win.i) continue;
         const float prob = expf(key2f(k) - smax) / esum;
-        const float q = qrow ? qrow[i] : philox_exp(p.seed, stream_id, static_cast<unsigned>(i));
+        const float q = qrow ? qrow[i] : philox_exp(*st.seed, stream_id, static_cast<unsigned>(i));
         second = better(second, ValIdx{prob / q, i});
       }
       second = block_argmax(second, sh_vi);
@@ -332,305 +333,6 @@ __global__ void __launch_bounds__(SNT) sample_step_kernel(RolloutState st, Rollo
       if (all || t + 1 >= p.Tmax) *st.done = 1;
       *st.arrive = 0;
     }
-  }
-}
-
-// =============================================================================
-// one-token self-attention
-// =============================================================================
-template <typename T>
-__global__ void __launch_bounds__(128) decode_self_attn_kernel(const T* __restrict__ qkv, T* __restrict__ kcache,
-                                                               T* __restrict__ vcache, T* __restrict__ ctx,
-                                                               RolloutState st, int Lmax) {
-  constexpr int NT = 128;
-  constexpr int VN = Vec16<T>::N;        // elements per 16-byte vector
-  constexpr int LPK = HD / VN;           // lanes per key
-  constexpr int NG = NT / LPK;           // key groups per block
-  __shared__ float qs[HD];
-  __shared__ float sc[512];
-  __shared__ float red[NG][HD];
-  __shared__ float sh_red[NT / kWarp];
-  if (*st.done) return;
-  const int r = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
-  if (st.finished[r]) return;
-  const int L = st.cur_len[r];           // slot of the new token; keys 0..L
-  const T* qrow = qkv + static_cast<long long>(r) * 3 * H + h * HD;
-  T* kbase = kcache + static_cast<long long>(r) * Lmax * H + h * HD;
-  T* vbase = vcache + static_cast<long long>(r) * Lmax * H + h * HD;
-  if (tid < HD) {
-    qs[tid] = to_f(qrow[tid]);
-    kbase[static_cast<long long>(L) * H + tid] = qrow[H + tid];
-  } else {
-    vbase[static_cast<long long>(L) * H + (tid - HD)] = qrow[2 * H + (tid - HD)];
-  }
-  __syncthreads();
-  const uint8_t* kv = st.key_valid + static_cast<long long>(r) * Lmax;
-  const int g = tid / LPK, sub = tid % LPK;
-  float qf[VN];
-#pragma unroll
-  for (int i = 0; i < VN; ++i) qf[i] = qs[sub * VN + i];
-  const int n = L + 1;
-  // warp-uniform trip count: every lane takes part in the group shuffles
-  for (int jb = 0; jb < n; jb += NG) {
-    const int j = jb + g;
-    const bool in = j < n;
-    float kf[VN];
-    if (in) {
-      Vec16<T> kvv;
-      kvv.load(kbase + static_cast<long long>(j) * H + sub * VN);
-      kvv.unpack(kf);
-    } else {
-#pragma unroll
-      for (int i = 0; i < VN; ++i) kf[i] = 0.f;
-    }
-    float d = 0.f;
-#pragma unroll
-    for (int i = 0; i < VN; ++i) d = fmaf(qf[i], kf[i], d);
-#pragma unroll
-    for (int o = LPK / 2; o > 0; o >>= 1) d += __shfl_xor_sync(kFull, d, o);
-    if (in && sub == 0) sc[j] = kv[j] ? d * 0.125f : -INFINITY;
-  }
-  __syncthreads();
-  // max and sum
-  float mx = -INFINITY;
-  for (int j = tid; j < n; j += NT) mx = fmaxf(mx, sc[j]);
-  mx = warp_max(mx);
-  if (tid % kWarp == 0) sh_red[tid / kWarp] = mx;
-  __syncthreads();
-  mx = fmaxf(fmaxf(sh_red[0], sh_red[1]), fmaxf(sh_red[2], sh_red[3]));
-  __syncthreads();
-  float sum = 0.f;
-  for (int j = tid; j < n; j += NT) {
-    const float e = (sc[j] == -INFINITY) ? 0.f : expf(sc[j] - mx);
-    sc[j] = e;
-    sum += e;
-  }
-  sum = warp_sum(sum);
-  if (tid % kWarp == 0) sh_red[tid / kWarp] = sum;
-  __syncthreads();
-  sum = sh_red[0] + sh_red[1] + sh_red[2] + sh_red[3];
-  float acc[VN];
-#pragma unroll
-  for (int i = 0; i < VN; ++i) acc[i] = 0.f;
-  for (int j = g; j < n; j += NG) {
-    const float pj = sc[j];
-    Vec16<T> vv;
-    vv.load(vbase + static_cast<long long>(j) * H + sub * VN);
-    float vf[VN];
-    vv.unpack(vf);
-#pragma unroll
-    for (int i = 0; i < VN; ++i) acc[i] = fmaf(pj, vf[i], acc[i]);
-  }
-#pragma unroll
-  for (int i = 0; i < VN; ++i) red[g][sub * VN + i] = acc[i];
-  __syncthreads();
-  if (tid < HD) {
-    float o = 0.f;
-#pragma unroll
-    for (int gg = 0; gg < NG; ++gg) o += red[gg][tid];
-    ctx[static_cast<long long>(r) * H + h * HD + tid] = from_f<T>(sum > 0.f ? o / sum : 0.f);
-  }
-}
-
-// =============================================================================
-// one-token cross-attention (NQ rows of one study share every K/V load)
-// =============================================================================
-template <typename T, int NQ>
-__global__ void __launch_bounds__(256) decode_cross_attn_kernel(const T* __restrict__ q, const T* __restrict__ kc,
-                                                                const T* __restrict__ vc, int ld,
-                                                                T* __restrict__ ctx,
-                                                                const int* __restrict__ kv_off,
-                                                                const int* __restrict__ kv_len, RolloutState st,
-                                                                int B, int nsplit, float* __restrict__ ws) {
-  constexpr int NT = 256;
-  constexpr int VN = Vec16<T>::N;
-  constexpr int LPK = HD / VN;
-  constexpr int NG = NT / LPK;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* sc = reinterpret_cast<float*>(smem_raw);      // [NQ][chunk]
-  __shared__ float qs[NQ][HD];
-  __shared__ float red[NG][NQ][HD];
-  __shared__ float sh_red[NQ][NT / kWarp];
-  if (*st.done) return;
-  const int b = blockIdx.x, h = blockIdx.y, s = blockIdx.z, tid = threadIdx.x;
-  bool all_fin = true;
-#pragma unroll
-  for (int i = 0; i < NQ; ++i) all_fin = all_fin && st.finished[b + i * B];
-  if (all_fin) return;
-  const int len = kv_len[b];
-  const int chunk = ceil_div(len, nsplit);
-  const int j0 = s * chunk, j1 = min(len, j0 + chunk);
-  const int n = max(j1 - j0, 0);
-  if (tid < NQ * HD) qs[tid / HD][tid % HD] = to_f(q[static_cast<long long>(b + (tid / HD) * B) * H + h * HD + tid % HD]);
-  __syncthreads();
-  const T* kbase = kc + (static_cast<long long>(kv_off[b]) + j0) * ld + h * HD;
-  const T* vbase = vc + (static_cast<long long>(kv_off[b]) + j0) * ld + h * HD;
-  const int g = tid / LPK, sub = tid % LPK;
-  float qf[NQ][VN];
-#pragma unroll
-  for (int i = 0; i < NQ; ++i)
-#pragma unroll
-    for (int e = 0; e < VN; ++e) qf[i][e] = qs[i][sub * VN + e];
-
-  // pass 1: scores (4 keys in flight per thread)
-  constexpr int U = 4;
-  // warp-uniform trip count: every lane takes part in the group shuffles
-  for (int jb = 0; jb < n; jb += NG * U) {
-    Vec16<T> kv[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int j = jb + u * NG + g;
-      if (j < n) {
-        kv[u].load_nc(kbase + static_cast<long long>(j) * ld + sub * VN);
-      } else {
-        float z[VN];
-#pragma unroll
-        for (int e = 0; e < VN; ++e) z[e] = 0.f;
-        kv[u].pack(z);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int j = jb + u * NG + g;
-      float kf[VN];
-      kv[u].unpack(kf);
-#pragma unroll
-      for (int i = 0; i < NQ; ++i) {
-        float d = 0.f;
-#pragma unroll
-        for (int e = 0; e < VN; ++e) d = fmaf(qf[i][e], kf[e], d);
-#pragma unroll
-        for (int o = LPK / 2; o > 0; o >>= 1) d += __shfl_xor_sync(kFull, d, o);
-        if (j < n && sub == 0) sc[i * chunk + j] = d * 0.125f;
-      }
-    }
-  }
-  __syncthreads();
-  float mx[NQ], sum[NQ];
-#pragma unroll
-  for (int i = 0; i < NQ; ++i) {
-    float m = -INFINITY;
-    for (int j = tid; j < n; j += NT) m = fmaxf(m, sc[i * chunk + j]);
-    m = warp_max(m);
-    if (tid % kWarp == 0) sh_red[i][tid / kWarp] = m;
-  }
-  __syncthreads();
-#pragma unroll
-  for (int i = 0; i < NQ; ++i) {
-    float m = -INFINITY;
-#pragma unroll
-    for (int w = 0; w < NT / kWarp; ++w) m = fmaxf(m, sh_red[i][w]);
-    mx[i] = m;
-  }
-  __syncthreads();
-#pragma unroll
-  for (int i = 0; i < NQ; ++i) {
-    float sm = 0.f;
-    for (int j = tid; j < n; j += NT) {
-      const float e = expf(sc[i * chunk + j] - mx[i]);
-      sc[i * chunk + j] = e;
-      sm += e;
-    }
-    sm = warp_sum(sm);
-    if (tid % kWarp == 0) sh_red[i][tid / kWarp] = sm;
-  }
-  __syncthreads();
-#pragma unroll
-  for (int i = 0; i < NQ; ++i) {
-    float sm = 0.f;
-#pragma unroll
-    for (int w = 0; w < NT / kWarp; ++w) sm += sh_red[i][w];
-    sum[i] = sm;
-  }
-  // pass 2: weighted sum of V
-  float acc[NQ][VN];
-#pragma unroll
-  for (int i = 0; i < NQ; ++i)
-#pragma unroll
-    for (int e = 0; e < VN; ++e) acc[i][e] = 0.f;
-  for (int jb = 0; jb < n; jb += NG * U) {
-    Vec16<T> vv[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int j = jb + u * NG + g;
-      if (j < n) vv[u].load_nc(vbase + static_cast<long long>(j) * ld + sub * VN);
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int j = jb + u * NG + g;
-      if (j >= n) continue;
-      float vf[VN];
-      vv[u].unpack(vf);
-#pragma unroll
-      for (int i = 0; i < NQ; ++i) {
-        const float pj = sc[i * chunk + j];
-#pragma unroll
-        for (int e = 0; e < VN; ++e) acc[i][e] = fmaf(pj, vf[e], acc[i][e]);
-      }
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < NQ; ++i)
-#pragma unroll
-    for (int e = 0; e < VN; ++e) red[g][i][sub * VN + e] = acc[i][e];
-  __syncthreads();
-  if (tid < NQ * HD) {
-    const int i = tid / HD, d = tid % HD;
-    float o = 0.f;
-#pragma unroll
-    for (int gg = 0; gg < NG; ++gg) o += red[gg][i][d];
-    const int r = b + i * B;
-    const float m_i = (i == 0) ? mx[0] : mx[NQ - 1];
-    const float s_i = (i == 0) ? sum[0] : sum[NQ - 1];
-    if (nsplit == 1) {
-      ctx[static_cast<long long>(r) * H + h * HD + d] = from_f<T>(s_i > 0.f ? o / s_i : 0.f);
-    } else {
-      float* w = ws + ((static_cast<long long>(r) * NH + h) * nsplit + s) * (HD + 2);
-      w[2 + d] = o;
-      if (d == 0) {
-        w[0] = (n > 0) ? m_i : -INFINITY;
-        w[1] = s_i;
-      }
-    }
-  }
-}
-
-template <typename T>
-__global__ void cross_combine_kernel(const float* __restrict__ ws, T* __restrict__ ctx, RolloutState st, int nsplit) {
-  if (*st.done) return;
-  const int r = blockIdx.x, h = blockIdx.y, d = threadIdx.x;
-  if (st.finished[r]) return;
-  const float* w = ws + (static_cast<long long>(r) * NH + h) * nsplit * (HD + 2);
-  float m = -INFINITY;
-  for (int s = 0; s < nsplit; ++s) m = fmaxf(m, w[s * (HD + 2)]);
-  float l = 0.f, o = 0.f;
-  for (int s = 0; s < nsplit; ++s) {
-    const float ms = w[s * (HD + 2)];
-    if (ms == -INFINITY) continue;
-    const float a = expf(ms - m);
-    l += a * w[s * (HD + 2) + 1];
-    o += a * w[s * (HD + 2) + 2 + d];
-  }
-  ctx[static_cast<long long>(r) * H + h * HD + d] = from_f<T>(l > 0.f ? o / l : 0.f);
-}
-
-template <typename T>
-__global__ void prefill_store_kv_kernel(const T* __restrict__ qkv, T* __restrict__ kcache, T* __restrict__ vcache,
-                                        int R, int P, int Lmax) {
-  constexpr int VN = Vec16<T>::N;
-  const int cv = H / VN;
-  const long long total = static_cast<long long>(R) * P * cv * 2;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % cv) * VN;
-    long long t = i / cv;
-    const int which = static_cast<int>(t % 2);
-    t /= 2;
-    const int pcol = static_cast<int>(t % P);
-    const long long r = t / P;
-    Vec16<T> v;
-    v.load(qkv + (r * P + pcol) * 3 * H + (1 + which) * H + c);
-    v.store((which ? vcache : kcache) + (r * Lmax + pcol) * H + c);
   }
 }
 
@@ -684,56 +386,6 @@ void sample_step(const RolloutState& st, const RolloutParams& p, const float* lo
 }
 
 template <typename T>
-void decode_self_attention(const T* qkv, T* kcache, T* vcache, T* ctx, const RolloutState& st, int R, int Lmax,
-                           cudaStream_t stream) {
-  CXRM_CHECK(Lmax <= 512, "decode_self_attention supports at most 512 cached tokens");
-  decode_self_attn_kernel<T><<<dim3(R, NH), 128, 0, stream>>>(qkv, kcache, vcache, ctx, st, Lmax);
-  check_launch("decode_self_attention");
-}
-
-size_t decode_cross_ws_bytes(int R, int nsplit) {
-  return static_cast<size_t>(R) * NH * nsplit * (HD + 2) * sizeof(float);
-}
-
-template <typename T>
-void decode_cross_attention(const T* q, const T* kc, const T* vc, int ld, T* ctx, const int* kv_off,
-                            const int* kv_len, const RolloutState& st, int R, int B, int max_len, int nsplit, float* ws,
-                            cudaStream_t stream) {
-  const int nq = R / B;
-  CXRM_CHECK(nq == 1 || nq == 2, "decode_cross_attention: 1 or 2 rows per study");
-  const int chunk = ceil_div(max_len, nsplit);
-  const size_t smem = static_cast<size_t>(nq) * chunk * sizeof(float);
-  CXRM_CHECK(smem <= 160 * 1024, "cross-attention chunk too large: raise nsplit");
-  auto launch = [&](auto kern) {
-    static size_t configured = 0;
-    if (smem > configured) {
-      CXRM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-      configured = smem;
-    }
-    kern<<<dim3(B, NH, nsplit), 256, smem, stream>>>(q, kc, vc, ld, ctx, kv_off, kv_len, st, B, nsplit, ws);
-  };
-  if (nq == 1)
-    launch(decode_cross_attn_kernel<T, 1>);
-  else
-    launch(decode_cross_attn_kernel<T, 2>);
-  check_launch("decode_cross_attention");
-  if (nsplit > 1) {
-    cross_combine_kernel<T><<<dim3(R, NH), HD, 0, stream>>>(ws, ctx, st, nsplit);
-    check_launch("cross_combine");
-  }
-}
-
-template <typename T>
-void prefill_store_kv(const T* qkv, T* kcache, T* vcache, int R, int P, int Lmax, cudaStream_t stream) {
-  const long long total = static_cast<long long>(R) * P * (H / Vec16<T>::N) * 2;
-  if (total <= 0) return;
-  long long grid = ceil_div_ll(total, 256);
-  if (grid > 148 * 32) grid = 148 * 32;
-  prefill_store_kv_kernel<T><<<static_cast<unsigned>(grid), 256, 0, stream>>>(qkv, kcache, vcache, R, P, Lmax);
-  check_launch("prefill_store_kv");
-}
-
-template <typename T>
 void take_last_token(const T* x, T* out, int R, int P, int C, cudaStream_t stream) {
   const long long total = static_cast<long long>(R) * C;
   take_last_kernel<T><<<static_cast<unsigned>(ceil_div_ll(total, 256)), 256, 0, stream>>>(x, out, R, P, C);
@@ -746,12 +398,7 @@ void cosine_rows(const float* a, const float* b, float* out, int n, int C, cudaS
   check_launch("cosine_rows");
 }
 
-#define INST(T)                                                                                                  \
-  template void decode_self_attention<T>(const T*, T*, T*, T*, const RolloutState&, int, int, cudaStream_t);      \
-  template void decode_cross_attention<T>(const T*, const T*, const T*, int, T*, const int*, const int*,          \
-                                          const RolloutState&, int, int, int, int, float*, cudaStream_t);         \
-  template void prefill_store_kv<T>(const T*, T*, T*, int, int, int, cudaStream_t);                               \
-  template void take_last_token<T>(const T*, T*, int, int, int, cudaStream_t);
+#define INST(T) template void take_last_token<T>(const T*, T*, int, int, int, cudaStream_t);
 INST(float)
 INST(bf16)
 #undef INST

@@ -378,12 +378,23 @@ class Engine : public EngineBase {
     st.step = dalloc<int>(1);
     st.done = dalloc<int>(1);
     st.arrive = dalloc<unsigned>(1);
+    st.seed = dalloc<unsigned long long>(1);
     pre_ids = dalloc<int>(static_cast<long long>(Rmax) * cfg.max_prompt);
     pre_types = dalloc<int>(static_cast<long long>(Rmax) * cfg.max_prompt);
     pre_pos = dalloc<int>(static_cast<long long>(Rmax) * cfg.max_prompt);
     prompt_dev = dalloc<int>(B * cfg.max_prompt);
-    cross_nsplit = 1;
-    cross_ws = dalloc<float>(static_cast<long long>(decode_cross_ws_bytes(Rmax, 64) / sizeof(float)));
+    // decode-attention work units (decode_attn.cu): partials + arrival tickets, zeroed once
+    attn_ch = decode_attn_chunk(sizeof(T));
+    cross_max_chunks = ceil_div(Smax, attn_ch);
+    cross_max_units = cfg.max_studies * cross_max_chunks;
+    self_max_chunks = ceil_div(Lmax, attn_ch);
+    cross_ws = dalloc<float>(static_cast<long long>(decode_attn_ws_floats(Rmax, cross_max_chunks)));
+    self_ws = dalloc<float>(static_cast<long long>(decode_attn_ws_floats(Rmax, self_max_chunks)));
+    cross_tickets = dalloc<unsigned>(static_cast<long long>(cfg.max_studies) * NHEAD);
+    self_tickets = dalloc<unsigned>(static_cast<long long>(Rmax) * NHEAD);
+    CXRM_CUDA_CHECK(cudaMemset(cross_tickets, 0, sizeof(unsigned) * cfg.max_studies * NHEAD));
+    CXRM_CUDA_CHECK(cudaMemset(self_tickets, 0, sizeof(unsigned) * Rmax * NHEAD));
+    unit_tab = dalloc<int>(4LL * cross_max_units + cfg.max_studies + 1);
 
     // scratch arena: max over the phases
     const long long e = sizeof(T);
@@ -456,8 +467,9 @@ class Engine : public EngineBase {
 
   // =========================================================================== GEMM dispatch
   void gemm(const T* A, int lda, const Lin& L, void* C, int ldc, long long M, int act, const T* residual, int ldr,
-            bool out_f32, const int* skip, cudaStream_t s, const char* tag = "gemm") {
+            bool out_f32, const int* skip, cudaStream_t s, const char* tag = "gemm", long long c_head_stride = 0) {
     GemmArgs g;
+    g.c_head_stride = c_head_stride;
     g.A = A; g.lda = lda; g.W = L.w; g.ldw = L.n_in; g.C = C; g.ldc = ldc;
     g.M = static_cast<int>(M); g.N = L.n_out; g.K = L.n_in;
     g.bias = L.b; g.act = act; g.residual = residual; g.ldr = ldr; g.out_f32 = out_f32 ? 1 : 0; g.skip_flag = skip;
@@ -620,16 +632,48 @@ class Engine : public EngineBase {
     check_launch("compact_rows");
     PF("gather", s, [&] { gather_rows<T>(mem, compact_idx, mem_compact, total, DH, s); });
     for (int l = 0; l < cfg.dec_layers; ++l) {
+      // head-major store: [k|v][head][token][64] (n / 64 = kv * 12 + head)
       T* kvl = cross_kv + static_cast<long long>(l) * cross_layer_stride();
-      gemm(mem_compact, DH, dec.layers[l].ckv, kvl, 2 * DH, total, ACT_NONE, nullptr, 0, false, nullptr, s);
+      gemm(mem_compact, DH, dec.layers[l].ckv, kvl, 2 * DH, total, ACT_NONE, nullptr, 0, false, nullptr, s, "gemm",
+           cross_head_stride());
     }
-    // split the per-study key range when there are too few (study, head) blocks to fill the GPU
-    const int blocks = B * NHEAD;
-    cross_nsplit = 1;
-    while (blocks * cross_nsplit < 2 * 148 && cross_nsplit < 16 && Smax / (cross_nsplit * 2) >= 64) cross_nsplit *= 2;
-    graph_valid = false;
+    // uniform work units of the decode-step cross-attention: (study, chunk of attn_ch tokens)
+    std::vector<int> tab(4 * static_cast<size_t>(cross_max_units) + cfg.max_studies + 1, 0);
+    int* u_study = tab.data();
+    int* u_j0 = u_study + cross_max_units;
+    int* u_n = u_j0 + cross_max_units;
+    int* u_chunk = u_n + cross_max_units;
+    int* n_chunks = u_chunk + cross_max_units;
+    int nu = 0;
+    for (int b = 0; b < B; ++b) {
+      const int nc = ceil_div(len[b], attn_ch);
+      n_chunks[b] = nc;
+      for (int c = 0; c < nc; ++c, ++nu) {
+        u_study[nu] = b;
+        u_j0[nu] = off[b] + c * attn_ch;
+        u_n[nu] = std::min(attn_ch, len[b] - c * attn_ch);
+        u_chunk[nu] = c;
+      }
+    }
+    n_chunks[cfg.max_studies] = nu;
+    CXRM_CUDA_CHECK(cudaMemcpyAsync(unit_tab, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+    CXRM_CUDA_CHECK(cudaStreamSynchronize(s));   // `tab` is pageable host memory going out of scope
   }
-  long long cross_layer_stride() const { return static_cast<long long>(cfg.max_studies) * Smax * 2 * DH; }
+  CrossUnits cross_units() const {
+    CrossUnits cu;
+    cu.study = unit_tab;
+    cu.j0 = unit_tab + cross_max_units;
+    cu.n = unit_tab + 2 * cross_max_units;
+    cu.chunk = unit_tab + 3 * cross_max_units;
+    cu.n_chunks = unit_tab + 4 * cross_max_units;
+    cu.n_units = cu.n_chunks + cfg.max_studies;
+    cu.max_units = cross_max_units;
+    cu.max_chunks = cross_max_chunks;
+    return cu;
+  }
+  long long cross_tok_cap() const { return static_cast<long long>(cfg.max_studies) * Smax; }
+  long long cross_head_stride() const { return cross_tok_cap() * 64; }
+  long long cross_layer_stride() const { return cross_tok_cap() * 2 * DH; }
 
   // =========================================================================== attention dispatch
   void attention(const AttnArgs& a, cudaStream_t s) { attention_simt<T>(a, s); }
@@ -673,10 +717,10 @@ class Engine : public EngineBase {
       gemm(b.x1, DH, w.cq, b.qkv, DH, M, ACT_NONE, nullptr, 0, false, nullptr, s);
       const T* kvl = cross_kv + static_cast<long long>(l) * cross_layer_stride();
       AttnArgs c{};
-      c.q = b.qkv; c.k = kvl; c.v = kvl + DH; c.o = b.ctx;
+      c.q = b.qkv; c.k = kvl; c.v = kvl + NHEAD * cross_head_stride(); c.o = b.ctx;
       c.q_bs = static_cast<long long>(q) * DH; c.q_hs = 64; c.q_ts = DH;
-      c.k_bs = 0; c.k_hs = 64; c.k_ts = 2 * DH;
-      c.v_bs = 0; c.v_hs = 64; c.v_ts = 2 * DH;
+      c.k_bs = 0; c.k_hs = cross_head_stride(); c.k_ts = 64;
+      c.v_bs = 0; c.v_hs = cross_head_stride(); c.v_ts = 64;
       c.o_bs = c.q_bs; c.o_hs = 64; c.o_ts = DH;
       c.batch = R; c.heads = NHEAD; c.Lq = q; c.Lk = kv_maxlen;
       c.Lk_per_batch = kv_len; c.kv_offset = kv_off; c.kv_batch_mod = B;
@@ -710,14 +754,14 @@ class Engine : public EngineBase {
       const BertLayerW& w = dec.layers[l];
       gemm(b.x, DH, w.qkv, b.qkv, 3 * DH, R, ACT_NONE, nullptr, 0, false, skip, s);
       PF("self_attn", s, [&] { decode_self_attention<T>(b.qkv, self_k + l * self_layer_stride(), self_v + l * self_layer_stride(), b.ctx, st, R,
-                               Lmax, s); });
+                               Lmax, self_ws, self_tickets, s); });
       gemm(b.ctx, DH, w.o, b.x1, DH, R, ACT_NONE, b.x, DH, false, skip, s);
       PF("layernorm", s, [&] { layernorm<T>(b.x1, DH, b.x1, DH, w.ln1.g, w.ln1.b, R, DH, LN_EPS_BERT, s); });
       gemm(b.x1, DH, w.cq, b.qkv, DH, R, ACT_NONE, nullptr, 0, false, skip, s);
       const T* kvl = cross_kv + static_cast<long long>(l) * cross_layer_stride();
-      // smem sized for the configured maximum so that the captured graph does not depend on the batch's image counts
-      PF("cross_attn", s, [&] { decode_cross_attention<T>(b.qkv, kvl, kvl + DH, 2 * DH, b.ctx, kv_off, kv_len, st, R, B, Smax, cross_nsplit,
-                                cross_ws, s); });
+      // the grid covers cross_max_units so that the captured graph does not depend on the batch's image counts
+      PF("cross_attn", s, [&] { decode_cross_attention<T>(b.qkv, DH, kvl, kvl + NHEAD * cross_head_stride(), cross_head_stride(), b.ctx,
+                                cross_units(), st, R, B, cross_ws, cross_tickets, s); });
       gemm(b.ctx, DH, w.co, b.x, DH, R, ACT_NONE, b.x1, DH, false, skip, s);
       PF("layernorm", s, [&] { layernorm<T>(b.x, DH, b.x, DH, w.ln2.g, w.ln2.b, R, DH, LN_EPS_BERT, s); });
       gemm(b.x, DH, w.fc1, b.hid, DFF, R, ACT_GELU, nullptr, 0, false, skip, s);
@@ -814,8 +858,7 @@ class Engine : public EngineBase {
     GraphKey key;
     std::memset(&key, 0, sizeof(key));
     key.R = rp.R; key.B = rp.B; key.P = rp.P; key.Tmax = rp.Tmax; key.top_k = rp.top_k;
-    key.temperature = rp.temperature; key.seed = rp.seed; key.noise = noise; key.buf = db.x;
-    key.nsplit = cross_nsplit;
+    key.temperature = rp.temperature; key.noise = noise; key.buf = db.x;
     key.mask_id = rp.mask_token_id; key.eos = rp.eos; key.pad = rp.pad;
     std::memcpy(key.special, rp.special_ids, sizeof(key.special));
     std::memcpy(key.sections, rp.sections, sizeof(key.sections));
@@ -1012,8 +1055,11 @@ class Engine : public EngineBase {
   T* memory = nullptr; uint8_t* mem_mask = nullptr; T* mem_compact = nullptr; int* compact_idx = nullptr;
   int* kv_off = nullptr; int* kv_len = nullptr; T* cross_kv = nullptr; T* self_k = nullptr; T* self_v = nullptr;
   float* logits = nullptr; uint8_t* valid_img = nullptr; int* img_idx = nullptr;
-  int enc_B = 0, enc_S = 0, kv_B = 0, kv_total = 0, kv_maxlen = 0, cross_nsplit = 1;
-  float* cross_ws = nullptr;
+  int enc_B = 0, enc_S = 0, kv_B = 0, kv_total = 0, kv_maxlen = 0;
+  int attn_ch = 0, cross_max_chunks = 0, cross_max_units = 0, self_max_chunks = 0;
+  float* cross_ws = nullptr; float* self_ws = nullptr;
+  unsigned* cross_tickets = nullptr; unsigned* self_tickets = nullptr;
+  int* unit_tab = nullptr;
   RolloutState st{};
   int* pre_ids = nullptr; int* pre_types = nullptr; int* pre_pos = nullptr; int* prompt_dev = nullptr;
   // host-step staging
@@ -1022,8 +1068,8 @@ class Engine : public EngineBase {
   int* id_map = nullptr; int bridge_cls = 0, bridge_sep = 0, bridge_bos = 1, bridge_sep_dec = 3;
   // CUDA graph of one decode step
   struct GraphKey {
-    int R, B, P, Tmax, top_k; float temperature; unsigned long long seed; const float* noise; const void* buf;
-    int kv_total, kv_maxlen, nsplit, mask_id, eos, pad;
+    int R, B, P, Tmax, top_k; float temperature; const float* noise; const void* buf;
+    int mask_id, eos, pad;
     int special[2][kMaxSpecial]; int sections[2][kMaxSpecial + 1]; int nspecial[2]; int modes[2];
   };
   GraphKey graph_key;

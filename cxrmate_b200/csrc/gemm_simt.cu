@@ -112,7 +112,9 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(GemmArgs g) {
       if (g.bias) v += g.bias[n];
       if (g.act == ACT_GELU) v = gelu_erf(v);
       if (R) v += to_f(R[m * g.ldr + n]);
-      if (g.out_f32)
+      if (g.c_head_stride > 0)
+        static_cast<T*>(g.C)[static_cast<long long>(n / 64) * g.c_head_stride + m * 64 + (n % 64)] = from_f<T>(v);
+      else if (g.out_f32)
         static_cast<float*>(g.C)[m * g.ldc + n] = v;
       else
         static_cast<T*>(g.C)[m * g.ldc + n] = from_f<T>(v);

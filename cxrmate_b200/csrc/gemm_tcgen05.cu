@@ -206,7 +206,16 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const __grid_constant
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
       }
-      if (full_chunk && vec_ok) {
+      if (g.c_head_stride > 0) {
+        // head-major K/V cache store: 32 consecutive columns never straddle a 64-wide head
+        bf16* cp = static_cast<bf16*>(g.C) + static_cast<long long>(nb / 64) * g.c_head_stride + m * 64 + (nb % 64);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          Vec16<bf16> ov;
+          ov.pack(v + 8 * q);
+          ov.store(cp + 8 * q);
+        }
+      } else if (full_chunk && vec_ok) {
         if (R) {
           const bf16* rp = R + m * g.ldr + nb;
 #pragma unroll
@@ -328,6 +337,9 @@ int gemm_tcgen05_supported(const GemmArgs& g) {
   if (g.K % 8 != 0 || g.lda % 8 != 0 || g.ldw % 8 != 0) return 2;
   if (reinterpret_cast<uintptr_t>(g.A) % 16 != 0 || reinterpret_cast<uintptr_t>(g.W) % 16 != 0) return 3;
   if (ceil_div(g.N, 32) > 65535) return 4;
+  if (g.c_head_stride > 0 && (g.N % 64 != 0 || g.out_f32 || g.residual || reinterpret_cast<uintptr_t>(g.C) % 16 != 0 ||
+                              g.c_head_stride % 8 != 0))
+    return 5;
   return 0;
 }
 

@@ -23,6 +23,8 @@ struct GemmArgs {
   const void* residual; int ldr;
   int out_f32;
   const int* skip_flag;   // nullable device flag: kernel returns immediately when *skip_flag != 0
+  // > 0: head-major store (K/V caches): element (m, n) goes to C[(n / 64) * c_head_stride + m * 64 + n % 64]
+  long long c_head_stride;
 };
 
 // strict-fp32 FMA path (validation mode; also the bf16-storage SIMT debug path)
@@ -132,6 +134,7 @@ struct RolloutState {
   int* step;             // scalar: decode steps executed so far
   int* done;             // scalar: 1 once every row is finished or the budget is spent
   unsigned* arrive;      // scalar: block-arrival counter of the sampling kernel
+  unsigned long long* seed;  // scalar: Philox seed of this rollout (device-resident so the step graph is reusable)
 };
 
 struct RolloutParams {
@@ -161,22 +164,36 @@ void rollout_init(const RolloutState& st, const RolloutParams& p, const int* pro
 void sample_step(const RolloutState& st, const RolloutParams& p, const float* logits, int ldl, const float* exp_noise,
                  cudaStream_t stream);
 
-// one-token self-attention over the row's KV cache; appends the new K/V first.
-// qkv [R, 3*768] (q | k | v); kcache/vcache [R, Lmax, 768] of this layer; ctx [R,768].
+// ---- one-token attention over the head-major K/V caches (decode_attn.cu) ----------------------------------
+// Work units of the cross-attention: (study, chunk of <= CH encoder tokens); built on the host at
+// cxrm_prefill_cross_kv, read by every decode step.  The grid is sized for max_units so that the captured
+// CUDA graph does not depend on the batch's image counts.
+struct CrossUnits {
+  const int* study;      // [max_units]
+  const int* j0;         // [max_units] first token of the chunk in the compact cache (kv_off[study] + chunk*CH)
+  const int* n;          // [max_units] tokens in the chunk
+  const int* chunk;      // [max_units] chunk index within its study
+  const int* n_chunks;   // [B] chunks per study
+  const int* n_units;    // scalar: live units
+  int max_units, max_chunks;
+};
+int decode_attn_chunk(size_t elem_size);                   // CH: keys per unit (192 bf16 / 96 fp32)
+size_t decode_attn_ws_floats(int rows, int max_chunks);    // fp32 partials (max, sum, out[64]) per (row, head, chunk)
+
+// self-attention of each row's new token over its cache [R][12][Lmax][64] (this layer); appends the new K/V.
+// qkv [R, 3*768] (q | k | v); ctx [R,768]; ws / tickets: partials and per-(row, head) arrival counters (zeroed once).
 template <typename T>
 void decode_self_attention(const T* qkv, T* kcache, T* vcache, T* ctx, const RolloutState& st, int R, int Lmax,
-                           cudaStream_t stream);
+                           float* ws, unsigned* tickets, cudaStream_t stream);
 
-// one-token cross-attention of the rows of each study over that study's encoder K/V.
-// q [R,768]; kc/vc [total_tokens, 768] with row stride ld, of this layer; study b owns tokens
-// [kv_off[b], kv_off[b]+kv_len[b]).  rows of study b: b, b+B, ... (R/B rows).  ws: fp32 workspace for split partials.
+// cross-attention of the R/B rows of each study over that study's encoder K/V, kc/vc [12][tokens][64] of this
+// layer (head_stride = tokens * 64).  q [R, ldq]; rows of study b: b, b+B.
 template <typename T>
-void decode_cross_attention(const T* q, const T* kc, const T* vc, int ld, T* ctx, const int* kv_off, const int* kv_len,
-                            const RolloutState& st, int R, int B, int max_len, int nsplit, float* ws,
+void decode_cross_attention(const T* q, int ldq, const T* kc, const T* vc, long long head_stride, T* ctx,
+                            const CrossUnits& cu, const RolloutState& st, int R, int B, float* ws, unsigned* tickets,
                             cudaStream_t stream);
-size_t decode_cross_ws_bytes(int R, int nsplit);
 
-// qkv [R*P, 3*768] -> kcache/vcache [R, Lmax, 768] columns [0,P)
+// qkv [R*P, 3*768] -> head-major kcache/vcache [R][12][Lmax][64] columns [0,P)
 template <typename T>
 void prefill_store_kv(const T* qkv, T* kcache, T* vcache, int R, int P, int Lmax, cudaStream_t stream);
 

@@ -1,0 +1,79 @@
+"""Host-side data-parallel logic on CPU: study sharding == DistributedSampler(shuffle=False), and the reward /
+baseline gather with world_size 2 over gloo."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from cxrmate_b200 import sharding
+
+
+@pytest.mark.parametrize("n,world", [(1, 1), (7, 2), (8, 2), (9, 4), (3, 8), (64, 8), (257, 8)])
+def test_shard_matches_distributed_sampler(n, world):
+    ds = list(range(n))
+    seen = []
+    for r in range(world):
+        ref = list(torch.utils.data.distributed.DistributedSampler(ds, num_replicas=world, rank=r, shuffle=False))
+        got = sharding.shard_studies(n, r, world)
+        assert got == ref
+        seen += got
+    assert set(seen) == set(ds)
+
+
+def test_shard_edge_cases():
+    assert sharding.shard_studies(0, 0, 4) == []
+    with pytest.raises(ValueError):
+        sharding.shard_studies(4, 4, 4)
+    assert sharding.batches([0, 2, 4, 6, 8], 2) == [[0, 2], [4, 6], [8]]
+
+
+def test_gather_without_process_group_is_identity():
+    r, b = torch.arange(4.0), torch.ones(4)
+    R, B = sharding.gather_rewards(r, b)
+    assert R.shape == (1, 4) and torch.equal(R[0], r) and torch.equal(B[0], b)
+    with pytest.raises(ValueError):
+        sharding.gather_rewards(torch.zeros(3), torch.zeros(4))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, n, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        mine = sharding.shard_studies(n, rank, world)
+        # stand-in for the engine: a deterministic per-study "reward" and "baseline"
+        reward = torch.tensor([0.25 * i - 1.0 for i in mine])
+        baseline = torch.tensor([0.5 * i + 2.0 for i in mine])
+        R, B = sharding.gather_rewards(reward, baseline)
+        ms = sharding.max_over_ranks(10.0 + rank, torch.device("cpu"))
+        q.put((rank, sharding.unshard(R, n).tolist(), sharding.unshard(B, n).tolist(), ms))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [8, 7])
+def test_gather_rewards_world2_gloo(n):
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    outs = [q.get(timeout=60) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want_r = [0.25 * i - 1.0 for i in range(n)]
+    want_b = [0.5 * i + 2.0 for i in range(n)]
+    for rank, r, b, ms in outs:
+        assert r == want_r and b == want_b          # every rank sees the whole batch in dataset order
+        assert ms == 11.0                           # max over ranks
