@@ -164,11 +164,33 @@ int cxrm_test_gemm(int impl, int dtype, const void* A, const void* W, void* C, i
     if (impl == 1) {
       if (dtype != CXRM_BF16 || gemm_tcgen05_supported(g) != 0) return CXRM_ERR_INVALID;
       gemm_tcgen05(g, s);
+    } else if (impl == 2) {
+      if (dtype != CXRM_BF16 || gemm_skinny_supported(g) != 0) return CXRM_ERR_INVALID;
+      gemm_tcgen05_skinny(g, nullptr, nullptr, s);
     } else if (dtype == CXRM_F32) {
       gemm_simt<float>(g, s);
     } else {
       gemm_simt<bf16>(g, s);
     }
+    return CXRM_OK;
+  } catch (const std::exception& ex) {
+    g_create_error = ex.what();
+    return CXRM_ERR_CUDA;
+  }
+}
+
+int cxrm_test_gemm_ln(const void* A, const void* W, void* out, int M, int N, int K, const float* bias, int act,
+                      const void* residual, const float* gamma, const float* beta, float eps, float* partial_ws,
+                      void* stream) {
+  try {
+    GemmArgs g;
+    g.A = A; g.lda = K; g.W = W; g.ldw = K; g.C = nullptr; g.ldc = 0; g.M = M; g.N = N; g.K = K;
+    g.bias = nullptr; g.act = 0; g.residual = nullptr; g.ldr = 0; g.out_f32 = 0; g.skip_flag = nullptr; g.c_head_stride = 0;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (gemm_skinny_supported(g) != 0 || N > 1024 || N % 4 != 0) return CXRM_ERR_INVALID;
+    int nsplit = 0;
+    gemm_tcgen05_skinny(g, partial_ws, &nsplit, s);
+    splitk_ln(partial_ws, nsplit, M, N, bias, act, residual, N, gamma, beta, eps, out, N, nullptr, s);
     return CXRM_OK;
   } catch (const std::exception& ex) {
     g_create_error = ex.what();

@@ -20,6 +20,10 @@
 // Reference semantics: HF modeling_bert.py:143-207 (self, cache append, key padding
 // mask as finfo.min == skipped keys) and :210-284 (cross, encoder mask: masked
 // tokens were dropped from the cache at cxrm_prefill_cross_kv).
+#include <cuda.h>
+
+#include <type_traits>
+
 #include "kernels.h"
 
 namespace cxrm {
@@ -371,6 +375,355 @@ __global__ void __launch_bounds__(NT) decode_self_units_kernel(const T* __restri
   }
 }
 
+
+// =====================================================================================================
+// bf16 path: the same units, but the two small contractions of a unit (scores = q.K^T, out = p.V) run on the
+// tensor cores through mma.sync.m16n8k16 with the NQ (1-2) query rows padded to the 16-row tile.  This is not
+// about FLOPs (the kernel is HBM-bound): the SIMT formulation needs ~5200 warp-instructions per 48 KiB unit
+// (unpack + shuffle reductions dominate) and ncu showed it issue-bound at 2.7 TB/s; the MMA formulation
+// needs ~450.  K/V chunks arrive by 2-D TMA (cp.async.bulk.tensor) with the 128-byte swizzle so that the
+// ldmatrix reads of 8 keys x 16 B are bank-conflict free.
+// =====================================================================================================
+constexpr int CHB = 192;            // keys per unit (bf16)
+constexpr int WKEYS = CHB / 4;      // keys per warp
+constexpr int SELF_BOX = 64;        // rows per TMA box of the self cache (a unit loads only the boxes it needs)
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                         uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+// byte offset of (key row r, 16-byte chunk c) inside a 128B-swizzled tile whose base is 1024-byte aligned
+__device__ __forceinline__ uint32_t swz(int r, int c) { return static_cast<uint32_t>(r * 128 + ((c ^ (r & 7)) << 4)); }
+
+// One warp: keys [w*48, w*48+48) of the chunk.  qrow[i]: global bf16 query rows (head slice, 64 dims).
+// Writes its (m, l, o[64]) per query row into wpart[w][i][66] (shared).  `valid`: nullable key mask of the chunk.
+template <int NQ>
+__device__ __forceinline__ void mma_warp_unit(uint32_t Ks, uint32_t Vs, uint64_t* bars, int n,
+                                              const bf16* const (&qrow)[NQ], const uint8_t* __restrict__ valid,
+                                              float* __restrict__ wpart) {
+  const int lane = threadIdx.x % kWarp, w = threadIdx.x / kWarp;
+  const int g = lane >> 2, t = lane & 3;
+  const int k0 = w * WKEYS;
+  float* mine = wpart + (w * NQ + (g < NQ ? g : 0)) * (HD + 2);
+  if (k0 >= n) {   // nothing for this warp (short last chunk)
+    if (g < NQ) {
+      if (t == 0) {
+        mine[0] = -INFINITY;
+        mine[1] = 0.f;
+      }
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        mine[2 + nt * 8 + 2 * t] = 0.f;
+        mine[2 + nt * 8 + 2 * t + 1] = 0.f;
+      }
+    }
+    return;
+  }
+  // ---- Q fragments (rows >= NQ of the 16-row tile are zero) ----
+  uint32_t qa0[4], qa2[4];
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    qa0[ks] = 0u;
+    qa2[ks] = 0u;
+  }
+#pragma unroll
+  for (int i = 0; i < NQ; ++i)
+    if (g == i) {
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        qa0[ks] = *reinterpret_cast<const uint32_t*>(qrow[i] + ks * 16 + 2 * t);
+        qa2[ks] = *reinterpret_cast<const uint32_t*>(qrow[i] + ks * 16 + 8 + 2 * t);
+      }
+    }
+  // ---- scores: 6 n-tiles of 8 keys ----
+  mbar_wait(&bars[0], 0);
+  float sc[6][4];
+  const int mi = lane >> 3, mr = lane & 7;   // ldmatrix: this lane addresses row mr of matrix mi
+#pragma unroll
+  for (int nt = 0; nt < 6; ++nt) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sc[nt][j] = 0.f;
+    const int key = k0 + nt * 8 + mr;
+    uint32_t b[4];
+    ldsm_x4(Ks + swz(key, mi), b[0], b[1], b[2], b[3]);          // dims 0..31
+    mma_bf16(sc[nt], qa0[0], 0u, qa2[0], 0u, b[0], b[1]);
+    mma_bf16(sc[nt], qa0[1], 0u, qa2[1], 0u, b[2], b[3]);
+    ldsm_x4(Ks + swz(key, 4 + mi), b[0], b[1], b[2], b[3]);      // dims 32..63
+    mma_bf16(sc[nt], qa0[2], 0u, qa2[2], 0u, b[0], b[1]);
+    mma_bf16(sc[nt], qa0[3], 0u, qa2[3], 0u, b[2], b[3]);
+  }
+  // ---- warp-local softmax statistics (row g lives in lanes 4g..4g+3: sc[nt][0..1] = keys k0+nt*8+2t, +1) ----
+  float m = -INFINITY;
+#pragma unroll
+  for (int nt = 0; nt < 6; ++nt)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int key = k0 + nt * 8 + 2 * t + j;
+      const bool vis = key < n && (!valid || valid[key]);
+      sc[nt][j] = vis ? sc[nt][j] * 0.125f : -INFINITY;
+      m = fmaxf(m, sc[nt][j]);
+    }
+  m = fmaxf(m, __shfl_xor_sync(kFull, m, 1));
+  m = fmaxf(m, __shfl_xor_sync(kFull, m, 2));
+  float l = 0.f;
+  uint32_t pa[6];
+#pragma unroll
+  for (int nt = 0; nt < 6; ++nt) {
+    const float p0 = (sc[nt][0] == -INFINITY) ? 0.f : expf(sc[nt][0] - m);
+    const float p1 = (sc[nt][1] == -INFINITY) ? 0.f : expf(sc[nt][1] - m);
+    l += p0 + p1;
+    pa[nt] = (g < NQ) ? pack_bf16(p0, p1) : 0u;
+  }
+  l += __shfl_xor_sync(kFull, l, 1);
+  l += __shfl_xor_sync(kFull, l, 2);
+  // ---- out = p.V : 3 k-steps of 16 keys x 8 n-tiles of 8 dims ----
+  mbar_wait(&bars[1], 0);
+  float o[8][4];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[nt][j] = 0.f;
+#pragma unroll
+  for (int kk = 0; kk < 3; ++kk) {
+    if (k0 + kk * 16 >= n) break;   // warp-uniform
+    const int key = k0 + kk * 16 + (mi & 1) * 8 + mr;
+#pragma unroll
+    for (int dp = 0; dp < 4; ++dp) {
+      uint32_t b[4];
+      ldsm_x4_t(Vs + swz(key, 2 * dp + (mi >> 1)), b[0], b[1], b[2], b[3]);
+      mma_bf16(o[2 * dp], pa[2 * kk], 0u, pa[2 * kk + 1], 0u, b[0], b[1]);
+      mma_bf16(o[2 * dp + 1], pa[2 * kk], 0u, pa[2 * kk + 1], 0u, b[2], b[3]);
+    }
+  }
+  if (g < NQ) {
+    if (t == 0) {
+      mine[0] = m;
+      mine[1] = l;
+    }
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      mine[2 + nt * 8 + 2 * t] = o[nt][0];
+      mine[2 + nt * 8 + 2 * t + 1] = o[nt][1];
+    }
+  }
+}
+
+// merge the 4 warp partials of the unit (shared) into the unit's global partial slot
+template <int NQ>
+__device__ __forceinline__ void merge_warps_to_global(const float* __restrict__ wpart, float* __restrict__ part,
+                                                      long long part_row_stride) {
+  const int tid = threadIdx.x;
+  if (tid < NQ * HD) {
+    const int i = tid / HD, d = tid % HD;
+    float m = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) m = fmaxf(m, wpart[(w * NQ + i) * (HD + 2)]);
+    float l = 0.f, o = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const float mw = wpart[(w * NQ + i) * (HD + 2)];
+      if (mw == -INFINITY) continue;
+      const float a = expf(mw - m);
+      l += a * wpart[(w * NQ + i) * (HD + 2) + 1];
+      o += a * wpart[(w * NQ + i) * (HD + 2) + 2 + d];
+    }
+    float* dst = part + i * part_row_stride;
+    dst[2 + d] = o;
+    if (d == 0) {
+      dst[0] = m;
+      dst[1] = l;
+    }
+  }
+}
+
+template <int NQ>
+__global__ void __launch_bounds__(NT) decode_cross_mma_kernel(const __grid_constant__ CUtensorMap tm_kv,
+                                                              int row_base_k, int row_base_v, int tok_cap,
+                                                              const bf16* __restrict__ q, int ldq,
+                                                              bf16* __restrict__ ctx, CrossUnits cu, RolloutState st,
+                                                              int B, float* __restrict__ ws,
+                                                              unsigned* __restrict__ tickets) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  float* wpart = reinterpret_cast<float*>(tiles + 2 * CHB * 128);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wpart + 4 * NQ * (HD + 2));
+  __shared__ int sh_last;
+
+  if (*st.done) return;
+  const int u = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
+  if (u >= *cu.n_units) return;
+  const int b = cu.study[u], j0 = cu.j0[u], n = cu.n[u], c = cu.chunk[u];
+  bool all_fin = true;
+#pragma unroll
+  for (int i = 0; i < NQ; ++i) all_fin = all_fin && st.finished[b + i * B];
+  if (all_fin) return;
+
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_expect_tx(&bars[0], CHB * 128);
+    tma_load_2d(tiles, &tm_kv, 0, row_base_k + h * tok_cap + j0, &bars[0]);
+    mbar_expect_tx(&bars[1], CHB * 128);
+    tma_load_2d(tiles + CHB * 128, &tm_kv, 0, row_base_v + h * tok_cap + j0, &bars[1]);
+  }
+  __syncthreads();   // barrier inits visible to every waiter
+  const bf16* qrow[NQ];
+#pragma unroll
+  for (int i = 0; i < NQ; ++i) qrow[i] = q + static_cast<long long>(b + i * B) * ldq + h * HD;
+  mma_warp_unit<NQ>(smem_u32(tiles), smem_u32(tiles + CHB * 128), bars, n, qrow, nullptr, wpart);
+  __syncthreads();
+
+  const int maxc = cu.max_chunks;
+  float* part = ws + ((static_cast<long long>(b) * NH + h) * maxc + c) * (HD + 2);
+  const long long row_stride = static_cast<long long>(B) * NH * maxc * (HD + 2);
+  merge_warps_to_global<NQ>(wpart, part, row_stride);
+
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned nchunk = static_cast<unsigned>(cu.n_chunks[b]);
+    const unsigned prev = atomicAdd(&tickets[b * NH + h], 1u);
+    sh_last = (prev == nchunk - 1) ? 1 : 0;
+    if (sh_last) tickets[b * NH + h] = 0;
+  }
+  __syncthreads();
+  if (sh_last) {
+    __threadfence();
+    if (tid < NQ * HD) {
+      const int i = tid / HD, d = tid % HD;
+      const int r = b + i * B;
+      const float* w = ws + i * row_stride + (static_cast<long long>(b) * NH + h) * maxc * (HD + 2);
+      merge_partials<bf16>(w, cu.n_chunks[b], ctx + static_cast<long long>(r) * H + h * HD, d);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(NT) decode_self_mma_kernel(const __grid_constant__ CUtensorMap tm_k,
+                                                             const __grid_constant__ CUtensorMap tm_v, int layer_row0,
+                                                             const bf16* __restrict__ qkv, bf16* __restrict__ kcache,
+                                                             bf16* __restrict__ vcache, bf16* __restrict__ ctx,
+                                                             RolloutState st, int Lmax, int max_chunks,
+                                                             float* __restrict__ ws, unsigned* __restrict__ tickets) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  float* wpart = reinterpret_cast<float*>(tiles + 2 * CHB * 128);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wpart + 4 * (HD + 2));
+  __shared__ int sh_last;
+
+  if (*st.done) return;
+  const int r = blockIdx.x / max_chunks, c = blockIdx.x % max_chunks, h = blockIdx.y, tid = threadIdx.x;
+  if (st.finished[r]) return;
+  const int L = st.cur_len[r];
+  const int ntot = L + 1;
+  const int nchunk = ceil_div(ntot, CHB);
+  if (c >= nchunk) return;
+  const int j0 = c * CHB, n = min(CHB, ntot - j0);
+  const bool has_new = (c == nchunk - 1);
+  const int n_cached = has_new ? n - 1 : n;
+  const int nbox = ceil_div(n_cached, SELF_BOX);
+
+  const long long base = (static_cast<long long>(r) * NH + h) * Lmax * HD;
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (nbox > 0) {
+      const int row0 = layer_row0 + (r * NH + h) * Lmax + j0;
+      mbar_expect_tx(&bars[0], nbox * SELF_BOX * 128);
+      for (int x = 0; x < nbox; ++x) tma_load_2d(tiles + x * SELF_BOX * 128, &tm_k, 0, row0 + x * SELF_BOX, &bars[0]);
+      mbar_expect_tx(&bars[1], nbox * SELF_BOX * 128);
+      for (int x = 0; x < nbox; ++x)
+        tma_load_2d(tiles + CHB * 128 + x * SELF_BOX * 128, &tm_v, 0, row0 + x * SELF_BOX, &bars[1]);
+    } else {
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars[0])) : "memory");
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars[1])) : "memory");
+    }
+  }
+  __syncthreads();
+  const bf16* qrow = qkv + static_cast<long long>(r) * 3 * H + h * HD;
+  if (has_new) {
+    // The new token's K/V: into the cache now; into the (swizzled) tile once the TMA boxes that cover its row landed.
+    const int row = n - 1;
+    const bool covered = row < nbox * SELF_BOX;   // a TMA box also writes this row: patch after it completes
+    if (!covered) {
+      // rows [nbox*64, row) do not exist (row == nbox*64 here); the MMAs also read the rest of this 16-key group
+      for (int x = tid; x < 16 * 8; x += NT) {
+        const int rr = nbox * SELF_BOX + x / 8, cc = x % 8;
+        if (rr < CHB) {
+          *reinterpret_cast<uint4*>(tiles + swz(rr, cc)) = make_uint4(0, 0, 0, 0);
+          *reinterpret_cast<uint4*>(tiles + CHB * 128 + swz(rr, cc)) = make_uint4(0, 0, 0, 0);
+        }
+      }
+      __syncthreads();
+    } else {
+      mbar_wait(&bars[0], 0);
+      mbar_wait(&bars[1], 0);
+    }
+    if (tid < HD) {
+      const bf16 kvn = qrow[H + tid];
+      *reinterpret_cast<bf16*>(tiles + swz(row, tid / 8) + (tid % 8) * 2) = kvn;
+      kcache[base + static_cast<long long>(L) * HD + tid] = kvn;
+    } else {
+      const int d = tid - HD;
+      const bf16 vvn = qrow[2 * H + d];
+      *reinterpret_cast<bf16*>(tiles + CHB * 128 + swz(row, d / 8) + (d % 8) * 2) = vvn;
+      vcache[base + static_cast<long long>(L) * HD + d] = vvn;
+    }
+    __syncthreads();
+  }
+  const bf16* qr[1] = {qrow};
+  mma_warp_unit<1>(smem_u32(tiles), smem_u32(tiles + CHB * 128), bars, n, qr,
+                   st.key_valid + static_cast<long long>(r) * Lmax + j0, wpart);
+  __syncthreads();
+  float* part = ws + ((static_cast<long long>(r) * NH + h) * max_chunks + c) * (HD + 2);
+  merge_warps_to_global<1>(wpart, part, 0);
+
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned prev = atomicAdd(&tickets[r * NH + h], 1u);
+    sh_last = (prev == static_cast<unsigned>(nchunk) - 1) ? 1 : 0;
+    if (sh_last) tickets[r * NH + h] = 0;
+  }
+  __syncthreads();
+  if (sh_last) {
+    __threadfence();
+    if (tid < HD)
+      merge_partials<bf16>(ws + (static_cast<long long>(r) * NH + h) * max_chunks * (HD + 2), nchunk,
+                           ctx + static_cast<long long>(r) * H + h * HD, tid);
+  }
+}
+
+constexpr size_t kMmaSmem = 2 * CHB * 128 + 4 * 2 * (HD + 2) * sizeof(float) + 64 + 1024;
+
 // qkv [R*P, 3*768] -> head-major caches [R][12][Lmax][64], columns [0,P)
 template <typename T>
 __global__ void prefill_store_kv_kernel(const T* __restrict__ qkv, T* __restrict__ kcache, T* __restrict__ vcache,
@@ -403,40 +756,72 @@ size_t decode_attn_ws_floats(int rows, int max_chunks) {
 
 template <typename T>
 void decode_self_attention(const T* qkv, T* kcache, T* vcache, T* ctx, const RolloutState& st, int R, int Lmax,
-                           float* ws, unsigned* tickets, cudaStream_t stream) {
+                           float* ws, unsigned* tickets, const AttnMaps* maps, int layer, cudaStream_t stream) {
   const int CH = decode_attn_chunk(sizeof(T));
   const int max_chunks = ceil_div(Lmax, CH);
-  const size_t smem = unit_smem_bytes<T, 1>(CH);
-  static size_t configured = 0;
-  if (smem > configured) {
-    CXRM_CUDA_CHECK(cudaFuncSetAttribute(decode_self_units_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(smem)));
-    configured = smem;
+  if constexpr (std::is_same<T, bf16>::value) {
+    CXRM_CHECK(maps != nullptr, "bf16 decode attention needs the cache tensor maps");
+    static bool configured = false;
+    if (!configured) {
+      CXRM_CUDA_CHECK(cudaFuncSetAttribute(decode_self_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(kMmaSmem)));
+      configured = true;
+    }
+    const int layer_row0 = layer * maps->self_rows_per_layer;
+    decode_self_mma_kernel<<<dim3(R * max_chunks, NH), NT, kMmaSmem, stream>>>(
+        maps->self_k, maps->self_v, layer_row0, qkv, kcache, vcache, ctx, st, Lmax, max_chunks, ws, tickets);
+  } else {
+    const size_t smem = unit_smem_bytes<T, 1>(CH);
+    static size_t configured = 0;
+    if (smem > configured) {
+      CXRM_CUDA_CHECK(cudaFuncSetAttribute(decode_self_units_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(smem)));
+      configured = smem;
+    }
+    decode_self_units_kernel<T><<<dim3(R * max_chunks, NH), NT, smem, stream>>>(qkv, kcache, vcache, ctx, st, Lmax, CH,
+                                                                               max_chunks, ws, tickets);
   }
-  decode_self_units_kernel<T><<<dim3(R * max_chunks, NH), NT, smem, stream>>>(qkv, kcache, vcache, ctx, st, Lmax, CH,
-                                                                             max_chunks, ws, tickets);
   check_launch("decode_self_attention");
 }
 
 template <typename T>
 void decode_cross_attention(const T* q, int ldq, const T* kc, const T* vc, long long head_stride, T* ctx,
                             const CrossUnits& cu, const RolloutState& st, int R, int B, float* ws, unsigned* tickets,
-                            cudaStream_t stream) {
+                            const AttnMaps* maps, int layer, cudaStream_t stream) {
   const int nq = R / B;
   CXRM_CHECK(nq == 1 || nq == 2, "decode_cross_attention: 1 or 2 rows per study");
   const int CH = decode_attn_chunk(sizeof(T));
-  auto launch = [&](auto kern, size_t smem) {
-    static size_t configured = 0;
-    if (smem > configured) {
-      CXRM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-      configured = smem;
+  if constexpr (std::is_same<T, bf16>::value) {
+    CXRM_CHECK(maps != nullptr, "bf16 decode attention needs the cache tensor maps");
+    const int tok_cap = static_cast<int>(head_stride / HD);
+    const int row_k = layer * 2 * NH * tok_cap, row_v = row_k + NH * tok_cap;
+    // (one flag for both instantiations: they share a function-pointer type, so a generic lambda would share it too)
+    static bool configured = false;
+    if (!configured) {
+      CXRM_CUDA_CHECK(cudaFuncSetAttribute(decode_cross_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(kMmaSmem)));
+      CXRM_CUDA_CHECK(cudaFuncSetAttribute(decode_cross_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(kMmaSmem)));
+      configured = true;
     }
-    kern<<<dim3(cu.max_units, NH), NT, smem, stream>>>(q, ldq, kc, vc, head_stride, ctx, cu, st, B, CH, ws, tickets);
-  };
-  if (nq == 1)
-    launch(decode_cross_units_kernel<T, 1>, unit_smem_bytes<T, 1>(CH));
-  else
-    launch(decode_cross_units_kernel<T, 2>, unit_smem_bytes<T, 2>(CH));
+    auto launch = [&](auto kern) {
+      kern<<<dim3(cu.max_units, NH), NT, kMmaSmem, stream>>>(maps->cross, row_k, row_v, tok_cap, q, ldq, ctx, cu, st, B,
+                                                              ws, tickets);
+    };
+    if (nq == 1)
+      launch(decode_cross_mma_kernel<1>);
+    else
+      launch(decode_cross_mma_kernel<2>);
+  } else {
+    auto launch = [&](auto kern, size_t smem) {
+      CXRM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+      kern<<<dim3(cu.max_units, NH), NT, smem, stream>>>(q, ldq, kc, vc, head_stride, ctx, cu, st, B, CH, ws, tickets);
+    };
+    if (nq == 1)
+      launch(decode_cross_units_kernel<T, 1>, unit_smem_bytes<T, 1>(CH));
+    else
+      launch(decode_cross_units_kernel<T, 2>, unit_smem_bytes<T, 2>(CH));
+  }
   check_launch("decode_cross_attention");
 }
 
@@ -452,9 +837,10 @@ void prefill_store_kv(const T* qkv, T* kcache, T* vcache, int R, int P, int Lmax
 
 #define INST(T)                                                                                                      \
   template void decode_self_attention<T>(const T*, T*, T*, T*, const RolloutState&, int, int, float*, unsigned*,      \
-                                         cudaStream_t);                                                               \
+                                         const AttnMaps*, int, cudaStream_t);                                         \
   template void decode_cross_attention<T>(const T*, int, const T*, const T*, long long, T*, const CrossUnits&,        \
-                                          const RolloutState&, int, int, float*, unsigned*, cudaStream_t);            \
+                                          const RolloutState&, int, int, float*, unsigned*, const AttnMaps*, int,     \
+                                          cudaStream_t);                                                              \
   template void prefill_store_kv<T>(const T*, T*, T*, int, int, int, cudaStream_t);
 INST(float)
 INST(bf16)

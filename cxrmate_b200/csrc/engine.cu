@@ -395,6 +395,12 @@ class Engine : public EngineBase {
     CXRM_CUDA_CHECK(cudaMemset(cross_tickets, 0, sizeof(unsigned) * cfg.max_studies * NHEAD));
     CXRM_CUDA_CHECK(cudaMemset(self_tickets, 0, sizeof(unsigned) * Rmax * NHEAD));
     unit_tab = dalloc<int>(4LL * cross_max_units + cfg.max_studies + 1);
+    // the tensor-core attention units multiply p = 0 with whatever lies behind a short chunk: keep the caches finite
+    CXRM_CUDA_CHECK(cudaMemset(cross_kv, 0, sizeof(T) * cfg.dec_layers * cross_layer_stride()));
+    CXRM_CUDA_CHECK(cudaMemset(self_k, 0, sizeof(T) * cfg.dec_layers * self_layer_stride()));
+    CXRM_CUDA_CHECK(cudaMemset(self_v, 0, sizeof(T) * cfg.dec_layers * self_layer_stride()));
+    setup_attn_maps();
+    skinny_ws = dalloc<float>(static_cast<long long>(gemm_skinny_partial_floats(DH)));
 
     // scratch arena: max over the phases
     const long long e = sizeof(T);
@@ -415,6 +421,7 @@ class Engine : public EngineBase {
     CXRM_CUDA_CHECK(cudaEventCreateWithFlags(&ev_b, cudaEventDisableTiming));
     std::memset(&graph_key, 0, sizeof(graph_key));
   }
+  void setup_attn_maps();
   size_t workspace_bytes() const override { return arena.capacity() + static_cast<size_t>(persistent_bytes); }
 
   // =========================================================================== per-kernel-class profiler
@@ -476,6 +483,34 @@ class Engine : public EngineBase {
     PF(tag, s, [&] { dispatch_gemm(g, s); });
   }
   void dispatch_gemm(const GemmArgs& g, cudaStream_t s);
+
+  // out = LayerNorm(act(A.W^T + bias) + residual), eps 1e-12 (every LN that follows a decoder GEMM).
+  // Decode steps in bf16 (M <= 64): skinny split-K GEMM into fp32 partials + one fused reduce/bias/residual/LN kernel;
+  // otherwise GEMM with fused epilogue followed by the LayerNorm kernel.  `out` may alias `residual`.
+  void gemm_ln(const T* A, int lda, const Lin& L, int act, const T* residual, int ldr, const LNp& ln, T* out, int ldo,
+               long long M, const int* skip, cudaStream_t s) {
+    if (use_skinny(M, L)) {
+      GemmArgs g = make_args(A, lda, L, nullptr, 0, M, ACT_NONE, nullptr, 0, false, skip);
+      int nsplit = 0;
+      PF("gemm", s, [&] { gemm_tcgen05_skinny(g, skinny_ws, &nsplit, s); });
+      PF("layernorm", s, [&] { splitk_ln(skinny_ws, nsplit, static_cast<int>(M), L.n_out, L.b, act, residual, ldr, ln.g, ln.b,
+                                         LN_EPS_BERT, out, ldo, skip, s); });
+      return;
+    }
+    T* tmp = out;
+    gemm(A, lda, L, tmp, ldo, M, act, residual, ldr, false, skip, s);
+    PF("layernorm", s, [&] { layernorm<T>(tmp, ldo, out, ldo, ln.g, ln.b, M, L.n_out, LN_EPS_BERT, s); });
+  }
+  bool use_skinny(long long M, const Lin& L) const;
+  GemmArgs make_args(const T* A, int lda, const Lin& L, void* C, int ldc, long long M, int act, const T* residual,
+                     int ldr, bool out_f32, const int* skip) const {
+    GemmArgs g;
+    g.c_head_stride = 0;
+    g.A = A; g.lda = lda; g.W = L.w; g.ldw = L.n_in; g.C = C; g.ldc = ldc;
+    g.M = static_cast<int>(M); g.N = L.n_out; g.K = L.n_in;
+    g.bias = L.b; g.act = act; g.residual = residual; g.ldr = ldr; g.out_f32 = out_f32 ? 1 : 0; g.skip_flag = skip;
+    return g;
+  }
 
   // =========================================================================== encoder
   // n images (indices img_idx_dev into `pixels`) -> proj [n*T2, 768] in the arena
@@ -738,8 +773,7 @@ class Engine : public EngineBase {
 
   // LM head on `rows` hidden rows -> fp32 logits (dense -> GELU -> LN -> tied decoder + bias)
   void lm_head(const T* hidden, long long rows, T* tmp, float* out, int ld_out, const int* skip, cudaStream_t s) {
-    gemm(hidden, DH, dec_head_t, tmp, DH, rows, ACT_GELU, nullptr, 0, false, skip, s);
-    PF("layernorm", s, [&] { layernorm<T>(tmp, DH, tmp, DH, dec_head_ln.g, dec_head_ln.b, rows, DH, LN_EPS_BERT, s); });
+    gemm_ln(hidden, DH, dec_head_t, ACT_GELU, nullptr, 0, dec_head_ln, tmp, DH, rows, skip, s);
     gemm(tmp, DH, dec_lm, out, ld_out, rows, ACT_NONE, nullptr, 0, true, skip, s);
   }
 
@@ -754,19 +788,16 @@ class Engine : public EngineBase {
       const BertLayerW& w = dec.layers[l];
       gemm(b.x, DH, w.qkv, b.qkv, 3 * DH, R, ACT_NONE, nullptr, 0, false, skip, s);
       PF("self_attn", s, [&] { decode_self_attention<T>(b.qkv, self_k + l * self_layer_stride(), self_v + l * self_layer_stride(), b.ctx, st, R,
-                               Lmax, self_ws, self_tickets, s); });
-      gemm(b.ctx, DH, w.o, b.x1, DH, R, ACT_NONE, b.x, DH, false, skip, s);
-      PF("layernorm", s, [&] { layernorm<T>(b.x1, DH, b.x1, DH, w.ln1.g, w.ln1.b, R, DH, LN_EPS_BERT, s); });
+                               Lmax, self_ws, self_tickets, attn_maps_ptr, l, s); });
+      gemm_ln(b.ctx, DH, w.o, ACT_NONE, b.x, DH, w.ln1, b.x1, DH, R, skip, s);
       gemm(b.x1, DH, w.cq, b.qkv, DH, R, ACT_NONE, nullptr, 0, false, skip, s);
       const T* kvl = cross_kv + static_cast<long long>(l) * cross_layer_stride();
       // the grid covers cross_max_units so that the captured graph does not depend on the batch's image counts
       PF("cross_attn", s, [&] { decode_cross_attention<T>(b.qkv, DH, kvl, kvl + NHEAD * cross_head_stride(), cross_head_stride(), b.ctx,
-                                cross_units(), st, R, B, cross_ws, cross_tickets, s); });
-      gemm(b.ctx, DH, w.co, b.x, DH, R, ACT_NONE, b.x1, DH, false, skip, s);
-      PF("layernorm", s, [&] { layernorm<T>(b.x, DH, b.x, DH, w.ln2.g, w.ln2.b, R, DH, LN_EPS_BERT, s); });
+                                cross_units(), st, R, B, cross_ws, cross_tickets, attn_maps_ptr, l, s); });
+      gemm_ln(b.ctx, DH, w.co, ACT_NONE, b.x1, DH, w.ln2, b.x, DH, R, skip, s);
       gemm(b.x, DH, w.fc1, b.hid, DFF, R, ACT_GELU, nullptr, 0, false, skip, s);
-      gemm(b.hid, DFF, w.fc2, b.x1, DH, R, ACT_NONE, b.x, DH, false, skip, s);
-      PF("layernorm", s, [&] { layernorm<T>(b.x1, DH, b.x, DH, w.ln3.g, w.ln3.b, R, DH, LN_EPS_BERT, s); });
+      gemm_ln(b.hid, DFF, w.fc2, ACT_NONE, b.x, DH, w.ln3, b.x, DH, R, skip, s);
     }
     lm_head(b.x, R, head_tmp, logits, cfg.vocab, skip, s);
     PF("sample", s, [&] { sample_step(st, rp, logits, cfg.vocab, noise, s); });
@@ -1060,6 +1091,9 @@ class Engine : public EngineBase {
   float* cross_ws = nullptr; float* self_ws = nullptr;
   unsigned* cross_tickets = nullptr; unsigned* self_tickets = nullptr;
   int* unit_tab = nullptr;
+  AttnMaps attn_maps{};
+  const AttnMaps* attn_maps_ptr = nullptr;
+  float* skinny_ws = nullptr;
   RolloutState st{};
   int* pre_ids = nullptr; int* pre_types = nullptr; int* pre_pos = nullptr; int* prompt_dev = nullptr;
   // host-step staging
@@ -1079,10 +1113,31 @@ class Engine : public EngineBase {
 };
 
 template <>
+void Engine<float>::setup_attn_maps() {}
+template <>
+void Engine<bf16>::setup_attn_maps() {
+  const long long cross_rows = static_cast<long long>(cfg.dec_layers) * 2 * NHEAD * cross_tok_cap();
+  const long long self_rows = static_cast<long long>(Rmax) * NHEAD * Lmax;
+  CXRM_CHECK(cross_rows < (1LL << 31) && self_rows * cfg.dec_layers < (1LL << 31), "cache too large for 32-bit TMA row coordinates");
+  attn_maps.cross = make_tensor_map_bf16(cross_kv, cross_rows, 64, 64, 192, 64);
+  attn_maps.self_k = make_tensor_map_bf16(self_k, self_rows * cfg.dec_layers, 64, 64, 64, 64);
+  attn_maps.self_v = make_tensor_map_bf16(self_v, self_rows * cfg.dec_layers, 64, 64, 64, 64);
+  attn_maps.self_rows_per_layer = static_cast<int>(self_rows);
+  attn_maps_ptr = &attn_maps;
+}
+template <>
+bool Engine<float>::use_skinny(long long, const Lin&) const { return false; }
+template <>
+bool Engine<bf16>::use_skinny(long long M, const Lin& L) const {
+  return cfg.use_tensor_cores && M <= 64 && L.n_out <= 1024 && L.n_out % 4 == 0 && L.n_in % 8 == 0;
+}
+template <>
 void Engine<float>::dispatch_gemm(const GemmArgs& g, cudaStream_t s) { gemm_simt<float>(g, s); }
 template <>
 void Engine<bf16>::dispatch_gemm(const GemmArgs& g, cudaStream_t s) {
-  if (cfg.use_tensor_cores && gemm_tcgen05_supported(g) == 0)
+  if (cfg.use_tensor_cores && g.M <= 64 && gemm_skinny_supported(g) == 0)
+    gemm_tcgen05_skinny(g, nullptr, nullptr, s);   // decode steps: latency-bound weight streaming
+  else if (cfg.use_tensor_cores && gemm_tcgen05_supported(g) == 0)
     gemm_tcgen05(g, s);
   else
     gemm_simt<bf16>(g, s);

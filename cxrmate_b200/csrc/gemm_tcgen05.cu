@@ -100,6 +100,80 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// Fused epilogue of one accumulator row segment: v[0..31] = D[m, nb .. nb+31] (fp32) ->
+// + bias -> act -> (+ residual) -> store as bf16 / fp32 / head-major bf16.
+__device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, float (&v)[32], long long m, int nb, int vec_ok) {
+  const bf16* __restrict__ R = static_cast<const bf16*>(g.residual);
+  const bool full_chunk = (nb + 32 <= g.N);
+  if (g.bias) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] += (full_chunk || nb + j < g.N) ? g.bias[nb + j] : 0.f;
+  }
+  if (g.act == ACT_GELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+  }
+  if (g.c_head_stride > 0) {
+    // head-major K/V cache store: 32 consecutive columns never straddle a 64-wide head
+    bf16* cp = static_cast<bf16*>(g.C) + static_cast<long long>(nb / 64) * g.c_head_stride + m * 64 + (nb % 64);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      Vec16<bf16> ov;
+      ov.pack(v + 8 * q);
+      ov.store(cp + 8 * q);
+    }
+  } else if (full_chunk && vec_ok) {
+    if (R) {
+      const bf16* rp = R + m * g.ldr + nb;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        Vec16<bf16> rv;
+        rv.load(rp + 8 * q);
+        float rf[8];
+        rv.unpack(rf);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[8 * q + j] += rf[j];
+      }
+    }
+    if (g.out_f32) {
+      float* cp = static_cast<float*>(g.C) + m * g.ldc + nb;
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        *reinterpret_cast<float4*>(cp + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    } else {
+      bf16* cp = static_cast<bf16*>(g.C) + m * g.ldc + nb;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        Vec16<bf16> ov;
+        ov.pack(v + 8 * q);
+        ov.store(cp + 8 * q);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int n = nb + j;
+      if (n >= g.N) continue;
+      float o = v[j];
+      if (R) o += to_f(R[m * g.ldr + n]);
+      if (g.out_f32)
+        static_cast<float*>(g.C)[m * g.ldc + n] = o;
+      else
+        static_cast<bf16*>(g.C)[m * g.ldc + n] = from_f<bf16>(o);
+    }
+  }
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 template <int BN>
 struct Cfg {
   static constexpr int B_BYTES = BN * BK * 2;
@@ -187,74 +261,15 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const __grid_constant
     tc_fence_after();
     const long long m = static_cast<long long>(m0) + quarter * 32 + lane;
     const bool row_ok = m < g.M;
-    const bf16* __restrict__ R = static_cast<const bf16*>(g.residual);
     for (int c0 = 0; c0 < BN; c0 += 32) {
       if (n0 + c0 >= g.N) break;   // warp-uniform
       uint32_t r[32];
       tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(c0), r);
       if (!row_ok) continue;
-      const int nb = n0 + c0;
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-      const bool full_chunk = (nb + 32 <= g.N);
-      if (g.bias) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += (full_chunk || nb + j < g.N) ? g.bias[nb + j] : 0.f;
-      }
-      if (g.act == ACT_GELU) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-      }
-      if (g.c_head_stride > 0) {
-        // head-major K/V cache store: 32 consecutive columns never straddle a 64-wide head
-        bf16* cp = static_cast<bf16*>(g.C) + static_cast<long long>(nb / 64) * g.c_head_stride + m * 64 + (nb % 64);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          Vec16<bf16> ov;
-          ov.pack(v + 8 * q);
-          ov.store(cp + 8 * q);
-        }
-      } else if (full_chunk && vec_ok) {
-        if (R) {
-          const bf16* rp = R + m * g.ldr + nb;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            Vec16<bf16> rv;
-            rv.load(rp + 8 * q);
-            float rf[8];
-            rv.unpack(rf);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[8 * q + j] += rf[j];
-          }
-        }
-        if (g.out_f32) {
-          float* cp = static_cast<float*>(g.C) + m * g.ldc + nb;
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-            *reinterpret_cast<float4*>(cp + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-        } else {
-          bf16* cp = static_cast<bf16*>(g.C) + m * g.ldc + nb;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            Vec16<bf16> ov;
-            ov.pack(v + 8 * q);
-            ov.store(cp + 8 * q);
-          }
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int n = nb + j;
-          if (n >= g.N) continue;
-          float o = v[j];
-          if (R) o += to_f(R[m * g.ldr + n]);
-          if (g.out_f32)
-            static_cast<float*>(g.C)[m * g.ldc + n] = o;
-          else
-            static_cast<bf16*>(g.C)[m * g.ldc + n] = from_f<bf16>(o);
-        }
-      }
+      epilogue_chunk(g, v, m, n0 + c0, vec_ok);
     }
   }
 
@@ -263,6 +278,207 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const __grid_constant
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C_::TMEM_COLS)
                  : "memory");
+  }
+}
+
+
+// =====================================================================================================
+// Skinny GEMM for the decode steps: M <= 64 rows (2B rollout rows), weights streamed from HBM once.
+// Such a GEMM is bound by the latency of its TMA round trips, not by the MMAs: the generic kernel's
+// 4-stage ring needs K/64/4 serial round trips (9.7 us for K = 768, 19.4 us for K = 3072 measured by ncu).
+// Here a CTA (a) loads only 64 A rows per stage (8 KiB; the MMA still spans 128 rows - rows 64..127 of the
+// accumulator are never read), (b) keeps up to 16 stages in flight so that a whole K slice is requested at
+// once, and (c) splits K across blockIdx.y so that enough CTAs pull weights concurrently.  With split-K the
+// fp32 partial tiles go to `partial[split][64][N]`; splitk_ln_kernel below reduces them and applies
+// bias / GELU / residual / LayerNorm in the same pass (every split GEMM of the decoder is followed by one).
+// =====================================================================================================
+constexpr int SK_ROWS = 64, SK_A_BYTES = SK_ROWS * BK * 2, SK_MAX_STAGES = 16, SK_SLACK = A_BYTES - SK_A_BYTES;
+
+template <int BN>
+__global__ void __launch_bounds__(NTHREADS) gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                  const __grid_constant__ CUtensorMap tmB, GemmArgs g,
+                                                                  int stages, int kb_per_split,
+                                                                  float* __restrict__ partial, int vec_ok) {
+  constexpr int B_BYTES = BN * BK * 2;
+  constexpr int STAGE_BYTES = SK_A_BYTES + B_BYTES;
+  constexpr int TMEM_COLS = BN <= 32 ? 32 : 64;
+  extern __shared__ uint8_t smem_raw[];
+  if (g.skip_flag && *g.skip_flag) return;
+
+  uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(tiles + stages * STAGE_BYTES + SK_SLACK);
+  uint64_t* empty = full + SK_MAX_STAGES;
+  uint64_t* tmem_full = empty + SK_MAX_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int n0 = blockIdx.x * BN, split = blockIdx.y;
+  const int num_kb = (g.K + BK - 1) / BK;
+  const int kb0 = split * kb_per_split;
+  const int nkb = min(kb_per_split, num_kb - kb0);   // >= 1 by construction of the grid
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % stages;
+        const uint32_t ph = (i / stages) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_expect_tx(&full[s], STAGE_BYTES);
+        uint8_t* a_dst = tiles + s * STAGE_BYTES;
+        tma_load_2d(a_dst, &tmA, (kb0 + i) * BK, 0, &full[s]);
+        tma_load_2d(a_dst + SK_A_BYTES, &tmB, (kb0 + i) * BK, n0, &full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BN);
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % stages;
+        const uint32_t ph = (i / stages) & 1;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(tiles + s * STAGE_BYTES);
+        const uint64_t da = make_desc(a_addr), db = make_desc(a_addr + SK_A_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k)
+          umma(tmem_base, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
+               (i | k) != 0 ? 1u : 0u);
+        umma_commit(&empty[s]);
+      }
+      umma_commit(tmem_full);
+    }
+  } else if (warp % 4 < 2) {
+    // ---- epilogue: warps 4,5 own TMEM lanes 0..63 = the 64 real rows ---------------------------
+    const int quarter = warp % 4;
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const long long m = quarter * 32 + lane;
+    const bool row_ok = m < g.M;
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      if (n0 + c0 >= g.N) break;
+      uint32_t r[32];
+      if (BN >= 32) {
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(c0), r);
+      } else {
+        tmem_ld16(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(c0), r);
+#pragma unroll
+        for (int j = 16; j < 32; ++j) r[j] = 0u;
+      }
+      if (!row_ok) continue;
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      const int nb = n0 + c0;
+      if (partial) {
+        float* dst = partial + (static_cast<long long>(split) * SK_ROWS + m) * g.N + nb;
+        constexpr int W = BN >= 32 ? 32 : BN;
+        if (nb + W <= g.N && (g.N % 4) == 0) {
+#pragma unroll
+          for (int q = 0; q < W / 4; ++q)
+            *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < W; ++j)
+            if (nb + j < g.N) dst[j] = v[j];
+        }
+      } else {
+        GemmArgs gl = g;
+        if (BN < 32) gl.N = min(g.N, nb + BN);   // columns beyond this CTA's tile belong to its neighbour
+        epilogue_chunk(gl, v, m, nb, (BN >= 32) ? vec_ok : 0);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+// out[m, :] = LayerNorm( act( sum_s partial[s][m][:] + bias ) + residual[m, :] ) for m < M; one CTA per row.
+__global__ void __launch_bounds__(256) splitk_ln_kernel(const float* __restrict__ partial, int nsplit, int N,
+                                                        const float* __restrict__ bias, int act,
+                                                        const bf16* __restrict__ residual, int ldr,
+                                                        const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, float eps,
+                                                        bf16* __restrict__ out, int ldo,
+                                                        const int* __restrict__ skip_flag) {
+  __shared__ float sh[8];
+  if (skip_flag && *skip_flag) return;
+  const int m = blockIdx.x, tid = threadIdx.x;
+  const int c = tid * 4;
+  float v[4] = {0.f, 0.f, 0.f, 0.f};
+  const bool on = c < N;   // N % 4 == 0, N <= 1024
+  if (on) {
+    for (int s = 0; s < nsplit; ++s) {
+      const float4 p = __ldcg(reinterpret_cast<const float4*>(partial + (static_cast<long long>(s) * SK_ROWS + m) * N + c));
+      v[0] += p.x; v[1] += p.y; v[2] += p.z; v[3] += p.w;
+    }
+    if (bias) {
+      const float4 b = *reinterpret_cast<const float4*>(bias + c);
+      v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+    }
+    if (act == ACT_GELU) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = gelu_erf(v[j]);
+    }
+    if (residual) {
+      const uint2 rr = *reinterpret_cast<const uint2*>(residual + static_cast<long long>(m) * ldr + c);
+      v[0] += __uint_as_float(rr.x << 16); v[1] += __uint_as_float(rr.x & 0xffff0000u);
+      v[2] += __uint_as_float(rr.y << 16); v[3] += __uint_as_float(rr.y & 0xffff0000u);
+    }
+    // the reference rounds the pre-LN sum to the storage type (bf16 GEMM output) before normalising
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
+  }
+  auto block_sum = [&](float x) {
+    x = warp_sum(x);
+    __syncthreads();
+    if (tid % kWarp == 0) sh[tid / kWarp] = x;
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sh[w];
+    return t;
+  };
+  const float mean = block_sum(on ? v[0] + v[1] + v[2] + v[3] : 0.f) / N;
+  float d2 = 0.f;
+  if (on) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) d2 += (v[j] - mean) * (v[j] - mean);
+  }
+  const float var = block_sum(d2) / N;
+  const float rstd = rsqrtf(var + eps);
+  if (on) {
+    const float4 gm = *reinterpret_cast<const float4*>(gamma + c), bt = *reinterpret_cast<const float4*>(beta + c);
+    const float o0 = (v[0] - mean) * rstd * gm.x + bt.x, o1 = (v[1] - mean) * rstd * gm.y + bt.y;
+    const float o2 = (v[2] - mean) * rstd * gm.z + bt.z, o3 = (v[3] - mean) * rstd * gm.w + bt.w;
+    __nv_bfloat162 a = __floats2bfloat162_rn(o0, o1), b = __floats2bfloat162_rn(o2, o3);
+    uint2 st;
+    st.x = *reinterpret_cast<uint32_t*>(&a);
+    st.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(out + static_cast<long long>(m) * ldo + c) = st;
   }
 }
 
@@ -330,6 +546,86 @@ void launch(const GemmArgs& g, cudaStream_t stream) {
   check_launch("gemm_tcgen05");
 }
 
+
+// ---- skinny path (M <= 64) -------------------------------------------------------------------------
+template <int BN>
+void launch_skinny(const GemmArgs& g, int stages, int nsplit, int kb_per_split, float* partial, cudaStream_t stream) {
+  const size_t smem = static_cast<size_t>(stages) * (SK_A_BYTES + BN * BK * 2) + SK_SLACK + 1024 + 512;
+  static size_t configured = 0;
+  if (smem > configured) {
+    CXRM_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_skinny_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem)));
+    configured = smem;
+  }
+  const CUtensorMap ta = make_map(g.A, g.M, g.K, g.lda, SK_ROWS);
+  const CUtensorMap tb = make_map(g.W, g.N, g.K, g.ldw, BN);
+  const int esz = g.out_f32 ? 4 : 2;
+  int vec_ok = (reinterpret_cast<uintptr_t>(g.C) % 16 == 0) && ((static_cast<long long>(g.ldc) * esz) % 16 == 0);
+  if (g.residual) vec_ok = vec_ok && (reinterpret_cast<uintptr_t>(g.residual) % 16 == 0) && (g.ldr % 8 == 0);
+  dim3 grid(ceil_div(g.N, BN), nsplit);
+  gemm_tc_skinny_kernel<BN><<<grid, NTHREADS, smem, stream>>>(ta, tb, g, stages, kb_per_split, partial, vec_ok);
+  check_launch("gemm_tcgen05_skinny");
+}
+
+}  // namespace
+
+CUtensorMap make_tensor_map_bf16(const void* ptr, long long rows, long long cols, long long ld, int box_rows,
+                                 int box_cols) {
+  CUtensorMap m;
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    throw std::runtime_error("cuTensorMapEncodeTiled failed (CUresult " + std::to_string(static_cast<int>(r)) + ")");
+  return m;
+}
+
+int gemm_skinny_supported(const GemmArgs& g) {
+  if (gemm_tcgen05_supported(g) != 0) return 1;
+  if (g.M > SK_ROWS) return 2;
+  return 0;
+}
+
+// nsplit_out: number of K splits written to `partial` (0 when the result was stored directly through the epilogue)
+void gemm_tcgen05_skinny(const GemmArgs& g, float* partial, int* nsplit_out, cudaStream_t stream) {
+  CXRM_CHECK(gemm_skinny_supported(g) == 0, "shape not supported by the skinny tcgen05 GEMM");
+  const int num_kb = ceil_div(g.K, BK);
+  int bn = 32, stages = SK_MAX_STAGES;
+  if (g.N >= 8192) {   // LM head: many tiles, two CTAs per SM
+    bn = 64;
+    stages = 6;
+  } else if (!partial && ceil_div(g.N, 32) < 48 && g.c_head_stride == 0) {
+    bn = 16;           // no split possible (direct epilogue): narrower tiles instead
+  }
+  int nsplit = 1;
+  if (partial && ceil_div(g.N, bn) < 64) nsplit = std::max(1, std::min(4, num_kb / 6));
+  const int kb_per_split = ceil_div(num_kb, nsplit);
+  nsplit = ceil_div(num_kb, kb_per_split);
+  stages = std::min(stages, kb_per_split);
+  if (nsplit_out) *nsplit_out = partial ? nsplit : 0;
+  switch (bn) {
+    case 16: launch_skinny<16>(g, stages, nsplit, kb_per_split, partial, stream); break;
+    case 64: launch_skinny<64>(g, stages, nsplit, kb_per_split, partial, stream); break;
+    default: launch_skinny<32>(g, stages, nsplit, kb_per_split, partial, stream); break;
+  }
+}
+
+void splitk_ln(const float* partial, int nsplit, int M, int N, const float* bias, int act, const void* residual,
+               int ldr, const float* gamma, const float* beta, float eps, void* out, int ldo, const int* skip_flag,
+               cudaStream_t stream) {
+  CXRM_CHECK(N % 4 == 0 && N <= 1024 && M <= SK_ROWS && ldo % 4 == 0 && (!residual || ldr % 4 == 0), "splitk_ln shape");
+  splitk_ln_kernel<<<M, 256, 0, stream>>>(partial, nsplit, N, bias, act, static_cast<const bf16*>(residual), ldr, gamma,
+                                          beta, eps, static_cast<bf16*>(out), ldo, skip_flag);
+  check_launch("splitk_ln");
+}
+
+size_t gemm_skinny_partial_floats(int N) { return static_cast<size_t>(4) * SK_ROWS * N; }
+
+namespace {
 }  // namespace
 
 int gemm_tcgen05_supported(const GemmArgs& g) {

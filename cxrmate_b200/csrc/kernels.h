@@ -2,6 +2,7 @@
 // All launchers are asynchronous on `stream`; pointers are device pointers.
 #pragma once
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -33,6 +34,15 @@ template <typename T> void gemm_simt(const GemmArgs& g, cudaStream_t stream);
 void gemm_tcgen05(const GemmArgs& g, cudaStream_t stream);
 // returns 0 when the tcgen05 path can take this shape
 int gemm_tcgen05_supported(const GemmArgs& g);
+// decode-step GEMMs (M <= 64): deep TMA ring, optional split-K into fp32 partials [nsplit][64][N]
+// (partial == nullptr: direct fused epilogue).  *nsplit_out = splits written (0 = direct).
+int gemm_skinny_supported(const GemmArgs& g);
+void gemm_tcgen05_skinny(const GemmArgs& g, float* partial, int* nsplit_out, cudaStream_t stream);
+size_t gemm_skinny_partial_floats(int N);
+// out[M, N] (bf16) = LayerNorm(act(sum_s partial[s] + bias) + residual): consumer of the split-K partials
+void splitk_ln(const float* partial, int nsplit, int M, int N, const float* bias, int act, const void* residual,
+               int ldr, const float* gamma, const float* beta, float eps, void* out, int ldo, const int* skip_flag,
+               cudaStream_t stream);
 
 // ---- elementwise / normalisation (elementwise.cu) -------------------------
 template <typename T>
@@ -177,6 +187,14 @@ struct CrossUnits {
   const int* n_units;    // scalar: live units
   int max_units, max_chunks;
 };
+// TMA descriptors of the bf16 caches (built once by the engine; nullptr in fp32 mode):
+//   cross: rows = layers * 2 * 12 * tok_cap of 64 bf16, box 192 rows;  self_k / self_v: rows = layers * R * 12 * Lmax, box 64 rows
+struct AttnMaps {
+  CUtensorMap cross, self_k, self_v;
+  int self_rows_per_layer;
+};
+// 2-D bf16 tensor map [rows, cols] (row pitch ld elements), box [box_cols, box_rows], 128-byte swizzle (gemm_tcgen05.cu)
+CUtensorMap make_tensor_map_bf16(const void* ptr, long long rows, long long cols, long long ld, int box_rows, int box_cols);
 int decode_attn_chunk(size_t elem_size);                   // CH: keys per unit (192 bf16 / 96 fp32)
 size_t decode_attn_ws_floats(int rows, int max_chunks);    // fp32 partials (max, sum, out[64]) per (row, head, chunk)
 
@@ -184,14 +202,14 @@ size_t decode_attn_ws_floats(int rows, int max_chunks);    // fp32 partials (max
 // qkv [R, 3*768] (q | k | v); ctx [R,768]; ws / tickets: partials and per-(row, head) arrival counters (zeroed once).
 template <typename T>
 void decode_self_attention(const T* qkv, T* kcache, T* vcache, T* ctx, const RolloutState& st, int R, int Lmax,
-                           float* ws, unsigned* tickets, cudaStream_t stream);
+                           float* ws, unsigned* tickets, const AttnMaps* maps, int layer, cudaStream_t stream);
 
 // cross-attention of the R/B rows of each study over that study's encoder K/V, kc/vc [12][tokens][64] of this
 // layer (head_stride = tokens * 64).  q [R, ldq]; rows of study b: b, b+B.
 template <typename T>
 void decode_cross_attention(const T* q, int ldq, const T* kc, const T* vc, long long head_stride, T* ctx,
                             const CrossUnits& cu, const RolloutState& st, int R, int B, float* ws, unsigned* tickets,
-                            cudaStream_t stream);
+                            const AttnMaps* maps, int layer, cudaStream_t stream);
 
 // qkv [R*P, 3*768] -> head-major kcache/vcache [R][12][Lmax][64] columns [0,P)
 template <typename T>

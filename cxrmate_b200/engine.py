@@ -285,10 +285,24 @@ def gemm_hook(impl: str, A, W, bias=None, act: int = 0, residual=None, out_f32: 
     N = W.shape[0]
     dt = _lib.CXRM_F32 if A.dtype == torch.float32 else _lib.CXRM_BF16
     out = torch.empty(M, N, dtype=torch.float32 if (out_f32 or dt == _lib.CXRM_F32) else torch.bfloat16, device=A.device)
-    rc = lib.cxrm_test_gemm(1 if impl == "tcgen05" else 0, dt, _ptr(A), _ptr(W), _ptr(out), M, N, K, _ptr(bias), act,
+    rc = lib.cxrm_test_gemm({"simt": 0, "tcgen05": 1, "skinny": 2}[impl], dt, _ptr(A), _ptr(W), _ptr(out), M, N, K, _ptr(bias), act,
                             _ptr(residual), int(out_f32), _stream())
     if rc != 0:
         raise RuntimeError(f"cxrm_test_gemm failed ({rc}): {lib.cxrm_last_error(None).decode()}")
+    return out
+
+
+def gemm_ln_hook(A, W, bias, act, residual, gamma, beta, eps=1e-12):
+    """bf16 decode-step pair: skinny split-K GEMM + fused reduce/bias/act/residual/LayerNorm.  A [M<=64,K], W [N,K]."""
+    lib = _lib.load()
+    M, K = A.shape
+    N = W.shape[0]
+    out = torch.empty(M, N, dtype=torch.bfloat16, device=A.device)
+    ws = torch.empty(4 * 64 * N, dtype=torch.float32, device=A.device)
+    rc = lib.cxrm_test_gemm_ln(_ptr(A), _ptr(W), _ptr(out), M, N, K, _ptr(bias), act, _ptr(residual), _ptr(gamma),
+                               _ptr(beta), float(eps), _ptr(ws), _stream())
+    if rc != 0:
+        raise RuntimeError(f"cxrm_test_gemm_ln failed ({rc}): {lib.cxrm_last_error(None).decode()}")
     return out
 
 

@@ -69,6 +69,8 @@ SYMBOLS = {
     "cxrm_profile_report": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t]),
     "cxrm_test_gemm": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                  C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "cxrm_test_gemm_ln": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),
     "cxrm_test_attention": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                       C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_void_p]),
 }

@@ -232,9 +232,14 @@ CXRM_API int cxrm_set_profile(cxrm_engine* e, int on);
 CXRM_API int cxrm_profile_report(cxrm_engine* e, char* buf, size_t len);
 
 /* Standalone GEMM entry used by the kernel tests: C = A[M,K] . W[N,K]^T (+bias, act, +residual).
- * impl: 0 = SIMT fp32-FMA, 1 = tcgen05.  dtype: cxrm_dtype of A/W/C/residual. */
+ * impl: 0 = SIMT fp32-FMA, 1 = tcgen05, 2 = tcgen05 skinny (M <= 64, deep TMA ring).  dtype: cxrm_dtype of A/W/C/residual. */
 CXRM_API int cxrm_test_gemm(int impl, int dtype, const void* A, const void* W, void* C, int M, int N, int K,
                    const float* bias, int act, const void* residual, int out_f32, void* stream);
+/* Decode-step pair used by the kernel tests: skinny split-K tcgen05 GEMM (M <= 64, bf16) into fp32 partials, then the
+ * fused reduce + bias + act + residual + LayerNorm kernel.  partial_ws: dev fp32 [4 * 64 * N]. */
+CXRM_API int cxrm_test_gemm_ln(const void* A, const void* W, void* out, int M, int N, int K, const float* bias, int act,
+                      const void* residual, const float* gamma, const float* beta, float eps, float* partial_ws,
+                      void* stream);
 /* Standalone attention entry used by the kernel tests (q,k,v,o: [batch, L, heads*64] token-major). */
 CXRM_API int cxrm_test_attention(int dtype, const void* q, const void* k, const void* v, void* o, int batch, int heads,
                         int Lq, int Lk, const uint8_t* key_mask, int causal, float scale, void* stream);

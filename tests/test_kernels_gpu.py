@@ -55,6 +55,49 @@ def test_gemm_tcgen05_matches_simt_bf16():
     assert (a - b).abs().max().item() < 1e-3
 
 
+SKINNY = [(64, 2304, 768), (64, 768, 768), (64, 768, 3072), (64, 3072, 768), (64, 30000, 768), (33, 30000, 768),
+          (2, 128, 768), (7, 768, 3072), (64, 100, 152), (1, 768, 64)]
+
+
+@pytest.mark.parametrize("M,N,K", SKINNY)
+def test_gemm_skinny(M, N, K):
+    """decode-step GEMM (M <= 64): deep TMA ring, 64-row A boxes, BN 16/32/64"""
+    from cxrmate_b200.engine import gemm_hook
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    W = (torch.randn(N, K, device="cuda", generator=g) * K ** -0.5).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    res = torch.randn(M, N, device="cuda", generator=g).bfloat16()
+    for use_bias, act, use_res, out_f32 in [(False, 0, False, False), (True, 1, False, False), (True, 0, True, False),
+                                            (True, 0, False, True)]:
+        out = gemm_hook("skinny", A, W, bias if use_bias else None, act, res if use_res else None, out_f32)
+        torch.cuda.synchronize()
+        ref = _ref_gemm(A, W, bias if use_bias else None, act, res if use_res else None)
+        err = (out.float() - ref).abs().max().item()
+        tol = 2e-3 if out_f32 else 2e-3 + ref.abs().max().item() * 2 ** -8
+        assert err < tol, f"skinny {M}x{N}x{K} bias={use_bias} act={act} res={use_res} f32={out_f32}: max err {err}"
+
+
+@pytest.mark.parametrize("M,N,K", [(64, 768, 768), (64, 768, 3072), (5, 768, 768), (64, 128, 768), (33, 1024, 512)])
+@pytest.mark.parametrize("act,use_res", [(0, True), (1, False)])
+def test_gemm_splitk_layernorm(M, N, K, act, use_res):
+    """skinny split-K GEMM -> fused reduce + bias + act + residual + LayerNorm(eps 1e-12)"""
+    from cxrmate_b200.engine import gemm_ln_hook
+    g = torch.Generator(device="cuda").manual_seed(M + N + K + act)
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    W = (torch.randn(N, K, device="cuda", generator=g) * K ** -0.5).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    res = torch.randn(M, N, device="cuda", generator=g).bfloat16() if use_res else None
+    gamma = 1 + 0.1 * torch.randn(N, device="cuda", generator=g)
+    beta = 0.1 * torch.randn(N, device="cuda", generator=g)
+    out = gemm_ln_hook(A, W, bias, act, res, gamma, beta)
+    torch.cuda.synchronize()
+    pre = _ref_gemm(A, W, bias, act, res).bfloat16().float()      # the GEMM result is stored as bf16 before the LN
+    ref = torch.nn.functional.layer_norm(pre, (N,), gamma, beta, 1e-12)
+    err = (out.float() - ref).abs().max().item()
+    assert err < 4e-2, f"gemm_ln {M}x{N}x{K} act={act} res={use_res}: max err {err}"   # one bf16 ulp at |y| ~ 4
+
+
 def _ref_attn(q, k, v, heads, key_mask, causal, scale):
     b, Lq, C = q.shape
     Lk = k.shape[1]

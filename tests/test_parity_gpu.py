@@ -254,6 +254,49 @@ def test_rollout_eos_and_ragged_finish_fp32(eng32, sd, gold):
     assert torch.allclose(lp, o.logprobs, atol=2e-3), (lp, o.logprobs)
 
 
+# ------------------------------------------------------------------------------ size-independent property, long caches
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_cached_decode_equals_teacher_forced_long(sd, dtype):
+    """KV-cached decode == uncached teacher-forced forward on the generated sequence (the property SURVEY.md
+    finding 4 pins for the reference), at sizes where the decode-attention units span several key chunks:
+    1..3 images of 384x384 (576..1728 encoder tokens), right-padded prompts up to 224 tokens + 40 new tokens."""
+    from cxrmate_b200.modelling import position_ids_from_mask, token_ids_to_token_type_ids
+    e = _engine(sd, None, dtype, max_studies=3, max_images=3, max_prompt=224, max_new_tokens=40)
+    try:
+        g = torch.Generator().manual_seed(77)
+        px = torch.randn(3, 3, 3, 384, 384, generator=g)
+        px[1, 1:] = 0.0
+        px[2, 2] = 0.0
+        P, T = 224, 40
+        prompt = torch.full((3, P), PAD, dtype=torch.int64)
+        for r, n in enumerate((224, 150, 201)):
+            body = torch.randint(12, 30000, (n,), generator=g)
+            body[0], body[n // 2], body[-1] = 8, PMT_SEP, BOS
+            prompt[r, :n] = body
+        e.encode(px.cuda())
+        e.prefill_cross_kv()
+        out = e.rollout(prompt.cuda(), mode="greedy", max_new_tokens=T, eos_token_id=EOS, pad_token_id=PAD,
+                        mask_token_id=PAD, special_greedy=[PMT_SEP, BOS, SEP], sections_greedy=[0, 1, 0, 1])
+        torch.cuda.synchronize()
+        assert out.steps == T
+        ids = out.sequences[:, : P + T - 1]                      # what the last executed step has seen
+        mask = (ids != PAD).int()
+        tt = token_ids_to_token_type_ids(ids, [PMT_SEP, BOS, SEP], [0, 1, 0, 1])
+        tf = e.decoder_forward(ids, tt, position_ids_from_mask(mask), mask, n_studies=3, last_only=True)
+        torch.cuda.synchronize()
+        if dtype == "fp32":
+            err = (tf - out.last_logits).abs().max().item()
+            print("cached vs teacher-forced fp32 max abs err:", err)
+            assert err < 2e-3
+            assert torch.equal(tf.argmax(-1), out.sequences[:, -1])
+        else:
+            err = rel_l2(out.last_logits, tf)
+            print("cached vs teacher-forced bf16 rel-L2:", err)
+            assert err < 3e-2
+    finally:
+        e.close()
+
+
 # ------------------------------------------------------------------------------ small ragged studies vs live oracle
 def test_small_images_ragged_fp32(sd):
     """64x64 images (16 tokens each), 3 studies with 3/1/2 valid images incl. a zero image in the MIDDLE of a study"""
