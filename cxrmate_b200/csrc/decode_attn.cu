@@ -22,6 +22,7 @@
 // tokens were dropped from the cache at cxrm_prefill_cross_kv).
 #include <cuda.h>
 
+#include <algorithm>
 #include <type_traits>
 
 #include "kernels.h"
@@ -420,48 +421,53 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 // byte offset of (key row r, 16-byte chunk c) inside a 128B-swizzled tile whose base is 1024-byte aligned
 __device__ __forceinline__ uint32_t swz(int r, int c) { return static_cast<uint32_t>(r * 128 + ((c ^ (r & 7)) << 4)); }
 
-// One warp: keys [w*48, w*48+48) of the chunk.  qrow[i]: global bf16 query rows (head slice, 64 dims).
-// Writes its (m, l, o[64]) per query row into wpart[w][i][66] (shared).  `valid`: nullable key mask of the chunk.
+// ---- persistent formulation ------------------------------------------------------------------------
+// One CTA per SM for the whole launch.  Warp 4 is the TMA producer: it walks the CTA's contiguous range of
+// work items and keeps a 4-stage ring of (K chunk, V chunk) tiles = 192 KiB per SM requested ahead of the
+// four consumer warps, so that HBM requests never drain while a tile is being reduced (the one-unit-per-CTA
+// version left the memory pipe idle during every unit's epilogue and CTA relaunch: 3.5 TB/s in ncu).
+// Consumers keep flash-style running (max, sum, out) state in registers across consecutive chunks of the same
+// (group, head) and only flush when the group changes, so most groups are finished by a single CTA without
+// touching the global partial buffer; groups that straddle CTAs use the ticket merge.
+constexpr int PSTAGES = 2;                      // per CTA; two CTAs per SM -> 4 x 48 KiB requested ahead per SM
+constexpr int TILE_BYTES = CHB * 128;           // one K or V chunk
+constexpr int ST_Q = 2 * TILE_BYTES;            // stage layout: K | V | q rows (2 x 128 B) | key mask (<= 192 B)
+constexpr int ST_MASK = ST_Q + 256;
+constexpr int STAGE_BYTES = ST_MASK + 256 + 512;   // 50176 = 49 KiB: keeps every stage 1024-byte aligned
+static_assert(STAGE_BYTES % 1024 == 0, "stage alignment (128B swizzle)");
+constexpr int NCONS = 128;                      // consumer threads (4 warps); warp 4 = producer
+constexpr int PNT = NCONS + 32;
+constexpr int MAXI = 128;                       // work items per CTA (metadata staged in shared memory)
+constexpr size_t kPersistSmem = static_cast<size_t>(PSTAGES) * STAGE_BYTES + 4 * 2 * (HD + 2) * sizeof(float) +
+                                5 * MAXI * sizeof(int) + 256 + 1024;
+
+__device__ __forceinline__ void cons_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// running flash state of one consumer warp: rows g < NQ live in lanes 4g..4g+3
+struct WarpAcc {
+  float m, l;
+  float o[8][2];
+  __device__ __forceinline__ void reset() {
+    m = -INFINITY;
+    l = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) o[nt][0] = o[nt][1] = 0.f;
+  }
+};
+
+// One consumer warp folds keys [w*48, w*48+48) of the staged chunk (n valid keys) into its running state.
 template <int NQ>
-__device__ __forceinline__ void mma_warp_unit(uint32_t Ks, uint32_t Vs, uint64_t* bars, int n,
-                                              const bf16* const (&qrow)[NQ], const uint8_t* __restrict__ valid,
-                                              float* __restrict__ wpart) {
+__device__ __forceinline__ void warp_tile_update(uint32_t Ks, uint32_t Vs, int n, const uint32_t (&qa0)[4],
+                                                 const uint32_t (&qa2)[4], const uint8_t* __restrict__ valid,
+                                                 WarpAcc& acc) {
   const int lane = threadIdx.x % kWarp, w = threadIdx.x / kWarp;
   const int g = lane >> 2, t = lane & 3;
   const int k0 = w * WKEYS;
-  float* mine = wpart + (w * NQ + (g < NQ ? g : 0)) * (HD + 2);
-  if (k0 >= n) {   // nothing for this warp (short last chunk)
-    if (g < NQ) {
-      if (t == 0) {
-        mine[0] = -INFINITY;
-        mine[1] = 0.f;
-      }
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        mine[2 + nt * 8 + 2 * t] = 0.f;
-        mine[2 + nt * 8 + 2 * t + 1] = 0.f;
-      }
-    }
-    return;
-  }
-  // ---- Q fragments (rows >= NQ of the 16-row tile are zero) ----
-  uint32_t qa0[4], qa2[4];
-#pragma unroll
-  for (int ks = 0; ks < 4; ++ks) {
-    qa0[ks] = 0u;
-    qa2[ks] = 0u;
-  }
-#pragma unroll
-  for (int i = 0; i < NQ; ++i)
-    if (g == i) {
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        qa0[ks] = *reinterpret_cast<const uint32_t*>(qrow[i] + ks * 16 + 2 * t);
-        qa2[ks] = *reinterpret_cast<const uint32_t*>(qrow[i] + ks * 16 + 8 + 2 * t);
-      }
-    }
+  if (k0 >= n) return;   // warp-uniform
   // ---- scores: 6 n-tiles of 8 keys ----
-  mbar_wait(&bars[0], 0);
   float sc[6][4];
   const int mi = lane >> 3, mr = lane & 7;   // ldmatrix: this lane addresses row mr of matrix mi
 #pragma unroll
@@ -477,8 +483,8 @@ __device__ __forceinline__ void mma_warp_unit(uint32_t Ks, uint32_t Vs, uint64_t
     mma_bf16(sc[nt], qa0[2], 0u, qa2[2], 0u, b[0], b[1]);
     mma_bf16(sc[nt], qa0[3], 0u, qa2[3], 0u, b[2], b[3]);
   }
-  // ---- warp-local softmax statistics (row g lives in lanes 4g..4g+3: sc[nt][0..1] = keys k0+nt*8+2t, +1) ----
-  float m = -INFINITY;
+  // ---- online softmax (row g: sc[nt][0..1] = keys k0 + nt*8 + 2t, +1) ----
+  float mt = -INFINITY;
 #pragma unroll
   for (int nt = 0; nt < 6; ++nt)
 #pragma unroll
@@ -486,28 +492,33 @@ __device__ __forceinline__ void mma_warp_unit(uint32_t Ks, uint32_t Vs, uint64_t
       const int key = k0 + nt * 8 + 2 * t + j;
       const bool vis = key < n && (!valid || valid[key]);
       sc[nt][j] = vis ? sc[nt][j] * 0.125f : -INFINITY;
-      m = fmaxf(m, sc[nt][j]);
+      mt = fmaxf(mt, sc[nt][j]);
     }
-  m = fmaxf(m, __shfl_xor_sync(kFull, m, 1));
-  m = fmaxf(m, __shfl_xor_sync(kFull, m, 2));
-  float l = 0.f;
+  mt = fmaxf(mt, __shfl_xor_sync(kFull, mt, 1));
+  mt = fmaxf(mt, __shfl_xor_sync(kFull, mt, 2));
+  const float m_new = fmaxf(acc.m, mt);
+  const float scale = (acc.m == -INFINITY) ? 0.f : expf(acc.m - m_new);   // m_new == -inf only if acc.m == -inf too
+  float ls = 0.f;
   uint32_t pa[6];
 #pragma unroll
   for (int nt = 0; nt < 6; ++nt) {
-    const float p0 = (sc[nt][0] == -INFINITY) ? 0.f : expf(sc[nt][0] - m);
-    const float p1 = (sc[nt][1] == -INFINITY) ? 0.f : expf(sc[nt][1] - m);
-    l += p0 + p1;
+    const float p0 = (sc[nt][0] == -INFINITY) ? 0.f : expf(sc[nt][0] - m_new);
+    const float p1 = (sc[nt][1] == -INFINITY) ? 0.f : expf(sc[nt][1] - m_new);
+    ls += p0 + p1;
     pa[nt] = (g < NQ) ? pack_bf16(p0, p1) : 0u;
   }
-  l += __shfl_xor_sync(kFull, l, 1);
-  l += __shfl_xor_sync(kFull, l, 2);
-  // ---- out = p.V : 3 k-steps of 16 keys x 8 n-tiles of 8 dims ----
-  mbar_wait(&bars[1], 0);
+  ls += __shfl_xor_sync(kFull, ls, 1);
+  ls += __shfl_xor_sync(kFull, ls, 2);
+  acc.l = acc.l * scale + ls;
+  acc.m = m_new;
+  // ---- out = out * scale + p.V : 3 k-steps of 16 keys x 8 n-tiles of 8 dims ----
   float o[8][4];
 #pragma unroll
-  for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) o[nt][j] = 0.f;
+  for (int nt = 0; nt < 8; ++nt) {
+    o[nt][0] = acc.o[nt][0] * scale;
+    o[nt][1] = acc.o[nt][1] * scale;
+    o[nt][2] = o[nt][3] = 0.f;
+  }
 #pragma unroll
   for (int kk = 0; kk < 3; ++kk) {
     if (k0 + kk * 16 >= n) break;   // warp-uniform
@@ -520,209 +531,337 @@ __device__ __forceinline__ void mma_warp_unit(uint32_t Ks, uint32_t Vs, uint64_t
       mma_bf16(o[2 * dp + 1], pa[2 * kk], 0u, pa[2 * kk + 1], 0u, b[2], b[3]);
     }
   }
-  if (g < NQ) {
-    if (t == 0) {
-      mine[0] = m;
-      mine[1] = l;
-    }
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      mine[2 + nt * 8 + 2 * t] = o[nt][0];
-      mine[2 + nt * 8 + 2 * t + 1] = o[nt][1];
+  for (int nt = 0; nt < 8; ++nt) {
+    acc.o[nt][0] = o[nt][0];
+    acc.o[nt][1] = o[nt][1];
+  }
+}
+
+// q rows staged in shared memory (row i at qs + i*128 bytes) -> A fragments of the 16-row tile (rows >= NQ zero)
+template <int NQ>
+__device__ __forceinline__ void load_q_frags(const unsigned char* qs, uint32_t (&qa0)[4], uint32_t (&qa2)[4]) {
+  const int lane = threadIdx.x % kWarp, g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    qa0[ks] = 0u;
+    qa2[ks] = 0u;
+  }
+  if (g < NQ) {
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      qa0[ks] = *reinterpret_cast<const uint32_t*>(qs + g * 128 + (ks * 16 + 2 * t) * 2);
+      qa2[ks] = *reinterpret_cast<const uint32_t*>(qs + g * 128 + (ks * 16 + 8 + 2 * t) * 2);
     }
   }
 }
 
-// merge the 4 warp partials of the unit (shared) into the unit's global partial slot
+// Consumers (128 threads): finish a (group, head): merge the 4 warps' states and store the context rows, directly
+// when this CTA saw every chunk of the group (n_parts == 1), else through the global partials + ticket.
+//   rows[i]: global row index of query row i; slot(i) = ws + ((rows[i]*NH + h)*maxp + part)*(HD+2)
 template <int NQ>
-__device__ __forceinline__ void merge_warps_to_global(const float* __restrict__ wpart, float* __restrict__ part,
-                                                      long long part_row_stride) {
-  const int tid = threadIdx.x;
+__device__ __forceinline__ void flush_group(const WarpAcc& acc, float* wpart, const int (&rows)[NQ], int h, int part,
+                                            int n_parts, int maxp, float* __restrict__ ws, unsigned* ticket,
+                                            bf16* __restrict__ ctx, int* sh_last) {
+  const int tid = threadIdx.x, lane = tid % kWarp, w = tid / kWarp, g = lane >> 2, t = lane & 3;
+  if (g < NQ) {
+    float* mine = wpart + (w * NQ + g) * (HD + 2);
+    if (t == 0) {
+      mine[0] = acc.m;
+      mine[1] = acc.l;
+    }
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      mine[2 + nt * 8 + 2 * t] = acc.o[nt][0];
+      mine[2 + nt * 8 + 2 * t + 1] = acc.o[nt][1];
+    }
+  }
+  cons_sync();
   if (tid < NQ * HD) {
     const int i = tid / HD, d = tid % HD;
     float m = -INFINITY;
 #pragma unroll
-    for (int w = 0; w < 4; ++w) m = fmaxf(m, wpart[(w * NQ + i) * (HD + 2)]);
+    for (int x = 0; x < 4; ++x) m = fmaxf(m, wpart[(x * NQ + i) * (HD + 2)]);
     float l = 0.f, o = 0.f;
 #pragma unroll
-    for (int w = 0; w < 4; ++w) {
-      const float mw = wpart[(w * NQ + i) * (HD + 2)];
+    for (int x = 0; x < 4; ++x) {
+      const float mw = wpart[(x * NQ + i) * (HD + 2)];
       if (mw == -INFINITY) continue;
       const float a = expf(mw - m);
-      l += a * wpart[(w * NQ + i) * (HD + 2) + 1];
-      o += a * wpart[(w * NQ + i) * (HD + 2) + 2 + d];
+      l += a * wpart[(x * NQ + i) * (HD + 2) + 1];
+      o += a * wpart[(x * NQ + i) * (HD + 2) + 2 + d];
     }
-    float* dst = part + i * part_row_stride;
-    dst[2 + d] = o;
-    if (d == 0) {
-      dst[0] = m;
-      dst[1] = l;
-    }
-  }
-}
-
-template <int NQ>
-__global__ void __launch_bounds__(NT) decode_cross_mma_kernel(const __grid_constant__ CUtensorMap tm_kv,
-                                                              int row_base_k, int row_base_v, int tok_cap,
-                                                              const bf16* __restrict__ q, int ldq,
-                                                              bf16* __restrict__ ctx, CrossUnits cu, RolloutState st,
-                                                              int B, float* __restrict__ ws,
-                                                              unsigned* __restrict__ tickets) {
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
-  unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  float* wpart = reinterpret_cast<float*>(tiles + 2 * CHB * 128);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(wpart + 4 * NQ * (HD + 2));
-  __shared__ int sh_last;
-
-  if (*st.done) return;
-  const int u = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
-  if (u >= *cu.n_units) return;
-  const int b = cu.study[u], j0 = cu.j0[u], n = cu.n[u], c = cu.chunk[u];
-  bool all_fin = true;
-#pragma unroll
-  for (int i = 0; i < NQ; ++i) all_fin = all_fin && st.finished[b + i * B];
-  if (all_fin) return;
-
-  if (tid == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    mbar_expect_tx(&bars[0], CHB * 128);
-    tma_load_2d(tiles, &tm_kv, 0, row_base_k + h * tok_cap + j0, &bars[0]);
-    mbar_expect_tx(&bars[1], CHB * 128);
-    tma_load_2d(tiles + CHB * 128, &tm_kv, 0, row_base_v + h * tok_cap + j0, &bars[1]);
-  }
-  __syncthreads();   // barrier inits visible to every waiter
-  const bf16* qrow[NQ];
-#pragma unroll
-  for (int i = 0; i < NQ; ++i) qrow[i] = q + static_cast<long long>(b + i * B) * ldq + h * HD;
-  mma_warp_unit<NQ>(smem_u32(tiles), smem_u32(tiles + CHB * 128), bars, n, qrow, nullptr, wpart);
-  __syncthreads();
-
-  const int maxc = cu.max_chunks;
-  float* part = ws + ((static_cast<long long>(b) * NH + h) * maxc + c) * (HD + 2);
-  const long long row_stride = static_cast<long long>(B) * NH * maxc * (HD + 2);
-  merge_warps_to_global<NQ>(wpart, part, row_stride);
-
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) {
-    const unsigned nchunk = static_cast<unsigned>(cu.n_chunks[b]);
-    const unsigned prev = atomicAdd(&tickets[b * NH + h], 1u);
-    sh_last = (prev == nchunk - 1) ? 1 : 0;
-    if (sh_last) tickets[b * NH + h] = 0;
-  }
-  __syncthreads();
-  if (sh_last) {
-    __threadfence();
-    if (tid < NQ * HD) {
-      const int i = tid / HD, d = tid % HD;
-      const int r = b + i * B;
-      const float* w = ws + i * row_stride + (static_cast<long long>(b) * NH + h) * maxc * (HD + 2);
-      merge_partials<bf16>(w, cu.n_chunks[b], ctx + static_cast<long long>(r) * H + h * HD, d);
-    }
-  }
-}
-
-__global__ void __launch_bounds__(NT) decode_self_mma_kernel(const __grid_constant__ CUtensorMap tm_k,
-                                                             const __grid_constant__ CUtensorMap tm_v, int layer_row0,
-                                                             const bf16* __restrict__ qkv, bf16* __restrict__ kcache,
-                                                             bf16* __restrict__ vcache, bf16* __restrict__ ctx,
-                                                             RolloutState st, int Lmax, int max_chunks,
-                                                             float* __restrict__ ws, unsigned* __restrict__ tickets) {
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
-  unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  float* wpart = reinterpret_cast<float*>(tiles + 2 * CHB * 128);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(wpart + 4 * (HD + 2));
-  __shared__ int sh_last;
-
-  if (*st.done) return;
-  const int r = blockIdx.x / max_chunks, c = blockIdx.x % max_chunks, h = blockIdx.y, tid = threadIdx.x;
-  if (st.finished[r]) return;
-  const int L = st.cur_len[r];
-  const int ntot = L + 1;
-  const int nchunk = ceil_div(ntot, CHB);
-  if (c >= nchunk) return;
-  const int j0 = c * CHB, n = min(CHB, ntot - j0);
-  const bool has_new = (c == nchunk - 1);
-  const int n_cached = has_new ? n - 1 : n;
-  const int nbox = ceil_div(n_cached, SELF_BOX);
-
-  const long long base = (static_cast<long long>(r) * NH + h) * Lmax * HD;
-  if (tid == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    if (nbox > 0) {
-      const int row0 = layer_row0 + (r * NH + h) * Lmax + j0;
-      mbar_expect_tx(&bars[0], nbox * SELF_BOX * 128);
-      for (int x = 0; x < nbox; ++x) tma_load_2d(tiles + x * SELF_BOX * 128, &tm_k, 0, row0 + x * SELF_BOX, &bars[0]);
-      mbar_expect_tx(&bars[1], nbox * SELF_BOX * 128);
-      for (int x = 0; x < nbox; ++x)
-        tma_load_2d(tiles + CHB * 128 + x * SELF_BOX * 128, &tm_v, 0, row0 + x * SELF_BOX, &bars[1]);
+    if (n_parts == 1) {
+      ctx[static_cast<long long>(rows[i]) * H + h * HD + d] = from_f<bf16>(l > 0.f ? o / l : 0.f);
     } else {
-      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars[0])) : "memory");
-      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars[1])) : "memory");
-    }
-  }
-  __syncthreads();
-  const bf16* qrow = qkv + static_cast<long long>(r) * 3 * H + h * HD;
-  if (has_new) {
-    // The new token's K/V: into the cache now; into the (swizzled) tile once the TMA boxes that cover its row landed.
-    const int row = n - 1;
-    const bool covered = row < nbox * SELF_BOX;   // a TMA box also writes this row: patch after it completes
-    if (!covered) {
-      // rows [nbox*64, row) do not exist (row == nbox*64 here); the MMAs also read the rest of this 16-key group
-      for (int x = tid; x < 16 * 8; x += NT) {
-        const int rr = nbox * SELF_BOX + x / 8, cc = x % 8;
-        if (rr < CHB) {
-          *reinterpret_cast<uint4*>(tiles + swz(rr, cc)) = make_uint4(0, 0, 0, 0);
-          *reinterpret_cast<uint4*>(tiles + CHB * 128 + swz(rr, cc)) = make_uint4(0, 0, 0, 0);
-        }
+      float* dst = ws + ((static_cast<long long>(rows[i]) * NH + h) * maxp + part) * (HD + 2);
+      dst[2 + d] = o;
+      if (d == 0) {
+        dst[0] = m;
+        dst[1] = l;
       }
-      __syncthreads();
-    } else {
-      mbar_wait(&bars[0], 0);
-      mbar_wait(&bars[1], 0);
     }
-    if (tid < HD) {
-      const bf16 kvn = qrow[H + tid];
-      *reinterpret_cast<bf16*>(tiles + swz(row, tid / 8) + (tid % 8) * 2) = kvn;
-      kcache[base + static_cast<long long>(L) * HD + tid] = kvn;
-    } else {
-      const int d = tid - HD;
-      const bf16 vvn = qrow[2 * H + d];
-      *reinterpret_cast<bf16*>(tiles + CHB * 128 + swz(row, d / 8) + (d % 8) * 2) = vvn;
-      vcache[base + static_cast<long long>(L) * HD + d] = vvn;
-    }
-    __syncthreads();
   }
-  const bf16* qr[1] = {qrow};
-  mma_warp_unit<1>(smem_u32(tiles), smem_u32(tiles + CHB * 128), bars, n, qr,
-                   st.key_valid + static_cast<long long>(r) * Lmax + j0, wpart);
-  __syncthreads();
-  float* part = ws + ((static_cast<long long>(r) * NH + h) * max_chunks + c) * (HD + 2);
-  merge_warps_to_global<1>(wpart, part, 0);
-
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) {
-    const unsigned prev = atomicAdd(&tickets[r * NH + h], 1u);
-    sh_last = (prev == static_cast<unsigned>(nchunk) - 1) ? 1 : 0;
-    if (sh_last) tickets[r * NH + h] = 0;
-  }
-  __syncthreads();
-  if (sh_last) {
+  if (n_parts > 1) {
     __threadfence();
-    if (tid < HD)
-      merge_partials<bf16>(ws + (static_cast<long long>(r) * NH + h) * max_chunks * (HD + 2), nchunk,
-                           ctx + static_cast<long long>(r) * H + h * HD, tid);
+    cons_sync();
+    if (tid == 0) {
+      const unsigned prev = atomicAdd(ticket, 1u);
+      *sh_last = (prev == static_cast<unsigned>(n_parts) - 1) ? 1 : 0;
+      if (*sh_last) *ticket = 0;   // ready for the next launch
+    }
+    cons_sync();
+    if (*sh_last) {
+      __threadfence();
+      if (tid < NQ * HD) {
+        const int i = tid / HD, d = tid % HD;
+        merge_partials<bf16>(ws + (static_cast<long long>(rows[i]) * NH + h) * maxp * (HD + 2), n_parts,
+                             ctx + static_cast<long long>(rows[i]) * H + h * HD, d);
+      }
+    }
   }
+  cons_sync();   // wpart / sh_last reusable
 }
 
-constexpr size_t kMmaSmem = 2 * CHB * 128 + 4 * 2 * (HD + 2) * sizeof(float) + 64 + 1024;
+// ---- cross-attention: items = (head, unit) with the unit fastest, so a CTA's range walks the chunks of a study in order
+template <int NQ>
+__global__ void __launch_bounds__(PNT, 2) decode_cross_persist_kernel(const __grid_constant__ CUtensorMap tm_kv,
+                                                                      int row_base_k, int row_base_v, int tok_cap,
+                                                                      const bf16* __restrict__ q, int ldq,
+                                                                      bf16* __restrict__ ctx, CrossUnits cu,
+                                                                      RolloutState st, int B, float* __restrict__ ws,
+                                                                      unsigned* __restrict__ tickets) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  float* wpart = reinterpret_cast<float*>(tiles + PSTAGES * STAGE_BYTES);
+  int* m_study = reinterpret_cast<int*>(wpart + 4 * 2 * (HD + 2));   // -1: skip (every row of the study finished)
+  int* m_j0 = m_study + MAXI;
+  int* m_n = m_j0 + MAXI;
+  int* m_first = m_n + MAXI;
+  int* m_nch = m_first + MAXI;
+  uint64_t* full = reinterpret_cast<uint64_t*>(m_nch + MAXI);
+  uint64_t* empty = full + PSTAGES;
+  __shared__ int sh_last;
+
+  if (*st.done) return;
+  const int tid = threadIdx.x, warp = tid / kWarp;
+  const int n_units = *cu.n_units;
+  const int n_items = n_units * NH;
+  const int per = ceil_div(n_items, static_cast<int>(gridDim.x));   // <= MAXI by the launcher's grid size
+  const int lo = blockIdx.x * per, hi = min(n_items, lo + per);
+  if (lo >= hi) return;
+
+  if (tid == 0) {
+    for (int s = 0; s < PSTAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  for (int x = tid; x < hi - lo; x += PNT) {
+    const int u = (lo + x) % n_units;
+    const int b = cu.study[u];
+    bool fin = true;
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) fin = fin && st.finished[b + i * B];
+    m_study[x] = fin ? -1 : b;
+    m_j0[x] = cu.j0[u];
+    m_n[x] = cu.n[u];
+    m_first[x] = cu.first_unit[b];
+    m_nch[x] = cu.n_chunks[b];
+  }
+  __syncthreads();
+
+  if (warp == 4) {
+    // ===== producer =====
+    if (tid % kWarp == 0) {
+      int k = 0;
+      for (int it = lo; it < hi; ++it) {
+        const int b = m_study[it - lo];
+        if (b < 0) continue;
+        const int h = it / n_units;
+        const int s = k % PSTAGES;
+        mbar_wait(&empty[s], ((k / PSTAGES) & 1) ^ 1);
+        unsigned char* dst = tiles + s * STAGE_BYTES;
+        mbar_expect_tx(&full[s], 2 * TILE_BYTES + NQ * 128);
+        tma_load_2d(dst, &tm_kv, 0, row_base_k + h * tok_cap + m_j0[it - lo], &full[s]);
+        tma_load_2d(dst + TILE_BYTES, &tm_kv, 0, row_base_v + h * tok_cap + m_j0[it - lo], &full[s]);
+#pragma unroll
+        for (int i = 0; i < NQ; ++i)
+          bulk_g2s(dst + ST_Q + i * 128, q + static_cast<long long>(b + i * B) * ldq + h * HD, 128, &full[s]);
+        ++k;
+      }
+    }
+    return;
+  }
+
+  // ===== consumers =====
+  WarpAcc acc;
+  acc.reset();
+  uint32_t qa0[4], qa2[4];
+  int cur_b = -1, cur_h = -1, cur_x = 0, k = 0;
+  auto finish = [&]() {
+    if (cur_b < 0) return;
+    const int first_item = cur_h * n_units + m_first[cur_x];
+    const int last_item = first_item + m_nch[cur_x] - 1;
+    const int p0 = first_item / per, n_parts = last_item / per - p0 + 1;
+    int rows[NQ];
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) rows[i] = cur_b + i * B;
+    flush_group<NQ>(acc, wpart, rows, cur_h, static_cast<int>(blockIdx.x) - p0, n_parts, cu.max_chunks, ws,
+                    &tickets[cur_b * NH + cur_h], ctx, &sh_last);
+    acc.reset();
+  };
+  for (int it = lo; it < hi; ++it) {
+    const int b = m_study[it - lo];
+    if (b < 0) continue;
+    const int h = it / n_units;
+    if (b != cur_b || h != cur_h) {
+      finish();
+      cur_b = b;
+      cur_h = h;
+      cur_x = it - lo;
+    }
+    const int s = k % PSTAGES;
+    mbar_wait(&full[s], (k / PSTAGES) & 1);
+    const unsigned char* stage = tiles + s * STAGE_BYTES;
+    load_q_frags<NQ>(stage + ST_Q, qa0, qa2);
+    const uint32_t base = smem_u32(stage);
+    warp_tile_update<NQ>(base, base + TILE_BYTES, m_n[it - lo], qa0, qa2, nullptr, acc);
+    __syncwarp();
+    if (tid % kWarp == 0) mbar_arrive(&empty[s]);
+    ++k;
+  }
+  finish();
+}
+
+// ---- self-attention: items = (head, row, chunk); every live row has the same cache length P + step
+__global__ void __launch_bounds__(PNT, 2) decode_self_persist_kernel(const __grid_constant__ CUtensorMap tm_k,
+                                                                     const __grid_constant__ CUtensorMap tm_v,
+                                                                     int layer_row0, const bf16* __restrict__ qkv,
+                                                                     bf16* __restrict__ kcache, bf16* __restrict__ vcache,
+                                                                     bf16* __restrict__ ctx, RolloutState st, int R,
+                                                                     int P, int Lmax, int max_chunks,
+                                                                     float* __restrict__ ws,
+                                                                     unsigned* __restrict__ tickets) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  float* wpart = reinterpret_cast<float*>(tiles + PSTAGES * STAGE_BYTES);
+  int* m_n = reinterpret_cast<int*>(wpart + 4 * 2 * (HD + 2));   // keys in the chunk; 0: skip
+  int* m_nch = m_n + MAXI;                                       // chunks of the row
+  int* m_len = m_nch + MAXI;                                     // cache slot of the token being fed
+  uint64_t* full = reinterpret_cast<uint64_t*>(m_n + 5 * MAXI);
+  uint64_t* empty = full + PSTAGES;
+  __shared__ int sh_last;
+
+  if (*st.done) return;
+  const int tid = threadIdx.x, warp = tid / kWarp, lane = tid % kWarp;
+  // live rows sit at slot P + step (rollout_init / sample_step keep cur_len uniform); chunks of the longest row
+  const int mc = ceil_div(P + *st.step + 1, CHB);
+  const int n_items = NH * R * mc;
+  const int per = ceil_div(n_items, static_cast<int>(gridDim.x));   // <= MAXI by the launcher's grid size
+  const int lo = blockIdx.x * per, hi = min(n_items, lo + per);
+  if (lo >= hi) return;
+
+  if (tid == 0) {
+    for (int s = 0; s < PSTAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  // item -> (h, r, c) = (it / (mc*R), (it / mc) % R, it % mc); dead when the row is finished or the chunk is beyond its cache
+  for (int x = tid; x < hi - lo; x += PNT) {
+    const int it = lo + x, c = it % mc, r = (it / mc) % R;
+    const int ntot = st.cur_len[r] + 1;
+    const int nchunk = ceil_div(ntot, CHB);
+    const bool live = !st.finished[r] && c < nchunk;
+    m_n[x] = live ? min(CHB, ntot - c * CHB) : 0;
+    m_nch[x] = nchunk;
+    m_len[x] = ntot - 1;
+  }
+  __syncthreads();
+
+  if (warp == 4) {
+    // ===== producer (whole warp: the append of the new token's K/V is a 32-lane copy) =====
+    int k = 0;
+    for (int it = lo; it < hi; ++it) {
+      const int n = m_n[it - lo];
+      if (n == 0) continue;
+      const int c = it % mc, r = (it / mc) % R, h = it / (mc * R);
+      const long long base = (static_cast<long long>(r) * NH + h) * Lmax * HD;
+      const bf16* qrow = qkv + static_cast<long long>(r) * 3 * H + h * HD;
+      if (c == m_nch[it - lo] - 1) {
+        // this chunk ends with the token being fed: its K/V go from the QKV projection into the cache first, so
+        // that the TMA boxes below already contain them (generic-proxy write -> async-proxy read: proxy fence)
+        const int L = m_len[it - lo];
+        const uint32_t kx = *reinterpret_cast<const uint32_t*>(qrow + H + 2 * lane);
+        const uint32_t vx = *reinterpret_cast<const uint32_t*>(qrow + 2 * H + 2 * lane);
+        *reinterpret_cast<uint32_t*>(kcache + base + static_cast<long long>(L) * HD + 2 * lane) = kx;
+        *reinterpret_cast<uint32_t*>(vcache + base + static_cast<long long>(L) * HD + 2 * lane) = vx;
+        __threadfence();
+        asm volatile("fence.proxy.async;" ::: "memory");
+        __syncwarp();
+      }
+      if (lane == 0) {
+        const int s = k % PSTAGES;
+        mbar_wait(&empty[s], ((k / PSTAGES) & 1) ^ 1);
+        unsigned char* dst = tiles + s * STAGE_BYTES;
+        const int nbox = ceil_div(n, SELF_BOX);
+        const int row0 = layer_row0 + (r * NH + h) * Lmax + c * CHB;
+        const int mbytes = min(CHB, Lmax - c * CHB);   // Lmax % 16 == 0
+        mbar_expect_tx(&full[s], 2 * nbox * SELF_BOX * 128 + 128 + mbytes);
+        for (int x = 0; x < nbox; ++x) {
+          tma_load_2d(dst + x * SELF_BOX * 128, &tm_k, 0, row0 + x * SELF_BOX, &full[s]);
+          tma_load_2d(dst + TILE_BYTES + x * SELF_BOX * 128, &tm_v, 0, row0 + x * SELF_BOX, &full[s]);
+        }
+        bulk_g2s(dst + ST_Q, qrow, 128, &full[s]);
+        bulk_g2s(dst + ST_MASK, st.key_valid + static_cast<long long>(r) * Lmax + c * CHB, mbytes, &full[s]);
+      }
+      ++k;
+    }
+    return;
+  }
+
+  // ===== consumers =====
+  WarpAcc acc;
+  acc.reset();
+  uint32_t qa0[4], qa2[4];
+  int cur_r = -1, cur_h = -1, cur_nchunk = 0, k = 0;
+  auto finish = [&]() {
+    if (cur_r < 0) return;
+    const int first_item = (cur_h * R + cur_r) * mc;
+    const int last_item = first_item + cur_nchunk - 1;
+    const int p0 = first_item / per, n_parts = last_item / per - p0 + 1;
+    const int rows[1] = {cur_r};
+    flush_group<1>(acc, wpart, rows, cur_h, static_cast<int>(blockIdx.x) - p0, n_parts, max_chunks, ws,
+                   &tickets[cur_r * NH + cur_h], ctx, &sh_last);
+    acc.reset();
+  };
+  for (int it = lo; it < hi; ++it) {
+    const int n = m_n[it - lo];
+    if (n == 0) continue;
+    const int r = (it / mc) % R, h = it / (mc * R);
+    if (r != cur_r || h != cur_h) {
+      finish();
+      cur_r = r;
+      cur_h = h;
+      cur_nchunk = m_nch[it - lo];
+    }
+    const int s = k % PSTAGES;
+    mbar_wait(&full[s], (k / PSTAGES) & 1);
+    const unsigned char* stage = tiles + s * STAGE_BYTES;
+    load_q_frags<1>(stage + ST_Q, qa0, qa2);
+    const uint32_t base = smem_u32(stage);
+    warp_tile_update<1>(base, base + TILE_BYTES, n, qa0, qa2, stage + ST_MASK, acc);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+    ++k;
+  }
+  finish();
+}
 
 // qkv [R*P, 3*768] -> head-major caches [R][12][Lmax][64], columns [0,P)
 template <typename T>
@@ -746,6 +885,16 @@ __global__ void prefill_store_kv_kernel(const T* __restrict__ qkv, T* __restrict
   }
 }
 
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    CXRM_CUDA_CHECK(cudaGetDevice(&dev));
+    CXRM_CUDA_CHECK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+  }
+  return n;
+}
+
 }  // namespace
 
 int decode_attn_chunk(size_t elem_size) { return elem_size == 2 ? 192 : 96; }
@@ -755,7 +904,7 @@ size_t decode_attn_ws_floats(int rows, int max_chunks) {
 }
 
 template <typename T>
-void decode_self_attention(const T* qkv, T* kcache, T* vcache, T* ctx, const RolloutState& st, int R, int Lmax,
+void decode_self_attention(const T* qkv, T* kcache, T* vcache, T* ctx, const RolloutState& st, int R, int P, int Lmax,
                            float* ws, unsigned* tickets, const AttnMaps* maps, int layer, cudaStream_t stream) {
   const int CH = decode_attn_chunk(sizeof(T));
   const int max_chunks = ceil_div(Lmax, CH);
@@ -763,13 +912,15 @@ void decode_self_attention(const T* qkv, T* kcache, T* vcache, T* ctx, const Rol
     CXRM_CHECK(maps != nullptr, "bf16 decode attention needs the cache tensor maps");
     static bool configured = false;
     if (!configured) {
-      CXRM_CUDA_CHECK(cudaFuncSetAttribute(decode_self_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           static_cast<int>(kMmaSmem)));
+      CXRM_CUDA_CHECK(cudaFuncSetAttribute(decode_self_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(kPersistSmem)));
       configured = true;
     }
     const int layer_row0 = layer * maps->self_rows_per_layer;
-    decode_self_mma_kernel<<<dim3(R * max_chunks, NH), NT, kMmaSmem, stream>>>(
-        maps->self_k, maps->self_v, layer_row0, qkv, kcache, vcache, ctx, st, Lmax, max_chunks, ws, tickets);
+    const int grid = std::max(2 * num_sms(), ceil_div(NH * R * max_chunks, MAXI));
+    decode_self_persist_kernel<<<grid, PNT, kPersistSmem, stream>>>(maps->self_k, maps->self_v, layer_row0, qkv,
+                                                                       kcache, vcache, ctx, st, R, P, Lmax, max_chunks,
+                                                                       ws, tickets);
   } else {
     const size_t smem = unit_smem_bytes<T, 1>(CH);
     static size_t configured = 0;
@@ -798,20 +949,21 @@ void decode_cross_attention(const T* q, int ldq, const T* kc, const T* vc, long 
     // (one flag for both instantiations: they share a function-pointer type, so a generic lambda would share it too)
     static bool configured = false;
     if (!configured) {
-      CXRM_CUDA_CHECK(cudaFuncSetAttribute(decode_cross_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           static_cast<int>(kMmaSmem)));
-      CXRM_CUDA_CHECK(cudaFuncSetAttribute(decode_cross_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           static_cast<int>(kMmaSmem)));
+      CXRM_CUDA_CHECK(cudaFuncSetAttribute(decode_cross_persist_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(kPersistSmem)));
+      CXRM_CUDA_CHECK(cudaFuncSetAttribute(decode_cross_persist_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(kPersistSmem)));
       configured = true;
     }
     auto launch = [&](auto kern) {
-      kern<<<dim3(cu.max_units, NH), NT, kMmaSmem, stream>>>(maps->cross, row_k, row_v, tok_cap, q, ldq, ctx, cu, st, B,
-                                                              ws, tickets);
+      const int grid = std::max(2 * num_sms(), ceil_div(NH * cu.max_units, MAXI));
+      kern<<<grid, PNT, kPersistSmem, stream>>>(maps->cross, row_k, row_v, tok_cap, q, ldq, ctx, cu, st, B, ws,
+                                                      tickets);
     };
     if (nq == 1)
-      launch(decode_cross_mma_kernel<1>);
+      launch(decode_cross_persist_kernel<1>);
     else
-      launch(decode_cross_mma_kernel<2>);
+      launch(decode_cross_persist_kernel<2>);
   } else {
     auto launch = [&](auto kern, size_t smem) {
       CXRM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -836,7 +988,7 @@ void prefill_store_kv(const T* qkv, T* kcache, T* vcache, int R, int P, int Lmax
 }
 
 #define INST(T)                                                                                                      \
-  template void decode_self_attention<T>(const T*, T*, T*, T*, const RolloutState&, int, int, float*, unsigned*,      \
+  template void decode_self_attention<T>(const T*, T*, T*, T*, const RolloutState&, int, int, int, float*, unsigned*, \
                                          const AttnMaps*, int, cudaStream_t);                                         \
   template void decode_cross_attention<T>(const T*, int, const T*, const T*, long long, T*, const CrossUnits&,        \
                                           const RolloutState&, int, int, float*, unsigned*, const AttnMaps*, int,     \

@@ -345,7 +345,7 @@ class Engine : public EngineBase {
     T2 = (cfg.image_h / 16) * (cfg.image_w / 16);
     Smax = cfg.max_images * T2;
     Rmax = 2 * cfg.max_studies;
-    Lmax = cfg.max_prompt + cfg.max_new_tokens;
+    Lmax = (cfg.max_prompt + cfg.max_new_tokens + 15) & ~15;   // row stride of the caches / key mask (16-byte bulk copies)
     const long long B = cfg.max_studies;
     // persistent buffers
     memory = dalloc<T>(B * Smax * DH);
@@ -394,7 +394,7 @@ class Engine : public EngineBase {
     self_tickets = dalloc<unsigned>(static_cast<long long>(Rmax) * NHEAD);
     CXRM_CUDA_CHECK(cudaMemset(cross_tickets, 0, sizeof(unsigned) * cfg.max_studies * NHEAD));
     CXRM_CUDA_CHECK(cudaMemset(self_tickets, 0, sizeof(unsigned) * Rmax * NHEAD));
-    unit_tab = dalloc<int>(4LL * cross_max_units + cfg.max_studies + 1);
+    unit_tab = dalloc<int>(4LL * cross_max_units + 2LL * cfg.max_studies + 1);
     // the tensor-core attention units multiply p = 0 with whatever lies behind a short chunk: keep the caches finite
     CXRM_CUDA_CHECK(cudaMemset(cross_kv, 0, sizeof(T) * cfg.dec_layers * cross_layer_stride()));
     CXRM_CUDA_CHECK(cudaMemset(self_k, 0, sizeof(T) * cfg.dec_layers * self_layer_stride()));
@@ -673,16 +673,18 @@ class Engine : public EngineBase {
            cross_head_stride());
     }
     // uniform work units of the decode-step cross-attention: (study, chunk of attn_ch tokens)
-    std::vector<int> tab(4 * static_cast<size_t>(cross_max_units) + cfg.max_studies + 1, 0);
+    std::vector<int> tab(4 * static_cast<size_t>(cross_max_units) + 2 * cfg.max_studies + 1, 0);
     int* u_study = tab.data();
     int* u_j0 = u_study + cross_max_units;
     int* u_n = u_j0 + cross_max_units;
     int* u_chunk = u_n + cross_max_units;
     int* n_chunks = u_chunk + cross_max_units;
+    int* first_unit = n_chunks + cfg.max_studies;
     int nu = 0;
     for (int b = 0; b < B; ++b) {
       const int nc = ceil_div(len[b], attn_ch);
       n_chunks[b] = nc;
+      first_unit[b] = nu;
       for (int c = 0; c < nc; ++c, ++nu) {
         u_study[nu] = b;
         u_j0[nu] = off[b] + c * attn_ch;
@@ -690,7 +692,7 @@ class Engine : public EngineBase {
         u_chunk[nu] = c;
       }
     }
-    n_chunks[cfg.max_studies] = nu;
+    first_unit[cfg.max_studies] = nu;
     CXRM_CUDA_CHECK(cudaMemcpyAsync(unit_tab, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice, s));
     CXRM_CUDA_CHECK(cudaStreamSynchronize(s));   // `tab` is pageable host memory going out of scope
   }
@@ -701,7 +703,8 @@ class Engine : public EngineBase {
     cu.n = unit_tab + 2 * cross_max_units;
     cu.chunk = unit_tab + 3 * cross_max_units;
     cu.n_chunks = unit_tab + 4 * cross_max_units;
-    cu.n_units = cu.n_chunks + cfg.max_studies;
+    cu.first_unit = cu.n_chunks + cfg.max_studies;
+    cu.n_units = cu.first_unit + cfg.max_studies;
     cu.max_units = cross_max_units;
     cu.max_chunks = cross_max_chunks;
     return cu;
@@ -788,7 +791,7 @@ class Engine : public EngineBase {
       const BertLayerW& w = dec.layers[l];
       gemm(b.x, DH, w.qkv, b.qkv, 3 * DH, R, ACT_NONE, nullptr, 0, false, skip, s);
       PF("self_attn", s, [&] { decode_self_attention<T>(b.qkv, self_k + l * self_layer_stride(), self_v + l * self_layer_stride(), b.ctx, st, R,
-                               Lmax, self_ws, self_tickets, attn_maps_ptr, l, s); });
+                               rp.P, Lmax, self_ws, self_tickets, attn_maps_ptr, l, s); });
       gemm_ln(b.ctx, DH, w.o, ACT_NONE, b.x, DH, w.ln1, b.x1, DH, R, skip, s);
       gemm(b.x1, DH, w.cq, b.qkv, DH, R, ACT_NONE, nullptr, 0, false, skip, s);
       const T* kvl = cross_kv + static_cast<long long>(l) * cross_layer_stride();

@@ -184,6 +184,7 @@ struct CrossUnits {
   const int* n;          // [max_units] tokens in the chunk
   const int* chunk;      // [max_units] chunk index within its study
   const int* n_chunks;   // [B] chunks per study
+  const int* first_unit; // [B] index of the study's first unit (units are ordered by study, then chunk)
   const int* n_units;    // scalar: live units
   int max_units, max_chunks;
 };
@@ -201,7 +202,7 @@ size_t decode_attn_ws_floats(int rows, int max_chunks);    // fp32 partials (max
 // self-attention of each row's new token over its cache [R][12][Lmax][64] (this layer); appends the new K/V.
 // qkv [R, 3*768] (q | k | v); ctx [R,768]; ws / tickets: partials and per-(row, head) arrival counters (zeroed once).
 template <typename T>
-void decode_self_attention(const T* qkv, T* kcache, T* vcache, T* ctx, const RolloutState& st, int R, int Lmax,
+void decode_self_attention(const T* qkv, T* kcache, T* vcache, T* ctx, const RolloutState& st, int R, int P, int Lmax,
                            float* ws, unsigned* tickets, const AttnMaps* maps, int layer, cudaStream_t stream);
 
 // cross-attention of the R/B rows of each study over that study's encoder K/V, kc/vc [12][tokens][64] of this
