@@ -188,6 +188,211 @@ __global__ void __launch_bounds__(NT) attention_simt_kernel(AttnArgs a) {
   }
 }
 
+
+// =====================================================================================================
+// bf16 tensor-core version (flash-attention-2 data flow): 64 queries per CTA (4 warps x 16 rows), K/V tiles of
+// 64 keys double-buffered in shared memory by cp.async (16-byte chunks, XOR-swizzled so that the ldmatrix
+// reads are bank-conflict free), S = Q.K^T and O += P.V by mma.sync.m16n8k16 with fp32 accumulation, online
+// softmax in registers, probabilities rounded to bf16 for the second product (as the reference's bf16
+// attention does).  Same AttnArgs contract as the SIMT kernel.
+// =====================================================================================================
+namespace tc {
+
+constexpr int TBQ = 64, TBK = 64, TNT = 128;
+constexpr int TILE_B = 64 * 128;   // one 64 x 64 bf16 tile
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                         uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+// byte offset of (row r, 16-byte chunk c) in a 64-row x 128-byte tile
+__device__ __forceinline__ uint32_t swz(int r, int c) { return static_cast<uint32_t>(r * 128 + ((c ^ (r & 7)) << 4)); }
+
+// 64 rows x 64 bf16 from global (row stride ts elements) into a swizzled tile; rows >= n_rows are zero-filled
+__device__ __forceinline__ void load_tile(uint32_t dst, const bf16* src, long long ts, int n_rows) {
+#pragma unroll
+  for (int x = 0; x < 4; ++x) {
+    const int idx = threadIdx.x + x * TNT;   // 512 chunks
+    const int r = idx >> 3, c = idx & 7;
+    const bool ok = r < n_rows;
+    cp_async16(dst + swz(r, c), ok ? static_cast<const void*>(src + r * ts + c * 8) : static_cast<const void*>(src), ok ? 16 : 0);
+  }
+}
+
+__global__ void __launch_bounds__(TNT) attention_mma_kernel(AttnArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~static_cast<uintptr_t>(127));
+  const uint32_t sQ = smem_u32(sm), sK = sQ + TILE_B, sV = sK + 2 * TILE_B;   // K, V double-buffered
+  const int tid = threadIdx.x, warp = tid / kWarp, lane = tid % kWarp;
+  const int g = lane >> 2, t = lane & 3, mi = lane >> 3, mr = lane & 7;
+  const int q0 = blockIdx.x * TBQ, h = blockIdx.y, b = blockIdx.z;
+  const int kvb = a.kv_batch_mod > 0 ? b % a.kv_batch_mod : b;
+  const int Lk = a.Lk_per_batch ? a.Lk_per_batch[kvb] : a.Lk;
+  const long long koff = a.kv_offset ? a.kv_offset[kvb] : 0;
+  const bf16* __restrict__ Q = static_cast<const bf16*>(a.q) + b * a.q_bs + h * a.q_hs;
+  const bf16* __restrict__ K = static_cast<const bf16*>(a.k) + kvb * a.k_bs + h * a.k_hs + koff * a.k_ts;
+  const bf16* __restrict__ V = static_cast<const bf16*>(a.v) + kvb * a.v_bs + h * a.v_hs + koff * a.v_ts;
+  const uint8_t* __restrict__ km =
+      a.key_mask ? a.key_mask + static_cast<long long>(a.key_mask_per_q_batch ? b : kvb) * a.key_mask_ld : nullptr;
+
+  int k_end = Lk;
+  if (a.causal) k_end = min(k_end, min(q0 + TBQ, a.Lq) + a.q_pos_offset);   // keys beyond the tile's last query
+  const int n_tiles = (k_end + TBK - 1) / TBK;
+
+  load_tile(sQ, Q + static_cast<long long>(q0) * a.q_ts, a.q_ts, a.Lq - q0);
+  if (n_tiles > 0) {
+    load_tile(sK, K, a.k_ts, Lk);
+    load_tile(sV, V, a.v_ts, Lk);
+  }
+  cp_commit();
+
+  float o[8][4], m_[2] = {-INFINITY, -INFINITY}, l_[2] = {0.f, 0.f};
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[nt][j] = 0.f;
+  uint32_t qf[4][4];
+  const float sl2 = a.scale * 1.4426950408889634f;   // scores are kept in the log2 domain
+  const int qi0 = q0 + warp * 16 + g;                // this lane's rows: qi0 and qi0 + 8
+
+  for (int it = 0; it < n_tiles; ++it) {
+    const int buf = it & 1;
+    if (it + 1 < n_tiles) {
+      const int kb = (it + 1) * TBK;
+      load_tile(sK + (buf ^ 1) * TILE_B, K + static_cast<long long>(kb) * a.k_ts, a.k_ts, Lk - kb);
+      load_tile(sV + (buf ^ 1) * TILE_B, V + static_cast<long long>(kb) * a.v_ts, a.v_ts, Lk - kb);
+      cp_commit();
+      cp_wait<1>();
+    } else {
+      cp_wait<0>();
+    }
+    __syncthreads();
+    if (it == 0) {
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+        ldsm_x4(sQ + swz(warp * 16 + (mi & 1) * 8 + mr, ks * 2 + (mi >> 1)), qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
+    }
+    const uint32_t kt = sK + buf * TILE_B, vt = sV + buf * TILE_B;
+    const int k0 = it * TBK;
+    // ---- S = Q.K^T ----
+    float s[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[nt][j] = 0.f;
+      uint32_t bb[4];
+      ldsm_x4(kt + swz(nt * 8 + mr, mi), bb[0], bb[1], bb[2], bb[3]);
+      mma_bf16(s[nt], qf[0][0], qf[0][1], qf[0][2], qf[0][3], bb[0], bb[1]);
+      mma_bf16(s[nt], qf[1][0], qf[1][1], qf[1][2], qf[1][3], bb[2], bb[3]);
+      ldsm_x4(kt + swz(nt * 8 + mr, 4 + mi), bb[0], bb[1], bb[2], bb[3]);
+      mma_bf16(s[nt], qf[2][0], qf[2][1], qf[2][2], qf[2][3], bb[0], bb[1]);
+      mma_bf16(s[nt], qf[3][0], qf[3][1], qf[3][2], qf[3][3], bb[2], bb[3]);
+    }
+    // ---- mask + online softmax (rows g and g+8; s[nt][0..1] row g, s[nt][2..3] row g+8; cols nt*8 + 2t, +1) ----
+    const bool need_mask = km != nullptr || (k0 + TBK > Lk) || (a.causal && (k0 + TBK - 1 > q0 + warp * 16 + a.q_pos_offset));
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float v = s[nt][j] * sl2;
+        if (need_mask) {
+          const int kj = k0 + nt * 8 + 2 * t + (j & 1);
+          const int qi = qi0 + (j >> 1) * 8;
+          const bool vis = kj < Lk && (!km || km[kj] != 0) && (!a.causal || kj <= qi + a.q_pos_offset);
+          v = vis ? v : -INFINITY;
+        }
+        s[nt][j] = v;
+        mx[j >> 1] = fmaxf(mx[j >> 1], v);
+      }
+    float alpha[2];
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      mx[rr] = fmaxf(mx[rr], __shfl_xor_sync(kFull, mx[rr], 1));
+      mx[rr] = fmaxf(mx[rr], __shfl_xor_sync(kFull, mx[rr], 2));
+      const float m_new = fmaxf(m_[rr], mx[rr]);
+      alpha[rr] = (m_[rr] == -INFINITY) ? 0.f : exp2f(m_[rr] - m_new);
+      m_[rr] = m_new;
+    }
+    float ps[2] = {0.f, 0.f};
+    uint32_t pa[8][2];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      float pv[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        pv[j] = (s[nt][j] == -INFINITY) ? 0.f : exp2f(s[nt][j] - m_[j >> 1]);
+        ps[j >> 1] += pv[j];
+      }
+      pa[nt][0] = pack_bf16(pv[0], pv[1]);
+      pa[nt][1] = pack_bf16(pv[2], pv[3]);
+    }
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      ps[rr] += __shfl_xor_sync(kFull, ps[rr], 1);
+      ps[rr] += __shfl_xor_sync(kFull, ps[rr], 2);
+      l_[rr] = l_[rr] * alpha[rr] + ps[rr];
+    }
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      o[nt][0] *= alpha[0]; o[nt][1] *= alpha[0];
+      o[nt][2] *= alpha[1]; o[nt][3] *= alpha[1];
+    }
+    // ---- O += P.V ----
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+      for (int dp = 0; dp < 4; ++dp) {
+        uint32_t bb[4];
+        ldsm_x4_t(vt + swz(kk * 16 + (mi & 1) * 8 + mr, 2 * dp + (mi >> 1)), bb[0], bb[1], bb[2], bb[3]);
+        mma_bf16(o[2 * dp], pa[2 * kk][0], pa[2 * kk][1], pa[2 * kk + 1][0], pa[2 * kk + 1][1], bb[0], bb[1]);
+        mma_bf16(o[2 * dp + 1], pa[2 * kk][0], pa[2 * kk][1], pa[2 * kk + 1][0], pa[2 * kk + 1][1], bb[2], bb[3]);
+      }
+    }
+    __syncthreads();   // this buffer is overwritten by the load issued in the next iteration
+  }
+  if (n_tiles == 0) cp_wait<0>();
+
+  bf16* __restrict__ O = static_cast<bf16*>(a.o) + b * a.o_bs + h * a.o_hs;
+#pragma unroll
+  for (int rr = 0; rr < 2; ++rr) {
+    const int qi = qi0 + rr * 8;
+    if (qi >= a.Lq) continue;
+    const float inv = l_[rr] > 0.f ? 1.f / l_[rr] : 0.f;
+    bf16* dst = O + static_cast<long long>(qi) * a.o_ts + 2 * t;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+      *reinterpret_cast<uint32_t*>(dst + nt * 8) = pack_bf16(o[nt][2 * rr] * inv, o[nt][2 * rr + 1] * inv);
+  }
+}
+
+}  // namespace tc
+
 }  // namespace
 
 template <typename T>
@@ -203,6 +408,32 @@ void attention_simt(const AttnArgs& a, cudaStream_t stream) {
   CXRM_CHECK(grid.z <= 65535 && grid.y <= 65535, "attention batch too large for grid.z");
   attention_simt_kernel<T><<<grid, NT, sizeof(Smem), stream>>>(a);
   check_launch("attention_simt");
+}
+
+int attention_mma_supported(const AttnArgs& a) {
+  auto al16 = [](const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
+  const long long st[] = {a.q_bs, a.q_hs, a.q_ts, a.k_bs, a.k_hs, a.k_ts, a.v_bs, a.v_hs, a.v_ts};
+  for (long long x : st)
+    if (x % 8 != 0) return 1;                       // 16-byte cp.async chunks
+  if (a.o_bs % 2 != 0 || a.o_hs % 2 != 0 || a.o_ts % 2 != 0) return 2;
+  if (!al16(a.q) || !al16(a.k) || !al16(a.v) || reinterpret_cast<uintptr_t>(a.o) % 4 != 0) return 3;
+  if (a.kv_offset && a.k_ts % 8 != 0) return 4;
+  return 0;
+}
+
+void attention_mma(const AttnArgs& a, cudaStream_t stream) {
+  if (a.batch <= 0 || a.Lq <= 0) return;
+  CXRM_CHECK(attention_mma_supported(a) == 0, "strides/alignment not supported by the tensor-core attention");
+  constexpr int smem = 5 * tc::TILE_B + 128;
+  static bool configured = false;
+  if (!configured) {
+    CXRM_CUDA_CHECK(cudaFuncSetAttribute(tc::attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  dim3 grid(ceil_div(a.Lq, tc::TBQ), a.heads, a.batch);
+  CXRM_CHECK(grid.z <= 65535 && grid.y <= 65535, "attention batch too large for grid.z");
+  tc::attention_mma_kernel<<<grid, tc::TNT, smem, stream>>>(a);
+  check_launch("attention_mma");
 }
 
 template void attention_simt<float>(const AttnArgs&, cudaStream_t);

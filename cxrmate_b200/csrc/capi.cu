@@ -179,6 +179,8 @@ int cxrm_test_gemm(int impl, int dtype, const void* A, const void* W, void* C, i
   }
 }
 
+void cxrm_test_set_pdl(int on) { g_pdl = on != 0; }
+
 int cxrm_test_gemm_ln(const void* A, const void* W, void* out, int M, int N, int K, const float* bias, int act,
                       const void* residual, const float* gamma, const float* beta, float eps, float* partial_ws,
                       void* stream) {
@@ -214,6 +216,8 @@ int cxrm_test_attention(int dtype, const void* q, const void* k, const void* v, 
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (dtype == CXRM_F32)
       attention_simt<float>(a, s);
+    else if (attention_mma_supported(a) == 0)
+      attention_mma(a, s);
     else
       attention_simt<bf16>(a, s);
     return CXRM_OK;

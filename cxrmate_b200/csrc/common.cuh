@@ -7,6 +7,7 @@
 
 #include <cmath>
 #include <stdexcept>
+#include <utility>
 #include <string>
 
 namespace cxrm {
@@ -37,6 +38,35 @@ inline void check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) throw std::runtime_error(std::string(what) + " launch failed: " + cudaGetErrorString(e));
 }
+
+// Programmatic dependent launch (PDL) for the decode-step kernel chain: while g_pdl is set, the chain's kernels are
+// launched with cudaLaunchAttributeProgrammaticStreamSerialization, so that kernel N+1 is scheduled as soon as every
+// CTA of kernel N has executed pdl_launch_dependents(); its prologue (barrier init, TMEM allocation, descriptor
+// prefetch, TMA loads of WEIGHT tiles - data that no kernel of the chain writes) overlaps kernel N, and it blocks in
+// pdl_wait() until kernel N has completed and flushed.  Rules for a chain kernel: call pdl_launch_dependents() early,
+// touch only chain-constant memory before pdl_wait(), and ALWAYS execute pdl_wait() (completion is transitive only
+// through it).  Both instructions are no-ops in a kernel that was launched without the attribute.
+extern bool g_pdl;   // engine.cu
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline void launch_chain(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+  if (e != cudaSuccess) throw std::runtime_error(std::string("cudaLaunchKernelEx failed: ") + cudaGetErrorString(e));
+}
+#endif
 
 constexpr int kWarp = 32;
 constexpr unsigned kFull = 0xffffffffu;

@@ -150,18 +150,75 @@ __device__ __forceinline__ float philox_exp(unsigned long long seed, unsigned lo
   return -logf(curand_uniform(&s));   // curand_uniform is in (0,1]
 }
 
+// k-th largest of arr[0..n) (sortable keys in shared memory): 4 x 8-bit radix select, MSB first.
+// Block-wide; hist/sh_prefix/sh_kk are shared scratch.  Returns the key of the k-th largest element.
+__device__ unsigned radix_kth(const unsigned* arr, int n, int k, int* hist, unsigned* sh_prefix, int* sh_kk) {
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    *sh_prefix = 0;
+    *sh_kk = k;
+  }
+  unsigned mask = 0;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    if (tid < 256) hist[tid] = 0;
+    __syncthreads();
+    const unsigned prefix = *sh_prefix;
+    for (int i = tid; i < n; i += SNT) {
+      const unsigned key = arr[i];
+      if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255], 1);
+    }
+    __syncthreads();
+    if (tid < kWarp) {
+      // lane l owns bins 255-8l .. 248-8l (descending)
+      int loc = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) loc += hist[255 - 8 * tid - j];
+      int inc = loc;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(kFull, inc, o);
+        if (tid >= o) inc += y;
+      }
+      const int before = inc - loc;
+      const int kk = *sh_kk;
+      if (before < kk && kk <= inc) {
+        int cum = before;
+        for (int j = 0; j < 8; ++j) {
+          const int bin = 255 - 8 * tid - j;
+          if (cum + hist[bin] >= kk) {
+            *sh_prefix = prefix | (static_cast<unsigned>(bin) << shift);
+            *sh_kk = kk - cum;
+            break;
+          }
+          cum += hist[bin];
+        }
+      }
+    }
+    mask |= 255u << shift;
+    __syncthreads();
+  }
+  return *sh_prefix;
+}
+
 __global__ void __launch_bounds__(SNT) sample_step_kernel(RolloutState st, RolloutParams p,
                                                           const float* __restrict__ logits, int ldl,
                                                           const float* __restrict__ exp_noise) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned* keys = reinterpret_cast<unsigned*>(smem_raw);   // [V]
+  constexpr int kCandCap = 1024;                             // elements >= the lower bound of the k-th value
+  constexpr int kListCap = 256;                              // survivors staged for the race (top-k + ties)
   __shared__ int hist[256];
   __shared__ ValIdx sh_vi[SNT / kWarp];
   __shared__ float sh_f[SNT / kWarp];
+  __shared__ unsigned tmax[SNT];
+  __shared__ int cand[kCandCap];
+  __shared__ int sv_idx[kListCap];
   __shared__ unsigned sh_prefix;
   __shared__ int sh_kk;
-  __shared__ int sh_cnt;
+  __shared__ int sh_cnt, sh_ncand;
 
+  pdl_launch_dependents();
+  pdl_wait();
   if (*st.done) return;
   const int r = blockIdx.x, tid = threadIdx.x;
   const int t = *st.step;
@@ -171,13 +228,14 @@ __global__ void __launch_bounds__(SNT) sample_step_kernel(RolloutState st, Rollo
   const float* lrow = logits + static_cast<long long>(r) * ldl;
   const bool was_finished = st.finished[r] != 0;
   const float inv_temp = (mode == 0 && p.temperature != 1.0f) ? 1.0f / p.temperature : 1.0f;
+  const bool diag = p.want_margin != 0;
 
   int next = p.pad;
   float lp = 0.f, margin = 0.f;
   int n_surv = 0;
 
   if (!was_finished) {
-    // ---- stage the row as sortable keys, find the maximum ---------------------
+    // ---- pass 1: stage the row as sortable keys; per-thread and block maximum ---------------------
     ValIdx best{-INFINITY, 0x7fffffff};
     for (int i = tid; i < V; i += SNT) {
       float s = lrow[i];
@@ -185,112 +243,127 @@ __global__ void __launch_bounds__(SNT) sample_step_kernel(RolloutState st, Rollo
       keys[i] = f2key(s);
       best = better(best, ValIdx{s, i});
     }
-    best = block_argmax(best, sh_vi);
+    tmax[tid] = (best.i != 0x7fffffff) ? f2key(best.v) : 0u;
+    best = block_argmax(best, sh_vi);   // (its barriers also publish keys / tmax)
     const float smax = best.v;
 
+    const bool filter = (mode == 0 && p.top_k > 0 && p.top_k < V);
     unsigned thr_key = 0;   // everything survives
-    if (mode == 0 && p.top_k > 0 && p.top_k < V) {
-      // ---- radix select of the k-th largest key (4 x 8 bits, MSB first) ---------
-      if (tid == 0) {
-        sh_prefix = 0;
-        sh_kk = p.top_k;
-      }
-      unsigned mask = 0;
-      for (int shift = 24; shift >= 0; shift -= 8) {
-        if (tid < 256) hist[tid] = 0;
-        __syncthreads();
-        const unsigned prefix = sh_prefix;
-        for (int i = tid; i < V; i += SNT) {
-          const unsigned k = keys[i];
-          if ((k & mask) == prefix) atomicAdd(&hist[(k >> shift) & 255], 1);
-        }
-        __syncthreads();
-        if (tid < kWarp) {
-          // lane l owns bins 255-8l .. 248-8l (descending)
-          int loc = 0;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) loc += hist[255 - 8 * tid - j];
-          int inc = loc;
-#pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            const int y = __shfl_up_sync(kFull, inc, o);
-            if (tid >= o) inc += y;
+    bool listed = false;    // sv_idx / sh_cnt hold exactly the survivors
+    if (tid == 0) {
+      sh_cnt = 0;
+      sh_ncand = 0;
+    }
+    __syncthreads();
+    if (filter) {
+      bool exact = false;
+      if (p.top_k <= SNT / 2) {
+        // The k largest per-thread maxima are k distinct elements, so the k-th largest of the 512 maxima is a LOWER
+        // bound of the k-th largest logit: one more pass collects the few elements above it, and the exact
+        // threshold (ties kept, as TopKLogitsWarper does) is found among those candidates only.
+        const unsigned lb = radix_kth(tmax, SNT, p.top_k, hist, &sh_prefix, &sh_kk);
+        for (int i = tid; i < V; i += SNT)
+          if (keys[i] >= lb) {
+            const int slot = atomicAdd(&sh_ncand, 1);
+            if (slot < kCandCap) cand[slot] = i;
           }
-          const int before = inc - loc;
-          const int kk = sh_kk;
-          const bool mine = before < kk && kk <= inc;
-          if (mine) {
-            int cum = before;
-            for (int j = 0; j < 8; ++j) {
-              const int b = 255 - 8 * tid - j;
-              if (cum + hist[b] >= kk) {
-                sh_prefix = prefix | (static_cast<unsigned>(b) << shift);
-                sh_kk = kk - cum;
-                break;
-              }
-              cum += hist[b];
+        __syncthreads();
+        const int nc = sh_ncand;
+        if (nc <= kCandCap) {
+          for (int x = tid; x < nc; x += SNT) {
+            const unsigned v = keys[cand[x]];
+            int gt = 0, ge = 0;
+            for (int y = 0; y < nc; ++y) {
+              const unsigned u = keys[cand[y]];
+              gt += u > v;
+              ge += u >= v;
             }
+            if (gt < p.top_k && p.top_k <= ge) sh_prefix = v;   // every such thread writes the same value
           }
+          __syncthreads();
+          thr_key = sh_prefix;
+          for (int x = tid; x < nc; x += SNT)
+            if (keys[cand[x]] >= thr_key) {
+              const int slot = atomicAdd(&sh_cnt, 1);
+              if (slot < kListCap) sv_idx[slot] = cand[x];
+            }
+          __syncthreads();
+          exact = true;
+          listed = sh_cnt <= kListCap;
         }
-        mask |= 255u << shift;
+      }
+      if (!exact) {   // very flat rows (more than kCandCap elements above the bound) or a large k: full radix select
+        thr_key = radix_kth(keys, V, p.top_k, hist, &sh_prefix, &sh_kk);
+        if (tid == 0) sh_cnt = 0;
+        __syncthreads();
+        for (int i = tid; i < V; i += SNT)
+          if (keys[i] >= thr_key) atomicAdd(&sh_cnt, 1);
         __syncthreads();
       }
-      thr_key = sh_prefix;
     }
 
-    // ---- softmax over the survivors -------------------------------------------
-    if (tid == 0) sh_cnt = 0;
+    // ---- softmax denominator over the survivors ------------------------------------------------
     float esum = 0.f;
-    for (int i = tid; i < V; i += SNT) {
-      const unsigned k = keys[i];
-      if (k >= thr_key) esum += expf(key2f(k) - smax);
+    if (listed) {
+      for (int x = tid; x < sh_cnt; x += SNT) esum += expf(key2f(keys[sv_idx[x]]) - smax);
+    } else {
+      for (int i = tid; i < V; i += SNT) {
+        const unsigned k = keys[i];
+        if (k >= thr_key) esum += expf(key2f(k) - smax);
+      }
     }
     esum = block_sum(esum, sh_f);
 
     if (mode == 1) {
       next = best.i;
       lp = -logf(esum);   // s_max - smax - log(sum)
-      // margin: top1 - top2 logit
-      ValIdx second{-INFINITY, 0x7fffffff};
-      for (int i = tid; i < V; i += SNT)
-        if (i != best.i) second = better(second, ValIdx{key2f(keys[i]), i});
-      second = block_argmax(second, sh_vi);
-      margin = smax - second.v;
+      if (diag) {         // margin: top1 - top2 logit
+        ValIdx second{-INFINITY, 0x7fffffff};
+        for (int i = tid; i < V; i += SNT)
+          if (i != best.i) second = better(second, ValIdx{key2f(keys[i]), i});
+        second = block_argmax(second, sh_vi);
+        margin = smax - second.v;
+      }
       n_surv = V;
     } else {
       // ---- exponential race among the survivors: argmax (e/sum) / q --------------
       const int nrow = r % p.B;
       const float* qrow = exp_noise ? exp_noise + (static_cast<long long>(t) * p.B + nrow) * V : nullptr;
       const unsigned long long stream_id = static_cast<unsigned long long>(t) * p.R + r;
-      ValIdx win{-INFINITY, 0x7fffffff};
+      const unsigned long long seed = *st.seed;
       const long long slot0 = (static_cast<long long>(r) * p.Tmax + t) * kTopKCap;
-      for (int i = tid; i < V; i += SNT) {
-        const unsigned k = keys[i];
-        if (k < thr_key) continue;
-        const float s = key2f(k);
-        const float prob = expf(s - smax) / esum;
-        const float q = qrow ? qrow[i] : philox_exp(*st.seed, stream_id, static_cast<unsigned>(i));
-        win = better(win, ValIdx{prob / q, i});
-        const int slot = atomicAdd(&sh_cnt, 1);
-        if (slot < kTopKCap) {
-          st.topk_idx[slot0 + slot] = i;
-          st.topk_val[slot0 + slot] = s;
+      n_surv = filter ? sh_cnt : V;
+      ValIdx win{-INFINITY, 0x7fffffff};
+      auto ratio = [&](int i) {
+        const float prob = expf(key2f(keys[i]) - smax) / esum;
+        const float q = qrow ? qrow[i] : philox_exp(seed, stream_id, static_cast<unsigned>(i));
+        return prob / q;
+      };
+      if (listed) {
+        for (int x = tid; x < n_surv; x += SNT) {
+          const int i = sv_idx[x];
+          win = better(win, ValIdx{ratio(i), i});
+          if (x < kTopKCap) {
+            st.topk_idx[slot0 + x] = i;
+            st.topk_val[slot0 + x] = key2f(keys[i]);
+          }
         }
+      } else {   // no top-k filter, or more ties at the threshold than the list holds: scan the row
+        for (int i = tid; i < V; i += SNT)
+          if (keys[i] >= thr_key) win = better(win, ValIdx{ratio(i), i});
       }
       win = block_argmax(win, sh_vi);
       next = win.i;
       lp = key2f(keys[next]) - smax - logf(esum);
-      ValIdx second{-INFINITY, 0x7fffffff};
-      for (int i = tid; i < V; i += SNT) {
-        const unsigned k = keys[i];
-        if (k < thr_key || i == win.i) continue;
-        const float prob = expf(key2f(k) - smax) / esum;
-        const float q = qrow ? qrow[i] : philox_exp(*st.seed, stream_id, static_cast<unsigned>(i));
-        second = better(second, ValIdx{prob / q, i});
+      if (diag) {
+        ValIdx second{-INFINITY, 0x7fffffff};
+        for (int i = tid; i < V; i += SNT) {
+          if (keys[i] < thr_key || i == win.i) continue;
+          second = better(second, ValIdx{ratio(i), i});
+        }
+        second = block_argmax(second, sh_vi);
+        margin = (win.v - second.v) / win.v;
       }
-      second = block_argmax(second, sh_vi);
-      margin = (win.v - second.v) / win.v;
-      n_surv = sh_cnt;
     }
   }
 
@@ -381,7 +454,7 @@ void sample_step(const RolloutState& st, const RolloutParams& p, const float* lo
                                          static_cast<int>(smem)));
     configured = smem;
   }
-  sample_step_kernel<<<p.R, SNT, smem, stream>>>(st, p, logits, ldl, exp_noise);
+  launch_chain(sample_step_kernel, dim3(p.R), dim3(SNT), smem, stream, st, p, logits, ldl, exp_noise);
   check_launch("sample_step");
 }
 

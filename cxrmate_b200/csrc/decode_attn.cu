@@ -643,6 +643,8 @@ __global__ void __launch_bounds__(PNT, 2) decode_cross_persist_kernel(const __gr
   uint64_t* empty = full + PSTAGES;
   __shared__ int sh_last;
 
+  pdl_launch_dependents();
+  pdl_wait();
   if (*st.done) return;
   const int tid = threadIdx.x, warp = tid / kWarp;
   const int n_units = *cu.n_units;
@@ -755,6 +757,8 @@ __global__ void __launch_bounds__(PNT, 2) decode_self_persist_kernel(const __gri
   uint64_t* empty = full + PSTAGES;
   __shared__ int sh_last;
 
+  pdl_launch_dependents();
+  pdl_wait();
   if (*st.done) return;
   const int tid = threadIdx.x, warp = tid / kWarp, lane = tid % kWarp;
   // live rows sit at slot P + step (rollout_init / sample_step keep cur_len uniform); chunks of the longest row
@@ -918,9 +922,8 @@ void decode_self_attention(const T* qkv, T* kcache, T* vcache, T* ctx, const Rol
     }
     const int layer_row0 = layer * maps->self_rows_per_layer;
     const int grid = std::max(2 * num_sms(), ceil_div(NH * R * max_chunks, MAXI));
-    decode_self_persist_kernel<<<grid, PNT, kPersistSmem, stream>>>(maps->self_k, maps->self_v, layer_row0, qkv,
-                                                                       kcache, vcache, ctx, st, R, P, Lmax, max_chunks,
-                                                                       ws, tickets);
+    launch_chain(decode_self_persist_kernel, dim3(grid), dim3(PNT), kPersistSmem, stream, maps->self_k, maps->self_v,
+                 layer_row0, qkv, kcache, vcache, ctx, st, R, P, Lmax, max_chunks, ws, tickets);
   } else {
     const size_t smem = unit_smem_bytes<T, 1>(CH);
     static size_t configured = 0;
@@ -957,8 +960,8 @@ void decode_cross_attention(const T* q, int ldq, const T* kc, const T* vc, long 
     }
     auto launch = [&](auto kern) {
       const int grid = std::max(2 * num_sms(), ceil_div(NH * cu.max_units, MAXI));
-      kern<<<grid, PNT, kPersistSmem, stream>>>(maps->cross, row_k, row_v, tok_cap, q, ldq, ctx, cu, st, B, ws,
-                                                      tickets);
+      launch_chain(kern, dim3(grid), dim3(PNT), kPersistSmem, stream, maps->cross, row_k, row_v, tok_cap, q, ldq, ctx, cu,
+                   st, B, ws, tickets);
     };
     if (nq == 1)
       launch(decode_cross_persist_kernel<1>);

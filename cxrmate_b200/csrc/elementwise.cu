@@ -53,6 +53,7 @@ __global__ void embed_ln_kernel(const int* __restrict__ ids, const int* __restri
                                 const float* __restrict__ beta, T* __restrict__ out, long long rows, int C, float eps) {
   const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) / kWarp;
   const int lane = threadIdx.x % kWarp;
+  pdl_launch_dependents();   // first kernel of the decode-step chain: lets the QKV GEMM prefetch its weights
   if (row >= rows) return;
   const T* w = word + static_cast<long long>(ids[row]) * C;
   const T* t = type_emb + static_cast<long long>(types ? types[row] : 0) * C;

@@ -10,6 +10,7 @@
 namespace cxrm {
 
 unsigned long long g_launch_count = 0;
+bool g_pdl = false;
 
 // ---- Arena --------------------------------------------------------------------
 void Arena::init(size_t bytes) {
@@ -502,6 +503,7 @@ class Engine : public EngineBase {
     PF("layernorm", s, [&] { layernorm<T>(tmp, ldo, out, ldo, ln.g, ln.b, M, L.n_out, LN_EPS_BERT, s); });
   }
   bool use_skinny(long long M, const Lin& L) const;
+  bool chain_pdl() const;
   GemmArgs make_args(const T* A, int lda, const Lin& L, void* C, int ldc, long long M, int act, const T* residual,
                      int ldr, bool out_f32, const int* skip) const {
     GemmArgs g;
@@ -714,7 +716,7 @@ class Engine : public EngineBase {
   long long cross_layer_stride() const { return cross_tok_cap() * 2 * DH; }
 
   // =========================================================================== attention dispatch
-  void attention(const AttnArgs& a, cudaStream_t s) { attention_simt<T>(a, s); }
+  void attention(const AttnArgs& a, cudaStream_t s);
 
   // =========================================================================== decoder trunk
   // tokens M = R*qlen already embedded in x [M,768]; returns the buffer holding the output hidden states
@@ -787,6 +789,11 @@ class Engine : public EngineBase {
     const int* skip = st.done;
     PF("embed_ln", s, [&] { embed_ln<T>(st.cur_token, st.cur_type, st.cur_pos, dec.word, dec.type, dec.pos, dec.emb_ln.g, dec.emb_ln.b, b.x, R,
                 DH, LN_EPS_BERT, s); });
+    // every following kernel of the step is a programmatic dependent launch of its predecessor (common.cuh)
+    struct PdlScope {
+      explicit PdlScope(bool on) { g_pdl = on; }
+      ~PdlScope() { g_pdl = false; }
+    } pdl_scope(chain_pdl() && !profiling);
     for (int l = 0; l < cfg.dec_layers; ++l) {
       const BertLayerW& w = dec.layers[l];
       gemm(b.x, DH, w.qkv, b.qkv, 3 * DH, R, ACT_NONE, nullptr, 0, false, skip, s);
@@ -838,6 +845,7 @@ class Engine : public EngineBase {
     }
     rp.mask_token_id = a.mask_token_id; rp.eos = a.eos_token_id; rp.pad = a.pad_token_id;
     rp.top_k = a.top_k; rp.temperature = a.temperature; rp.seed = a.seed;
+    rp.want_margin = a.margins ? 1 : 0;
     // the kernels index logprob/topk buffers with Tmax = Tn
     PF("init", s, [&] { rollout_init(st, rp, a.prompt_ids, pre_ids, pre_types, pre_pos, s); });
 
@@ -893,7 +901,7 @@ class Engine : public EngineBase {
     std::memset(&key, 0, sizeof(key));
     key.R = rp.R; key.B = rp.B; key.P = rp.P; key.Tmax = rp.Tmax; key.top_k = rp.top_k;
     key.temperature = rp.temperature; key.noise = noise; key.buf = db.x;
-    key.mask_id = rp.mask_token_id; key.eos = rp.eos; key.pad = rp.pad;
+    key.mask_id = rp.mask_token_id; key.eos = rp.eos; key.pad = rp.pad; key.want_margin = rp.want_margin;
     std::memcpy(key.special, rp.special_ids, sizeof(key.special));
     std::memcpy(key.sections, rp.sections, sizeof(key.sections));
     std::memcpy(key.nspecial, rp.n_special, sizeof(key.nspecial));
@@ -1106,7 +1114,7 @@ class Engine : public EngineBase {
   // CUDA graph of one decode step
   struct GraphKey {
     int R, B, P, Tmax, top_k; float temperature; const float* noise; const void* buf;
-    int mask_id, eos, pad;
+    int mask_id, eos, pad, want_margin;
     int special[2][kMaxSpecial]; int sections[2][kMaxSpecial + 1]; int nspecial[2]; int modes[2];
   };
   GraphKey graph_key;
@@ -1115,6 +1123,15 @@ class Engine : public EngineBase {
   unsigned long long graph_nodes = 0;
 };
 
+template <>
+void Engine<float>::attention(const AttnArgs& a, cudaStream_t s) { attention_simt<float>(a, s); }
+template <>
+void Engine<bf16>::attention(const AttnArgs& a, cudaStream_t s) {
+  if (cfg.use_tensor_cores && attention_mma_supported(a) == 0)
+    attention_mma(a, s);
+  else
+    attention_simt<bf16>(a, s);
+}
 template <>
 void Engine<float>::setup_attn_maps() {}
 template <>
@@ -1128,6 +1145,10 @@ void Engine<bf16>::setup_attn_maps() {
   attn_maps.self_rows_per_layer = static_cast<int>(self_rows);
   attn_maps_ptr = &attn_maps;
 }
+template <>
+bool Engine<float>::chain_pdl() const { return false; }
+template <>
+bool Engine<bf16>::chain_pdl() const { return cfg.use_tensor_cores != 0; }
 template <>
 bool Engine<float>::use_skinny(long long, const Lin&) const { return false; }
 template <>

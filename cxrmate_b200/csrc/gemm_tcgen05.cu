@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_skinny_kernel(const __grid_c
   constexpr int STAGE_BYTES = SK_A_BYTES + B_BYTES;
   constexpr int TMEM_COLS = BN <= 32 ? 32 : 64;
   extern __shared__ uint8_t smem_raw[];
-  if (g.skip_flag && *g.skip_flag) return;
+  pdl_launch_dependents();   // the next kernel of the chain may start its own prologue now
 
   uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(tiles + stages * STAGE_BYTES + SK_SLACK);
@@ -336,33 +336,50 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_skinny_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // After a skip (every rollout row finished) only the loads already requested are drained; no MMA, no stores.
+  const int npre = min(nkb, stages);
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % stages;
-        const uint32_t ph = (i / stages) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
-        mbar_expect_tx(&full[s], STAGE_BYTES);
-        uint8_t* a_dst = tiles + s * STAGE_BYTES;
-        tma_load_2d(a_dst, &tmA, (kb0 + i) * BK, 0, &full[s]);
-        tma_load_2d(a_dst + SK_A_BYTES, &tmB, (kb0 + i) * BK, n0, &full[s]);
+      // weight tiles do not depend on the previous kernel: request the first ring-full BEFORE the dependency wait
+      for (int i = 0; i < npre; ++i) {
+        mbar_expect_tx(&full[i], STAGE_BYTES);
+        tma_load_2d(tiles + i * STAGE_BYTES + SK_A_BYTES, &tmB, (kb0 + i) * BK, n0, &full[i]);
+      }
+      pdl_wait();
+      const bool skip = g.skip_flag && *g.skip_flag;
+      for (int i = 0; i < npre; ++i) tma_load_2d(tiles + i * STAGE_BYTES, &tmA, (kb0 + i) * BK, 0, &full[i]);
+      if (!skip) {
+        for (int i = npre; i < nkb; ++i) {
+          const int s = i % stages;
+          const uint32_t ph = (i / stages) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_expect_tx(&full[s], STAGE_BYTES);
+          uint8_t* a_dst = tiles + s * STAGE_BYTES;
+          tma_load_2d(a_dst, &tmA, (kb0 + i) * BK, 0, &full[s]);
+          tma_load_2d(a_dst + SK_A_BYTES, &tmB, (kb0 + i) * BK, n0, &full[s]);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
+      pdl_wait();
+      const bool skip = g.skip_flag && *g.skip_flag;
+      const int n_do = skip ? npre : nkb;
       constexpr uint32_t idesc = make_idesc(BN);
-      for (int i = 0; i < nkb; ++i) {
+      for (int i = 0; i < n_do; ++i) {
         const int s = i % stages;
         const uint32_t ph = (i / stages) & 1;
         mbar_wait(&full[s], ph);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(tiles + s * STAGE_BYTES);
-        const uint64_t da = make_desc(a_addr), db = make_desc(a_addr + SK_A_BYTES);
+        if (!skip) {
+          const uint32_t a_addr = smem_u32(tiles + s * STAGE_BYTES);
+          const uint64_t da = make_desc(a_addr), db = make_desc(a_addr + SK_A_BYTES);
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k)
-          umma(tmem_base, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
-               (i | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < BK / 16; ++k)
+            umma(tmem_base, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
+                 (i | k) != 0 ? 1u : 0u);
+        }
         umma_commit(&empty[s]);
       }
       umma_commit(tmem_full);
@@ -370,12 +387,14 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_skinny_kernel(const __grid_c
   } else if (warp % 4 < 2) {
     // ---- epilogue: warps 4,5 own TMEM lanes 0..63 = the 64 real rows ---------------------------
     const int quarter = warp % 4;
+    pdl_wait();
+    const bool skip = g.skip_flag && *g.skip_flag;
     mbar_wait(tmem_full, 0);
     tc_fence_after();
     const long long m = quarter * 32 + lane;
-    const bool row_ok = m < g.M;
+    const bool row_ok = m < g.M && !skip;
     for (int c0 = 0; c0 < BN; c0 += 32) {
-      if (n0 + c0 >= g.N) break;
+      if (n0 + c0 >= g.N || skip) break;
       uint32_t r[32];
       if (BN >= 32) {
         tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(c0), r);
@@ -407,6 +426,8 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_skinny_kernel(const __grid_c
         epilogue_chunk(gl, v, m, nb, (BN >= 32) ? vec_ok : 0);
       }
     }
+  } else {
+    pdl_wait();   // every thread of a chain kernel passes the dependency wait
   }
 
   tc_fence_before();
@@ -425,6 +446,8 @@ __global__ void __launch_bounds__(256) splitk_ln_kernel(const float* __restrict_
                                                         bf16* __restrict__ out, int ldo,
                                                         const int* __restrict__ skip_flag) {
   __shared__ float sh[8];
+  pdl_launch_dependents();
+  pdl_wait();
   if (skip_flag && *skip_flag) return;
   const int m = blockIdx.x, tid = threadIdx.x;
   const int c = tid * 4;
@@ -563,7 +586,7 @@ void launch_skinny(const GemmArgs& g, int stages, int nsplit, int kb_per_split, 
   int vec_ok = (reinterpret_cast<uintptr_t>(g.C) % 16 == 0) && ((static_cast<long long>(g.ldc) * esz) % 16 == 0);
   if (g.residual) vec_ok = vec_ok && (reinterpret_cast<uintptr_t>(g.residual) % 16 == 0) && (g.ldr % 8 == 0);
   dim3 grid(ceil_div(g.N, BN), nsplit);
-  gemm_tc_skinny_kernel<BN><<<grid, NTHREADS, smem, stream>>>(ta, tb, g, stages, kb_per_split, partial, vec_ok);
+  launch_chain(gemm_tc_skinny_kernel<BN>, grid, dim3(NTHREADS), smem, stream, ta, tb, g, stages, kb_per_split, partial, vec_ok);
   check_launch("gemm_tcgen05_skinny");
 }
 
@@ -618,8 +641,8 @@ void splitk_ln(const float* partial, int nsplit, int M, int N, const float* bias
                int ldr, const float* gamma, const float* beta, float eps, void* out, int ldo, const int* skip_flag,
                cudaStream_t stream) {
   CXRM_CHECK(N % 4 == 0 && N <= 1024 && M <= SK_ROWS && ldo % 4 == 0 && (!residual || ldr % 4 == 0), "splitk_ln shape");
-  splitk_ln_kernel<<<M, 256, 0, stream>>>(partial, nsplit, N, bias, act, static_cast<const bf16*>(residual), ldr, gamma,
-                                          beta, eps, static_cast<bf16*>(out), ldo, skip_flag);
+  launch_chain(splitk_ln_kernel, dim3(M), dim3(256), 0, stream, partial, nsplit, N, bias, act,
+               static_cast<const bf16*>(residual), ldr, gamma, beta, eps, static_cast<bf16*>(out), ldo, skip_flag);
   check_launch("splitk_ln");
 }
 

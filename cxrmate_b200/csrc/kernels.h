@@ -116,6 +116,9 @@ struct AttnArgs {
   float scale;
 };
 template <typename T> void attention_simt(const AttnArgs& a, cudaStream_t stream);
+// bf16 tensor-core (mma.sync m16n8k16) flash attention with the same contract; returns 0 from _supported when usable
+int attention_mma_supported(const AttnArgs& a);
+void attention_mma(const AttnArgs& a, cudaStream_t stream);
 
 }  // namespace cxrm
 
@@ -162,6 +165,7 @@ struct RolloutParams {
   int top_k;
   float temperature;
   unsigned long long seed;
+  int want_margin;       // 1: also compute the decision margins (two more passes over the row; diagnostics)
 };
 
 // state from the prompt (reference modelling_longitudinal.py:274-282): types (full rule), positions,

@@ -240,6 +240,9 @@ CXRM_API int cxrm_test_gemm(int impl, int dtype, const void* A, const void* W, v
 CXRM_API int cxrm_test_gemm_ln(const void* A, const void* W, void* out, int M, int N, int K, const float* bias, int act,
                       const void* residual, const float* gamma, const float* beta, float eps, float* partial_ws,
                       void* stream);
+/* Micro-benchmark switch: launch the decode-chain kernels reached through the test hooks as programmatic dependent
+ * launches (the engine sets this itself inside a decode step). */
+CXRM_API void cxrm_test_set_pdl(int on);
 /* Standalone attention entry used by the kernel tests (q,k,v,o: [batch, L, heads*64] token-major). */
 CXRM_API int cxrm_test_attention(int dtype, const void* q, const void* k, const void* v, void* o, int batch, int heads,
                         int Lq, int Lk, const uint8_t* key_mask, int causal, float scale, void* stream);
