@@ -237,11 +237,40 @@ __global__ void __launch_bounds__(SNT) sample_step_kernel(RolloutState st, Rollo
   if (!was_finished) {
     // ---- pass 1: stage the row as sortable keys; per-thread and block maximum ---------------------
     ValIdx best{-INFINITY, 0x7fffffff};
-    for (int i = tid; i < V; i += SNT) {
-      float s = lrow[i];
-      if (inv_temp != 1.0f) s = s / p.temperature;
-      keys[i] = f2key(s);
-      best = better(best, ValIdx{s, i});
+    if ((V % 4) == 0 && (ldl % 4) == 0 && (reinterpret_cast<uintptr_t>(logits) % 16) == 0) {
+      // 128-bit streaming loads, four in flight per thread (a scalar loop serialises ~60 L2 round trips)
+      const float4* l4 = reinterpret_cast<const float4*>(lrow);
+      const int nv4 = V / 4;
+      for (int base = tid; base < nv4; base += 4 * SNT) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int idx = base + u * SNT;
+          v[u] = (idx < nv4) ? __ldcs(l4 + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int idx = base + u * SNT;
+          if (idx >= nv4) continue;
+          float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+          uint4 kq;
+          unsigned* kp = reinterpret_cast<unsigned*>(&kq);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (inv_temp != 1.0f) e[j] = e[j] / p.temperature;
+            kp[j] = f2key(e[j]);
+            best = better(best, ValIdx{e[j], 4 * idx + j});
+          }
+          *reinterpret_cast<uint4*>(keys + 4 * idx) = kq;
+        }
+      }
+    } else {
+      for (int i = tid; i < V; i += SNT) {
+        float s = lrow[i];
+        if (inv_temp != 1.0f) s = s / p.temperature;
+        keys[i] = f2key(s);
+        best = better(best, ValIdx{s, i});
+      }
     }
     tmax[tid] = (best.i != 0x7fffffff) ? f2key(best.v) : 0u;
     best = block_argmax(best, sh_vi);   // (its barriers also publish keys / tmax)

@@ -23,6 +23,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 
 #include "kernels.h"
@@ -630,7 +631,7 @@ __global__ void __launch_bounds__(PNT, 2) decode_cross_persist_kernel(const __gr
                                                                       const bf16* __restrict__ q, int ldq,
                                                                       bf16* __restrict__ ctx, CrossUnits cu,
                                                                       RolloutState st, int B, float* __restrict__ ws,
-                                                                      unsigned* __restrict__ tickets) {
+                                                                      unsigned* __restrict__ tickets, int dbg_nocompute) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   float* wpart = reinterpret_cast<float*>(tiles + PSTAGES * STAGE_BYTES);
@@ -730,7 +731,7 @@ __global__ void __launch_bounds__(PNT, 2) decode_cross_persist_kernel(const __gr
     const unsigned char* stage = tiles + s * STAGE_BYTES;
     load_q_frags<NQ>(stage + ST_Q, qa0, qa2);
     const uint32_t base = smem_u32(stage);
-    warp_tile_update<NQ>(base, base + TILE_BYTES, m_n[it - lo], qa0, qa2, nullptr, acc);
+    if (!dbg_nocompute) warp_tile_update<NQ>(base, base + TILE_BYTES, m_n[it - lo], qa0, qa2, nullptr, acc);
     __syncwarp();
     if (tid % kWarp == 0) mbar_arrive(&empty[s]);
     ++k;
@@ -746,7 +747,7 @@ __global__ void __launch_bounds__(PNT, 2) decode_self_persist_kernel(const __gri
                                                                      bf16* __restrict__ ctx, RolloutState st, int R,
                                                                      int P, int Lmax, int max_chunks,
                                                                      float* __restrict__ ws,
-                                                                     unsigned* __restrict__ tickets) {
+                                                                     unsigned* __restrict__ tickets, int dbg_nocompute) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   float* wpart = reinterpret_cast<float*>(tiles + PSTAGES * STAGE_BYTES);
@@ -859,7 +860,7 @@ __global__ void __launch_bounds__(PNT, 2) decode_self_persist_kernel(const __gri
     const unsigned char* stage = tiles + s * STAGE_BYTES;
     load_q_frags<1>(stage + ST_Q, qa0, qa2);
     const uint32_t base = smem_u32(stage);
-    warp_tile_update<1>(base, base + TILE_BYTES, n, qa0, qa2, stage + ST_MASK, acc);
+    if (!dbg_nocompute) warp_tile_update<1>(base, base + TILE_BYTES, n, qa0, qa2, stage + ST_MASK, acc);
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[s]);
     ++k;
@@ -887,6 +888,13 @@ __global__ void prefill_store_kv_kernel(const T* __restrict__ qkv, T* __restrict
     const int h = c / HD, d = c % HD;
     v.store((which ? vcache : kcache) + ((r * NH + h) * Lmax + pcol) * HD + d);
   }
+}
+
+// timing experiment only: CXRM_ATTN_NOCOMPUTE=1 keeps the TMA pipeline but skips the MMAs (memory-side ceiling)
+int dbg_nocompute() {
+  static int v = -1;
+  if (v < 0) v = std::getenv("CXRM_ATTN_NOCOMPUTE") ? 1 : 0;
+  return v;
 }
 
 int num_sms() {
@@ -923,7 +931,7 @@ void decode_self_attention(const T* qkv, T* kcache, T* vcache, T* ctx, const Rol
     const int layer_row0 = layer * maps->self_rows_per_layer;
     const int grid = std::max(2 * num_sms(), ceil_div(NH * R * max_chunks, MAXI));
     launch_chain(decode_self_persist_kernel, dim3(grid), dim3(PNT), kPersistSmem, stream, maps->self_k, maps->self_v,
-                 layer_row0, qkv, kcache, vcache, ctx, st, R, P, Lmax, max_chunks, ws, tickets);
+                 layer_row0, qkv, kcache, vcache, ctx, st, R, P, Lmax, max_chunks, ws, tickets, dbg_nocompute());
   } else {
     const size_t smem = unit_smem_bytes<T, 1>(CH);
     static size_t configured = 0;
@@ -961,7 +969,7 @@ void decode_cross_attention(const T* q, int ldq, const T* kc, const T* vc, long 
     auto launch = [&](auto kern) {
       const int grid = std::max(2 * num_sms(), ceil_div(NH * cu.max_units, MAXI));
       launch_chain(kern, dim3(grid), dim3(PNT), kPersistSmem, stream, maps->cross, row_k, row_v, tok_cap, q, ldq, ctx, cu,
-                   st, B, ws, tickets);
+                   st, B, ws, tickets, dbg_nocompute());
     };
     if (nq == 1)
       launch(decode_cross_persist_kernel<1>);

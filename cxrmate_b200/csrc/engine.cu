@@ -5,6 +5,7 @@
 #include "engine.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 namespace cxrm {
@@ -783,34 +784,78 @@ class Engine : public EngineBase {
   }
 
   // one decode step for R rows (all inputs come from the device-side rollout state)
+  // Timing aid (never set in production): CXRM_ABLATE=<comma list of gemm,ln,self,cross,sample,embed> drops those
+  // launches from the decode step, so that bench.py differences give each class's in-graph cost.
+  static unsigned ablate_mask() {
+    static int m = -1;
+    if (m < 0) {
+      m = 0;
+      const char* e = std::getenv("CXRM_ABLATE");
+      if (e) {
+        const std::string v(e);
+        const char* names[6] = {"gemm", "ln", "self", "cross", "sample", "embed"};
+        for (int i = 0; i < 6; ++i)
+          if (v.find(names[i]) != std::string::npos) m |= 1 << i;
+      }
+    }
+    return static_cast<unsigned>(m);
+  }
+
   void decode_step(DecBufs& b, T* head_tmp, const RolloutParams& rp, const float* noise, cudaStream_t s) {
     phase = "decode";
     const int R = rp.R, B = rp.B;
     const int* skip = st.done;
-    PF("embed_ln", s, [&] { embed_ln<T>(st.cur_token, st.cur_type, st.cur_pos, dec.word, dec.type, dec.pos, dec.emb_ln.g, dec.emb_ln.b, b.x, R,
-                DH, LN_EPS_BERT, s); });
+    const unsigned abl = ablate_mask();
+    const bool no_gemm = abl & 1, no_ln = abl & 2, no_self = abl & 4, no_cross = abl & 8, no_sample = abl & 16, no_embed = abl & 32;
+    if (!no_embed)
+      PF("embed_ln", s, [&] { embed_ln<T>(st.cur_token, st.cur_type, st.cur_pos, dec.word, dec.type, dec.pos, dec.emb_ln.g, dec.emb_ln.b, b.x, R,
+                  DH, LN_EPS_BERT, s); });
     // every following kernel of the step is a programmatic dependent launch of its predecessor (common.cuh)
     struct PdlScope {
       explicit PdlScope(bool on) { g_pdl = on; }
       ~PdlScope() { g_pdl = false; }
     } pdl_scope(chain_pdl() && !profiling);
+    auto G = [&](const T* A, int lda, const Lin& L, void* C, int ldc, int act) {
+      if (!no_gemm) gemm(A, lda, L, C, ldc, R, act, nullptr, 0, false, skip, s);
+    };
+    auto GL = [&](const T* A, int lda, const Lin& L, int act, const T* res, const LNp& ln, T* out) {
+      if (no_gemm && no_ln) return;
+      if (no_gemm || no_ln) {   // ablation only: one half of the pair
+        if (!no_gemm) gemm(A, lda, L, out, DH, R, act, res, DH, false, skip, s);
+        if (!no_ln) PF("layernorm", s, [&] { layernorm<T>(out, DH, out, DH, ln.g, ln.b, R, DH, LN_EPS_BERT, s); });
+        return;
+      }
+      gemm_ln(A, lda, L, act, res, DH, ln, out, DH, R, skip, s);
+    };
     for (int l = 0; l < cfg.dec_layers; ++l) {
       const BertLayerW& w = dec.layers[l];
-      gemm(b.x, DH, w.qkv, b.qkv, 3 * DH, R, ACT_NONE, nullptr, 0, false, skip, s);
-      PF("self_attn", s, [&] { decode_self_attention<T>(b.qkv, self_k + l * self_layer_stride(), self_v + l * self_layer_stride(), b.ctx, st, R,
-                               rp.P, Lmax, self_ws, self_tickets, attn_maps_ptr, l, s); });
-      gemm_ln(b.ctx, DH, w.o, ACT_NONE, b.x, DH, w.ln1, b.x1, DH, R, skip, s);
-      gemm(b.x1, DH, w.cq, b.qkv, DH, R, ACT_NONE, nullptr, 0, false, skip, s);
+      G(b.x, DH, w.qkv, b.qkv, 3 * DH, ACT_NONE);
+      if (!no_self)
+        PF("self_attn", s, [&] { decode_self_attention<T>(b.qkv, self_k + l * self_layer_stride(), self_v + l * self_layer_stride(), b.ctx, st, R,
+                                 rp.P, Lmax, self_ws, self_tickets, attn_maps_ptr, l, s); });
+      GL(b.ctx, DH, w.o, ACT_NONE, b.x, w.ln1, b.x1);
+      G(b.x1, DH, w.cq, b.qkv, DH, ACT_NONE);
       const T* kvl = cross_kv + static_cast<long long>(l) * cross_layer_stride();
       // the grid covers cross_max_units so that the captured graph does not depend on the batch's image counts
-      PF("cross_attn", s, [&] { decode_cross_attention<T>(b.qkv, DH, kvl, kvl + NHEAD * cross_head_stride(), cross_head_stride(), b.ctx,
-                                cross_units(), st, R, B, cross_ws, cross_tickets, attn_maps_ptr, l, s); });
-      gemm_ln(b.ctx, DH, w.co, ACT_NONE, b.x1, DH, w.ln2, b.x, DH, R, skip, s);
-      gemm(b.x, DH, w.fc1, b.hid, DFF, R, ACT_GELU, nullptr, 0, false, skip, s);
-      gemm_ln(b.hid, DFF, w.fc2, ACT_NONE, b.x, DH, w.ln3, b.x, DH, R, skip, s);
+      if (!no_cross)
+        PF("cross_attn", s, [&] { decode_cross_attention<T>(b.qkv, DH, kvl, kvl + NHEAD * cross_head_stride(), cross_head_stride(), b.ctx,
+                                  cross_units(), st, R, B, cross_ws, cross_tickets, attn_maps_ptr, l, s); });
+      GL(b.ctx, DH, w.co, ACT_NONE, b.x1, w.ln2, b.x);
+      G(b.x, DH, w.fc1, b.hid, DFF, ACT_GELU);
+      GL(b.hid, DFF, w.fc2, ACT_NONE, b.x, w.ln3, b.x);
     }
-    lm_head(b.x, R, head_tmp, logits, cfg.vocab, skip, s);
-    PF("sample", s, [&] { sample_step(st, rp, logits, cfg.vocab, noise, s); });
+    if (!no_gemm || !no_ln) {
+      if (no_gemm || no_ln) {
+        if (!no_ln) PF("layernorm", s, [&] { layernorm<T>(head_tmp, DH, head_tmp, DH, dec_head_ln.g, dec_head_ln.b, R, DH, LN_EPS_BERT, s); });
+        if (!no_gemm) {
+          gemm(b.x, DH, dec_head_t, head_tmp, DH, R, ACT_GELU, nullptr, 0, false, skip, s);
+          gemm(head_tmp, DH, dec_lm, logits, cfg.vocab, R, ACT_NONE, nullptr, 0, true, skip, s);
+        }
+      } else {
+        lm_head(b.x, R, head_tmp, logits, cfg.vocab, skip, s);
+      }
+    }
+    if (!no_sample) PF("sample", s, [&] { sample_step(st, rp, logits, cfg.vocab, noise, s); });
   }
 
   void rollout(const cxrm_rollout_args& a, cudaStream_t s_user) override {
