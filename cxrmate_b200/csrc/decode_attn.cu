@@ -440,7 +440,7 @@ constexpr int NCONS = 128;                      // consumer threads (4 warps); w
 constexpr int PNT = NCONS + 32;
 constexpr int MAXI = 128;                       // work items per CTA (metadata staged in shared memory)
 constexpr size_t kPersistSmem = static_cast<size_t>(PSTAGES) * STAGE_BYTES + 4 * 2 * (HD + 2) * sizeof(float) +
-                                5 * MAXI * sizeof(int) + 256 + 1024;
+                                5 * MAXI * sizeof(int) + MAXI + 256 + 1024;
 
 __device__ __forceinline__ void cons_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -624,7 +624,10 @@ __device__ __forceinline__ void flush_group(const WarpAcc& acc, float* wpart, co
   cons_sync();   // wpart / sh_last reusable
 }
 
-// ---- cross-attention: items = (head, unit) with the unit fastest, so a CTA's range walks the chunks of a study in order
+// ---- cross-attention: items = (head, unit) with the unit fastest, so a CTA's range walks the chunks of a study in order.
+// The encoder K/V cache and the unit table are constants of the whole rollout, so the first PSTAGES tiles of the
+// CTA are requested BEFORE the programmatic-dependency wait: they stream in while the preceding Q-projection GEMM
+// (a latency-bound kernel on a few dozen SMs) is still running.  Only q and the finished flags wait.
 template <int NQ>
 __global__ void __launch_bounds__(PNT, 2) decode_cross_persist_kernel(const __grid_constant__ CUtensorMap tm_kv,
                                                                       int row_base_k, int row_base_v, int tok_cap,
@@ -635,25 +638,26 @@ __global__ void __launch_bounds__(PNT, 2) decode_cross_persist_kernel(const __gr
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   float* wpart = reinterpret_cast<float*>(tiles + PSTAGES * STAGE_BYTES);
-  int* m_study = reinterpret_cast<int*>(wpart + 4 * 2 * (HD + 2));   // -1: skip (every row of the study finished)
+  int* m_study = reinterpret_cast<int*>(wpart + 4 * 2 * (HD + 2));
   int* m_j0 = m_study + MAXI;
   int* m_n = m_j0 + MAXI;
   int* m_first = m_n + MAXI;
   int* m_nch = m_first + MAXI;
   uint64_t* full = reinterpret_cast<uint64_t*>(m_nch + MAXI);
   uint64_t* empty = full + PSTAGES;
+  uint8_t* m_fin = reinterpret_cast<uint8_t*>(empty + PSTAGES);   // [MAXI] every row of the item's study finished
   __shared__ int sh_last;
 
   pdl_launch_dependents();
-  pdl_wait();
-  if (*st.done) return;
   const int tid = threadIdx.x, warp = tid / kWarp;
   const int n_units = *cu.n_units;
   const int n_items = n_units * NH;
   const int per = ceil_div(n_items, static_cast<int>(gridDim.x));   // <= MAXI by the launcher's grid size
   const int lo = blockIdx.x * per, hi = min(n_items, lo + per);
-  if (lo >= hi) return;
-
+  if (lo >= hi) {
+    pdl_wait();
+    return;
+  }
   if (tid == 0) {
     for (int s = 0; s < PSTAGES; ++s) {
       mbar_init(&full[s], 1);
@@ -665,24 +669,47 @@ __global__ void __launch_bounds__(PNT, 2) decode_cross_persist_kernel(const __gr
   for (int x = tid; x < hi - lo; x += PNT) {
     const int u = (lo + x) % n_units;
     const int b = cu.study[u];
-    bool fin = true;
-#pragma unroll
-    for (int i = 0; i < NQ; ++i) fin = fin && st.finished[b + i * B];
-    m_study[x] = fin ? -1 : b;
+    m_study[x] = b;
     m_j0[x] = cu.j0[u];
     m_n[x] = cu.n[u];
     m_first[x] = cu.first_unit[b];
     m_nch[x] = cu.n_chunks[b];
   }
   __syncthreads();
+  const int npre = min(PSTAGES, hi - lo);   // items whose K/V are requested ahead of the dependency wait
+  if (tid == NCONS) {
+    for (int x = 0; x < npre; ++x) {
+      const int h = (lo + x) / n_units;
+      unsigned char* dst = tiles + x * STAGE_BYTES;
+      mbar_expect_tx(&full[x], 2 * TILE_BYTES + NQ * 128);
+      tma_load_2d(dst, &tm_kv, 0, row_base_k + h * tok_cap + m_j0[x], &full[x]);
+      tma_load_2d(dst + TILE_BYTES, &tm_kv, 0, row_base_v + h * tok_cap + m_j0[x], &full[x]);
+    }
+  }
+  pdl_wait();
+  const bool done = *st.done != 0;
+  for (int x = tid; x < hi - lo; x += PNT) {
+    bool fin = true;
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) fin = fin && st.finished[m_study[x] + i * B];
+    m_fin[x] = (fin || done) ? 1 : 0;
+  }
+  __syncthreads();
 
   if (warp == 4) {
     // ===== producer =====
     if (tid % kWarp == 0) {
-      int k = 0;
-      for (int it = lo; it < hi; ++it) {
+      // q rows of the prefetched items (also when the study is finished: the stage's barrier expects them)
+      for (int x = 0; x < npre; ++x) {
+        const int h = (lo + x) / n_units, b = m_study[x];
+#pragma unroll
+        for (int i = 0; i < NQ; ++i)
+          bulk_g2s(tiles + x * STAGE_BYTES + ST_Q + i * 128, q + static_cast<long long>(b + i * B) * ldq + h * HD, 128, &full[x]);
+      }
+      int k = npre;
+      for (int it = lo + npre; it < hi; ++it) {
+        if (m_fin[it - lo]) continue;
         const int b = m_study[it - lo];
-        if (b < 0) continue;
         const int h = it / n_units;
         const int s = k % PSTAGES;
         mbar_wait(&empty[s], ((k / PSTAGES) & 1) ^ 1);
@@ -717,23 +744,26 @@ __global__ void __launch_bounds__(PNT, 2) decode_cross_persist_kernel(const __gr
     acc.reset();
   };
   for (int it = lo; it < hi; ++it) {
-    const int b = m_study[it - lo];
-    if (b < 0) continue;
-    const int h = it / n_units;
-    if (b != cur_b || h != cur_h) {
-      finish();
-      cur_b = b;
-      cur_h = h;
-      cur_x = it - lo;
-    }
+    const int x = it - lo;
+    const bool fin = m_fin[x] != 0;
+    if (fin && x >= npre) continue;          // never requested
     const int s = k % PSTAGES;
     mbar_wait(&full[s], (k / PSTAGES) & 1);
-    const unsigned char* stage = tiles + s * STAGE_BYTES;
-    load_q_frags<NQ>(stage + ST_Q, qa0, qa2);
-    const uint32_t base = smem_u32(stage);
-    if (!dbg_nocompute) warp_tile_update<NQ>(base, base + TILE_BYTES, m_n[it - lo], qa0, qa2, nullptr, acc);
+    if (!fin) {
+      const int b = m_study[x], h = it / n_units;
+      if (b != cur_b || h != cur_h) {
+        finish();
+        cur_b = b;
+        cur_h = h;
+        cur_x = x;
+      }
+      const unsigned char* stage = tiles + s * STAGE_BYTES;
+      load_q_frags<NQ>(stage + ST_Q, qa0, qa2);
+      const uint32_t base = smem_u32(stage);
+      if (!dbg_nocompute) warp_tile_update<NQ>(base, base + TILE_BYTES, m_n[x], qa0, qa2, nullptr, acc);
+    }
     __syncwarp();
-    if (tid % kWarp == 0) mbar_arrive(&empty[s]);
+    if (tid % kWarp == 0) mbar_arrive(&empty[s]);   // a prefetched tile of a finished study is simply released
     ++k;
   }
   finish();

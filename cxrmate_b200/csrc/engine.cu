@@ -492,6 +492,11 @@ class Engine : public EngineBase {
   void gemm_ln(const T* A, int lda, const Lin& L, int act, const T* residual, int ldr, const LNp& ln, T* out, int ldo,
                long long M, const int* skip, cudaStream_t s) {
     if (use_skinny(M, L)) {
+      GemmArgs gc = make_args(A, lda, L, out, ldo, M, act, residual, ldr, false, skip);
+      if (!no_cluster_ln() && gemm_ln_cluster_supported(gc) == 0) {
+        PF("gemm_ln", s, [&] { gemm_ln_cluster(gc, ln.g, ln.b, LN_EPS_BERT, s); });
+        return;
+      }
       GemmArgs g = make_args(A, lda, L, nullptr, 0, M, ACT_NONE, nullptr, 0, false, skip);
       int nsplit = 0;
       PF("gemm", s, [&] { gemm_tcgen05_skinny(g, skinny_ws, &nsplit, s); });
@@ -502,6 +507,14 @@ class Engine : public EngineBase {
     T* tmp = out;
     gemm(A, lda, L, tmp, ldo, M, act, residual, ldr, false, skip, s);
     PF("layernorm", s, [&] { layernorm<T>(tmp, ldo, out, ldo, ln.g, ln.b, M, L.n_out, LN_EPS_BERT, s); });
+  }
+  // The single-kernel cluster GEMM+LayerNorm (gemm_ln_cluster) is correct but MEASURED SLOWER than the split-K pair
+  // (17 us vs 8 us per call in tools/microbench_decode.py: the three cluster barriers dominate, ncu UCGABAR_WAIT), so
+  // it is opt-in for experiments only: CXRM_CLUSTER_LN=1.
+  static bool no_cluster_ln() {
+    static int v = -1;
+    if (v < 0) v = std::getenv("CXRM_CLUSTER_LN") ? 0 : 1;
+    return v != 0;
   }
   bool use_skinny(long long M, const Lin& L) const;
   bool chain_pdl() const;

@@ -387,6 +387,14 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_skinny_kernel(const __grid_c
   } else if (warp % 4 < 2) {
     // ---- epilogue: warps 4,5 own TMEM lanes 0..63 = the 64 real rows ---------------------------
     const int quarter = warp % 4;
+    // the bias is a constant of the chain: fetch this CTA's slice before the dependency wait / the accumulator
+    constexpr int BW = BN >= 32 ? BN : 32;
+    float bpre[BW];
+    const bool pre_bias = g.bias != nullptr && partial == nullptr;
+    if (pre_bias) {
+#pragma unroll
+      for (int j = 0; j < BW; ++j) bpre[j] = (j < BN && n0 + j < g.N) ? g.bias[n0 + j] : 0.f;
+    }
     pdl_wait();
     const bool skip = g.skip_flag && *g.skip_flag;
     mbar_wait(tmem_full, 0);
@@ -423,11 +431,228 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_skinny_kernel(const __grid_c
       } else {
         GemmArgs gl = g;
         if (BN < 32) gl.N = min(g.N, nb + BN);   // columns beyond this CTA's tile belong to its neighbour
+        if (pre_bias) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += bpre[c0 + j];
+          gl.bias = nullptr;
+        }
         epilogue_chunk(gl, v, m, nb, (BN >= 32) ? vec_ok : 0);
       }
     }
   } else {
     pdl_wait();   // every thread of a chain kernel passes the dependency wait
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+
+// =====================================================================================================
+// Decoder GEMM + LayerNorm in ONE kernel: out = LN(act(A.W^T + bias) + residual) for the 768-wide
+// projections that are followed by a post-LN (attention output, cross-attention output, FFN output, LM-head
+// transform).  A thread-block CLUSTER of 8 CTAs covers the 768 output columns (96 each, UMMA 128 x 96 x 16);
+// the row statistics LayerNorm needs are reduced across the cluster through distributed shared memory
+// (two rounds: mean, then variance about the mean - the same two-pass arithmetic as the reference), so the
+// pre-LN activations never leave registers.  Replaces the split-K GEMM + splitk_ln pair: one dependent launch
+// (~5 us in the step chain) less per LayerNorm, 19 per decode step.
+// =====================================================================================================
+constexpr int CL_SIZE = 8, CL_BN = 96, CL_N = CL_SIZE * CL_BN;
+constexpr int CL_B_BYTES = CL_BN * BK * 2;                 // 12 KiB
+constexpr int CL_STAGE = SK_A_BYTES + CL_B_BYTES;          // 20 KiB
+constexpr int CL_MAX_STAGES = 8;
+
+__device__ __forceinline__ void cluster_sync_all() {
+  __syncwarp();   // the single-lane producer / MMA roles reconverge before the warp-aligned barrier
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_f32(uint32_t local_addr, uint32_t peer, float v) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(peer));
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(v) : "memory");
+}
+
+__global__ void __cluster_dims__(CL_SIZE, 1, 1) __launch_bounds__(NTHREADS)
+    gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmArgs g,
+                           const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int stages) {
+  constexpr int TMEM_COLS = 128;
+  extern __shared__ uint8_t smem_raw[];
+  pdl_launch_dependents();
+
+  uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(tiles + stages * CL_STAGE + SK_SLACK);
+  uint64_t* empty = full + CL_MAX_STAGES;
+  uint64_t* tmem_full = empty + CL_MAX_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  float* xch = reinterpret_cast<float*>(tmem_slot + 2);          // [2 rounds][CL_SIZE][64 rows]
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const uint32_t rank = cluster_rank();
+  const int n0 = static_cast<int>(rank) * CL_BN;
+  const int nkb = (g.K + BK - 1) / BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int npre = min(nkb, stages);
+  cluster_sync_all();   // every CTA of the cluster is running before anyone writes into a peer's shared memory
+
+  float v[CL_BN];       // this thread's row slice (epilogue warps only)
+  const int quarter = warp % 4;
+  const int m = quarter * 32 + lane;
+  const bool epi = warp >= 2 && quarter < 2;
+  const bool row_ok = epi && m < g.M;
+  bool skip = false;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < npre; ++i) {   // weights first: they do not depend on the previous kernel
+        mbar_expect_tx(&full[i], CL_STAGE);
+        tma_load_2d(tiles + i * CL_STAGE + SK_A_BYTES, &tmB, i * BK, n0, &full[i]);
+      }
+      pdl_wait();
+      skip = g.skip_flag && *g.skip_flag;
+      for (int i = 0; i < npre; ++i) tma_load_2d(tiles + i * CL_STAGE, &tmA, i * BK, 0, &full[i]);
+      if (!skip) {
+        for (int i = npre; i < nkb; ++i) {
+          const int s = i % stages;
+          mbar_wait(&empty[s], ((i / stages) & 1) ^ 1);
+          mbar_expect_tx(&full[s], CL_STAGE);
+          tma_load_2d(tiles + s * CL_STAGE, &tmA, i * BK, 0, &full[s]);
+          tma_load_2d(tiles + s * CL_STAGE + SK_A_BYTES, &tmB, i * BK, n0, &full[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      pdl_wait();
+      skip = g.skip_flag && *g.skip_flag;
+      const int n_do = skip ? npre : nkb;
+      constexpr uint32_t idesc = make_idesc(CL_BN);
+      for (int i = 0; i < n_do; ++i) {
+        const int s = i % stages;
+        mbar_wait(&full[s], (i / stages) & 1);
+        tc_fence_after();
+        if (!skip) {
+          const uint32_t a_addr = smem_u32(tiles + s * CL_STAGE);
+          const uint64_t da = make_desc(a_addr), db = make_desc(a_addr + SK_A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma(tmem_base, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
+                 (i | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(tmem_full);
+    }
+  } else {
+    pdl_wait();
+    skip = g.skip_flag && *g.skip_flag;
+    if (epi) {
+      mbar_wait(tmem_full, 0);
+      tc_fence_after();
+      if (!skip) {
+#pragma unroll
+        for (int c0 = 0; c0 < CL_BN; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(c0), r);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[c0 + j] = __uint_as_float(r[j]);
+        }
+      }
+    }
+  }
+  // ---- LayerNorm across the cluster: every thread of every CTA passes the two cluster barriers ----
+  float psum = 0.f;
+  if (row_ok && !skip) {
+    const bf16* __restrict__ R = static_cast<const bf16*>(g.residual);
+#pragma unroll
+    for (int c = 0; c < CL_BN; ++c) {
+      float x = v[c] + (g.bias ? g.bias[n0 + c] : 0.f);
+      if (g.act == ACT_GELU) x = gelu_erf(x);
+      v[c] = x;
+    }
+    if (R) {
+      const bf16* rp = R + static_cast<long long>(m) * g.ldr + n0;
+#pragma unroll
+      for (int q = 0; q < CL_BN / 8; ++q) {
+        Vec16<bf16> rv;
+        rv.load(rp + 8 * q);
+        float rf[8];
+        rv.unpack(rf);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[8 * q + j] += rf[j];
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < CL_BN; ++c) {
+      v[c] = __bfloat162float(__float2bfloat16_rn(v[c]));   // the reference stores the pre-LN sum in bf16
+      psum += v[c];
+    }
+  }
+  if (epi) {
+    const uint32_t slot = smem_u32(&xch[(0 * CL_SIZE + rank) * SK_ROWS + m]);
+#pragma unroll
+    for (uint32_t peer = 0; peer < CL_SIZE; ++peer) st_cluster_f32(slot, peer, psum);
+  }
+  cluster_sync_all();
+  float mean = 0.f, pvar = 0.f;
+  if (epi) {
+#pragma unroll
+    for (int r2 = 0; r2 < CL_SIZE; ++r2) mean += xch[(0 * CL_SIZE + r2) * SK_ROWS + m];
+    mean *= (1.0f / CL_N);
+    if (row_ok && !skip) {
+#pragma unroll
+      for (int c = 0; c < CL_BN; ++c) pvar += (v[c] - mean) * (v[c] - mean);
+    }
+    const uint32_t slot = smem_u32(&xch[(1 * CL_SIZE + rank) * SK_ROWS + m]);
+#pragma unroll
+    for (uint32_t peer = 0; peer < CL_SIZE; ++peer) st_cluster_f32(slot, peer, pvar);
+  }
+  cluster_sync_all();
+  if (row_ok && !skip) {
+    float var = 0.f;
+#pragma unroll
+    for (int r2 = 0; r2 < CL_SIZE; ++r2) var += xch[(1 * CL_SIZE + r2) * SK_ROWS + m];
+    const float rstd = rsqrtf(var * (1.0f / CL_N) + eps);
+    bf16* dst = static_cast<bf16*>(g.C) + static_cast<long long>(m) * g.ldc + n0;
+#pragma unroll
+    for (int q = 0; q < CL_BN / 8; ++q) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = 8 * q + j;
+        o[j] = (v[c] - mean) * rstd * gamma[n0 + c] + beta[n0 + c];
+      }
+      Vec16<bf16> ov;
+      ov.pack(o);
+      ov.store(dst + 8 * q);
+    }
   }
 
   tc_fence_before();
@@ -447,27 +672,38 @@ __global__ void __launch_bounds__(256) splitk_ln_kernel(const float* __restrict_
                                                         const int* __restrict__ skip_flag) {
   __shared__ float sh[8];
   pdl_launch_dependents();
-  pdl_wait();
-  if (skip_flag && *skip_flag) return;
   const int m = blockIdx.x, tid = threadIdx.x;
   const int c = tid * 4;
-  float v[4] = {0.f, 0.f, 0.f, 0.f};
   const bool on = c < N;   // N % 4 == 0, N <= 1024
+  // parameters are constants of the chain: fetch them while the producing GEMM is still running
+  float4 bs = make_float4(0.f, 0.f, 0.f, 0.f), gm = bs, bt = bs;
   if (on) {
-    for (int s = 0; s < nsplit; ++s) {
-      const float4 p = __ldcg(reinterpret_cast<const float4*>(partial + (static_cast<long long>(s) * SK_ROWS + m) * N + c));
-      v[0] += p.x; v[1] += p.y; v[2] += p.z; v[3] += p.w;
+    if (bias) bs = *reinterpret_cast<const float4*>(bias + c);
+    gm = *reinterpret_cast<const float4*>(gamma + c);
+    bt = *reinterpret_cast<const float4*>(beta + c);
+  }
+  pdl_wait();
+  if (skip_flag && *skip_flag) return;
+  float v[4] = {0.f, 0.f, 0.f, 0.f};
+  if (on) {
+    // all loads first (one L2 round trip instead of a dependent chain), then the arithmetic
+    float4 p[4];
+    uint2 rr = make_uint2(0u, 0u);
+#pragma unroll
+    for (int s = 0; s < 4; ++s)
+      p[s] = (s < nsplit) ? __ldcg(reinterpret_cast<const float4*>(partial + (static_cast<long long>(s) * SK_ROWS + m) * N + c))
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (residual) rr = *reinterpret_cast<const uint2*>(residual + static_cast<long long>(m) * ldr + c);
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      v[0] += p[s].x; v[1] += p[s].y; v[2] += p[s].z; v[3] += p[s].w;
     }
-    if (bias) {
-      const float4 b = *reinterpret_cast<const float4*>(bias + c);
-      v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
-    }
+    v[0] += bs.x; v[1] += bs.y; v[2] += bs.z; v[3] += bs.w;
     if (act == ACT_GELU) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) v[j] = gelu_erf(v[j]);
     }
     if (residual) {
-      const uint2 rr = *reinterpret_cast<const uint2*>(residual + static_cast<long long>(m) * ldr + c);
       v[0] += __uint_as_float(rr.x << 16); v[1] += __uint_as_float(rr.x & 0xffff0000u);
       v[2] += __uint_as_float(rr.y << 16); v[3] += __uint_as_float(rr.y & 0xffff0000u);
     }
@@ -494,7 +730,6 @@ __global__ void __launch_bounds__(256) splitk_ln_kernel(const float* __restrict_
   const float var = block_sum(d2) / N;
   const float rstd = rsqrtf(var + eps);
   if (on) {
-    const float4 gm = *reinterpret_cast<const float4*>(gamma + c), bt = *reinterpret_cast<const float4*>(beta + c);
     const float o0 = (v[0] - mean) * rstd * gm.x + bt.x, o1 = (v[1] - mean) * rstd * gm.y + bt.y;
     const float o2 = (v[2] - mean) * rstd * gm.z + bt.z, o3 = (v[3] - mean) * rstd * gm.w + bt.w;
     __nv_bfloat162 a = __floats2bfloat162_rn(o0, o1), b = __floats2bfloat162_rn(o2, o3);
@@ -605,6 +840,33 @@ CUtensorMap make_tensor_map_bf16(const void* ptr, long long rows, long long cols
   if (r != CUDA_SUCCESS)
     throw std::runtime_error("cuTensorMapEncodeTiled failed (CUresult " + std::to_string(static_cast<int>(r)) + ")");
   return m;
+}
+
+
+int gemm_ln_cluster_supported(const GemmArgs& g) {
+  if (gemm_tcgen05_supported(g) != 0) return 1;
+  if (g.M > SK_ROWS || g.N != CL_N) return 2;
+  if (g.ldc % 8 != 0 || reinterpret_cast<uintptr_t>(g.C) % 16 != 0) return 3;
+  if (g.residual && (g.ldr % 8 != 0 || reinterpret_cast<uintptr_t>(g.residual) % 16 != 0)) return 4;
+  return 0;
+}
+
+// C (bf16) = LayerNorm(act(A.W^T + bias) + residual) with gamma/beta/eps; M <= 64, N == 768
+void gemm_ln_cluster(const GemmArgs& g, const float* gamma, const float* beta, float eps, cudaStream_t stream) {
+  CXRM_CHECK(gemm_ln_cluster_supported(g) == 0, "shape not supported by the cluster GEMM+LayerNorm");
+  const int nkb = ceil_div(g.K, BK);
+  const int stages = std::min(CL_MAX_STAGES, nkb);
+  const size_t smem = static_cast<size_t>(stages) * CL_STAGE + SK_SLACK + 1024 + 512 + 2 * CL_SIZE * SK_ROWS * sizeof(float);
+  static size_t configured = 0;
+  if (smem > configured) {
+    CXRM_CUDA_CHECK(cudaFuncSetAttribute(gemm_ln_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem)));
+    configured = smem;
+  }
+  const CUtensorMap ta = make_map(g.A, g.M, g.K, g.lda, SK_ROWS);
+  const CUtensorMap tb = make_map(g.W, g.N, g.K, g.ldw, CL_BN);
+  launch_chain(gemm_ln_cluster_kernel, dim3(CL_SIZE), dim3(NTHREADS), smem, stream, ta, tb, g, gamma, beta, eps, stages);
+  check_launch("gemm_ln_cluster");
 }
 
 int gemm_skinny_supported(const GemmArgs& g) {

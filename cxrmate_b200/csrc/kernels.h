@@ -39,6 +39,10 @@ int gemm_tcgen05_supported(const GemmArgs& g);
 int gemm_skinny_supported(const GemmArgs& g);
 void gemm_tcgen05_skinny(const GemmArgs& g, float* partial, int* nsplit_out, cudaStream_t stream);
 size_t gemm_skinny_partial_floats(int N);
+// one kernel: C (bf16) = LayerNorm(act(A.W^T + bias) + residual); 8-CTA cluster, row statistics through DSMEM.
+// M <= 64, N == 768 (the decoder's hidden width).
+int gemm_ln_cluster_supported(const GemmArgs& g);
+void gemm_ln_cluster(const GemmArgs& g, const float* gamma, const float* beta, float eps, cudaStream_t stream);
 // out[M, N] (bf16) = LayerNorm(act(sum_s partial[s] + bias) + residual): consumer of the split-K partials
 void splitk_ln(const float* partial, int nsplit, int M, int N, const float* bias, int act, const void* residual,
                int ldr, const float* gamma, const float* beta, float eps, void* out, int ldo, const int* skip_flag,
