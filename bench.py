@@ -302,9 +302,19 @@ def run_b200(a):
                 bytes_per_launch = tok * 2 * 768 * esz                  # K and V rows of ONE layer, read once per study
                 dur = ca["ms"] / ca["n"] / 1000.0
                 ach = bytes_per_launch / dur / 1e9
-                roofline = {"kernel": "decode_cross_attn_kernel (one layer, all studies, sample+greedy rows share K/V)",
+                traffic = None
+                try:   # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu capture
+                    tj = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+                    if tj.get("valid_images") == n_valid_images and tj.get("dtype") == a.dtype:
+                        traffic = tj["bytes_per_launch"]
+                except Exception:
+                    pass
+                roofline = {"kernel": "decode_cross_persist_kernel<2> (decode-step cross-attention of ONE layer: all studies, "
+                                      "sample+greedy rows share each K/V read)",
                             "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
-                            "traffic": None, "peak_source": which, "algorithmic_bytes_per_launch": bytes_per_launch,
+                            "traffic": traffic, "peak_source": which, "algorithmic_bytes_per_launch": bytes_per_launch,
+                            "timing": "CUDA event pair around each launch on the launching stream (engine profiler, graph "
+                                      "bypassed; includes ~3 us of launch/event overhead per launch)",
                             "mean_launch_us": dur * 1e6, "launches_profiled": ca["n"],
                             "share_of_step": round(ca["ms"] / total, 4)}
             if a.profile_out:
