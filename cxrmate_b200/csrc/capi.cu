@@ -154,15 +154,19 @@ int cxrm_profile_report(cxrm_engine* e, char* buf, size_t len) {
   });
 }
 
+static unsigned long long* g_trace_buf = nullptr;
+void cxrm_test_set_gemm_trace(unsigned long long* dev_buf) { g_trace_buf = dev_buf; }
+
 int cxrm_test_gemm(int impl, int dtype, const void* A, const void* W, void* C, int M, int N, int K, const float* bias,
                    int act, const void* residual, int out_f32, void* stream) {
   try {
     GemmArgs g;
     g.A = A; g.lda = K; g.W = W; g.ldw = K; g.C = C; g.ldc = N; g.M = M; g.N = N; g.K = K;
-    g.bias = bias; g.act = act; g.residual = residual; g.ldr = N; g.out_f32 = out_f32; g.skip_flag = nullptr; g.c_head_stride = 0;
+    g.bias = bias; g.act = act; g.residual = residual; g.ldr = N; g.out_f32 = out_f32; g.skip_flag = nullptr; g.c_head_stride = 0; g.trace = nullptr;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (impl == 1) {
       if (dtype != CXRM_BF16 || gemm_tcgen05_supported(g) != 0) return CXRM_ERR_INVALID;
+      g.trace = g_trace_buf;
       gemm_tcgen05(g, s);
     } else if (impl == 2) {
       if (dtype != CXRM_BF16 || gemm_skinny_supported(g) != 0) return CXRM_ERR_INVALID;
@@ -181,13 +185,14 @@ int cxrm_test_gemm(int impl, int dtype, const void* A, const void* W, void* C, i
 
 void cxrm_test_set_pdl(int on) { g_pdl = on != 0; }
 
+
 int cxrm_test_gemm_ln(const void* A, const void* W, void* out, int M, int N, int K, const float* bias, int act,
                       const void* residual, const float* gamma, const float* beta, float eps, float* partial_ws,
                       void* stream) {
   try {
     GemmArgs g;
     g.A = A; g.lda = K; g.W = W; g.ldw = K; g.C = nullptr; g.ldc = 0; g.M = M; g.N = N; g.K = K;
-    g.bias = nullptr; g.act = 0; g.residual = nullptr; g.ldr = 0; g.out_f32 = 0; g.skip_flag = nullptr; g.c_head_stride = 0;
+    g.bias = nullptr; g.act = 0; g.residual = nullptr; g.ldr = 0; g.out_f32 = 0; g.skip_flag = nullptr; g.c_head_stride = 0; g.trace = nullptr;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (gemm_skinny_supported(g) != 0 || N > 1024 || N % 4 != 0) return CXRM_ERR_INVALID;
     if (partial_ws == nullptr) {   // cluster kernel: GEMM + LayerNorm fused

@@ -132,4 +132,19 @@ __device__ __forceinline__ float warp_max(float v) {
 // exact-erf GELU (nn.GELU() default / ACT2FN["gelu"])
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
+
+// GELU(x) = x * Phi(x) with erf from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7): used by the bf16 tensor-core
+// epilogues, where the result is rounded to 8 mantissa bits anyway; ~12 instructions instead of erff's ~30.
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));   // MUFU.RCP: 1 ulp-ish, far below bf16 rounding
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float erf_abs = 1.0f - p * t * __expf(-z * z);
+  const float erf_x = copysignf(erf_abs, x);
+  return 0.5f * x * (1.0f + erf_x);
+}
+
 }  // namespace cxrm

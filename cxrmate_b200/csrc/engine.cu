@@ -479,9 +479,15 @@ class Engine : public EngineBase {
             bool out_f32, const int* skip, cudaStream_t s, const char* tag = "gemm", long long c_head_stride = 0) {
     GemmArgs g;
     g.c_head_stride = c_head_stride;
+    g.trace = nullptr;
     g.A = A; g.lda = lda; g.W = L.w; g.ldw = L.n_in; g.C = C; g.ldc = ldc;
     g.M = static_cast<int>(M); g.N = L.n_out; g.K = L.n_in;
     g.bias = L.b; g.act = act; g.residual = residual; g.ldr = ldr; g.out_f32 = out_f32 ? 1 : 0; g.skip_flag = skip;
+    std::string shaped;
+    if (profiling) {   // per-shape attribution: gemm[N x K]
+      shaped = std::string(tag) + "[" + std::to_string(g.N) + "x" + std::to_string(g.K) + "]";
+      tag = shaped.c_str();
+    }
     PF(tag, s, [&] { dispatch_gemm(g, s); });
   }
   void dispatch_gemm(const GemmArgs& g, cudaStream_t s);
@@ -521,7 +527,7 @@ class Engine : public EngineBase {
   GemmArgs make_args(const T* A, int lda, const Lin& L, void* C, int ldc, long long M, int act, const T* residual,
                      int ldr, bool out_f32, const int* skip) const {
     GemmArgs g;
-    g.c_head_stride = 0;
+    g.c_head_stride = 0; g.trace = nullptr;
     g.A = A; g.lda = lda; g.W = L.w; g.ldw = L.n_in; g.C = C; g.ldc = ldc;
     g.M = static_cast<int>(M); g.N = L.n_out; g.K = L.n_in;
     g.bias = L.b; g.act = act; g.residual = residual; g.ldr = ldr; g.out_f32 = out_f32 ? 1 : 0; g.skip_flag = skip;

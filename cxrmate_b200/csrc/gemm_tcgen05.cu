@@ -21,7 +21,7 @@ namespace cxrm {
 
 namespace {
 
-constexpr int BM = 128, BK = 64, STAGES = 4, NTHREADS = 192;
+constexpr int BM = 128, BK = 64, MAX_STAGES = 4, NTHREADS = 192;
 constexpr int A_BYTES = BM * BK * 2;   // 16 KiB
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -52,6 +52,15 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define TRACE(i)                                                                                         \
+  do {                                                                                                   \
+    if (g.trace) g.trace[(static_cast<long long>(blockIdx.y) * gridDim.x + blockIdx.x) * 8 + (i)] = gtimer(); \
+  } while (0)
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -111,7 +120,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, float (&v)[32]
   }
   if (g.act == ACT_GELU) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+    for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
   }
   if (g.c_head_stride > 0) {
     // head-major K/V cache store: 32 consecutive columns never straddle a 64-wide head
@@ -178,27 +187,32 @@ template <int BN>
 struct Cfg {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
-  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  static constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;   // power of two >= BN
+  static constexpr int smem(int stages) { return stages * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ + BN * 4 /*bias*/; }
 };
 
 template <int BN>
 __global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                           const __grid_constant__ CUtensorMap tmB, GemmArgs g,
-                                                           int vec_ok) {
+                                                           const __grid_constant__ CUtensorMap tmB,
+                                                           const __grid_constant__ CUtensorMap tmC, GemmArgs g,
+                                                           int vec_ok, int STAGES, int tma_store) {
+  // STAGES (1..4) is a launch parameter: short-K GEMMs (CvT stage 1: K = 64) take one stage of shared memory, so
+  // several CTAs share an SM and one CTA's epilogue overlaps another's loads and MMAs.
   using C_ = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   if (g.skip_flag && *g.skip_flag) return;
 
   uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(tiles + STAGES * C_::STAGE_BYTES);
-  uint64_t* empty = full + STAGES;
-  uint64_t* tmem_full = empty + STAGES;
+  uint64_t* empty = full + MAX_STAGES;
+  uint64_t* tmem_full = empty + MAX_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  float* sbias = reinterpret_cast<float*>(tmem_slot + 2);   // [BN]
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   const int num_kb = (g.K + BK - 1) / BK;
+  if (threadIdx.x == 0) TRACE(0);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -219,6 +233,7 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) TRACE(1);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -242,6 +257,7 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const __grid_constant
         const uint32_t ph = (kb / STAGES) & 1;
         mbar_wait(&full[s], ph);
         tc_fence_after();
+        if (kb == 0) TRACE(2);
         const uint32_t a_addr = smem_u32(tiles + s * C_::STAGE_BYTES);
         const uint64_t da = make_desc(a_addr), db = make_desc(a_addr + A_BYTES);
 #pragma unroll
@@ -253,28 +269,105 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const __grid_constant
         umma_commit(&empty[s]);   // frees the stage once these MMAs have read it
       }
       umma_commit(tmem_full);     // accumulator complete
+      TRACE(3);
     }
   } else {
     // ---- epilogue: 4 warps x 32 TMEM lanes ---------------------------------------
+    // Everything the epilogue needs from global memory is fetched WHILE the mainloop runs: the tile's bias slice into
+    // shared memory, this thread's residual row into registers.  (Loading them per 32-column chunk after the
+    // accumulator was ready serialised two L2 round trips per chunk: ncu showed the tensor pipe 1-4 % busy.)
     const int quarter = warp % 4;
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
+    const int et = threadIdx.x - 64;   // 0..127
     const long long m = static_cast<long long>(m0) + quarter * 32 + lane;
     const bool row_ok = m < g.M;
+    for (int j = et; j < BN; j += 128) sbias[j] = (g.bias && n0 + j < g.N) ? g.bias[n0 + j] : 0.f;
+    constexpr int RPRE = BN < 128 ? BN : 128;   // residual columns held in registers (the rest are loaded in the loop)
+    uint4 rres[RPRE / 8];
+    const bf16* __restrict__ R = static_cast<const bf16*>(g.residual);
+    const bool res_pre = R != nullptr && vec_ok && row_ok && g.c_head_stride == 0 && (n0 + BN <= g.N);
+    if (res_pre) {
+#pragma unroll
+      for (int q = 0; q < RPRE / 8; ++q) rres[q] = __ldg(reinterpret_cast<const uint4*>(R + m * g.ldr + n0 + 8 * q));
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");   // bias slice visible to the four epilogue warps
+    if (et == 0) TRACE(4);
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    if (et == 0) TRACE(5);
     for (int c0 = 0; c0 < BN; c0 += 32) {
       if (n0 + c0 >= g.N) break;   // warp-uniform
       uint32_t r[32];
       tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(c0), r);
-      if (!row_ok) continue;
+      if (!row_ok && !tma_store) continue;   // (TMA store: every thread fills its panel row; out-of-range rows are clipped)
       float v[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-      epilogue_chunk(g, v, m, n0 + c0, vec_ok);
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + sbias[c0 + j];
+      GemmArgs gl = g;
+      gl.bias = nullptr;
+      if (g.act == ACT_GELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+        gl.act = ACT_NONE;
+      }
+      if (res_pre && c0 < RPRE) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          Vec16<bf16> rv;
+          rv.raw = rres[c0 / 8 + q];
+          float rf[8];
+          rv.unpack(rf);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[8 * q + j] += rf[j];
+        }
+        gl.residual = nullptr;
+      }
+      if (tma_store) {
+        // Row-per-thread 16-byte global stores hit 32 different rows per warp instruction (the globaltimer trace showed
+        // the epilogue at 3-11 us per tile, several times the mainloop).  Instead the thread's 64 bytes go into a
+        // 64B-swizzled [128 rows x 32 cols] panel in shared memory (the pipeline stages are idle by now) ...
+        if (gl.residual && row_ok) {
+          const bf16* rp = static_cast<const bf16*>(gl.residual) + m * g.ldr + n0 + c0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            Vec16<bf16> rv;
+            rv.load(rp + 8 * q);
+            float rf[8];
+            rv.unpack(rf);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[8 * q + j] += rf[j];
+          }
+        }
+        const int row = quarter * 32 + lane;
+        uint8_t* panel = tiles + (c0 / 32) * (BM * 64);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          Vec16<bf16> ov;
+          ov.pack(v + 8 * q);
+          *reinterpret_cast<uint4*>(panel + row * 64 + ((q ^ ((row >> 1) & 3)) << 4)) = ov.raw;
+        }
+      } else {
+        epilogue_chunk(gl, v, m, n0 + c0, vec_ok);
+      }
+      if (tma_store) {
+        // ... and one thread hands the panel to the TMA unit: a coalesced, asynchronous, bounds-clipped store.
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (et == 0) {
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                           reinterpret_cast<uint64_t>(&tmC)),
+                       "r"(smem_u32(tiles + (c0 / 32) * (BM * 64))), "r"(n0 + c0), "r"(m0)
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
     }
+    if (tma_store && et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem read out before exit
+    if (et == 0) TRACE(6);
   }
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) TRACE(7);
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C_::TMEM_COLS)
                  : "memory");
@@ -594,7 +687,7 @@ __global__ void __cluster_dims__(CL_SIZE, 1, 1) __launch_bounds__(NTHREADS)
 #pragma unroll
     for (int c = 0; c < CL_BN; ++c) {
       float x = v[c] + (g.bias ? g.bias[n0 + c] : 0.f);
-      if (g.act == ACT_GELU) x = gelu_erf(x);
+      if (g.act == ACT_GELU) x = gelu_fast(x);
       v[c] = x;
     }
     if (R) {
@@ -701,7 +794,7 @@ __global__ void __launch_bounds__(256) splitk_ln_kernel(const float* __restrict_
     v[0] += bs.x; v[1] += bs.y; v[2] += bs.z; v[3] += bs.w;
     if (act == ACT_GELU) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) v[j] = gelu_erf(v[j]);
+      for (int j = 0; j < 4; ++j) v[j] = gelu_fast(v[j]);
     }
     if (residual) {
       v[0] += __uint_as_float(rr.x << 16); v[1] += __uint_as_float(rr.x & 0xffff0000u);
@@ -774,23 +867,44 @@ CUtensorMap make_map(const void* ptr, long long rows, long long cols, long long 
   return m;
 }
 
-int pick_bn(int M, int N) {
-  if (M <= 256) {
-    // weight-streaming regime (decode steps): many narrow tiles so that enough CTAs pull weights concurrently
-    if (N <= 32 || N >= 512) return 32;
-  }
-  if (N <= 32) return 32;
-  if (N <= 64) return 64;
-  if (N <= 128) return 128;
-  if (N % 256 != 0 && N % 192 == 0 && N <= 768) return 192;
-  return 256;
+// C tile for the TMA-store epilogue: bf16 [rows, cols], box = 32 columns (64 B) x 128 rows, 64-byte swizzle
+CUtensorMap make_map_out(const void* ptr, long long rows, long long cols, long long ld) {
+  CUtensorMap m;
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  const cuuint32_t box[2] = {32u, static_cast<cuuint32_t>(BM)};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    throw std::runtime_error("cuTensorMapEncodeTiled (output) failed (CUresult " + std::to_string(static_cast<int>(r)) + ")");
+  return m;
+}
+
+// Tile width and ring depth.  Shared memory per CTA = stages * (16 KiB + BN * 128 B); the aim is two or more CTAs
+// per SM (one CTA's epilogue then overlaps another's mainloop) unless K is long enough for the mainloop to dominate.
+void pick_tile(int M, int N, int K, int* bn_out, int* stages_out) {
+  const int num_kb = ceil_div(K, BK);
+  int bn;
+  if (N <= 32) bn = 32;
+  else if (N <= 64) bn = 64;
+  else if (N % 128 == 0) bn = (num_kb >= 16 && N % 256 == 0) ? 256 : 128;
+  else if (N % 96 == 0) bn = 96;
+  else if (N <= 128) bn = 128;
+  else bn = (N % 192 == 0 && N <= 768) ? 192 : 256;
+  if (M <= 256 && N >= 512) bn = 32;   // few rows: many narrow tiles so that enough CTAs pull weights concurrently
+  int stages = std::min(num_kb, bn >= 192 ? 4 : 3);
+  *bn_out = bn;
+  *stages_out = std::max(stages, 1);
 }
 
 template <int BN>
-void launch(const GemmArgs& g, cudaStream_t stream) {
+void launch(const GemmArgs& g, int stages, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    CXRM_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM));
+    CXRM_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg<BN>::smem(MAX_STAGES)));
     configured = true;
   }
   const CUtensorMap ta = make_map(g.A, g.M, g.K, g.lda, BM);
@@ -799,11 +913,15 @@ void launch(const GemmArgs& g, cudaStream_t stream) {
   int vec_ok = (reinterpret_cast<uintptr_t>(g.C) % 16 == 0) && ((static_cast<long long>(g.ldc) * esz) % 16 == 0);
   if (g.residual)
     vec_ok = vec_ok && (reinterpret_cast<uintptr_t>(g.residual) % 16 == 0) && (g.ldr % 8 == 0);
+  // TMA-store epilogue: bf16 row-major output, 16-byte aligned rows, whole 32-column panels inside N's padding rules
+  // (a partial last panel is clipped by the tensor map); the staging panels reuse the pipeline stages.
+  const int tma_store = (!g.out_f32 && g.c_head_stride == 0 && vec_ok && g.N % 8 == 0 &&
+                         stages * Cfg<BN>::STAGE_BYTES >= BM * BN * 2 && (!g.residual || g.N % 32 == 0)) ? 1 : 0;
+  const CUtensorMap tc = tma_store ? make_map_out(g.C, g.M, g.N, g.ldc) : ta;
   dim3 grid(ceil_div(g.M, BM), ceil_div(g.N, BN));
-  gemm_tc_kernel<BN><<<grid, NTHREADS, Cfg<BN>::SMEM, stream>>>(ta, tb, g, vec_ok);
+  gemm_tc_kernel<BN><<<grid, NTHREADS, Cfg<BN>::smem(stages), stream>>>(ta, tb, tc, g, vec_ok, stages, tma_store);
   check_launch("gemm_tcgen05");
 }
-
 
 // ---- skinny path (M <= 64) -------------------------------------------------------------------------
 template <int BN>
@@ -926,12 +1044,15 @@ int gemm_tcgen05_supported(const GemmArgs& g) {
 
 void gemm_tcgen05(const GemmArgs& g, cudaStream_t stream) {
   CXRM_CHECK(gemm_tcgen05_supported(g) == 0, "shape/alignment not supported by the tcgen05 GEMM");
-  switch (pick_bn(g.M, g.N)) {
-    case 32: launch<32>(g, stream); break;
-    case 64: launch<64>(g, stream); break;
-    case 128: launch<128>(g, stream); break;
-    case 192: launch<192>(g, stream); break;
-    default: launch<256>(g, stream); break;
+  int bn = 128, stages = 3;
+  pick_tile(g.M, g.N, g.K, &bn, &stages);
+  switch (bn) {
+    case 32: launch<32>(g, stages, stream); break;
+    case 64: launch<64>(g, stages, stream); break;
+    case 96: launch<96>(g, stages, stream); break;
+    case 128: launch<128>(g, stages, stream); break;
+    case 192: launch<192>(g, stages, stream); break;
+    default: launch<256>(g, stages, stream); break;
   }
 }
 

@@ -26,6 +26,7 @@ struct GemmArgs {
   const int* skip_flag;   // nullable device flag: kernel returns immediately when *skip_flag != 0
   // > 0: head-major store (K/V caches): element (m, n) goes to C[(n / 64) * c_head_stride + m * 64 + n % 64]
   long long c_head_stride;
+  unsigned long long* trace;   // nullable debug buffer: 8 globaltimer stamps per CTA (gemm_tc_kernel only)
 };
 
 // strict-fp32 FMA path (validation mode; also the bf16-storage SIMT debug path)

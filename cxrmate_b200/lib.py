@@ -72,6 +72,7 @@ SYMBOLS = {
     "cxrm_test_gemm_ln": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),
     "cxrm_test_set_pdl": (None, [C.c_int]),
+    "cxrm_test_set_gemm_trace": (None, [C.c_void_p]),
     "cxrm_test_attention": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                       C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_void_p]),
 }

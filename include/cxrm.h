@@ -244,6 +244,8 @@ CXRM_API int cxrm_test_gemm_ln(const void* A, const void* W, void* out, int M, i
 /* Micro-benchmark switch: launch the decode-chain kernels reached through the test hooks as programmatic dependent
  * launches (the engine sets this itself inside a decode step). */
 CXRM_API void cxrm_test_set_pdl(int on);
+/* Debug: when non-NULL, cxrm_test_gemm(impl 1) writes 8 %globaltimer stamps per CTA into dev_buf (phase timeline). */
+CXRM_API void cxrm_test_set_gemm_trace(unsigned long long* dev_buf);
 /* Standalone attention entry used by the kernel tests (q,k,v,o: [batch, L, heads*64] token-major). */
 CXRM_API int cxrm_test_attention(int dtype, const void* q, const void* k, const void* v, void* o, int batch, int heads,
                         int Lq, int Lk, const uint8_t* key_mask, int causal, float scale, void* stream);
