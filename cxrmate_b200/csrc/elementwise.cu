@@ -2,6 +2,8 @@
 // im2col for the CvT convolutional token embeddings, the depth-wise
 // convolutional q/k/v projections with folded BatchNorm, row gathers/scatters
 // and the weight-packing helpers.  All math in fp32; storage type T.
+#include <algorithm>
+
 #include "kernels.h"
 
 namespace cxrm {
@@ -142,6 +144,174 @@ __global__ void im2col_tokens_kernel(const T* __restrict__ in, T* __restrict__ o
     }
     v.store(out + i * V);
   }
+}
+
+
+// ---- LayerNorm, vectorised: LPR lanes per row, 16-byte loads, rows held in registers -------------------------
+// Same two-pass fp32 arithmetic as layernorm_kernel.  STATS: write (mean, rstd) per row instead of the normalised
+// row (consumed by ln_dwconv_qkv_kernel, which normalises on load).
+constexpr int kLnMaxVec = 6;   // 16-byte vectors per lane
+template <typename T, int LPR, bool STATS>
+__global__ void __launch_bounds__(256) ln_rows_kernel(const T* __restrict__ x, int ldx, T* __restrict__ y, int ldy,
+                                                      float2* __restrict__ stats, const float* __restrict__ gamma,
+                                                      const float* __restrict__ beta, long long rows, int C, float eps) {
+  constexpr int V = Vec16<T>::N;
+  const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) / LPR;
+  const int sub = threadIdx.x % LPR;
+  if (row >= rows) return;   // LPR divides the warp size and rows are LPR-aligned in the warp: whole groups leave together
+  const int cv = C / V;
+  const T* xr = x + row * ldx;
+  float v[kLnMaxVec][V];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    const int vi = sub + i * LPR;
+    if (vi < cv) {
+      Vec16<T> t;
+      t.load(xr + vi * V);
+      t.unpack(v[i]);
+#pragma unroll
+      for (int j = 0; j < V; ++j) s += v[i][j];
+    }
+  }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(kFull, s, o);
+  const float mean = s / C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    if (sub + i * LPR < cv) {
+#pragma unroll
+      for (int j = 0; j < V; ++j) q += (v[i][j] - mean) * (v[i][j] - mean);
+    }
+  }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(kFull, q, o);
+  const float rstd = rsqrtf(q / C + eps);
+  if (STATS) {
+    if (sub == 0) stats[row] = make_float2(mean, rstd);
+    return;
+  }
+  T* yr = y + row * ldy;
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    const int vi = sub + i * LPR;
+    if (vi < cv) {
+      float o[V];
+#pragma unroll
+      for (int j = 0; j < V; ++j) o[j] = (v[i][j] - mean) * rstd * gamma[vi * V + j] + beta[vi * V + j];
+      Vec16<T> t;
+      t.pack(o);
+      t.store(yr + vi * V);
+    }
+  }
+}
+
+// ---- CvT attention front end in one pass: LayerNorm (from per-token stats) -> depth-wise 3x3 (pad 1) + folded
+// BatchNorm for q (stride 1) and k, v (stride 2), HF modeling_cvt.py:124-141,215-228,371-377.
+// A thread owns one 16-byte channel vector of one image column and walks TY output rows with a rolling 3x3 window
+// of NORMALISED values in registers: every input token is fetched 3 times per channel vector (its own column and
+// both neighbours - L1 hits inside the block) instead of 9 + 9/4 times, the LayerNorm output is never written, and
+// the stride-2 k/v outputs (window centre (2a, 2b) == the q window at even coordinates) come from the same registers.
+template <typename T, int TY>
+__global__ void __launch_bounds__(256) ln_dwconv_qkv_kernel(const T* __restrict__ x, T* __restrict__ q,
+                                                            T* __restrict__ k, T* __restrict__ v,
+                                                            const float2* __restrict__ stats,
+                                                            const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, const float* __restrict__ w,
+                                                            const float* __restrict__ scale,
+                                                            const float* __restrict__ shift, int H, int W, int C, int cls,
+                                                            int Hk, int Wk, int cols) {
+  constexpr int V = Vec16<T>::N;
+  const int cv = C / V;
+  const int tc = threadIdx.x % cv, tcol = threadIdx.x / cv;
+  const int ox = blockIdx.x * cols + tcol;
+  if (tcol >= cols || ox >= W) return;
+  const int oy0 = blockIdx.y * TY, n = blockIdx.z, c = tc * V;
+  const long long tok0 = static_cast<long long>(n) * (cls + H * W) + cls;
+  float g[V], b[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    g[j] = gamma[c + j];
+    b[j] = beta[c + j];
+  }
+  float win[3][3][V];
+  auto load_row = [&](int iy, float (&dst)[3][V]) {
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) {
+      const int ix = ox - 1 + dx;
+      if (iy < 0 || iy >= H || ix < 0 || ix >= W) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) dst[dx][j] = 0.f;   // the convolution pads the NORMALISED map with zeros
+      } else {
+        const long long tok = tok0 + static_cast<long long>(iy) * W + ix;
+        Vec16<T> t;
+        t.load(x + tok * C + c);
+        float xf[V];
+        t.unpack(xf);
+        const float2 st = stats[tok];
+#pragma unroll
+        for (int j = 0; j < V; ++j) dst[dx][j] = (xf[j] - st.x) * st.y * g[j] + b[j];
+      }
+    }
+  };
+  load_row(oy0 - 1, win[0]);
+  load_row(oy0, win[1]);
+#pragma unroll
+  for (int t = 0; t < TY; ++t) {
+    const int oy = oy0 + t;
+    if (oy >= H) break;
+    load_row(oy + 1, win[(t + 2) % 3]);
+    const bool kv = ((oy | ox) & 1) == 0;
+#pragma unroll
+    for (int o = 0; o < 3; ++o) {
+      if (o > 0 && !kv) break;
+      float acc[V];
+#pragma unroll
+      for (int j = 0; j < V; ++j) acc[j] = 0.f;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const float* wt = w + (static_cast<long long>(o) * 9 + ky * 3 + kx) * C + c;
+          float wf[V];
+#pragma unroll
+          for (int j = 0; j < V; j += 4) {
+            const float4 w4 = __ldg(reinterpret_cast<const float4*>(wt + j));
+            wf[j] = w4.x; wf[j + 1] = w4.y; wf[j + 2] = w4.z; wf[j + 3] = w4.w;
+          }
+#pragma unroll
+          for (int j = 0; j < V; ++j) acc[j] = fmaf(win[(t + ky) % 3][kx][j], wf[j], acc[j]);
+        }
+      float of[V];
+#pragma unroll
+      for (int j = 0; j < V; ++j) of[j] = fmaf(acc[j], scale[o * C + c + j], shift[o * C + c + j]);
+      Vec16<T> ov;
+      ov.pack(of);
+      if (o == 0) {
+        ov.store(q + (tok0 + static_cast<long long>(oy) * W + ox) * C + c);
+      } else {
+        const long long orow = static_cast<long long>(n) * (cls + Hk * Wk) + cls + static_cast<long long>(oy >> 1) * Wk + (ox >> 1);
+        ov.store((o == 1 ? k : v) + orow * C + c);
+      }
+    }
+  }
+}
+
+// cls rows bypass the convolution: q = k = v = LayerNorm(x[cls]) (modeling_cvt.py:215-228)
+template <typename T>
+__global__ void ln_cls_kernel(const T* __restrict__ x, const float2* __restrict__ stats, const float* __restrict__ gamma,
+                              const float* __restrict__ beta, T* __restrict__ q, T* __restrict__ k, T* __restrict__ v,
+                              int n_img, int HWq, int HWk, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_img * C) return;
+  const int n = i / C, c = i % C;
+  const long long row = static_cast<long long>(n) * (1 + HWq);
+  const float2 st = stats[row];
+  const T val = from_f<T>((to_f(x[row * C + c]) - st.x) * st.y * gamma[c] + beta[c]);
+  q[row * C + c] = val;
+  k[static_cast<long long>(n) * (1 + HWk) * C + c] = val;
+  v[static_cast<long long>(n) * (1 + HWk) * C + c] = val;
 }
 
 // ---- depth-wise 3x3 + BN(eval) ------------------------------------------------
@@ -337,11 +507,33 @@ inline unsigned grid_for(long long total, int block, long long cap = 148LL * 32)
 
 }  // namespace
 
+
+// vectorised LayerNorm / row statistics; false when the shape or alignment needs the scalar kernel
+template <typename T, bool STATS>
+bool ln_rows_launch(const T* x, int ldx, T* y, int ldy, float2* stats, const float* gamma, const float* beta,
+                    long long rows, int C, float eps, cudaStream_t stream) {
+  constexpr int V = Vec16<T>::N;
+  if (C % V != 0 || ldx % V != 0 || reinterpret_cast<uintptr_t>(x) % 16 != 0) return false;
+  if (!STATS && (ldy % V != 0 || reinterpret_cast<uintptr_t>(y) % 16 != 0)) return false;
+  const int cv = C / V;
+  if (cv > 32 * kLnMaxVec) return false;
+  const int lpr = cv <= 8 * kLnMaxVec ? 8 : cv <= 16 * kLnMaxVec ? 16 : 32;
+  const unsigned grid = static_cast<unsigned>(ceil_div_ll(rows * lpr, 256));
+  switch (lpr) {
+    case 8: ln_rows_kernel<T, 8, STATS><<<grid, 256, 0, stream>>>(x, ldx, y, ldy, stats, gamma, beta, rows, C, eps); break;
+    case 16: ln_rows_kernel<T, 16, STATS><<<grid, 256, 0, stream>>>(x, ldx, y, ldy, stats, gamma, beta, rows, C, eps); break;
+    default: ln_rows_kernel<T, 32, STATS><<<grid, 256, 0, stream>>>(x, ldx, y, ldy, stats, gamma, beta, rows, C, eps); break;
+  }
+  check_launch(STATS ? "ln_stats" : "layernorm_vec");
+  return true;
+}
+
 template <typename T>
 void layernorm(const T* x, int ldx, T* y, int ldy, const float* gamma, const float* beta, long long rows, int C,
                float eps, cudaStream_t stream) {
   if (rows <= 0) return;
   CXRM_CHECK(C <= kMaxPerLane * kWarp, "layernorm supports C <= 768");
+  if (ln_rows_launch<T, false>(x, ldx, y, ldy, nullptr, gamma, beta, rows, C, eps, stream)) return;
   const int block = 256;
   const long long grid = ceil_div_ll(rows * kWarp, block);
   layernorm_kernel<T><<<static_cast<unsigned>(grid), block, 0, stream>>>(x, ldx, y, ldy, gamma, beta, rows, C, eps);
@@ -404,6 +596,32 @@ void dwconv_bn_qkv(const T* y, T* q, T* k, T* v, const float* w, const float* sc
   if (cls) {
     copy_cls_kernel<T><<<ceil_div(n_img * C, 256), 256, 0, stream>>>(y, q, k, v, n_img, H * W, Hk * Wk, C);
     check_launch("copy_cls");
+  }
+}
+
+
+template <typename T>
+void ln_dwconv_qkv(const T* x, T* q, T* k, T* v, float* stats, const float* gamma, const float* beta, float eps,
+                   const float* w, const float* scale, const float* shift, int n_img, int H, int W, int C, int cls,
+                   cudaStream_t stream) {
+  if (n_img <= 0) return;
+  constexpr int V = Vec16<T>::N, TY = 8;
+  const int cv = C / V;
+  CXRM_CHECK(C % V == 0 && cv <= 256 && C % 4 == 0, "ln_dwconv_qkv: unsupported channel count");
+  const int Hk = (H + 2 - 3) / 2 + 1, Wk = (W + 2 - 3) / 2 + 1;   // stride-2 window centres are the even coordinates
+  float2* st = reinterpret_cast<float2*>(stats);
+  const long long rows = static_cast<long long>(n_img) * (cls + H * W);
+  const bool ok = ln_rows_launch<T, true>(x, C, nullptr, 0, st, nullptr, nullptr, rows, C, eps, stream);
+  CXRM_CHECK(ok, "ln_dwconv_qkv: row statistics need 16-byte aligned rows");
+  const int cols = std::min(W, 256 / cv);
+  dim3 grid(ceil_div(W, cols), ceil_div(H, TY), n_img);
+  CXRM_CHECK(grid.z <= 65535, "ln_dwconv_qkv: too many images per chunk");
+  ln_dwconv_qkv_kernel<T, TY><<<grid, cols * cv, 0, stream>>>(x, q, k, v, st, gamma, beta, w, scale, shift, H, W, C, cls,
+                                                              Hk, Wk, cols);
+  check_launch("ln_dwconv_qkv");
+  if (cls) {
+    ln_cls_kernel<T><<<ceil_div(n_img * C, 256), 256, 0, stream>>>(x, st, gamma, beta, q, k, v, n_img, H * W, Hk * Wk, C);
+    check_launch("ln_cls");
   }
 }
 
@@ -489,6 +707,8 @@ void pack_dw(const float* src, float* dst, int C, cudaStream_t stream) {
   template void im2col_tokens<T>(const T*, T*, int, int, int, int, int, int, int, cudaStream_t);                      \
   template void dwconv_bn_qkv<T>(const T*, T*, T*, T*, const float*, const float*, const float*, int, int, int, int,  \
                                  int, cudaStream_t);                                                                  \
+  template void ln_dwconv_qkv<T>(const T*, T*, T*, T*, float*, const float*, const float*, float, const float*,        \
+                                 const float*, const float*, int, int, int, int, int, cudaStream_t);                  \
   template void cat_cls<T>(const T*, const float*, T*, int, int, int, cudaStream_t);                                  \
   template void drop_cls<T>(const T*, T*, int, int, int, cudaStream_t);                                               \
   template void gather_rows<T>(const T*, const int*, T*, long long, int, cudaStream_t);                               \

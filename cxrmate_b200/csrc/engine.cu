@@ -133,6 +133,10 @@ class Engine : public EngineBase {
     arena.release();
     if (graph_exec) cudaGraphExecDestroy(graph_exec);
     if (side_stream) cudaStreamDestroy(side_stream);
+    if (pf_stream) cudaStreamDestroy(pf_stream);
+    for (cudaEvent_t e : ev_pf)
+      if (e) cudaEventDestroy(e);
+    if (ev_pf_join) cudaEventDestroy(ev_pf_join);
   }
 
   // =========================================================================== weights
@@ -411,7 +415,7 @@ class Engine : public EngineBase {
     const long long nimg = cfg.enc_chunk;
     const long long big = nimg * tok0 * 64 + nimg * 384 * 2;            // mirrors encode_chunk()
     const long long enc_elems = 5 * big + 4 * (big / 4 + nimg * 384) + std::max<long long>(nimg * tok0 * 152, 4 * big);
-    const long long enc_bytes = enc_elems * e + (1 << 20);
+    const long long enc_bytes = enc_elems * e + 8 * (nimg * tok0 + nimg) + (1 << 20);
     const long long dec_tok = static_cast<long long>(Rmax) * std::max(cfg.max_prompt, 1);
     const long long per_tok = (4LL * DH + 3 * DH + DFF) * e + 64;
     const long long dec_bytes = (dec_tok + 4LL * Rmax) * per_tok + (1 << 20);
@@ -421,6 +425,9 @@ class Engine : public EngineBase {
     CXRM_CUDA_CHECK(cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking));
     CXRM_CUDA_CHECK(cudaEventCreateWithFlags(&ev_a, cudaEventDisableTiming));
     CXRM_CUDA_CHECK(cudaEventCreateWithFlags(&ev_b, cudaEventDisableTiming));
+    CXRM_CUDA_CHECK(cudaStreamCreateWithFlags(&pf_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < kMaxForks; ++i) CXRM_CUDA_CHECK(cudaEventCreateWithFlags(&ev_pf[i], cudaEventDisableTiming));
+    CXRM_CUDA_CHECK(cudaEventCreateWithFlags(&ev_pf_join, cudaEventDisableTiming));
     std::memset(&graph_key, 0, sizeof(graph_key));
   }
   void setup_attn_maps();
@@ -514,6 +521,59 @@ class Engine : public EngineBase {
     gemm(A, lda, L, tmp, ldo, M, act, residual, ldr, false, skip, s);
     PF("layernorm", s, [&] { layernorm<T>(tmp, ldo, out, ldo, ln.g, ln.b, M, L.n_out, LN_EPS_BERT, s); });
   }
+  // ---- software L2 prefetch of the decode step: EXPERIMENT, off by default (fractions via CXRM_PF_CROSS /
+  // CXRM_PF_SELF).  Measured on B200 (profiles/l2_prefetch_r01.md): the attention kernels run no faster from an
+  // L2-resident cache - L2 delivers ~6.2 TB/s (the LTS cap), the same as streaming HBM - and the extra branch costs
+  // 2-8 % of the step, so the idle HBM time of the GEMM/LayerNorm chain cannot be bought back this way.
+  static float env_frac(const char* name, float dflt) {
+    const char* e = std::getenv(name);
+    return e ? std::min(1.0f, std::max(0.0f, static_cast<float>(std::atof(e)))) : dflt;
+  }
+  L2Prefetch pf_cross(int l) {
+    static const float frac = env_frac("CXRM_PF_CROSS", 0.0f);
+    if (sizeof(T) != 2 || frac <= 0.f) return L2Prefetch{};
+    const T* kvl = cross_kv + static_cast<long long>(l) * cross_layer_stride();
+    L2Prefetch p;
+    p.base[0] = reinterpret_cast<const char*>(kvl);
+    p.base[1] = reinterpret_cast<const char*>(kvl + NHEAD * cross_head_stride());
+    p.seg_stride = cross_head_stride() * static_cast<long long>(sizeof(T));
+    p.n_seg = NHEAD;
+    p.seg_bytes = static_cast<int>(static_cast<long long>(frac * kv_total) * 64 * sizeof(T));
+    return p;
+  }
+  L2Prefetch pf_self(int l, int R, int P, int extra) {
+    static const float frac = env_frac("CXRM_PF_SELF", 0.0f);
+    if (sizeof(T) != 2 || frac <= 0.f) return L2Prefetch{};
+    L2Prefetch p;
+    p.base[0] = reinterpret_cast<const char*>(self_k + l * self_layer_stride());
+    p.base[1] = reinterpret_cast<const char*>(self_v + l * self_layer_stride());
+    p.seg_stride = static_cast<long long>(Lmax) * 64 * sizeof(T);
+    p.n_seg = static_cast<int>(R * NHEAD * frac);
+    p.dyn = st.step;
+    p.dyn_add = P + extra;
+    p.dyn_unit = 64 * sizeof(T);
+    return p;
+  }
+  // Fork: the prefetch kernel depends on everything launched on `s` so far and runs on pf_stream beside the chain
+  // (a parallel branch of the captured step graph); decode_step joins the branch at the end of the step.
+  void fork_prefetch(const L2Prefetch& p, cudaStream_t s) {
+    if (p.n_seg <= 0) return;
+    if (profiling) {   // serialised on the main stream so that the event profiler sees its duration and its effect
+      PF("prefetch", s, [&] { l2_prefetch(p, s); });
+      return;
+    }
+    CXRM_CHECK(pf_forks < kMaxForks, "too many prefetch forks in one decode step");
+    cudaEvent_t ev = ev_pf[pf_forks++];
+    CXRM_CUDA_CHECK(cudaEventRecord(ev, s));
+    CXRM_CUDA_CHECK(cudaStreamWaitEvent(pf_stream, ev, 0));
+    l2_prefetch(p, pf_stream);
+  }
+  void join_prefetch(cudaStream_t s) {
+    if (pf_forks == 0) return;
+    CXRM_CUDA_CHECK(cudaEventRecord(ev_pf_join, pf_stream));
+    CXRM_CUDA_CHECK(cudaStreamWaitEvent(s, ev_pf_join, 0));
+    pf_forks = 0;
+  }
   // The single-kernel cluster GEMM+LayerNorm (gemm_ln_cluster) is correct but MEASURED SLOWER than the split-K pair
   // (17 us vs 8 us per call in tools/microbench_decode.py: the three cluster barriers dominate, ncu UCGABAR_WAIT), so
   // it is opt-in for experiments only: CXRM_CLUSTER_LN=1.
@@ -555,6 +615,7 @@ class Engine : public EngineBase {
     T* vp = arena.get<T>(big / 4 + n * 384);
     const long long hid_elems = std::max<long long>(nt * 152, 4 * big);
     T* hid = arena.get<T>(hid_elems);   // im2col buffer and MLP hidden share storage
+    float* ln_stats = arena.get<float>(2 * (nt + n));   // (mean, rstd) per token of the largest stage
     T* prev = nullptr;                  // previous stage's tokens [n, Hp*Wp, Cp]
     int Hp = 0, Wp = 0;
     for (int s_ = 0; s_ < 3; ++s_) {
@@ -581,8 +642,9 @@ class Engine : public EngineBase {
       const int Tk = cls + Hk * Wk;
       const long long rq = static_cast<long long>(n) * Tq, rk = static_cast<long long>(n) * Tk;
       for (const CvtLayerW& L : sw.layers) {
-        PF("layernorm", s, [&] { layernorm<T>(x, C, y, C, L.ln1.g, L.ln1.b, rq, C, LN_EPS_CVT, s); });
-        PF("dwconv", s, [&] { dwconv_bn_qkv<T>(y, q, k, v, L.dw, L.bn_scale, L.bn_shift, n, Ho, Wo, C, cls, s); });
+        // LayerNorm-before + convolutional projections in one pass over x (the normalised map is never stored)
+        PF("ln_dwconv", s, [&] { ln_dwconv_qkv<T>(x, q, k, v, ln_stats, L.ln1.g, L.ln1.b, LN_EPS_CVT, L.dw, L.bn_scale, L.bn_shift, n, Ho, Wo,
+                                                  C, cls, s); });
         gemm(q, C, L.q, qp, C, rq, ACT_NONE, nullptr, 0, false, nullptr, s);
         gemm(k, C, L.k, kp, C, rk, ACT_NONE, nullptr, 0, false, nullptr, s);
         gemm(v, C, L.v, vp, C, rk, ACT_NONE, nullptr, 0, false, nullptr, s);
@@ -852,6 +914,7 @@ class Engine : public EngineBase {
       if (!no_self)
         PF("self_attn", s, [&] { decode_self_attention<T>(b.qkv, self_k + l * self_layer_stride(), self_v + l * self_layer_stride(), b.ctx, st, R,
                                  rp.P, Lmax, self_ws, self_tickets, attn_maps_ptr, l, s); });
+      fork_prefetch(pf_cross(l), s);   // this layer's encoder K/V stream into L2 beside O-proj / LN / cross-Q
       GL(b.ctx, DH, w.o, ACT_NONE, b.x, w.ln1, b.x1);
       G(b.x1, DH, w.cq, b.qkv, DH, ACT_NONE);
       const T* kvl = cross_kv + static_cast<long long>(l) * cross_layer_stride();
@@ -859,6 +922,8 @@ class Engine : public EngineBase {
       if (!no_cross)
         PF("cross_attn", s, [&] { decode_cross_attention<T>(b.qkv, DH, kvl, kvl + NHEAD * cross_head_stride(), cross_head_stride(), b.ctx,
                                   cross_units(), st, R, B, cross_ws, cross_tickets, attn_maps_ptr, l, s); });
+      // ... and the next self-attention's K/V (layer 0 of the NEXT step after the last layer) beside cross-out / FFN
+      fork_prefetch(l + 1 < cfg.dec_layers ? pf_self(l + 1, R, rp.P, 0) : pf_self(0, R, rp.P, 1), s);
       GL(b.ctx, DH, w.co, ACT_NONE, b.x1, w.ln2, b.x);
       G(b.x, DH, w.fc1, b.hid, DFF, ACT_GELU);
       GL(b.hid, DFF, w.fc2, ACT_NONE, b.x, w.ln3, b.x);
@@ -875,6 +940,7 @@ class Engine : public EngineBase {
       }
     }
     if (!no_sample) PF("sample", s, [&] { sample_step(st, rp, logits, cfg.vocab, noise, s); });
+    join_prefetch(s);
   }
 
   void rollout(const cxrm_rollout_args& a, cudaStream_t s_user) override {
@@ -1169,6 +1235,11 @@ class Engine : public EngineBase {
   AttnMaps attn_maps{};
   const AttnMaps* attn_maps_ptr = nullptr;
   float* skinny_ws = nullptr;
+  static constexpr int kMaxForks = 16;
+  cudaStream_t pf_stream = nullptr;
+  cudaEvent_t ev_pf[kMaxForks] = {};
+  cudaEvent_t ev_pf_join = nullptr;
+  int pf_forks = 0;
   RolloutState st{};
   int* pre_ids = nullptr; int* pre_types = nullptr; int* pre_pos = nullptr; int* prompt_dev = nullptr;
   // host-step staging

@@ -12,6 +12,20 @@ namespace cxrm {
 
 enum Act : int { ACT_NONE = 0, ACT_GELU = 1 };
 
+// Software L2 prefetch of the decode step (l2_prefetch_kernel, decode.cu): the GEMM/LayerNorm chain between two
+// attention kernels is latency-bound and leaves HBM idle, so a kernel on a PARALLEL graph branch pulls the next
+// attention kernel's K/V (rollout constants / already-written cache rows) into the 126 MB L2 while the chain runs.
+//   n_seg segments per base pointer at base[i] + s * seg_stride, the first `seg_bytes` of each
+//   (or (*dyn + dyn_add) * dyn_unit bytes when dyn != nullptr, clamped to seg_stride).  n_seg == 0: nothing.
+struct L2Prefetch {
+  const char* base[2] = {nullptr, nullptr};
+  long long seg_stride = 0;
+  int n_seg = 0;
+  int seg_bytes = 0;
+  const int* dyn = nullptr;
+  int dyn_add = 0, dyn_unit = 0;
+};
+
 // C[M,N] = epi(A[M,K] . W[N,K]^T): + bias[N] (fp32, nullable) -> act -> + residual[M,N] (T, nullable);
 // stored as T, or as fp32 when out_f32.  K % 8 == 0, lda/ldw % 8 == 0.
 struct GemmArgs {
@@ -69,6 +83,12 @@ void im2col_tokens(const T* in, T* out, int n_img, int H, int W, int C, int ksz,
 template <typename T>
 void dwconv_bn_qkv(const T* y, T* q, T* k, T* v, const float* w, const float* scale, const float* shift, int n_img,
                    int H, int W, int C, int cls, cudaStream_t stream);
+// The same front end fused with the preceding LayerNorm (gamma/beta/eps): x [n_img, cls+H*W, C] -> q, k, v as above.
+// stats: scratch of 2 floats per token (mean, rstd).
+template <typename T>
+void ln_dwconv_qkv(const T* x, T* q, T* k, T* v, float* stats, const float* gamma, const float* beta, float eps,
+                   const float* w, const float* scale, const float* shift, int n_img, int H, int W, int C, int cls,
+                   cudaStream_t stream);
 // x[n_img, 1+HW, C] <- cat(cls_token[C], tokens[n_img, HW, C])
 template <typename T>
 void cat_cls(const T* tokens, const float* cls_token, T* out, int n_img, int HW, int C, cudaStream_t stream);
@@ -224,6 +244,9 @@ void decode_cross_attention(const T* q, int ldq, const T* kc, const T* vc, long 
 // qkv [R*P, 3*768] -> head-major kcache/vcache [R][12][Lmax][64] columns [0,P)
 template <typename T>
 void prefill_store_kv(const T* qkv, T* kcache, T* vcache, int R, int P, int Lmax, cudaStream_t stream);
+
+// issue the prefetch described by p (plain launch: belongs on a side stream / parallel graph branch)
+void l2_prefetch(const L2Prefetch& p, cudaStream_t stream);
 
 // copy rows [r, P-1] of x [R*P, C] into out [R, C]
 template <typename T>
