@@ -13,7 +13,8 @@ Synthetic data and random-init weights of the named architecture (no network, no
 
 `value`  : reports/s, inputs resident in HBM, device-timed (CUDA events), max over ranks.
 `e2e`    : the same step through the C ABI with HOST (pinned) buffers: H2D of pixels/prompts/labels and D2H of
-           sequences/log-probs/rewards inside the timed region (cxrm_scst_step_host).
+           sequences/log-probs/rewards inside the timed region (cxrm_scst_step_host; only the valid images of the
+           padded pixel tensor cross PCIe, one encoder chunk at a time, overlapped with the encoding).
 `roofline`: the dominant kernel (decode cross-attention over the encoder K/V cache), algorithmic bytes per launch /
            its mean launch duration from the engine's event profiler, vs the measured HBM copy peak.
 `cpu_baseline`: the CPU oracle (port of the reference modules) on a bounded sample, all host cores.
@@ -273,7 +274,9 @@ def run_b200(a):
             t2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
             if world > 1:
                 dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-            h2d = px_h.numel() * 4 + prompt_h.numel() * 4 + lab_h.numel() * 4 + lab_len_h.numel() * 4
+            # the engine copies only the valid (non-padding) images of the host pixel tensor, chunk by chunk
+            h2d = (n_valid_images * px_h[0, 0].numel() * 4 + B * N + prompt_h.numel() * 4 + lab_h.numel() * 4 +
+                   lab_len_h.numel() * 4)
             d2h = sum(v.numel() * v.element_size() for v in outs.values())
             e2e = {"value": world * B * a.steps / (float(t2.item()) / 1000.0), "unit": UNIT,
                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 
 namespace cxrm {
 
@@ -137,6 +138,7 @@ class Engine : public EngineBase {
     for (cudaEvent_t e : ev_pf)
       if (e) cudaEventDestroy(e);
     if (ev_pf_join) cudaEventDestroy(ev_pf_join);
+    for (cudaEvent_t e : ev_chunk) cudaEventDestroy(e);
   }
 
   // =========================================================================== weights
@@ -182,7 +184,7 @@ class Engine : public EngineBase {
     CXRM_CUDA_CHECK(cudaMemcpyAsync(d, t.data, n * sizeof(float), cudaMemcpyDeviceToDevice, 0));
     return d;
   }
-  struct Lin { T* w = nullptr; float* b = nullptr; int n_out = 0, n_in = 0; };
+  struct Lin { T* w = nullptr; float* b = nullptr; int n_out = 0, n_in = 0; float* s = nullptr; /* LN-folded: column sums; b = c */ };
   struct LNp { float* g = nullptr; float* b = nullptr; };
   LNp lnp(const std::string& prefix, int n) { return LNp{vecf(prefix + ".weight", n), vecf(prefix + ".bias", n)}; }
   Lin lin(const std::string& prefix, int n_out, int n_in, bool bias = true) {
@@ -224,9 +226,44 @@ class Engine : public EngineBase {
     return L;
   }
 
+  // ---- LN-folded weights of the decode step (bf16 tensor-core mode only; kernels.h LnFold) ----
+  // W' = W.diag(gamma) in bf16, s = row sums of W', c = bias + W.beta; `parts` stacks several [n_each, n_in]
+  // matrices (q|k|v), each with its optional LoRA update merged first.
+  Lin lin_fold(const std::vector<std::string>& parts, int n_each, int n_in, const std::string& ln_prefix) {
+    Lin L;
+    if constexpr (std::is_same<T, bf16>::value) {
+      const float* gamma = need(ln_prefix + ".weight", {n_in}).data;
+      const float* beta = need(ln_prefix + ".bias", {n_in}).data;
+      L.n_out = n_each * static_cast<int>(parts.size());
+      L.n_in = n_in;
+      L.w = dalloc<T>(static_cast<long long>(L.n_out) * n_in);
+      L.b = dalloc<float>(L.n_out);
+      L.s = dalloc<float>(L.n_out);
+      float* tmp = nullptr;
+      CXRM_CUDA_CHECK(cudaMalloc(&tmp, static_cast<size_t>(n_each) * n_in * sizeof(float)));
+      for (size_t i = 0; i < parts.size(); ++i) {
+        const std::string& p = parts[i];
+        const RawTensor& w = need(p + ".weight", {n_each, n_in});
+        const float* bias = has(p + ".bias") ? need(p + ".bias", {n_each}).data : nullptr;
+        CXRM_CUDA_CHECK(cudaMemcpyAsync(tmp, w.data, static_cast<size_t>(n_each) * n_in * sizeof(float), cudaMemcpyDeviceToDevice, 0));
+        if (has(p + ".lora_A.weight")) {
+          const RawTensor& A = raw.at(p + ".lora_A.weight");
+          const RawTensor& Bm = raw.at(p + ".lora_B.weight");
+          lora_merge(tmp, A.data, Bm.data, n_each, n_in, static_cast<int>(A.shape[0]), LORA_SCALE, 0);
+        }
+        fold_ln_weights(tmp, n_each, n_in, gamma, beta, bias, L.w + static_cast<long long>(i) * n_each * n_in,
+                        L.s + i * n_each, L.b + i * n_each, 0);
+      }
+      CXRM_CUDA_CHECK(cudaStreamSynchronize(0));
+      cudaFree(tmp);
+    }
+    return L;
+  }
+
   struct CvtLayerW { LNp ln1, ln2; float* dw; float* bn_scale; float* bn_shift; Lin q, k, v, o, fc1, fc2; };
   struct CvtStageW { Lin emb; LNp emb_ln; std::vector<CvtLayerW> layers; };
-  struct BertLayerW { Lin qkv, o; LNp ln1; Lin cq, ckv, co; LNp ln2; Lin fc1, fc2; LNp ln3; };
+  struct BertLayerW { Lin qkv, o; LNp ln1; Lin cq, ckv, co; LNp ln2; Lin fc1, fc2; LNp ln3;
+                      Lin cq_f, fc1_f; /* decode step, bf16: consumers of a folded LayerNorm (kernels.h LnFold) */ };
   struct BertW { T* word = nullptr; T* pos = nullptr; T* type = nullptr; LNp emb_ln; std::vector<BertLayerW> layers; int vocab = 0; };
 
   T* table(const std::string& name, int rows, int cols) {
@@ -324,6 +361,16 @@ class Engine : public EngineBase {
     dec_lm.b = dec_vocab_bias;
     dec_lm.n_out = cfg.vocab;
     dec_lm.n_in = DH;
+    if (std::is_same<T, bf16>::value && cfg.use_tensor_cores) {
+      for (int l = 0; l < cfg.dec_layers; ++l) {
+        const std::string p = "decoder.bert.encoder.layer." + std::to_string(l) + ".";
+        BertLayerW& w = dec.layers[l];
+        w.cq_f = lin_fold({p + "crossattention.self.query"}, DH, DH, p + "attention.output.LayerNorm");
+        w.fc1_f = lin_fold({p + "intermediate.dense"}, DFF, DH, p + "crossattention.output.LayerNorm");
+      }
+      dec_stats = dalloc<float2>(2LL * kStatTiles * 64);
+      CXRM_CUDA_CHECK(cudaMemset(dec_stats, 0, sizeof(float2) * 2 * kStatTiles * 64));
+    }
     // ---- reward model ----
     if (cfg.rwd_layers > 0 && has("reward.bert.embeddings.word_embeddings.weight")) {
       load_bert(rwd, "reward.bert.", cfg.rwd_layers, cfg.rwd_vocab, false);
@@ -693,28 +740,40 @@ class Engine : public EngineBase {
     std::vector<int> idx;
     for (int i = 0; i < n_all; ++i)
       if (valid[i]) idx.push_back(i);
+    encode_valid(pixels, B, N, idx, idx, nullptr, s);
+    if (memory_out)
+      CXRM_CUDA_CHECK(cudaMemcpyAsync(memory_out, memory, static_cast<size_t>(B) * enc_S * DH * sizeof(T), cudaMemcpyDeviceToDevice, s));
+    if (mask_out)
+      CXRM_CUDA_CHECK(cudaMemcpyAsync(mask_out, mem_mask, static_cast<size_t>(B) * enc_S, cudaMemcpyDeviceToDevice, s));
+  }
+
+  // Encode the valid images: the k-th one is image src[k] of `pixels` and lands in slot dst[k] (= b*N + n) of the
+  // encoder memory [B, N*T2, 768]; valid_img (device flags per slot) must be set.  chunk_ready (nullable): event c
+  // is awaited before chunk c is touched (host-buffer path: the chunk's pixels arrive on the copy stream meanwhile).
+  void encode_valid(const float* pixels, int B, int N, const std::vector<int>& src, const std::vector<int>& dst,
+                    const cudaEvent_t* chunk_ready, cudaStream_t s) {
+    const int n_all = B * N;
     enc_B = B;
     enc_S = N * T2;
     fill_zero(memory, static_cast<size_t>(B) * enc_S * DH * sizeof(T), s);
     expand_mask_kernel<<<static_cast<unsigned>(ceil_div_ll(static_cast<long long>(n_all) * T2, 256)), 256, 0, s>>>(
         valid_img, mem_mask, n_all, T2);
     check_launch("expand_mask");
-    if (!idx.empty()) {
-      CXRM_CUDA_CHECK(cudaMemcpyAsync(img_idx, idx.data(), idx.size() * sizeof(int), cudaMemcpyHostToDevice, s));
-      for (size_t c0 = 0; c0 < idx.size(); c0 += cfg.enc_chunk) {
-        const int n = static_cast<int>(std::min<size_t>(cfg.enc_chunk, idx.size() - c0));
-        T* proj = encode_chunk(pixels, img_idx + c0, n, s);
-        for (int i = 0; i < n; ++i) {
-          const long long dst_img = idx[c0 + i];   // = b*N + slot, i.e. row block dst_img*T2 of memory [B, N*T2, 768]
-          CXRM_CUDA_CHECK(cudaMemcpyAsync(memory + dst_img * T2 * DH, proj + static_cast<long long>(i) * T2 * DH,
-                                          static_cast<size_t>(T2) * DH * sizeof(T), cudaMemcpyDeviceToDevice, s));
-        }
+    if (dst.empty()) return;
+    CXRM_CUDA_CHECK(cudaMemcpyAsync(img_idx, src.data(), src.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+    for (size_t c0 = 0, c = 0; c0 < dst.size(); c0 += cfg.enc_chunk, ++c) {
+      const int n = static_cast<int>(std::min<size_t>(cfg.enc_chunk, dst.size() - c0));
+      if (chunk_ready) CXRM_CUDA_CHECK(cudaStreamWaitEvent(s, chunk_ready[c], 0));
+      T* proj = encode_chunk(pixels, img_idx + c0, n, s);
+      for (int i = 0; i < n;) {   // consecutive slots leave as one copy
+        int j = i + 1;
+        while (j < n && dst[c0 + j] == dst[c0 + j - 1] + 1) ++j;
+        const long long d0 = dst[c0 + i];
+        CXRM_CUDA_CHECK(cudaMemcpyAsync(memory + d0 * T2 * DH, proj + static_cast<long long>(i) * T2 * DH,
+                                        static_cast<size_t>(j - i) * T2 * DH * sizeof(T), cudaMemcpyDeviceToDevice, s));
+        i = j;
       }
     }
-    if (memory_out)
-      CXRM_CUDA_CHECK(cudaMemcpyAsync(memory_out, memory, static_cast<size_t>(B) * enc_S * DH * sizeof(T), cudaMemcpyDeviceToDevice, s));
-    if (mask_out)
-      CXRM_CUDA_CHECK(cudaMemcpyAsync(mask_out, mem_mask, static_cast<size_t>(B) * enc_S, cudaMemcpyDeviceToDevice, s));
   }
 
   // =========================================================================== cross K/V
@@ -882,7 +941,80 @@ class Engine : public EngineBase {
     return static_cast<unsigned>(m);
   }
 
+  // ---- decode step with the attention-output and cross-attention-output LayerNorms folded into their neighbours
+  // (bf16 tensor-core mode; kernels.h LnFold): per layer QKV, self, O, cross-Q, cross, cross-O, FFN1, FFN2, LN = 9
+  // launches instead of 11.  The O / cross-O projections lose their split-K (the pre-LN sum must leave the GEMM
+  // complete), which K = 768 affords; FFN2 (K = 3072) keeps split-K + the fused reduce/LayerNorm kernel, whose
+  // residual LN2(x2_pre) is recomputed inside it.
+  // EXPERIMENT, off by default (CXRM_LNFOLD=1): parity-green but MEASURED 3.5 % SLOWER than the unfused chain on B200
+  // (213.6 vs 206.2 ms per step): the un-split O projections and the heavier epilogue code cost more than the 12
+  // LayerNorm launches they remove (profiles/decode_chain_r01.md).
+  bool use_lnfold() const {
+    static int v = -1;
+    if (v < 0) v = std::getenv("CXRM_LNFOLD") ? 1 : 0;
+    return v != 0 && std::is_same<T, bf16>::value && cfg.use_tensor_cores && dec_stats != nullptr && ablate_mask() == 0;
+  }
+  void decode_step_folded(DecBufs& b, T* head_tmp, const RolloutParams& rp, const float* noise, cudaStream_t s) {
+    phase = "decode";
+    const int R = rp.R, B = rp.B;
+    const int* skip = st.done;
+    PF("embed_ln", s, [&] { embed_ln<T>(st.cur_token, st.cur_type, st.cur_pos, dec.word, dec.type, dec.pos, dec.emb_ln.g, dec.emb_ln.b, b.x, R,
+                DH, LN_EPS_BERT, s); });
+    struct PdlScope {
+      explicit PdlScope(bool on) { g_pdl = on; }
+      ~PdlScope() { g_pdl = false; }
+    } pdl_scope(chain_pdl() && !profiling);
+    float2* st1 = dec_stats, *st2 = dec_stats + kStatTiles * 64;
+    T* xp1 = fold_buf[0]; T* xp2 = fold_buf[1];
+    constexpr int kCols = DH / kStatTiles;
+    // consumer: C = act(LN(A_pre).W^T + b) with the LayerNorm folded into L (L.s set)
+    auto consume = [&](const T* A, const Lin& L, const float2* stats, void* C, int ldc, int act) {
+      GemmArgs g = make_args(A, DH, L, C, ldc, R, act, nullptr, 0, false, skip);
+      FoldArgs f;
+      f.ln_in.stats = stats; f.ln_in.tiles = kStatTiles; f.ln_in.cols = kCols; f.ln_in.s = L.s; f.ln_in.eps = LN_EPS_BERT;
+      PF("gemm", s, [&] { gemm_tcgen05_skinny(g, nullptr, nullptr, s, &f); });
+    };
+    // producer: out_pre = A.W^T + b + residual (LayerNorm of res_pre recomputed when res_stats), + tile statistics
+    auto produce = [&](const T* A, const Lin& L, const T* res, const float2* res_stats, const LNp* res_ln, T* out,
+                       float2* stats_out) {
+      GemmArgs g = make_args(A, DH, L, out, DH, R, ACT_NONE, res, DH, false, skip);
+      FoldArgs f;
+      if (res_stats) {
+        f.ln_res.stats = res_stats; f.ln_res.tiles = kStatTiles; f.ln_res.cols = kCols;
+        f.ln_res.gamma = res_ln->g; f.ln_res.beta = res_ln->b; f.ln_res.eps = LN_EPS_BERT;
+      }
+      f.stats_out = stats_out;
+      CXRM_CHECK(gemm_skinny_tile_n(g, false) == kCols, "producer tile width != statistics tile width");
+      PF("gemm", s, [&] { gemm_tcgen05_skinny(g, nullptr, nullptr, s, &f); });
+    };
+    for (int l = 0; l < cfg.dec_layers; ++l) {
+      const BertLayerW& w = dec.layers[l];
+      gemm(b.x, DH, w.qkv, b.qkv, 3 * DH, R, ACT_NONE, nullptr, 0, false, skip, s);
+      PF("self_attn", s, [&] { decode_self_attention<T>(b.qkv, self_k + l * self_layer_stride(), self_v + l * self_layer_stride(), b.ctx, st, R,
+                               rp.P, Lmax, self_ws, self_tickets, attn_maps_ptr, l, s); });
+      produce(b.ctx, w.o, b.x, nullptr, nullptr, xp1, st1);                 // x1_pre = ctx.Wo + b + x
+      consume(xp1, w.cq_f, st1, b.qkv, DH, ACT_NONE);                       // q = LN1(x1_pre).Wq + b
+      const T* kvl = cross_kv + static_cast<long long>(l) * cross_layer_stride();
+      PF("cross_attn", s, [&] { decode_cross_attention<T>(b.qkv, DH, kvl, kvl + NHEAD * cross_head_stride(), cross_head_stride(), b.ctx,
+                                cross_units(), st, R, B, cross_ws, cross_tickets, attn_maps_ptr, l, s); });
+      produce(b.ctx, w.co, xp1, st1, &w.ln1, xp2, st2);                     // x2_pre = ctx.Wco + b + LN1(x1_pre)
+      consume(xp2, w.fc1_f, st2, b.hid, DFF, ACT_GELU);                     // hid = GELU(LN2(x2_pre).W1 + b)
+      // x = LN3(hid.W2 + b + LN2(x2_pre)): split-K partials + one reduce / residual-LayerNorm / LayerNorm kernel
+      GemmArgs g = make_args(b.hid, DFF, w.fc2, nullptr, 0, R, ACT_NONE, nullptr, 0, false, skip);
+      int nsplit = 0;
+      PF("gemm", s, [&] { gemm_tcgen05_skinny(g, skinny_ws, &nsplit, s); });
+      PF("layernorm", s, [&] { splitk_ln(skinny_ws, nsplit, R, DH, w.fc2.b, ACT_NONE, xp2, DH, w.ln3.g, w.ln3.b, LN_EPS_BERT, b.x, DH, skip, s,
+                                         w.ln2.g, w.ln2.b); });
+    }
+    lm_head(b.x, R, head_tmp, logits, cfg.vocab, skip, s);
+    PF("sample", s, [&] { sample_step(st, rp, logits, cfg.vocab, noise, s); });
+  }
+
   void decode_step(DecBufs& b, T* head_tmp, const RolloutParams& rp, const float* noise, cudaStream_t s) {
+    if (use_lnfold()) {
+      decode_step_folded(b, head_tmp, rp, noise, s);
+      return;
+    }
     phase = "decode";
     const int R = rp.R, B = rp.B;
     const int* skip = st.done;
@@ -984,6 +1116,7 @@ class Engine : public EngineBase {
     DecBufs db = dec_bufs(R);     // first: keeps the decode-step pointers (and the captured graph) independent of P
     T* last = arena.get<T>(static_cast<long long>(R) * DH);
     T* head_tmp = arena.get<T>(static_cast<long long>(R) * DH);
+    for (T*& fb : fold_buf) fb = arena.get<T>(static_cast<long long>(R) * DH);
     DecBufs pb = dec_bufs(M);
     PF("embed_ln", s, [&] { embed_ln<T>(pre_ids, pre_types, pre_pos, dec.word, dec.type, dec.pos, dec.emb_ln.g, dec.emb_ln.b, pb.x, M, DH,
                 LN_EPS_BERT, s); });
@@ -1159,15 +1292,52 @@ class Engine : public EngineBase {
       h_out = dalloc<float>(3LL * cfg.max_studies);
       h_labels = dalloc<int>(static_cast<long long>(cfg.max_studies) * cfg.rwd_max_len);
     }
-    const size_t px = static_cast<size_t>(B) * N * 3 * cfg.image_h * cfg.image_w * sizeof(float);
-    const float* px_dev = pixels;
-    if (!on_device) {
-      CXRM_CUDA_CHECK(cudaMemcpyAsync(h_pixels, pixels, px, cudaMemcpyHostToDevice, s));
-      px_dev = h_pixels;
-    }
     // cudaMemcpyDefault: the direction is inferred from the (unified) addresses, host or device
     CXRM_CUDA_CHECK(cudaMemcpyAsync(prompt_dev, prompt_ids, static_cast<size_t>(B) * P * sizeof(int), cudaMemcpyDefault, s));
-    encode(px_dev, B, N, nullptr, nullptr, s);
+    if (on_device) {
+      encode(pixels, B, N, nullptr, nullptr, s);
+    } else {
+      // Host pixels: padding is detected on the host (pixel_values[b, n, 0, 0, 0] != 0, modelling_longitudinal.py:83),
+      // only the valid images cross PCIe, compacted, one encoder chunk at a time on the copy stream, so that chunk
+      // c + 1 is in flight while chunk c is being encoded.
+      const int n_all = B * N;
+      const long long img_stride = 3LL * cfg.image_h * cfg.image_w;
+      std::vector<uint8_t> valid(n_all);
+      std::vector<int> src, dst;
+      for (int i = 0; i < n_all; ++i) {
+        valid[i] = pixels[i * img_stride] != 0.0f ? 1 : 0;
+        if (valid[i]) {
+          src.push_back(static_cast<int>(dst.size()));
+          dst.push_back(i);
+        }
+      }
+      CXRM_CUDA_CHECK(cudaMemcpyAsync(valid_img, valid.data(), n_all, cudaMemcpyHostToDevice, s));
+      const size_t n_chunks = (dst.size() + cfg.enc_chunk - 1) / cfg.enc_chunk;
+      while (ev_chunk.size() < n_chunks + 1) {
+        cudaEvent_t e;
+        CXRM_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ev_chunk.push_back(e);
+      }
+      // h_pixels may still be read by work queued on s (a previous step): the copy stream starts behind it
+      CXRM_CUDA_CHECK(cudaEventRecord(ev_chunk[n_chunks], s));
+      CXRM_CUDA_CHECK(cudaStreamWaitEvent(pf_stream, ev_chunk[n_chunks], 0));
+      h2d_pixel_bytes = 0;
+      for (size_t c = 0; c < n_chunks; ++c) {
+        const size_t k0 = c * cfg.enc_chunk, k1 = std::min(dst.size(), k0 + cfg.enc_chunk);
+        for (size_t k = k0; k < k1;) {   // consecutive source slots travel as one copy
+          size_t j = k + 1;
+          while (j < k1 && dst[j] == dst[j - 1] + 1) ++j;
+          const size_t bytes = (j - k) * img_stride * sizeof(float);
+          CXRM_CUDA_CHECK(cudaMemcpyAsync(h_pixels + static_cast<long long>(k) * img_stride, pixels + dst[k] * img_stride, bytes,
+                                          cudaMemcpyHostToDevice, pf_stream));
+          h2d_pixel_bytes += bytes;
+          k = j;
+        }
+        CXRM_CUDA_CHECK(cudaEventRecord(ev_chunk[c], pf_stream));
+      }
+      CXRM_CHECK(B >= 1 && N >= 1, "scst_step_host shape");
+      encode_valid(h_pixels, B, N, src, dst, ev_chunk.data(), s);
+    }
     prefill_cross_kv(nullptr, nullptr, 0, 0, s);
     cxrm_rollout_args a = tmpl;
     a.mode = CXRM_BOTH; a.B = B; a.P = P; a.prompt_ids = prompt_dev;
@@ -1219,6 +1389,9 @@ class Engine : public EngineBase {
   Lin head_proj;
   BertW dec, rwd;
   Lin dec_head_t, dec_lm, rp1, rp2;
+  static constexpr int kStatTiles = 48;           // 768 columns / 16-column producer tiles
+  float2* dec_stats = nullptr;                    // [2][64][kStatTiles]: tile statistics of x1_pre, x2_pre
+  T* fold_buf[2] = {nullptr, nullptr};            // pre-LN tensors x1, x2 (arena, set by rollout)
   LNp dec_head_ln, rp_ln;
   float* dec_vocab_bias = nullptr;
   // geometry
@@ -1240,6 +1413,8 @@ class Engine : public EngineBase {
   cudaEvent_t ev_pf[kMaxForks] = {};
   cudaEvent_t ev_pf_join = nullptr;
   int pf_forks = 0;
+  std::vector<cudaEvent_t> ev_chunk;      // host-buffer step: pixels of encoder chunk c have arrived
+  size_t h2d_pixel_bytes = 0;             // pixel bytes copied by the last host-buffer step
   RolloutState st{};
   int* pre_ids = nullptr; int* pre_types = nullptr; int* pre_pos = nullptr; int* prompt_dev = nullptr;
   // host-step staging

@@ -12,7 +12,9 @@
 // MMA issuer, warps 2..5 = epilogue (warp w owns TMEM lanes 32*(w%4)..+31).
 #include <cuda.h>
 
+#include <cstdlib>
 #include <mutex>
+#include <type_traits>
 #include <unordered_map>
 
 #include "kernels.h"
@@ -387,11 +389,19 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const __grid_constant
 // =====================================================================================================
 constexpr int SK_ROWS = 64, SK_A_BYTES = SK_ROWS * BK * 2, SK_MAX_STAGES = 16, SK_SLACK = A_BYTES - SK_A_BYTES;
 
-template <int BN>
+struct NoFold {};
+// EPI selects a LEAN epilogue.  The decode-step kernels are latency-bound launches whose code is fetched cold on
+// every launch (~330 KB of distinct kernels per step against a 128 KB instruction cache; ncu: `no_instruction` is the
+// third-largest stall of the skinny GEMM), so the chain runs specialisations that carry only the path they execute:
+//   0 general (every flag of GemmArgs; test hooks and odd shapes)   1 split-K fp32 partial tile
+//   2 bias -> bf16, 16-byte stores   3 bias -> GELU -> bf16   4 bias -> fp32 (LM head; last tile may be partial)
+// 1-3 need whole tiles (N % BN == 0) and 16-byte aligned rows, no residual, no head-major store.
+template <int BN, bool FOLD, int EPI = 0>
 __global__ void __launch_bounds__(NTHREADS) gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                   const __grid_constant__ CUtensorMap tmB, GemmArgs g,
                                                                   int stages, int kb_per_split,
-                                                                  float* __restrict__ partial, int vec_ok) {
+                                                                  float* __restrict__ partial, int vec_ok,
+                                                                  std::conditional_t<FOLD, FoldArgs, NoFold> fa) {
   constexpr int B_BYTES = BN * BK * 2;
   constexpr int STAGE_BYTES = SK_A_BYTES + B_BYTES;
   constexpr int TMEM_COLS = BN <= 32 ? 32 : 64;
@@ -477,11 +487,209 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_skinny_kernel(const __grid_c
       }
       umma_commit(tmem_full);
     }
+  } else if (FOLD && warp % 4 < 2) {
+   if constexpr (FOLD) {
+    // ---- epilogue with folded LayerNorms (kernels.h LnFold): thread <-> output row ----------------
+    const int quarter = warp % 4;
+    constexpr int W = BN >= 32 ? 32 : BN;          // columns per TMEM load
+    float* cst = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full) + 512);   // [4][BN]: bias|c, s, gamma, beta
+    const int et = threadIdx.x - 128;              // 0..63
+    for (int j = et; j < BN; j += 64) {            // constants of the chain: staged before the dependency wait
+      const int n = n0 + j;
+      const bool ok = n < g.N;
+      cst[j] = (ok && g.bias) ? g.bias[n] : 0.f;
+      cst[BN + j] = (ok && fa.ln_in.stats) ? fa.ln_in.s[n] : 0.f;
+      cst[2 * BN + j] = (ok && fa.ln_res.stats) ? fa.ln_res.gamma[n] : 0.f;
+      cst[3 * BN + j] = (ok && fa.ln_res.stats) ? fa.ln_res.beta[n] : 0.f;
+    }
+    asm volatile("bar.sync 2, 64;" ::: "memory");
+    pdl_wait();
+    const bool skip = g.skip_flag && *g.skip_flag;
+    const int m = quarter * 32 + lane;
+    const bool row_ok = m < g.M && !skip;
+    // per-row (mean, rstd) from the producers' column-tile statistics: shifted sums, equal tile sizes
+    auto row_stats = [&](const float2* st, int tiles, int cols, float eps, float& mu, float& rstd) {
+      // the row's tile statistics are contiguous ([64][tiles]): every 16-byte load is issued before the first use
+      constexpr int MAXT = 48;
+      float4 pp[MAXT / 2];
+      const float4* src = reinterpret_cast<const float4*>(st + static_cast<long long>(m) * tiles);
+#pragma unroll
+      for (int t = 0; t < MAXT / 2; ++t)
+        if (2 * t < tiles) pp[t] = __ldcg(src + t);
+      const float2 p0 = make_float2(pp[0].x, pp[0].y);
+      float sd = 0.f, sd2 = 0.f, sm2 = 0.f;
+#pragma unroll
+      for (int t = 0; t < MAXT / 2; ++t)
+        if (2 * t < tiles) {
+          const float d0 = pp[t].x - p0.x, d1 = pp[t].z - p0.x;
+          sd += d0 + d1;
+          sd2 += d0 * d0 + d1 * d1;
+          sm2 += pp[t].y + pp[t].w;
+        }
+      const float md = sd / tiles;
+      mu = p0.x + md;
+      const float m2 = sm2 + cols * fmaxf(sd2 - tiles * md * md, 0.f);
+      rstd = rsqrtf(m2 / (tiles * cols) + eps);
+    };
+    float mu_in = 0.f, r_in = 1.f, mu_rs = 0.f, r_rs = 1.f;
+    if (fa.ln_in.stats) row_stats(fa.ln_in.stats, fa.ln_in.tiles, fa.ln_in.cols, fa.ln_in.eps, mu_in, r_in);
+    if (fa.ln_res.stats) row_stats(fa.ln_res.stats, fa.ln_res.tiles, fa.ln_res.cols, fa.ln_res.eps, mu_rs, r_rs);
+    const bf16* __restrict__ R = static_cast<const bf16*>(g.residual);
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    float ssum = 0.f, vals[BN >= 32 ? 32 : W];     // stats_out needs BN <= 32 (one chunk): checked by the launcher
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      if (n0 + c0 >= g.N || skip) break;
+      uint32_t r[32];
+      if (BN >= 32) {
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(c0), r);
+      } else {
+        tmem_ld16(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(c0), r);
+      }
+      if (!row_ok) continue;
+      const int nb = n0 + c0;
+      float v[W];
+#pragma unroll
+      for (int j = 0; j < W; ++j) {
+        float a = __uint_as_float(r[j]);
+        a = fa.ln_in.stats ? fmaf(r_in, a - mu_in * cst[BN + c0 + j], cst[c0 + j]) : a + cst[c0 + j];
+        v[j] = a;
+      }
+      if (g.act == ACT_GELU) {
+#pragma unroll
+        for (int j = 0; j < W; ++j) v[j] = gelu_fast(v[j]);
+      }
+      const bool full_w = nb + W <= g.N;
+      if (R) {
+        const bf16* rp = R + static_cast<long long>(m) * g.ldr + nb;
+#pragma unroll
+        for (int q = 0; q < W / 8; ++q) {
+          float rf[8];
+          if (full_w && vec_ok) {
+            Vec16<bf16> rv;
+            rv.load(rp + 8 * q);
+            rv.unpack(rf);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) rf[j] = (nb + 8 * q + j < g.N) ? to_f(rp[8 * q + j]) : 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float x = rf[j];
+            if (fa.ln_res.stats)
+              x = to_f(from_f<bf16>((x - mu_rs) * r_rs * cst[2 * BN + c0 + 8 * q + j] + cst[3 * BN + c0 + 8 * q + j]));
+            v[8 * q + j] += x;
+          }
+        }
+      }
+      if (g.out_f32) {
+        float* cp = static_cast<float*>(g.C) + static_cast<long long>(m) * g.ldc + nb;
+        if (full_w && vec_ok) {
+#pragma unroll
+          for (int q = 0; q < W / 4; ++q)
+            *reinterpret_cast<float4*>(cp + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < W; ++j)
+            if (nb + j < g.N) cp[j] = v[j];
+        }
+      } else {
+        bf16* cp = static_cast<bf16*>(g.C) + static_cast<long long>(m) * g.ldc + nb;
+        if (full_w && vec_ok) {
+#pragma unroll
+          for (int q = 0; q < W / 8; ++q) {
+            Vec16<bf16> ov;
+            ov.pack(v + 8 * q);
+            ov.store(cp + 8 * q);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < W; ++j)
+            if (nb + j < g.N) cp[j] = from_f<bf16>(v[j]);
+        }
+        if (fa.stats_out) {      // statistics of the values as stored (bf16-rounded), like a LayerNorm over the stored tensor
+#pragma unroll
+          for (int j = 0; j < W; ++j) {
+            vals[j] = to_f(from_f<bf16>(v[j]));
+            ssum += vals[j];
+          }
+        }
+      }
+    }
+    if (fa.stats_out && row_ok) {
+      const float mean = ssum / W;
+      float m2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < W; ++j) m2 += (vals[j] - mean) * (vals[j] - mean);
+      fa.stats_out[static_cast<long long>(m) * gridDim.x + blockIdx.x] = make_float2(mean, m2);
+    }
+   }
+  } else if (EPI != 0 && warp % 4 < 2) {
+   if constexpr (EPI != 0) {
+    // ---- lean epilogues (see the template comment) ------------------------------------------------
+    const int quarter = warp % 4;
+    constexpr int W = BN >= 32 ? 32 : BN;
+    float bpre[EPI == 1 ? 1 : BN];
+    if (EPI != 1) {
+#pragma unroll
+      for (int j = 0; j < BN; ++j) bpre[j] = (g.bias && (EPI != 4 || n0 + j < g.N)) ? g.bias[n0 + j] : 0.f;
+    }
+    pdl_wait();
+    const bool skip = g.skip_flag && *g.skip_flag;
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const long long m = quarter * 32 + lane;
+    const bool row_ok = m < g.M && !skip;
+#pragma unroll
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      if (skip || (EPI == 4 && n0 + c0 >= g.N)) break;
+      uint32_t r[32];
+      if (BN >= 32) tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(c0), r);
+      else tmem_ld16(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(c0), r);
+      if (!row_ok) continue;
+      const int nb = n0 + c0;
+      if (EPI == 1) {
+        float4* dst = reinterpret_cast<float4*>(partial + (static_cast<long long>(split) * SK_ROWS + m) * g.N + nb);
+#pragma unroll
+        for (int q = 0; q < W / 4; ++q)
+          dst[q] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
+                               __uint_as_float(r[4 * q + 3]));
+      } else if (EPI == 2 || EPI == 3) {
+        bf16* cp = static_cast<bf16*>(g.C) + m * g.ldc + nb;
+#pragma unroll
+        for (int q = 0; q < W / 8; ++q) {
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            v[j] = __uint_as_float(r[8 * q + j]) + bpre[c0 + 8 * q + j];
+            if (EPI == 3) v[j] = gelu_fast(v[j]);
+          }
+          Vec16<bf16> ov;
+          ov.pack(v);
+          ov.store(cp + 8 * q);
+        }
+      } else {
+        float* cp = static_cast<float*>(g.C) + m * g.ldc + nb;
+        if (nb + 32 <= g.N) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(cp + 4 * q) =
+                make_float4(__uint_as_float(r[4 * q]) + bpre[c0 + 4 * q], __uint_as_float(r[4 * q + 1]) + bpre[c0 + 4 * q + 1],
+                            __uint_as_float(r[4 * q + 2]) + bpre[c0 + 4 * q + 2], __uint_as_float(r[4 * q + 3]) + bpre[c0 + 4 * q + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (nb + j < g.N) cp[j] = __uint_as_float(r[j]) + bpre[c0 + j];
+        }
+      }
+    }
+   }
   } else if (warp % 4 < 2) {
     // ---- epilogue: warps 4,5 own TMEM lanes 0..63 = the 64 real rows ---------------------------
     const int quarter = warp % 4;
     // the bias is a constant of the chain: fetch this CTA's slice before the dependency wait / the accumulator
     constexpr int BW = BN >= 32 ? BN : 32;
+    if constexpr (EPI == 0) {
     float bpre[BW];
     const bool pre_bias = g.bias != nullptr && partial == nullptr;
     if (pre_bias) {
@@ -531,6 +739,7 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_skinny_kernel(const __grid_c
         }
         epilogue_chunk(gl, v, m, nb, (BN >= 32) ? vec_ok : 0);
       }
+    }
     }
   } else {
     pdl_wait();   // every thread of a chain kernel passes the dependency wait
@@ -762,48 +971,27 @@ __global__ void __launch_bounds__(256) splitk_ln_kernel(const float* __restrict_
                                                         const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float eps,
                                                         bf16* __restrict__ out, int ldo,
-                                                        const int* __restrict__ skip_flag) {
+                                                        const int* __restrict__ skip_flag,
+                                                        const float* __restrict__ res_gamma,
+                                                        const float* __restrict__ res_beta) {
   __shared__ float sh[8];
   pdl_launch_dependents();
   const int m = blockIdx.x, tid = threadIdx.x;
   const int c = tid * 4;
   const bool on = c < N;   // N % 4 == 0, N <= 1024
   // parameters are constants of the chain: fetch them while the producing GEMM is still running
-  float4 bs = make_float4(0.f, 0.f, 0.f, 0.f), gm = bs, bt = bs;
+  float4 bs = make_float4(0.f, 0.f, 0.f, 0.f), gm = bs, bt = bs, rg = bs, rb = bs;
   if (on) {
     if (bias) bs = *reinterpret_cast<const float4*>(bias + c);
     gm = *reinterpret_cast<const float4*>(gamma + c);
     bt = *reinterpret_cast<const float4*>(beta + c);
+    if (res_gamma) {
+      rg = *reinterpret_cast<const float4*>(res_gamma + c);
+      rb = *reinterpret_cast<const float4*>(res_beta + c);
+    }
   }
   pdl_wait();
   if (skip_flag && *skip_flag) return;
-  float v[4] = {0.f, 0.f, 0.f, 0.f};
-  if (on) {
-    // all loads first (one L2 round trip instead of a dependent chain), then the arithmetic
-    float4 p[4];
-    uint2 rr = make_uint2(0u, 0u);
-#pragma unroll
-    for (int s = 0; s < 4; ++s)
-      p[s] = (s < nsplit) ? __ldcg(reinterpret_cast<const float4*>(partial + (static_cast<long long>(s) * SK_ROWS + m) * N + c))
-                          : make_float4(0.f, 0.f, 0.f, 0.f);
-    if (residual) rr = *reinterpret_cast<const uint2*>(residual + static_cast<long long>(m) * ldr + c);
-#pragma unroll
-    for (int s = 0; s < 4; ++s) {
-      v[0] += p[s].x; v[1] += p[s].y; v[2] += p[s].z; v[3] += p[s].w;
-    }
-    v[0] += bs.x; v[1] += bs.y; v[2] += bs.z; v[3] += bs.w;
-    if (act == ACT_GELU) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) v[j] = gelu_fast(v[j]);
-    }
-    if (residual) {
-      v[0] += __uint_as_float(rr.x << 16); v[1] += __uint_as_float(rr.x & 0xffff0000u);
-      v[2] += __uint_as_float(rr.y << 16); v[3] += __uint_as_float(rr.y & 0xffff0000u);
-    }
-    // the reference rounds the pre-LN sum to the storage type (bf16 GEMM output) before normalising
-#pragma unroll
-    for (int j = 0; j < 4; ++j) v[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
-  }
   auto block_sum = [&](float x) {
     x = warp_sum(x);
     __syncthreads();
@@ -814,6 +1002,55 @@ __global__ void __launch_bounds__(256) splitk_ln_kernel(const float* __restrict_
     for (int w = 0; w < 8; ++w) t += sh[w];
     return t;
   };
+  float v[4] = {0.f, 0.f, 0.f, 0.f};
+  float rln[4] = {0.f, 0.f, 0.f, 0.f};   // residual as a recomputed LayerNorm output
+  if (res_gamma) {
+    float x[4] = {0.f, 0.f, 0.f, 0.f};
+    if (on) {
+      const uint2 rr = *reinterpret_cast<const uint2*>(residual + static_cast<long long>(m) * ldr + c);
+      x[0] = __uint_as_float(rr.x << 16); x[1] = __uint_as_float(rr.x & 0xffff0000u);
+      x[2] = __uint_as_float(rr.y << 16); x[3] = __uint_as_float(rr.y & 0xffff0000u);
+    }
+    const float rmean = block_sum(x[0] + x[1] + x[2] + x[3]) / N;
+    float q2 = 0.f;
+    if (on) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) q2 += (x[j] - rmean) * (x[j] - rmean);
+    }
+    const float rrstd = rsqrtf(block_sum(q2) / N + eps);
+    const float g4[4] = {rg.x, rg.y, rg.z, rg.w}, b4[4] = {rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) rln[j] = __bfloat162float(__float2bfloat16_rn((x[j] - rmean) * rrstd * g4[j] + b4[j]));
+  }
+  if (on) {
+    // all loads first (one L2 round trip instead of a dependent chain), then the arithmetic
+    float4 p[4];
+    uint2 rr = make_uint2(0u, 0u);
+#pragma unroll
+    for (int s = 0; s < 4; ++s)
+      p[s] = (s < nsplit) ? __ldcg(reinterpret_cast<const float4*>(partial + (static_cast<long long>(s) * SK_ROWS + m) * N + c))
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (residual && !res_gamma) rr = *reinterpret_cast<const uint2*>(residual + static_cast<long long>(m) * ldr + c);
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      v[0] += p[s].x; v[1] += p[s].y; v[2] += p[s].z; v[3] += p[s].w;
+    }
+    v[0] += bs.x; v[1] += bs.y; v[2] += bs.z; v[3] += bs.w;
+    if (act == ACT_GELU) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = gelu_fast(v[j]);
+    }
+    if (res_gamma) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] += rln[j];
+    } else if (residual) {
+      v[0] += __uint_as_float(rr.x << 16); v[1] += __uint_as_float(rr.x & 0xffff0000u);
+      v[2] += __uint_as_float(rr.y << 16); v[3] += __uint_as_float(rr.y & 0xffff0000u);
+    }
+    // the reference rounds the pre-LN sum to the storage type (bf16 GEMM output) before normalising
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
+  }
   const float mean = block_sum(on ? v[0] + v[1] + v[2] + v[3] : 0.f) / N;
   float d2 = 0.f;
   if (on) {
@@ -830,6 +1067,29 @@ __global__ void __launch_bounds__(256) splitk_ln_kernel(const float* __restrict_
     st.x = *reinterpret_cast<uint32_t*>(&a);
     st.y = *reinterpret_cast<uint32_t*>(&b);
     *reinterpret_cast<uint2*>(out + static_cast<long long>(m) * ldo + c) = st;
+  }
+}
+
+
+// ---- weight preparation for the LN-folded decode GEMMs: one warp per output row ----
+__global__ void fold_ln_weights_kernel(const float* __restrict__ W, int n_out, int n_in, const float* __restrict__ gamma,
+                                       const float* __restrict__ beta, const float* __restrict__ bias,
+                                       bf16* __restrict__ Wf, float* __restrict__ s, float* __restrict__ c) {
+  const int n = (blockIdx.x * blockDim.x + threadIdx.x) / kWarp, lane = threadIdx.x % kWarp;
+  if (n >= n_out) return;
+  float ss = 0.f, cc = 0.f;
+  for (int k = lane; k < n_in; k += kWarp) {
+    const float w = W[static_cast<long long>(n) * n_in + k];
+    const bf16 wf = __float2bfloat16_rn(w * gamma[k]);
+    Wf[static_cast<long long>(n) * n_in + k] = wf;
+    ss += __bfloat162float(wf);
+    cc += beta[k] * w;
+  }
+  ss = warp_sum(ss);
+  cc = warp_sum(cc);
+  if (lane == 0) {
+    s[n] = ss;
+    c[n] = cc + (bias ? bias[n] : 0.f);
   }
 }
 
@@ -925,21 +1185,53 @@ void launch(const GemmArgs& g, int stages, cudaStream_t stream) {
 
 // ---- skinny path (M <= 64) -------------------------------------------------------------------------
 template <int BN>
-void launch_skinny(const GemmArgs& g, int stages, int nsplit, int kb_per_split, float* partial, cudaStream_t stream) {
-  const size_t smem = static_cast<size_t>(stages) * (SK_A_BYTES + BN * BK * 2) + SK_SLACK + 1024 + 512;
-  static size_t configured = 0;
-  if (smem > configured) {
-    CXRM_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_skinny_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(smem)));
-    configured = smem;
-  }
+void launch_skinny(const GemmArgs& g, int stages, int nsplit, int kb_per_split, float* partial, cudaStream_t stream,
+                   const FoldArgs* fold) {
+  // tiles | slack | barriers (512 B) | per-CTA column constants of the LN-folded epilogue (4 x BN floats) | alignment
+  const size_t smem = static_cast<size_t>(stages) * (SK_A_BYTES + BN * BK * 2) + SK_SLACK + 1024 + 512 +
+                      (fold ? 4 * BN * sizeof(float) : 0);
   const CUtensorMap ta = make_map(g.A, g.M, g.K, g.lda, SK_ROWS);
   const CUtensorMap tb = make_map(g.W, g.N, g.K, g.ldw, BN);
   const int esz = g.out_f32 ? 4 : 2;
   int vec_ok = (reinterpret_cast<uintptr_t>(g.C) % 16 == 0) && ((static_cast<long long>(g.ldc) * esz) % 16 == 0);
   if (g.residual) vec_ok = vec_ok && (reinterpret_cast<uintptr_t>(g.residual) % 16 == 0) && (g.ldr % 8 == 0);
   dim3 grid(ceil_div(g.N, BN), nsplit);
-  launch_chain(gemm_tc_skinny_kernel<BN>, grid, dim3(NTHREADS), smem, stream, ta, tb, g, stages, kb_per_split, partial, vec_ok);
+  if (fold) {
+    static size_t configured = 0;
+    if (smem > configured) {
+      CXRM_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_skinny_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(smem)));
+      configured = smem;
+    }
+    launch_chain(gemm_tc_skinny_kernel<BN, true>, grid, dim3(NTHREADS), smem, stream, ta, tb, g, stages, kb_per_split, partial,
+                 vec_ok, *fold);
+  } else {
+    // lean epilogue when the call fits one (always the case for the decode step), else the general kernel
+    int epi = 0;
+    static const bool lean = std::getenv("CXRM_NO_LEAN_EPILOGUE") == nullptr;
+    if (lean && g.c_head_stride == 0 && !g.residual && vec_ok) {
+      if (partial && g.N % BN == 0) epi = 1;
+      else if (!partial && !g.out_f32 && g.N % BN == 0 && g.M <= SK_ROWS) epi = g.act == ACT_GELU ? 3 : 2;
+      else if (!partial && g.out_f32 && g.act == ACT_NONE && BN == 64) epi = 4;
+    }
+    auto go = [&](auto kern) {
+      // keyed by the function: the instantiations share one function-pointer type, so a static in this lambda would too
+      static std::unordered_map<const void*, size_t> configured;
+      size_t& have = configured[reinterpret_cast<const void*>(kern)];
+      if (smem > have) {
+        CXRM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        have = smem;
+      }
+      launch_chain(kern, grid, dim3(NTHREADS), smem, stream, ta, tb, g, stages, kb_per_split, partial, vec_ok, NoFold{});
+    };
+    switch (epi) {
+      case 1: go(gemm_tc_skinny_kernel<BN, false, 1>); break;
+      case 2: go(gemm_tc_skinny_kernel<BN, false, 2>); break;
+      case 3: go(gemm_tc_skinny_kernel<BN, false, 3>); break;
+      case 4: go(gemm_tc_skinny_kernel<BN, false, 4>); break;
+      default: go(gemm_tc_skinny_kernel<BN, false, 0>); break;
+    }
+  }
   check_launch("gemm_tcgen05_skinny");
 }
 
@@ -994,15 +1286,24 @@ int gemm_skinny_supported(const GemmArgs& g) {
 }
 
 // nsplit_out: number of K splits written to `partial` (0 when the result was stored directly through the epilogue)
-void gemm_tcgen05_skinny(const GemmArgs& g, float* partial, int* nsplit_out, cudaStream_t stream) {
+int gemm_skinny_tile_n(const GemmArgs& g, bool split_allowed) {
+  if (g.N >= 8192) return 64;   // LM head: many tiles, two CTAs per SM
+  if (!split_allowed && ceil_div(g.N, 32) < 48 && g.c_head_stride == 0) return 16;   // no split possible: narrower tiles
+  return 32;
+}
+
+void gemm_tcgen05_skinny(const GemmArgs& g, float* partial, int* nsplit_out, cudaStream_t stream, const FoldArgs* fold) {
   CXRM_CHECK(gemm_skinny_supported(g) == 0, "shape not supported by the skinny tcgen05 GEMM");
   const int num_kb = ceil_div(g.K, BK);
-  int bn = 32, stages = SK_MAX_STAGES;
-  if (g.N >= 8192) {   // LM head: many tiles, two CTAs per SM
-    bn = 64;
-    stages = 6;
-  } else if (!partial && ceil_div(g.N, 32) < 48 && g.c_head_stride == 0) {
-    bn = 16;           // no split possible (direct epilogue): narrower tiles instead
+  const int bn = gemm_skinny_tile_n(g, partial != nullptr);
+  int stages = bn == 64 ? 6 : SK_MAX_STAGES;
+  if (fold && !fold->any()) fold = nullptr;
+  if (fold) {
+    CXRM_CHECK(!partial && g.c_head_stride == 0, "LN-folded epilogue: direct bf16/fp32 stores only");
+    CXRM_CHECK(!fold->stats_out || (bn <= 32 && g.N % bn == 0 && !g.out_f32), "stats_out needs whole tiles of <= 32 bf16 columns");
+    CXRM_CHECK(!fold->ln_res.stats || g.residual, "ln_res without a residual tensor");
+    CXRM_CHECK(fold->ln_in.tiles <= 48 && fold->ln_res.tiles <= 48 && fold->ln_in.tiles % 2 == 0 && fold->ln_res.tiles % 2 == 0,
+               "LN-folded epilogue: at most 48 (even) statistics tiles per row");
   }
   int nsplit = 1;
   if (partial && ceil_div(g.N, bn) < 64) nsplit = std::max(1, std::min(4, num_kb / 6));
@@ -1011,19 +1312,28 @@ void gemm_tcgen05_skinny(const GemmArgs& g, float* partial, int* nsplit_out, cud
   stages = std::min(stages, kb_per_split);
   if (nsplit_out) *nsplit_out = partial ? nsplit : 0;
   switch (bn) {
-    case 16: launch_skinny<16>(g, stages, nsplit, kb_per_split, partial, stream); break;
-    case 64: launch_skinny<64>(g, stages, nsplit, kb_per_split, partial, stream); break;
-    default: launch_skinny<32>(g, stages, nsplit, kb_per_split, partial, stream); break;
+    case 16: launch_skinny<16>(g, stages, nsplit, kb_per_split, partial, stream, fold); break;
+    case 64: launch_skinny<64>(g, stages, nsplit, kb_per_split, partial, stream, fold); break;
+    default: launch_skinny<32>(g, stages, nsplit, kb_per_split, partial, stream, fold); break;
   }
 }
 
 void splitk_ln(const float* partial, int nsplit, int M, int N, const float* bias, int act, const void* residual,
                int ldr, const float* gamma, const float* beta, float eps, void* out, int ldo, const int* skip_flag,
-               cudaStream_t stream) {
+               cudaStream_t stream, const float* res_gamma, const float* res_beta) {
+  CXRM_CHECK(!res_gamma || (residual && res_beta), "splitk_ln: residual LayerNorm needs the pre-LN residual rows");
   CXRM_CHECK(N % 4 == 0 && N <= 1024 && M <= SK_ROWS && ldo % 4 == 0 && (!residual || ldr % 4 == 0), "splitk_ln shape");
   launch_chain(splitk_ln_kernel, dim3(M), dim3(256), 0, stream, partial, nsplit, N, bias, act,
-               static_cast<const bf16*>(residual), ldr, gamma, beta, eps, static_cast<bf16*>(out), ldo, skip_flag);
+               static_cast<const bf16*>(residual), ldr, gamma, beta, eps, static_cast<bf16*>(out), ldo, skip_flag, res_gamma,
+               res_beta);
   check_launch("splitk_ln");
+}
+
+void fold_ln_weights(const float* W, int n_out, int n_in, const float* gamma, const float* beta, const float* bias,
+                     void* Wf_bf16, float* s, float* c, cudaStream_t stream) {
+  fold_ln_weights_kernel<<<ceil_div(n_out * kWarp, 256), 256, 0, stream>>>(W, n_out, n_in, gamma, beta, bias,
+                                                                          static_cast<bf16*>(Wf_bf16), s, c);
+  check_launch("fold_ln_weights");
 }
 
 size_t gemm_skinny_partial_floats(int N) { return static_cast<size_t>(4) * SK_ROWS * N; }

@@ -401,3 +401,50 @@ def test_model_api_generate_matches_reference_call_shapes(eng32, gold):
     fin = torch.isfinite(ref)
     assert torch.equal(torch.isfinite(s1), fin)
     assert (s1[fin] - ref[fin]).abs().max().item() < 2e-3
+
+
+# ------------------------------------------------------------------------------ whole SCST step: host buffers == device buffers
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_scst_step_host_equals_device(sd, rsd, dtype):
+    """cxrm_scst_step_host (pinned host tensors: only the valid images cross PCIe, chunk by chunk on the copy stream)
+    must give exactly what cxrm_scst_step_device gives for device-resident inputs - same kernels, same order - with
+    padding images at the start, in the middle and at the end of studies, and more valid images than one encoder chunk."""
+    from cxrmate_b200 import synthetic as S
+    e = _engine(sd, rsd, dtype, image_size=64, max_studies=4, max_images=3, max_prompt=8, max_new_tokens=6,
+                rwd_max_len=32, rwd_max_seqs=12, enc_chunk=4)
+    try:
+        e.set_id_map(S.id_map(), S.RWD_CLS, S.RWD_SEP, S.BOS, S.SEP)
+        g = torch.Generator().manual_seed(17)
+        px = torch.randn(4, 3, 3, 64, 64, generator=g)
+        px[0, 0] = 0.0          # leading padding slot
+        px[1, 1] = 0.0          # hole in the middle
+        px[2, 1:] = 0.0         # trailing padding
+        prompt = torch.tensor([[S.PMT, 300, 301, S.PMT_SEP, 400, S.BOS], [S.PMT, S.NPF, S.PMT_SEP, S.NPI, S.BOS, S.PAD],
+                               [S.PMT, 700, S.PMT_SEP, 800, 801, S.BOS], [S.PMT, 900, 901, S.PMT_SEP, 902, S.BOS]],
+                              dtype=torch.int32)
+        lab, lab_len = S.make_label_ids(4, 8, 16, seed=2)
+        lab, lab_len = lab.to(torch.int32), lab_len.to(torch.int32)
+        kw = dict(max_new_tokens=6, eos_token_id=S.EOS, pad_token_id=S.PAD, mask_token_id=S.PAD,
+                  special_sample=S.SPECIAL_SAMPLE, sections_sample=S.SECTIONS[:3], special_greedy=S.SPECIAL_GREEDY,
+                  sections_greedy=S.SECTIONS, top_k=50, temperature=1.0, seed=5)
+        d = e.scst_step(px.cuda(), prompt.cuda(), lab.cuda(), lab_len.cuda(), **kw)
+        torch.cuda.synchronize()
+        d = {k: v.cpu().clone() for k, v in d.items()}
+        d2 = e.scst_step(px.cuda(), prompt.cuda(), lab.cuda(), lab_len.cuda(), **kw)
+        torch.cuda.synchronize()
+        print("device vs device (run-to-run): logprob max diff", (d2["logprobs"].cpu() - d["logprobs"]).abs().max().item())
+        # token ids / step count exact; floating-point outputs to the run-to-run reproducibility of the engine
+        # (the decode attention merges cross-CTA partials in arrival order)
+        tol = 1e-4 if dtype == "fp32" else 5e-2
+        for rep in range(2):    # twice: the staging buffers and chunk events are reused
+            h = e.scst_step(px.pin_memory(), prompt.pin_memory(), lab.pin_memory(), lab_len.pin_memory(), **kw)
+            for k in ("sequences", "steps"):
+                assert torch.equal(h[k], d[k]), (rep, k, h[k], d[k])
+            for k in ("logprobs", "reward", "baseline", "advantage"):
+                err = (h[k] - d[k]).abs().max().item()
+                print("host vs device", rep, k, "max abs diff", err)
+                assert err <= tol, (rep, k, err)
+        assert torch.isfinite(d["reward"]).all() and (d["reward"].abs() <= 1 + 1e-5).all()
+        assert torch.allclose(d["advantage"], d["reward"] - d["baseline"])
+    finally:
+        e.close()
