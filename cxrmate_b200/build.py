@@ -24,6 +24,8 @@ FLAGS = [
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
     "-Xptxas", "-v" if os.environ.get("CXRM_PTXAS_V") else "-O3",
 ]
+# experiment knobs: extra -D definitions, e.g. CXRM_DEFINES="CXRM_CHB=128 CXRM_PSTAGES=3"
+FLAGS += ["-D" + d for d in os.environ.get("CXRM_DEFINES", "").split()]
 
 
 def _sources():

@@ -386,8 +386,17 @@ __global__ void __launch_bounds__(NT) decode_self_units_kernel(const T* __restri
 // needs ~450.  K/V chunks arrive by 2-D TMA (cp.async.bulk.tensor) with the 128-byte swizzle so that the
 // ldmatrix reads of 8 keys x 16 B are bank-conflict free.
 // =====================================================================================================
-constexpr int CHB = 192;            // keys per unit (bf16)
+#ifndef CXRM_CHB
+#define CXRM_CHB 192
+#endif
+#ifndef CXRM_PSTAGES
+#define CXRM_PSTAGES 2
+#endif
+constexpr int CHB = CXRM_CHB;       // keys per unit (bf16): 192 or 128 (4 warps x a multiple of 16 keys)
 constexpr int WKEYS = CHB / 4;      // keys per warp
+constexpr int WNT = WKEYS / 8;      // 8-key score tiles per warp
+constexpr int WKK = WKEYS / 16;     // 16-key steps of p.V per warp
+static_assert(CHB % 64 == 0 && CHB <= 256, "CHB: whole 64-row TMA boxes of the self cache, one TMA box of the cross cache");
 constexpr int SELF_BOX = 64;        // rows per TMA box of the self cache (a unit loads only the boxes it needs)
 
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
@@ -430,7 +439,7 @@ __device__ __forceinline__ uint32_t swz(int r, int c) { return static_cast<uint3
 // Consumers keep flash-style running (max, sum, out) state in registers across consecutive chunks of the same
 // (group, head) and only flush when the group changes, so most groups are finished by a single CTA without
 // touching the global partial buffer; groups that straddle CTAs use the ticket merge.
-constexpr int PSTAGES = 2;                      // per CTA; two CTAs per SM -> 4 x 48 KiB requested ahead per SM
+constexpr int PSTAGES = CXRM_PSTAGES;           // per CTA; two CTAs per SM -> 4 x 48 KiB requested ahead per SM (CHB 192, 2 stages)
 constexpr int TILE_BYTES = CHB * 128;           // one K or V chunk
 constexpr int ST_Q = 2 * TILE_BYTES;            // stage layout: K | V | q rows (2 x 128 B) | key mask (<= 192 B)
 constexpr int ST_MASK = ST_Q + 256;
@@ -469,10 +478,10 @@ __device__ __forceinline__ void warp_tile_update(uint32_t Ks, uint32_t Vs, int n
   const int k0 = w * WKEYS;
   if (k0 >= n) return;   // warp-uniform
   // ---- scores: 6 n-tiles of 8 keys ----
-  float sc[6][4];
+  float sc[WNT][4];
   const int mi = lane >> 3, mr = lane & 7;   // ldmatrix: this lane addresses row mr of matrix mi
 #pragma unroll
-  for (int nt = 0; nt < 6; ++nt) {
+  for (int nt = 0; nt < WNT; ++nt) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) sc[nt][j] = 0.f;
     const int key = k0 + nt * 8 + mr;
@@ -487,7 +496,7 @@ __device__ __forceinline__ void warp_tile_update(uint32_t Ks, uint32_t Vs, int n
   // ---- online softmax (row g: sc[nt][0..1] = keys k0 + nt*8 + 2t, +1) ----
   float mt = -INFINITY;
 #pragma unroll
-  for (int nt = 0; nt < 6; ++nt)
+  for (int nt = 0; nt < WNT; ++nt)
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       const int key = k0 + nt * 8 + 2 * t + j;
@@ -500,9 +509,9 @@ __device__ __forceinline__ void warp_tile_update(uint32_t Ks, uint32_t Vs, int n
   const float m_new = fmaxf(acc.m, mt);
   const float scale = (acc.m == -INFINITY) ? 0.f : expf(acc.m - m_new);   // m_new == -inf only if acc.m == -inf too
   float ls = 0.f;
-  uint32_t pa[6];
+  uint32_t pa[WNT];
 #pragma unroll
-  for (int nt = 0; nt < 6; ++nt) {
+  for (int nt = 0; nt < WNT; ++nt) {
     const float p0 = (sc[nt][0] == -INFINITY) ? 0.f : expf(sc[nt][0] - m_new);
     const float p1 = (sc[nt][1] == -INFINITY) ? 0.f : expf(sc[nt][1] - m_new);
     ls += p0 + p1;
@@ -521,7 +530,7 @@ __device__ __forceinline__ void warp_tile_update(uint32_t Ks, uint32_t Vs, int n
     o[nt][2] = o[nt][3] = 0.f;
   }
 #pragma unroll
-  for (int kk = 0; kk < 3; ++kk) {
+  for (int kk = 0; kk < WKK; ++kk) {
     if (k0 + kk * 16 >= n) break;   // warp-uniform
     const int key = k0 + kk * 16 + (mi & 1) * 8 + mr;
 #pragma unroll
@@ -939,7 +948,7 @@ int num_sms() {
 
 }  // namespace
 
-int decode_attn_chunk(size_t elem_size) { return elem_size == 2 ? 192 : 96; }
+int decode_attn_chunk(size_t elem_size) { return elem_size == 2 ? CHB : 96; }
 
 size_t decode_attn_ws_floats(int rows, int max_chunks) {
   return static_cast<size_t>(rows) * NH * max_chunks * (HD + 2);

@@ -1449,7 +1449,7 @@ void Engine<bf16>::setup_attn_maps() {
   const long long cross_rows = static_cast<long long>(cfg.dec_layers) * 2 * NHEAD * cross_tok_cap();
   const long long self_rows = static_cast<long long>(Rmax) * NHEAD * Lmax;
   CXRM_CHECK(cross_rows < (1LL << 31) && self_rows * cfg.dec_layers < (1LL << 31), "cache too large for 32-bit TMA row coordinates");
-  attn_maps.cross = make_tensor_map_bf16(cross_kv, cross_rows, 64, 64, 192, 64);
+  attn_maps.cross = make_tensor_map_bf16(cross_kv, cross_rows, 64, 64, attn_ch, 64);   // one TMA box per K / V chunk
   attn_maps.self_k = make_tensor_map_bf16(self_k, self_rows * cfg.dec_layers, 64, 64, 64, 64);
   attn_maps.self_v = make_tensor_map_bf16(self_v, self_rows * cfg.dec_layers, 64, 64, 64, 64);
   attn_maps.self_rows_per_layer = static_cast<int>(self_rows);

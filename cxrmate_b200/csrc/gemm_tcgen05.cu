@@ -421,6 +421,7 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_skinny_kernel(const __grid_c
   const int nkb = min(kb_per_split, num_kb - kb0);   // >= 1 by construction of the grid
 
   if (threadIdx.x == 0) {
+#pragma unroll 1   // (code size: every launch of this latency-bound kernel fetches its instructions cold)
     for (int s = 0; s < stages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
@@ -445,14 +446,17 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_skinny_kernel(const __grid_c
   if (warp == 0) {
     if (lane == 0) {
       // weight tiles do not depend on the previous kernel: request the first ring-full BEFORE the dependency wait
+#pragma unroll 1
       for (int i = 0; i < npre; ++i) {
         mbar_expect_tx(&full[i], STAGE_BYTES);
         tma_load_2d(tiles + i * STAGE_BYTES + SK_A_BYTES, &tmB, (kb0 + i) * BK, n0, &full[i]);
       }
       pdl_wait();
       const bool skip = g.skip_flag && *g.skip_flag;
+#pragma unroll 1
       for (int i = 0; i < npre; ++i) tma_load_2d(tiles + i * STAGE_BYTES, &tmA, (kb0 + i) * BK, 0, &full[i]);
       if (!skip) {
+#pragma unroll 1
         for (int i = npre; i < nkb; ++i) {
           const int s = i % stages;
           const uint32_t ph = (i / stages) & 1;
@@ -470,6 +474,7 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_skinny_kernel(const __grid_c
       const bool skip = g.skip_flag && *g.skip_flag;
       const int n_do = skip ? npre : nkb;
       constexpr uint32_t idesc = make_idesc(BN);
+#pragma unroll 1
       for (int i = 0; i < n_do; ++i) {
         const int s = i % stages;
         const uint32_t ph = (i / stages) & 1;

@@ -10,5 +10,5 @@ run() {  # label, dir, env...
 for i in $(seq 1 ${1:-2}); do
   run ref _ab A=1
   run new . A=1 $AB_ENV
-  run new-alt . CXRM_NO_LEAN_EPILOGUE=1
+  if [ -n "$AB_ALT" ]; then run new-alt . $AB_ALT; fi
 done | tee gpurun_out/ab.txt
