@@ -193,7 +193,12 @@ struct Cfg {
   static constexpr int smem(int stages) { return stages * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ + BN * 4 /*bias*/; }
 };
 
-template <int BN>
+// EPI: 0 = general epilogue (every GemmArgs flag), 1 = TMA-store epilogue only (bf16 row-major output, bias, optional
+// residual), 2 = the same with GELU.  The specialisations exist for code size: the general epilogue of the 256-wide
+// tile is 210 KB of straight-line SASS (8 unrolled 32-column chunks x every store variant), far beyond the
+// instruction cache, and its speed then depends on code placement (the same GEMM measured 145 us and 305 us in two
+// builds that differed elsewhere).
+template <int BN, int EPI = 0>
 __global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                            const __grid_constant__ CUtensorMap tmB,
                                                            const __grid_constant__ CUtensorMap tmC, GemmArgs g,
@@ -286,7 +291,8 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const __grid_constant
     constexpr int RPRE = BN < 128 ? BN : 128;   // residual columns held in registers (the rest are loaded in the loop)
     uint4 rres[RPRE / 8];
     const bf16* __restrict__ R = static_cast<const bf16*>(g.residual);
-    const bool res_pre = R != nullptr && vec_ok && row_ok && g.c_head_stride == 0 && (n0 + BN <= g.N);
+    // (EPI 2, the GELU epilogue, keeps its chunk loop rolled for code size: no register-resident residual there)
+    const bool res_pre = EPI != 2 && R != nullptr && vec_ok && row_ok && g.c_head_stride == 0 && (n0 + BN <= g.N);
     if (res_pre) {
 #pragma unroll
       for (int q = 0; q < RPRE / 8; ++q) rres[q] = __ldg(reinterpret_cast<const uint4*>(R + m * g.ldr + n0 + 8 * q));
@@ -296,20 +302,19 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const __grid_constant
     mbar_wait(tmem_full, 0);
     tc_fence_after();
     if (et == 0) TRACE(5);
+#pragma unroll(EPI == 2 ? 1 : BN / 32)
     for (int c0 = 0; c0 < BN; c0 += 32) {
       if (n0 + c0 >= g.N) break;   // warp-uniform
       uint32_t r[32];
       tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(c0), r);
-      if (!row_ok && !tma_store) continue;   // (TMA store: every thread fills its panel row; out-of-range rows are clipped)
+      if (EPI == 0 && !row_ok && !tma_store) continue;   // (TMA store: every thread fills its panel row; out-of-range rows are clipped)
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + sbias[c0 + j];
-      GemmArgs gl = g;
-      gl.bias = nullptr;
-      if (g.act == ACT_GELU) {
+      const void* res_left = g.residual;     // residual still to be added by the store path (nullptr: done / none)
+      if (EPI == 2 || (EPI == 0 && g.act == ACT_GELU)) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
-        gl.act = ACT_NONE;
       }
       if (res_pre && c0 < RPRE) {
 #pragma unroll
@@ -321,14 +326,14 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const __grid_constant
 #pragma unroll
           for (int j = 0; j < 8; ++j) v[8 * q + j] += rf[j];
         }
-        gl.residual = nullptr;
+        res_left = nullptr;
       }
-      if (tma_store) {
+      if (EPI != 0 || tma_store) {
         // Row-per-thread 16-byte global stores hit 32 different rows per warp instruction (the globaltimer trace showed
         // the epilogue at 3-11 us per tile, several times the mainloop).  Instead the thread's 64 bytes go into a
         // 64B-swizzled [128 rows x 32 cols] panel in shared memory (the pipeline stages are idle by now) ...
-        if (gl.residual && row_ok) {
-          const bf16* rp = static_cast<const bf16*>(gl.residual) + m * g.ldr + n0 + c0;
+        if (res_left && row_ok) {
+          const bf16* rp = static_cast<const bf16*>(res_left) + m * g.ldr + n0 + c0;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             Vec16<bf16> rv;
@@ -347,10 +352,14 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const __grid_constant
           ov.pack(v + 8 * q);
           *reinterpret_cast<uint4*>(panel + row * 64 + ((q ^ ((row >> 1) & 3)) << 4)) = ov.raw;
         }
-      } else {
+      } else if constexpr (EPI == 0) {
+        GemmArgs gl = g;
+        gl.bias = nullptr;
+        gl.act = ACT_NONE;
+        gl.residual = res_left;
         epilogue_chunk(gl, v, m, n0 + c0, vec_ok);
       }
-      if (tma_store) {
+      if (EPI != 0 || tma_store) {
         // ... and one thread hands the panel to the TMA unit: a coalesced, asynchronous, bounds-clipped store.
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -363,7 +372,7 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const __grid_constant
         }
       }
     }
-    if (tma_store && et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem read out before exit
+    if ((EPI != 0 || tma_store) && et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem read out before exit
     if (et == 0) TRACE(6);
   }
 
@@ -1168,8 +1177,9 @@ template <int BN>
 void launch(const GemmArgs& g, int stages, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    CXRM_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg<BN>::smem(MAX_STAGES)));
+    CXRM_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::smem(MAX_STAGES)));
+    CXRM_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::smem(MAX_STAGES)));
+    CXRM_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::smem(MAX_STAGES)));
     configured = true;
   }
   const CUtensorMap ta = make_map(g.A, g.M, g.K, g.lda, BM);
@@ -1184,7 +1194,13 @@ void launch(const GemmArgs& g, int stages, cudaStream_t stream) {
                          stages * Cfg<BN>::STAGE_BYTES >= BM * BN * 2 && (!g.residual || g.N % 32 == 0)) ? 1 : 0;
   const CUtensorMap tc = tma_store ? make_map_out(g.C, g.M, g.N, g.ldc) : ta;
   dim3 grid(ceil_div(g.M, BM), ceil_div(g.N, BN));
-  gemm_tc_kernel<BN><<<grid, NTHREADS, Cfg<BN>::smem(stages), stream>>>(ta, tb, tc, g, vec_ok, stages, tma_store);
+  const size_t smem = Cfg<BN>::smem(stages);
+  if (tma_store && g.act == ACT_GELU)
+    gemm_tc_kernel<BN, 2><<<grid, NTHREADS, smem, stream>>>(ta, tb, tc, g, vec_ok, stages, tma_store);
+  else if (tma_store)
+    gemm_tc_kernel<BN, 1><<<grid, NTHREADS, smem, stream>>>(ta, tb, tc, g, vec_ok, stages, tma_store);
+  else
+    gemm_tc_kernel<BN, 0><<<grid, NTHREADS, smem, stream>>>(ta, tb, tc, g, vec_ok, stages, tma_store);
   check_launch("gemm_tcgen05");
 }
 
