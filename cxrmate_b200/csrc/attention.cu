@@ -230,6 +230,12 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+// 2^x in one MUFU instruction (relative error 2^-22; the probabilities are rounded to bf16 right after); 2^-inf = +0
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 // byte offset of (row r, 16-byte chunk c) in a 64-row x 128-byte tile
 __device__ __forceinline__ uint32_t swz(int r, int c) { return static_cast<uint32_t>(r * 128 + ((c ^ (r & 7)) << 4)); }
 
@@ -314,29 +320,34 @@ __global__ void __launch_bounds__(TNT) attention_mma_kernel(AttnArgs a) {
       mma_bf16(s[nt], qf[3][0], qf[3][1], qf[3][2], qf[3][3], bb[2], bb[3]);
     }
     // ---- mask + online softmax (rows g and g+8; s[nt][0..1] row g, s[nt][2..3] row g+8; cols nt*8 + 2t, +1) ----
+    // Scores stay RAW; the scale and the running maximum enter through one FFMA per element:
+    // p = 2^(s * sl2 - m), m = running maximum in the log2 domain.  (The softmax is 3/4 of this kernel's
+    // instructions - ncu: tensor pipe 33 %, issue slots 61 % - so every per-element instruction counts.)
     const bool need_mask = km != nullptr || (k0 + TBK > Lk) || (a.causal && (k0 + TBK - 1 > q0 + warp * 16 + a.q_pos_offset));
     float mx[2] = {-INFINITY, -INFINITY};
+    if (need_mask) {
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
+      for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float v = s[nt][j] * sl2;
-        if (need_mask) {
+        for (int j = 0; j < 4; ++j) {
           const int kj = k0 + nt * 8 + 2 * t + (j & 1);
           const int qi = qi0 + (j >> 1) * 8;
           const bool vis = kj < Lk && (!km || km[kj] != 0) && (!a.causal || kj <= qi + a.q_pos_offset);
-          v = vis ? v : -INFINITY;
+          s[nt][j] = vis ? s[nt][j] : -INFINITY;
         }
-        s[nt][j] = v;
-        mx[j >> 1] = fmaxf(mx[j >> 1], v);
-      }
-    float alpha[2];
+    }
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) mx[j >> 1] = fmaxf(mx[j >> 1], s[nt][j]);
+    float alpha[2], msub[2];
 #pragma unroll
     for (int rr = 0; rr < 2; ++rr) {
       mx[rr] = fmaxf(mx[rr], __shfl_xor_sync(kFull, mx[rr], 1));
       mx[rr] = fmaxf(mx[rr], __shfl_xor_sync(kFull, mx[rr], 2));
-      const float m_new = fmaxf(m_[rr], mx[rr]);
-      alpha[rr] = (m_[rr] == -INFINITY) ? 0.f : exp2f(m_[rr] - m_new);
+      const float m_new = fmaxf(m_[rr], mx[rr] * sl2);             // sl2 > 0: the maximum commutes with the scale
+      msub[rr] = (m_new == -INFINITY) ? 0.f : m_new;               // every key masked so far: 2^(-inf - 0) = 0
+      alpha[rr] = (m_[rr] == -INFINITY) ? 0.f : ex2_approx(m_[rr] - msub[rr]);
       m_[rr] = m_new;
     }
     float ps[2] = {0.f, 0.f};
@@ -346,7 +357,7 @@ __global__ void __launch_bounds__(TNT) attention_mma_kernel(AttnArgs a) {
       float pv[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        pv[j] = (s[nt][j] == -INFINITY) ? 0.f : exp2f(s[nt][j] - m_[j >> 1]);
+        pv[j] = ex2_approx(fmaf(s[nt][j], sl2, -msub[j >> 1]));     // masked: fma(-inf) = -inf -> 0
         ps[j >> 1] += pv[j];
       }
       pa[nt][0] = pack_bf16(pv[0], pv[1]);

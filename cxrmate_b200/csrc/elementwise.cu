@@ -207,14 +207,33 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const T* __restrict__ x, i
   }
 }
 
+// VW consecutive elements of T as one 8- or 16-byte access
+template <typename T, int VW> struct VecW;
+template <typename T> struct VecW<T, Vec16<T>::N> : Vec16<T> {};
+template <> struct VecW<bf16, 4> {
+  uint2 raw;
+  __device__ __forceinline__ void load(const bf16* p) { raw = *reinterpret_cast<const uint2*>(p); }
+  __device__ __forceinline__ void store(bf16* p) const { *reinterpret_cast<uint2*>(p) = raw; }
+  __device__ __forceinline__ void unpack(float* f) const {
+    f[0] = __uint_as_float(raw.x << 16); f[1] = __uint_as_float(raw.x & 0xffff0000u);
+    f[2] = __uint_as_float(raw.y << 16); f[3] = __uint_as_float(raw.y & 0xffff0000u);
+  }
+  __device__ __forceinline__ void pack(const float* f) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(f[0], f[1]), b = __floats2bfloat162_rn(f[2], f[3]);
+    raw = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+  }
+};
+
 // ---- CvT attention front end in one pass: LayerNorm (from per-token stats) -> depth-wise 3x3 (pad 1) + folded
 // BatchNorm for q (stride 1) and k, v (stride 2), HF modeling_cvt.py:124-141,215-228,371-377.
 // A thread owns one 16-byte channel vector of one image column and walks TY output rows with a rolling 3x3 window
 // of NORMALISED values in registers: every input token is fetched 3 times per channel vector (its own column and
 // both neighbours - L1 hits inside the block) instead of 9 + 9/4 times, the LayerNorm output is never written, and
 // the stride-2 k/v outputs (window centre (2a, 2b) == the q window at even coordinates) come from the same registers.
-template <typename T, int TY>
-__global__ void __launch_bounds__(256) ln_dwconv_qkv_kernel(const T* __restrict__ x, T* __restrict__ q,
+// (bf16 runs with 4 channels per thread: the rolling window is 9 x V registers, and at V = 8 the kernel needed 189
+// registers = one 256-thread CTA per SM, 141 us for a 38 MB map in ncu; 4 channels halve that.)
+template <typename T, int TY, int V>
+__global__ void __launch_bounds__(256, 3) ln_dwconv_qkv_kernel(const T* __restrict__ x, T* __restrict__ q,
                                                             T* __restrict__ k, T* __restrict__ v,
                                                             const float2* __restrict__ stats,
                                                             const float* __restrict__ gamma,
@@ -222,7 +241,6 @@ __global__ void __launch_bounds__(256) ln_dwconv_qkv_kernel(const T* __restrict_
                                                             const float* __restrict__ scale,
                                                             const float* __restrict__ shift, int H, int W, int C, int cls,
                                                             int Hk, int Wk, int cols) {
-  constexpr int V = Vec16<T>::N;
   const int cv = C / V;
   const int tc = threadIdx.x % cv, tcol = threadIdx.x / cv;
   const int ox = blockIdx.x * cols + tcol;
@@ -245,7 +263,7 @@ __global__ void __launch_bounds__(256) ln_dwconv_qkv_kernel(const T* __restrict_
         for (int j = 0; j < V; ++j) dst[dx][j] = 0.f;   // the convolution pads the NORMALISED map with zeros
       } else {
         const long long tok = tok0 + static_cast<long long>(iy) * W + ix;
-        Vec16<T> t;
+        VecW<T, V> t;
         t.load(x + tok * C + c);
         float xf[V];
         t.unpack(xf);
@@ -257,11 +275,12 @@ __global__ void __launch_bounds__(256) ln_dwconv_qkv_kernel(const T* __restrict_
   };
   load_row(oy0 - 1, win[0]);
   load_row(oy0, win[1]);
-#pragma unroll
+  // rolled on purpose: unrolled, the compiler keeps all 27 x V weights live across the rows (189 registers, spills)
+#pragma unroll 1
   for (int t = 0; t < TY; ++t) {
     const int oy = oy0 + t;
     if (oy >= H) break;
-    load_row(oy + 1, win[(t + 2) % 3]);
+    load_row(oy + 1, win[2]);
     const bool kv = ((oy | ox) & 1) == 0;
 #pragma unroll
     for (int o = 0; o < 3; ++o) {
@@ -277,16 +296,18 @@ __global__ void __launch_bounds__(256) ln_dwconv_qkv_kernel(const T* __restrict_
           float wf[V];
 #pragma unroll
           for (int j = 0; j < V; j += 4) {
-            const float4 w4 = __ldg(reinterpret_cast<const float4*>(wt + j));
-            wf[j] = w4.x; wf[j + 1] = w4.y; wf[j + 2] = w4.z; wf[j + 3] = w4.w;
+            // volatile asm: re-read (L1 hit) every row instead of 27 x V loop-invariant registers
+            asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(wf[j]), "=f"(wf[j + 1]), "=f"(wf[j + 2]), "=f"(wf[j + 3])
+                         : "l"(wt + j));
           }
 #pragma unroll
-          for (int j = 0; j < V; ++j) acc[j] = fmaf(win[(t + ky) % 3][kx][j], wf[j], acc[j]);
+          for (int j = 0; j < V; ++j) acc[j] = fmaf(win[ky][kx][j], wf[j], acc[j]);
         }
       float of[V];
 #pragma unroll
       for (int j = 0; j < V; ++j) of[j] = fmaf(acc[j], scale[o * C + c + j], shift[o * C + c + j]);
-      Vec16<T> ov;
+      VecW<T, V> ov;
       ov.pack(of);
       if (o == 0) {
         ov.store(q + (tok0 + static_cast<long long>(oy) * W + ox) * C + c);
@@ -295,6 +316,14 @@ __global__ void __launch_bounds__(256) ln_dwconv_qkv_kernel(const T* __restrict_
         ov.store((o == 1 ? k : v) + orow * C + c);
       }
     }
+    // slide the window one row down
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        win[0][dx][j] = win[1][dx][j];
+        win[1][dx][j] = win[2][dx][j];
+      }
   }
 }
 
@@ -605,9 +634,9 @@ void ln_dwconv_qkv(const T* x, T* q, T* k, T* v, float* stats, const float* gamm
                    const float* w, const float* scale, const float* shift, int n_img, int H, int W, int C, int cls,
                    cudaStream_t stream) {
   if (n_img <= 0) return;
-  constexpr int V = Vec16<T>::N, TY = 8;
+  constexpr int V = 4, TY = 8;   // channels per thread (8- / 16-byte accesses for bf16 / fp32)
   const int cv = C / V;
-  CXRM_CHECK(C % V == 0 && cv <= 256 && C % 4 == 0, "ln_dwconv_qkv: unsupported channel count");
+  CXRM_CHECK(C % V == 0 && cv <= 256, "ln_dwconv_qkv: unsupported channel count");
   const int Hk = (H + 2 - 3) / 2 + 1, Wk = (W + 2 - 3) / 2 + 1;   // stride-2 window centres are the even coordinates
   float2* st = reinterpret_cast<float2*>(stats);
   const long long rows = static_cast<long long>(n_img) * (cls + H * W);
@@ -616,7 +645,7 @@ void ln_dwconv_qkv(const T* x, T* q, T* k, T* v, float* stats, const float* gamm
   const int cols = std::min(W, 256 / cv);
   dim3 grid(ceil_div(W, cols), ceil_div(H, TY), n_img);
   CXRM_CHECK(grid.z <= 65535, "ln_dwconv_qkv: too many images per chunk");
-  ln_dwconv_qkv_kernel<T, TY><<<grid, cols * cv, 0, stream>>>(x, q, k, v, st, gamma, beta, w, scale, shift, H, W, C, cls,
+  ln_dwconv_qkv_kernel<T, TY, V><<<grid, cols * cv, 0, stream>>>(x, q, k, v, st, gamma, beta, w, scale, shift, H, W, C, cls,
                                                               Hk, Wk, cols);
   check_launch("ln_dwconv_qkv");
   if (cls) {
