@@ -296,7 +296,8 @@ __global__ void __launch_bounds__(256, 3) ln_dwconv_qkv_kernel(const T* __restri
           float wf[V];
 #pragma unroll
           for (int j = 0; j < V; j += 4) {
-            // volatile asm: re-read (L1 hit) every row instead of 27 x V loop-invariant registers
+            // volatile asm: re-read (L1 hit) every row instead of 27 x V loop-invariant registers (keeping the 9 q taps
+            // in registers at 2 CTAs/SM measured slower: 67.6 vs 60.5 us per launch)
             asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];"
                          : "=f"(wf[j]), "=f"(wf[j + 1]), "=f"(wf[j + 2]), "=f"(wf[j + 3])
                          : "l"(wt + j));
@@ -546,9 +547,14 @@ bool ln_rows_launch(const T* x, int ldx, T* y, int ldy, float2* stats, const flo
   if (!STATS && (ldy % V != 0 || reinterpret_cast<uintptr_t>(y) % 16 != 0)) return false;
   const int cv = C / V;
   if (cv > 32 * kLnMaxVec) return false;
-  const int lpr = cv <= 8 * kLnMaxVec ? 8 : cv <= 16 * kLnMaxVec ? 16 : 32;
+  // fewest lanes per row that still hold the row in kLnMaxVec vectors per lane: up to 6 independent 16-byte loads in
+  // flight per thread (one load per thread left the kernel latency-bound: 1.5 TB/s in ncu)
+  int lpr = 2;
+  while (lpr * kLnMaxVec < cv) lpr *= 2;
   const unsigned grid = static_cast<unsigned>(ceil_div_ll(rows * lpr, 256));
   switch (lpr) {
+    case 2: ln_rows_kernel<T, 2, STATS><<<grid, 256, 0, stream>>>(x, ldx, y, ldy, stats, gamma, beta, rows, C, eps); break;
+    case 4: ln_rows_kernel<T, 4, STATS><<<grid, 256, 0, stream>>>(x, ldx, y, ldy, stats, gamma, beta, rows, C, eps); break;
     case 8: ln_rows_kernel<T, 8, STATS><<<grid, 256, 0, stream>>>(x, ldx, y, ldy, stats, gamma, beta, rows, C, eps); break;
     case 16: ln_rows_kernel<T, 16, STATS><<<grid, 256, 0, stream>>>(x, ldx, y, ldy, stats, gamma, beta, rows, C, eps); break;
     default: ln_rows_kernel<T, 32, STATS><<<grid, 256, 0, stream>>>(x, ldx, y, ldy, stats, gamma, beta, rows, C, eps); break;
