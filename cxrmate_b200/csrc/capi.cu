@@ -238,4 +238,37 @@ int cxrm_test_attention(int dtype, const void* q, const void* k, const void* v, 
   }
 }
 
+int cxrm_test_layernorm(int dtype, const void* x, void* y, const float* gamma, const float* beta, long long rows, int C,
+                        float eps, void* stream) {
+  try {
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dtype == CXRM_F32)
+      layernorm<float>(static_cast<const float*>(x), C, static_cast<float*>(y), C, gamma, beta, rows, C, eps, s);
+    else
+      layernorm<bf16>(static_cast<const bf16*>(x), C, static_cast<bf16*>(y), C, gamma, beta, rows, C, eps, s);
+    return CXRM_OK;
+  } catch (const std::exception& ex) {
+    g_create_error = ex.what();
+    return CXRM_ERR_CUDA;
+  }
+}
+
+int cxrm_test_ln_dwconv(int dtype, const void* x, void* q, void* k, void* v, float* stats, const float* gamma,
+                        const float* beta, float eps, const float* w, const float* scale, const float* shift, int n_img,
+                        int H, int W, int C, int cls, void* stream) {
+  try {
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dtype == CXRM_F32)
+      ln_dwconv_qkv<float>(static_cast<const float*>(x), static_cast<float*>(q), static_cast<float*>(k),
+                           static_cast<float*>(v), stats, gamma, beta, eps, w, scale, shift, n_img, H, W, C, cls, s);
+    else
+      ln_dwconv_qkv<bf16>(static_cast<const bf16*>(x), static_cast<bf16*>(q), static_cast<bf16*>(k), static_cast<bf16*>(v),
+                          stats, gamma, beta, eps, w, scale, shift, n_img, H, W, C, cls, s);
+    return CXRM_OK;
+  } catch (const std::exception& ex) {
+    g_create_error = ex.what();
+    return CXRM_ERR_CUDA;
+  }
+}
+
 }  // extern "C"

@@ -495,25 +495,36 @@ __device__ __forceinline__ void warp_tile_update(uint32_t Ks, uint32_t Vs, int n
   }
   // ---- online softmax (row g: sc[nt][0..1] = keys k0 + nt*8 + 2t, +1) ----
   float mt = -INFINITY;
+  if (n < k0 + WKEYS || valid) {   // warp-uniform: a short chunk or a key-padding mask
 #pragma unroll
-  for (int nt = 0; nt < WNT; ++nt)
+    for (int nt = 0; nt < WNT; ++nt)
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const int key = k0 + nt * 8 + 2 * t + j;
-      const bool vis = key < n && (!valid || valid[key]);
-      sc[nt][j] = vis ? sc[nt][j] * 0.125f : -INFINITY;
-      mt = fmaxf(mt, sc[nt][j]);
-    }
+      for (int j = 0; j < 2; ++j) {
+        const int key = k0 + nt * 8 + 2 * t + j;
+        const bool vis = key < n && (!valid || valid[key]);
+        sc[nt][j] = vis ? sc[nt][j] * 0.125f : -INFINITY;
+        mt = fmaxf(mt, sc[nt][j]);
+      }
+  } else {
+#pragma unroll
+    for (int nt = 0; nt < WNT; ++nt)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        sc[nt][j] *= 0.125f;
+        mt = fmaxf(mt, sc[nt][j]);
+      }
+  }
   mt = fmaxf(mt, __shfl_xor_sync(kFull, mt, 1));
   mt = fmaxf(mt, __shfl_xor_sync(kFull, mt, 2));
   const float m_new = fmaxf(acc.m, mt);
-  const float scale = (acc.m == -INFINITY) ? 0.f : expf(acc.m - m_new);   // m_new == -inf only if acc.m == -inf too
+  // __expf = one FMUL + MUFU.EX2 (the probabilities are rounded to bf16 right below); __expf(-inf) = 0
+  const float scale = (acc.m == -INFINITY) ? 0.f : __expf(acc.m - m_new);   // m_new == -inf only if acc.m == -inf too
   float ls = 0.f;
   uint32_t pa[WNT];
 #pragma unroll
   for (int nt = 0; nt < WNT; ++nt) {
-    const float p0 = (sc[nt][0] == -INFINITY) ? 0.f : expf(sc[nt][0] - m_new);
-    const float p1 = (sc[nt][1] == -INFINITY) ? 0.f : expf(sc[nt][1] - m_new);
+    const float p0 = (sc[nt][0] == -INFINITY) ? 0.f : __expf(sc[nt][0] - m_new);
+    const float p1 = (sc[nt][1] == -INFINITY) ? 0.f : __expf(sc[nt][1] - m_new);
     ls += p0 + p1;
     pa[nt] = (g < NQ) ? pack_bf16(p0, p1) : 0u;
   }

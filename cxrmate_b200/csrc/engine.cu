@@ -5,6 +5,7 @@
 #include "engine.cuh"
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <type_traits>
@@ -1279,6 +1280,16 @@ class Engine : public EngineBase {
     CXRM_CHECK(finalized && have_reward && id_map, "scst_step_host needs all weights and cxrm_set_id_map");
     CXRM_CHECK(B <= cfg.max_studies && N <= cfg.max_images && P <= cfg.max_prompt, "scst_step_host shape");
     CXRM_CHECK(3 * B <= cfg.rwd_max_seqs && L_label <= cfg.rwd_max_len, "reward batch exceeds rwd_max_seqs");
+    // timing aid: CXRM_PHASE_TIMES=1 prints the device time of each phase of the step (events on the step's stream)
+    static const bool phase_times = std::getenv("CXRM_PHASE_TIMES") != nullptr;
+    cudaEvent_t pe[6] = {};
+    int n_pe = 0;
+    auto mark = [&]() {
+      if (!phase_times) return;
+      CXRM_CUDA_CHECK(cudaEventCreate(&pe[n_pe]));
+      CXRM_CUDA_CHECK(cudaEventRecord(pe[n_pe++], s));
+    };
+    mark();
     const int Tn = tmpl.max_new_tokens, R = 2 * B, Lseq = P + Tn;
     // longest possible reward input: [CLS] + generated words + [SEP], or the longest label
     const int Lr = std::min(cfg.rwd_max_len, std::max(Tn + 2, L_label));
@@ -1338,13 +1349,16 @@ class Engine : public EngineBase {
       CXRM_CHECK(B >= 1 && N >= 1, "scst_step_host shape");
       encode_valid(h_pixels, B, N, src, dst, ev_chunk.data(), s);
     }
+    mark();
     prefill_cross_kv(nullptr, nullptr, 0, 0, s);
+    mark();
     cxrm_rollout_args a = tmpl;
     a.mode = CXRM_BOTH; a.B = B; a.P = P; a.prompt_ids = prompt_dev;
     a.sequences = h_seq; a.logprobs = h_lp;
     a.margins = nullptr; a.topk_idx = nullptr; a.topk_val = nullptr; a.topk_cnt = nullptr; a.last_logits = nullptr;
     a.steps_out = nullptr;
     rollout(a, s);
+    mark();
     // text bridge: sample rows [0,B), greedy rows [B,2B) -> reward ids rows [0,2B); labels -> rows [2B,3B)
     bridge_ids_kernel<<<ceil_div(R, 64), 64, 0, s>>>(h_seq, Lseq, Lseq, R, bridge_bos, bridge_sep_dec, a.eos_token_id,
                                                       12, id_map, bridge_cls, bridge_sep, h_rids, h_rlens, Lr);
@@ -1365,7 +1379,19 @@ class Engine : public EngineBase {
     CXRM_CUDA_CHECK(cudaMemcpyAsync(baseline, h_out + B, B * sizeof(float), cudaMemcpyDefault, s));
     CXRM_CUDA_CHECK(cudaMemcpyAsync(advantage, h_out + 2 * B, B * sizeof(float), cudaMemcpyDefault, s));
     if (steps_out) CXRM_CUDA_CHECK(cudaMemcpyAsync(steps_out, st.step, sizeof(int), cudaMemcpyDefault, s));
+    mark();
     CXRM_CUDA_CHECK(cudaStreamSynchronize(s));
+    if (phase_times) {
+      const char* names[4] = {"encode", "cross_kv", "rollout", "reward+copy"};
+      std::string line = "[cxrm phases ms]";
+      for (int i = 0; i + 1 < n_pe; ++i) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, pe[i], pe[i + 1]);
+        line += std::string(" ") + names[i] + " " + std::to_string(ms);
+      }
+      fprintf(stderr, "%s\n", line.c_str());
+      for (int i = 0; i < n_pe; ++i) cudaEventDestroy(pe[i]);
+    }
   }
 
  private:

@@ -320,3 +320,32 @@ def attention_hook(q, k, v, key_mask=None, causal: bool = False, scale: float = 
     if rc != 0:
         raise RuntimeError(f"cxrm_test_attention failed ({rc}): {lib.cxrm_last_error(None).decode()}")
     return o
+
+
+def layernorm_hook(x, gamma, beta, eps: float):
+    """x [rows, C] fp32 | bf16 -> LayerNorm(x) like x (the vectorised kernel when rows are 16-byte aligned)."""
+    lib = _lib.load()
+    dt = _lib.CXRM_F32 if x.dtype == torch.float32 else _lib.CXRM_BF16
+    y = torch.empty_like(x)
+    rc = lib.cxrm_test_layernorm(dt, _ptr(x), _ptr(y), _ptr(gamma), _ptr(beta), x.shape[0], x.shape[1], float(eps), _stream())
+    if rc != 0:
+        raise RuntimeError(f"cxrm_test_layernorm failed ({rc}): {lib.cxrm_last_error(None).decode()}")
+    return y
+
+
+def ln_dwconv_hook(x, H: int, W: int, cls: int, gamma, beta, eps: float, w, scale, shift):
+    """x [n, cls + H*W, C]; w [3, 9, C] fp32 (q, k, v; tap-major); scale / shift [3, C] (folded BatchNorm).
+    Returns q [n, cls + H*W, C], k, v [n, cls + Hk*Wk, C]."""
+    lib = _lib.load()
+    n, _, Cc = x.shape
+    Hk, Wk = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
+    dt = _lib.CXRM_F32 if x.dtype == torch.float32 else _lib.CXRM_BF16
+    q = torch.empty_like(x)
+    k = torch.empty(n, cls + Hk * Wk, Cc, dtype=x.dtype, device=x.device)
+    v = torch.empty_like(k)
+    stats = torch.empty(n * (cls + H * W) * 2, dtype=torch.float32, device=x.device)
+    rc = lib.cxrm_test_ln_dwconv(dt, _ptr(x), _ptr(q), _ptr(k), _ptr(v), _ptr(stats), _ptr(gamma), _ptr(beta), float(eps),
+                                 _ptr(w), _ptr(scale), _ptr(shift), n, H, W, Cc, cls, _stream())
+    if rc != 0:
+        raise RuntimeError(f"cxrm_test_ln_dwconv failed ({rc}): {lib.cxrm_last_error(None).decode()}")
+    return q, k, v

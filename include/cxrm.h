@@ -250,6 +250,16 @@ CXRM_API void cxrm_test_set_gemm_trace(unsigned long long* dev_buf);
 CXRM_API int cxrm_test_attention(int dtype, const void* q, const void* k, const void* v, void* o, int batch, int heads,
                         int Lq, int Lk, const uint8_t* key_mask, int causal, float scale, void* stream);
 
+/* LayerNorm of rows [rows, C] (eps as given), dtype = cxrm_dtype of x / y. */
+CXRM_API int cxrm_test_layernorm(int dtype, const void* x, void* y, const float* gamma, const float* beta, long long rows,
+                        int C, float eps, void* stream);
+/* CvT attention front end (HF modeling_cvt.py:124-141,215-228,371-377): x [n_img, cls + H*W, C] ->
+ * q [n_img, cls + H*W, C], k, v [n_img, cls + Hk*Wk, C] = BatchNorm_eval(dwconv3x3(LayerNorm(x))) with stride 1 / 2
+ * (BatchNorm folded to scale/shift [3][C]; w [3][9][C] tap-major; stats: scratch of 2 floats per token). */
+CXRM_API int cxrm_test_ln_dwconv(int dtype, const void* x, void* q, void* k, void* v, float* stats, const float* gamma,
+                        const float* beta, float eps, const float* w, const float* scale, const float* shift,
+                        int n_img, int H, int W, int C, int cls, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

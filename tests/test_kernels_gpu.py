@@ -159,3 +159,53 @@ def test_attention(dtype, b, h, Lq, Lk, masked, causal):
     err = (o.float() - ref).abs().max().item()
     tol = 2e-5 if dtype == torch.float32 else 2e-2
     assert err < tol, f"attention {dtype} b={b} h={h} {Lq}x{Lk} masked={masked} causal={causal}: max err {err}"
+
+
+# ------------------------------------------------------------------------------ LayerNorm / CvT attention front end
+@pytest.mark.parametrize("rows,C", [(1000, 64), (577, 192), (333, 384), (64, 768), (50, 128), (7, 100)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_layernorm(rows, C, dtype):
+    """vectorised LayerNorm (2..32 lanes per row) and the scalar fallback (C = 100) vs torch, eps of CvT and of BERT"""
+    from cxrmate_b200.engine import layernorm_hook
+    g = torch.Generator(device="cuda").manual_seed(rows + C)
+    x = (torch.randn(rows, C, device="cuda", generator=g) * 3 + 1.5).to(dtype)
+    gamma = torch.randn(C, device="cuda", generator=g)
+    beta = torch.randn(C, device="cuda", generator=g)
+    for eps in (1e-5, 1e-12):
+        y = layernorm_hook(x, gamma, beta, eps)
+        torch.cuda.synchronize()
+        ref = torch.nn.functional.layer_norm(x.float(), (C,), gamma, beta, eps)
+        err = (y.float() - ref).abs().max().item()
+        tol = 2e-5 if dtype == torch.float32 else ref.abs().max().item() * 2 ** -8 + 1e-3
+        assert err < tol, f"layernorm {rows}x{C} {dtype} eps {eps}: max err {err}"
+
+
+@pytest.mark.parametrize("n,H,W,C,cls", [(2, 16, 16, 64, 0), (3, 8, 8, 192, 0), (2, 4, 4, 384, 1), (1, 24, 24, 384, 1),
+                                         (2, 3, 5, 64, 0), (1, 7, 7, 192, 1)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_ln_dwconv_qkv(n, H, W, C, cls, dtype):
+    """fused LayerNorm -> depth-wise 3x3 (+ folded BatchNorm) q/k/v projections vs torch (HF modeling_cvt.py:124-141,
+    215-228): even, odd and non-square maps, with and without the cls token (which bypasses the convolution)."""
+    from cxrmate_b200.engine import ln_dwconv_hook
+    g = torch.Generator(device="cuda").manual_seed(n * 1000 + H * 10 + C)
+    x = torch.randn(n, cls + H * W, C, device="cuda", generator=g).to(dtype)
+    gamma = 1 + 0.1 * torch.randn(C, device="cuda", generator=g)
+    beta = 0.1 * torch.randn(C, device="cuda", generator=g)
+    wconv = 0.3 * torch.randn(3, C, 1, 3, 3, device="cuda", generator=g)            # q, k, v depth-wise kernels
+    scale = 1 + 0.1 * torch.randn(3, C, device="cuda", generator=g)
+    shift = 0.1 * torch.randn(3, C, device="cuda", generator=g)
+    w = wconv.reshape(3, C, 9).permute(0, 2, 1).contiguous()                       # [3][9][C]
+    q, k, v = ln_dwconv_hook(x, H, W, cls, gamma, beta, 1e-5, w, scale, shift)
+    torch.cuda.synchronize()
+    y = torch.nn.functional.layer_norm(x.float(), (C,), gamma, beta, 1e-5)
+    ycls, ymap = y[:, :cls], y[:, cls:].transpose(1, 2).reshape(n, C, H, W)
+    outs = []
+    for i, stride in enumerate((1, 2, 2)):
+        o = torch.nn.functional.conv2d(ymap, wconv[i], stride=stride, padding=1, groups=C)
+        o = o * scale[i][None, :, None, None] + shift[i][None, :, None, None]
+        outs.append(torch.cat((ycls, o.flatten(2).transpose(1, 2)), 1))
+    for name, got, ref in zip("qkv", (q, k, v), outs):
+        assert got.shape == ref.shape, (name, got.shape, ref.shape)
+        err = (got.float() - ref).abs().max().item()
+        tol = 1e-4 if dtype == torch.float32 else ref.abs().max().item() * 2 ** -7 + 5e-3
+        assert err < tol, f"{name} {n}x{H}x{W}x{C} cls={cls} {dtype}: max err {err}"
