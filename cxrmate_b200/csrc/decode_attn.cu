@@ -809,15 +809,20 @@ __global__ void __launch_bounds__(PNT, 2) decode_self_persist_kernel(const __gri
   __shared__ int sh_last;
 
   pdl_launch_dependents();
-  pdl_wait();
-  if (*st.done) return;
   const int tid = threadIdx.x, warp = tid / kWarp, lane = tid % kWarp;
+  // The rollout state (step, done, cur_len, finished, key_valid) is written by the sampling kernel of the PREVIOUS
+  // step, and a step opens with a plain (fully serialised) launch: it is readable ahead of the dependency wait, and
+  // so are all cache rows except the slot of the token being fed.  Only q/k/v of the QKV projection wait.
+  const bool done = *st.done != 0;
   // live rows sit at slot P + step (rollout_init / sample_step keep cur_len uniform); chunks of the longest row
   const int mc = ceil_div(P + *st.step + 1, CHB);
   const int n_items = NH * R * mc;
   const int per = ceil_div(n_items, static_cast<int>(gridDim.x));   // <= MAXI by the launcher's grid size
   const int lo = blockIdx.x * per, hi = min(n_items, lo + per);
-  if (lo >= hi) return;
+  if (done || lo >= hi) {
+    pdl_wait();
+    return;
+  }
 
   if (tid == 0) {
     for (int s = 0; s < PSTAGES; ++s) {
@@ -841,8 +846,50 @@ __global__ void __launch_bounds__(PNT, 2) decode_self_persist_kernel(const __gri
 
   if (warp == 4) {
     // ===== producer (whole warp: the append of the new token's K/V is a 32-lane copy) =====
-    int k = 0;
-    for (int it = lo; it < hi; ++it) {
+    // K/V and mask of one item -> stage s (the barrier also expects the 128 q bytes, sent after the dependency wait)
+    auto request_kv = [&](int it, int s) {
+      const int n = m_n[it - lo];
+      const int c = it % mc, r = (it / mc) % R, h = it / (mc * R);
+      unsigned char* dst = tiles + s * STAGE_BYTES;
+      const int nbox = ceil_div(n, SELF_BOX);
+      const int row0 = layer_row0 + (r * NH + h) * Lmax + c * CHB;
+      const int mbytes = min(CHB, Lmax - c * CHB);   // Lmax % 16 == 0
+      mbar_expect_tx(&full[s], 2 * nbox * SELF_BOX * 128 + 128 + mbytes);
+      for (int x = 0; x < nbox; ++x) {
+        tma_load_2d(dst + x * SELF_BOX * 128, &tm_k, 0, row0 + x * SELF_BOX, &full[s]);
+        tma_load_2d(dst + TILE_BYTES + x * SELF_BOX * 128, &tm_v, 0, row0 + x * SELF_BOX, &full[s]);
+      }
+      bulk_g2s(dst + ST_MASK, st.key_valid + static_cast<long long>(r) * Lmax + c * CHB, mbytes, &full[s]);
+    };
+    // ahead of the dependency wait: the leading live items that do not end with the token being fed stream in while
+    // the QKV projection is still running
+    int it0 = lo, npre = 0, pre_it[PSTAGES];
+#pragma unroll
+    for (int x = 0; x < PSTAGES; ++x) pre_it[x] = 0;
+    if (lane == 0) {
+      for (; it0 < hi && npre < PSTAGES; ++it0) {
+        if (m_n[it0 - lo] == 0) continue;
+        if (it0 % mc == m_nch[it0 - lo] - 1) break;
+        request_kv(it0, npre);
+#pragma unroll
+        for (int x = 0; x < PSTAGES; ++x)
+          if (x == npre) pre_it[x] = it0;
+        ++npre;
+      }
+    }
+    it0 = __shfl_sync(kFull, it0, 0);
+    npre = __shfl_sync(kFull, npre, 0);
+    pdl_wait();
+    if (lane == 0) {
+#pragma unroll
+      for (int x = 0; x < PSTAGES; ++x)
+        if (x < npre) {
+          const int r = (pre_it[x] / mc) % R, h = pre_it[x] / (mc * R);
+          bulk_g2s(tiles + x * STAGE_BYTES + ST_Q, qkv + static_cast<long long>(r) * 3 * H + h * HD, 128, &full[x]);
+        }
+    }
+    int k = npre;
+    for (int it = it0; it < hi; ++it) {
       const int n = m_n[it - lo];
       if (n == 0) continue;
       const int c = it % mc, r = (it / mc) % R, h = it / (mc * R);
@@ -863,22 +910,14 @@ __global__ void __launch_bounds__(PNT, 2) decode_self_persist_kernel(const __gri
       if (lane == 0) {
         const int s = k % PSTAGES;
         mbar_wait(&empty[s], ((k / PSTAGES) & 1) ^ 1);
-        unsigned char* dst = tiles + s * STAGE_BYTES;
-        const int nbox = ceil_div(n, SELF_BOX);
-        const int row0 = layer_row0 + (r * NH + h) * Lmax + c * CHB;
-        const int mbytes = min(CHB, Lmax - c * CHB);   // Lmax % 16 == 0
-        mbar_expect_tx(&full[s], 2 * nbox * SELF_BOX * 128 + 128 + mbytes);
-        for (int x = 0; x < nbox; ++x) {
-          tma_load_2d(dst + x * SELF_BOX * 128, &tm_k, 0, row0 + x * SELF_BOX, &full[s]);
-          tma_load_2d(dst + TILE_BYTES + x * SELF_BOX * 128, &tm_v, 0, row0 + x * SELF_BOX, &full[s]);
-        }
-        bulk_g2s(dst + ST_Q, qrow, 128, &full[s]);
-        bulk_g2s(dst + ST_MASK, st.key_valid + static_cast<long long>(r) * Lmax + c * CHB, mbytes, &full[s]);
+        request_kv(it, s);
+        bulk_g2s(tiles + s * STAGE_BYTES + ST_Q, qrow, 128, &full[s]);
       }
       ++k;
     }
     return;
   }
+  pdl_wait();   // consumers: every thread of a chain kernel passes the dependency wait
 
   // ===== consumers =====
   WarpAcc acc;
