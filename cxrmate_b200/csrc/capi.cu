@@ -106,6 +106,11 @@ int cxrm_reward_embed(cxrm_engine* e, const int32_t* ids, const int32_t* lens, i
                       void* stream) {
   CXRM_GUARD(e, e->impl->reward_embed(ids, lens, n, L, emb_out, static_cast<cudaStream_t>(stream)));
 }
+int cxrm_reinforce_loss(cxrm_engine* e, const float* logprobs, int ld, const float* advantage, int B, int T, float* loss_out,
+                        void* stream) {
+  CXRM_GUARD(e, reinforce_loss(logprobs, ld, advantage, B, T, loss_out, static_cast<cudaStream_t>(stream)));
+}
+
 int cxrm_cosine(cxrm_engine* e, const float* a, const float* b, int n, int dim, float* out, void* stream) {
   CXRM_GUARD(e, cosine_rows(a, b, out, n, dim, static_cast<cudaStream_t>(stream)));
 }

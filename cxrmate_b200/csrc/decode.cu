@@ -550,6 +550,36 @@ void cosine_rows(const float* a, const float* b, float* out, int n, int C, cudaS
   check_launch("cosine_rows");
 }
 
+// REINFORCE loss of one rollout batch (reference scst/gen_prompt.py:350-364):
+//   loss = mean_b( -sum_t logprob[b, t] * advantage[b] ),
+// logprob = log-softmax of the top-k-masked scores at the sampled id, 0 at PAD positions (sample_step stores it so),
+// which is nll_loss(log_softmax(scores), ids, ignore_index=pad, 'none').sum(-1) * reward, .mean().
+// One block; fixed summation order (thread b sums its row, then a shared-memory tree): reproducible.
+__global__ void __launch_bounds__(256) reinforce_loss_kernel(const float* __restrict__ logprob, int ld,
+                                                             const float* __restrict__ advantage, int B, int T,
+                                                             float* __restrict__ loss) {
+  __shared__ float sh[256];
+  float acc = 0.f;
+  for (int b = threadIdx.x; b < B; b += 256) {
+    float srow = 0.f;
+    for (int t = 0; t < T; ++t) srow += logprob[static_cast<long long>(b) * ld + t];
+    acc += -srow * advantage[b];
+  }
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *loss = sh[0] / B;
+}
+
+void reinforce_loss(const float* logprob, int ld, const float* advantage, int B, int T, float* loss, cudaStream_t stream) {
+  CXRM_CHECK(B >= 1 && T >= 1 && ld >= T, "reinforce_loss shape");
+  reinforce_loss_kernel<<<1, 256, 0, stream>>>(logprob, ld, advantage, B, T, loss);
+  check_launch("reinforce_loss");
+}
+
 #define INST(T) template void take_last_token<T>(const T*, T*, int, int, int, cudaStream_t);
 INST(float)
 INST(bf16)

@@ -292,6 +292,9 @@ void l2_prefetch(const L2Prefetch& p, cudaStream_t stream);
 template <typename T>
 void take_last_token(const T* x, T* out, int R, int P, int C, cudaStream_t stream);
 
+// loss[0] = mean_b( -sum_t logprob[b * ld + t] * advantage[b] )  (reinforce_loss, scst/gen_prompt.py:350-364)
+void reinforce_loss(const float* logprob, int ld, const float* advantage, int B, int T, float* loss, cudaStream_t stream);
+
 // cosine similarity of rows: out[i] = <a_i, b_i> / (max(|a_i|, eps) * max(|b_i|, eps))  (torch eps 1e-8)
 void cosine_rows(const float* a, const float* b, float* out, int n, int C, cudaStream_t stream);
 

@@ -209,6 +209,17 @@ class Engine:
                     "cxrm_cosine")
         return out
 
+    def reinforce_loss(self, logprobs: torch.Tensor, advantage: torch.Tensor) -> torch.Tensor:
+        """reference `reinforce_loss` (scst/gen_prompt.py:331-366) from the sample rollout's log-probs [B, T] (0 at PAD)
+        and the advantage [B]: mean_b(-sum_t logprob * advantage) -> 0-dim fp32 tensor on the device."""
+        assert logprobs.dim() == 2 and advantage.shape == (logprobs.shape[0],)
+        lp, adv = logprobs.float(), advantage.contiguous().float()
+        assert lp.stride(1) == 1
+        out = torch.empty(1, dtype=torch.float32, device=lp.device)
+        self._check(self.lib.cxrm_reinforce_loss(self.h, _ptr(lp), lp.stride(0), _ptr(adv), lp.shape[0], lp.shape[1], _ptr(out),
+                                                 _stream()), "cxrm_reinforce_loss")
+        return out[0]
+
     def reward(self, pred_ids, pred_lens, label_ids, label_lens) -> torch.Tensor:
         n = pred_ids.shape[0]
         p32, pl = pred_ids.to(torch.int32).contiguous(), pred_lens.to(torch.int32).contiguous()

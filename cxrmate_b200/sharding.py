@@ -73,3 +73,63 @@ def max_over_ranks(ms: float, device) -> float:
     t = torch.tensor([ms], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Generated-prompt SCST: subjects, not studies, are the unit of sharding.
+# Study k's greedy report is study k+1's prompt, so all studies of a subject must visit ONE (rank, batch slot) in
+# chronological order.  Restates PreviousReportSubset.allocate_subjects_to_rank (reference data/prompt.py:142-213),
+# pinned against the real method by tests/golden/subject_schedule.json.
+# ---------------------------------------------------------------------------------------------------------------
+def subject_study_lists(subject_ids, study_ids) -> List[List[int]]:
+    """`df.drop_duplicates(subset=['study_id']).groupby('subject_id')['study_id'].apply(list).tolist()`
+    (data/prompt.py:160-162) without pandas: subjects in ascending id order, each subject's studies in first-occurrence
+    order of the table, every study once."""
+    seen, per_subject = set(), {}
+    for subj, study in zip(subject_ids, study_ids):
+        if study in seen:
+            continue
+        seen.add(study)
+        per_subject.setdefault(subj, []).append(study)
+    return [per_subject[s] for s in sorted(per_subject)]
+
+
+def allocate_subjects(subject_lists: List[List[int]], world: int, mbatch: int, seed=None,
+                      shuffle_subjects: bool = True) -> List[int]:
+    """Order in which the dataset serves study ids so that, with DistributedSampler(shuffle=False) and
+    batch_size=mbatch, every subject stays on one (rank, batch slot) lane with its studies in consecutive batches.
+
+    Same algorithm as the reference: subjects sorted by number of studies (stable, largest first) are packed
+    greedily onto the currently shortest of world*mbatch lanes (numpy argmin: first minimum), lanes are optionally
+    shuffled per lane with `random.seed(seed); random.sample(...)`, flattened, and interleaved element-wise.
+    The reference interleaves with zip(), which silently requires equally long lanes; here an unequal packing raises
+    (the reference's final assert fails in that case)."""
+    import itertools
+    import random
+
+    if world < 1 or mbatch < 1:
+        raise ValueError("world and mbatch must be positive")
+    lanes_n = world * mbatch
+    lists = sorted(subject_lists, key=len, reverse=True)          # list.sort is stable, like the reference's
+    lanes: List[List[List[int]]] = [[] for _ in range(lanes_n)]
+    total = [0] * lanes_n
+    for studies in lists:
+        i = total.index(min(total))                                # np.argmin: first occurrence of the minimum
+        lanes[i].append(studies)
+        total[i] += len(studies)
+    if len(set(total)) != 1:
+        raise ValueError(f"lanes are not equally long after packing ({min(total)}..{max(total)} studies): the reference "
+                         "pads by oversampling single-study subjects before interleaving")
+    if shuffle_subjects:
+        random.seed(seed)
+        flat = [list(itertools.chain(*random.sample(lane, k=len(lane)))) for lane in lanes]
+    else:
+        flat = [list(itertools.chain(*lane)) for lane in lanes]
+    return [study for row in zip(*flat) for study in row]
+
+
+def lane_of_position(pos: int, world: int, mbatch: int) -> Tuple[int, int, int]:
+    """(rank, batch index on that rank, slot inside the batch) of position `pos` of the served order under
+    DistributedSampler(shuffle=False) + DataLoader(batch_size=mbatch)."""
+    rank, k = pos % world, pos // world
+    return rank, k // mbatch, k % mbatch

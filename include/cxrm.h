@@ -192,6 +192,12 @@ CXRM_API int cxrm_decoder_forward(cxrm_engine* e, const int32_t* ids, const int3
 CXRM_API int cxrm_reward_embed(cxrm_engine* e, const int32_t* ids, const int32_t* lens, int n, int L, float* emb_out,
                       void* stream);
 CXRM_API int cxrm_cosine(cxrm_engine* e, const float* a, const float* b, int n, int dim, float* out, void* stream);
+/* REINFORCE loss of the SCST step (reference scst/gen_prompt.py:331-366 `reinforce_loss`):
+ *   loss_out[0] = mean_b( -sum_t logprobs[b * ld + t] * advantage[b] )
+ * logprobs: dev fp32, the SAMPLE rows of cxrm_rollout's `logprobs` output (log-softmax of the top-k-masked scores at
+ * the sampled id, 0 at PAD positions = nll_loss(..., ignore_index=pad)); advantage dev fp32 [B]; loss_out dev fp32 [1]. */
+CXRM_API int cxrm_reinforce_loss(cxrm_engine* e, const float* logprobs, int ld, const float* advantage, int B, int T,
+                        float* loss_out, void* stream);
 CXRM_API int cxrm_reward(cxrm_engine* e, const int32_t* pred_ids, const int32_t* pred_lens, int L_pred,
                 const int32_t* label_ids, const int32_t* label_lens, int L_label, int n, float* reward_out,
                 void* stream);

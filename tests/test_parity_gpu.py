@@ -334,6 +334,13 @@ def test_small_images_ragged_fp32(sd):
         fin = torch.isfinite(o_s.scores[-1])
         cnt = out.topk_cnt[:3, T - 1].cpu()
         assert torch.equal(cnt, fin.sum(-1).int())
+        # REINFORCE loss (reference reinforce_loss: nll of the sampled ids under the stacked masked scores x advantage)
+        from oracle import scst
+        adv = torch.tensor([0.3, -0.2, 0.1])
+        loss_ref = scst.reinforce_loss(torch.stack(o_s.scores, dim=-1), o_s.sequences[:, prompt.shape[1]:], adv)
+        loss = e.reinforce_loss(out.logprobs[:3], adv.cuda())
+        print("reinforce loss", loss.item(), "oracle", loss_ref.item())
+        assert abs(loss.item() - loss_ref.item()) < 2e-3 * max(1.0, abs(loss_ref.item()))
     finally:
         e.close()
 

@@ -77,3 +77,52 @@ def test_gather_rewards_world2_gloo(n):
     for rank, r, b, ms in outs:
         assert r == want_r and b == want_b          # every rank sees the whole batch in dataset order
         assert ms == 11.0                           # max over ranks
+
+
+# ------------------------------------------------------------------------------ generated-prompt subject schedule
+def _schedule_cases():
+    import json
+    import os
+    path = os.path.join(os.path.dirname(__file__), "golden", "subject_schedule.json")
+    return json.load(open(path))
+
+
+def test_allocate_subjects_matches_reference_golden():
+    """tests/golden/subject_schedule.json was written by the real PreviousReportSubset.allocate_subjects_to_rank
+    (tests/golden/gen_subject_schedule.py): same served order for every world size / mini-batch / shuffle setting"""
+    from cxrmate_b200 import sharding as S
+    cases = _schedule_cases()
+    assert len(cases) >= 20
+    for c in cases:
+        lists = S.subject_study_lists(c["subject_ids"], c["study_ids"])
+        got = S.allocate_subjects(lists, c["world"], c["mbatch"], seed=c["seed"], shuffle_subjects=c["shuffle"])
+        assert got == c["examples"], (c["world"], c["mbatch"], c["seed"], c["shuffle"])
+
+
+def test_subject_stays_on_one_lane_in_order():
+    """the property the schedule exists for: all studies of a subject are served to one (rank, slot), in consecutive
+    batches and in the subject's own order, so that study k's greedy report can prompt study k+1"""
+    from cxrmate_b200 import sharding as S
+    for c in _schedule_cases():
+        world, mb = c["world"], c["mbatch"]
+        lists = S.subject_study_lists(c["subject_ids"], c["study_ids"])
+        order = S.allocate_subjects(lists, world, mb, seed=c["seed"], shuffle_subjects=c["shuffle"])
+        where = {study: S.lane_of_position(p, world, mb) for p, study in enumerate(order)}
+        assert sorted(order) == sorted(s for l in lists for s in l)          # every study exactly once
+        for studies in lists:
+            lanes = [where[s] for s in studies]
+            assert len({(r, slot) for r, _, slot in lanes}) == 1
+            batches_ = [b for _, b, _ in lanes]
+            assert batches_ == list(range(batches_[0], batches_[0] + len(studies)))
+        # and the rank-local view agrees with shard_studies
+        for r in range(world):
+            mine = [order[i] for i in S.shard_studies(len(order), r, world)]
+            assert all(where[s][0] == r for s in mine)
+
+
+def test_allocate_subjects_rejects_unbalanced_packing():
+    from cxrmate_b200 import sharding as S
+    with pytest.raises(ValueError):
+        S.allocate_subjects([[1, 2, 3], [4]], world=2, mbatch=1, shuffle_subjects=False)
+    with pytest.raises(ValueError):
+        S.allocate_subjects([[1]], world=0, mbatch=1)
