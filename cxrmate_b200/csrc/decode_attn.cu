@@ -817,7 +817,9 @@ __global__ void __launch_bounds__(PNT, 2) decode_self_persist_kernel(const __gri
   // live rows sit at slot P + step (rollout_init / sample_step keep cur_len uniform); chunks of the longest row
   const int mc = ceil_div(P + *st.step + 1, CHB);
   const int n_items = NH * R * mc;
-  const int per = ceil_div(n_items, static_cast<int>(gridDim.x));   // <= MAXI by the launcher's grid size
+  // whole (row, head) groups per CTA (a multiple of mc items): no group straddles two CTAs, so the cross-CTA ticket
+  // merge (global partials, fences, atomics) never runs in this kernel; a few CTAs at the end of the grid stay idle
+  const int per = ceil_div(ceil_div(n_items, static_cast<int>(gridDim.x)), mc) * mc;   // <= MAXI by the launcher's grid size
   const int lo = blockIdx.x * per, hi = min(n_items, lo + per);
   if (done || lo >= hi) {
     pdl_wait();
@@ -1018,7 +1020,9 @@ void decode_self_attention(const T* qkv, T* kcache, T* vcache, T* ctx, const Rol
       configured = true;
     }
     const int layer_row0 = layer * maps->self_rows_per_layer;
-    const int grid = std::max(2 * num_sms(), ceil_div(NH * R * max_chunks, MAXI));
+    // the kernel rounds its per-CTA item count up to whole (row, head) groups: leave max_chunks of head room in MAXI
+    CXRM_CHECK(max_chunks < MAXI / 2, "self-attention cache too long for the per-CTA work list");
+    const int grid = std::max(2 * num_sms(), ceil_div(NH * R * max_chunks, MAXI - max_chunks));
     launch_chain(decode_self_persist_kernel, dim3(grid), dim3(PNT), kPersistSmem, stream, maps->self_k, maps->self_v,
                  layer_row0, qkv, kcache, vcache, ctx, st, R, P, Lmax, max_chunks, ws, tickets, dbg_nocompute());
   } else {

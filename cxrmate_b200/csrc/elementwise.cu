@@ -344,78 +344,6 @@ __global__ void ln_cls_kernel(const T* __restrict__ x, const float2* __restrict_
   v[static_cast<long long>(n) * (1 + HWk) * C + c] = val;
 }
 
-// ---- depth-wise 3x3 + BN(eval) ------------------------------------------------
-// HF modeling_cvt.py:124-141 (Conv2d groups=C, bias=False -> BatchNorm2d).
-// BatchNorm in eval mode is the affine map y*scale + shift with
-// scale = gamma / sqrt(var + eps), shift = beta - mean * scale.
-template <typename T, int NOUT>
-__global__ void dwconv_bn_kernel(const T* __restrict__ y, T* __restrict__ o0, T* __restrict__ o1,
-                                 const float* __restrict__ w, const float* __restrict__ scale,
-                                 const float* __restrict__ shift, int n_img, int H, int W, int C, int cls, int stride,
-                                 int Ho, int Wo, int which0) {
-  constexpr int V = Vec16<T>::N;
-  const int cv = C / V;
-  const long long total = static_cast<long long>(n_img) * Ho * Wo * cv;
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int c = static_cast<int>(i % cv) * V;
-  long long r = i / cv;
-  const int ox = static_cast<int>(r % Wo);
-  const int oy = static_cast<int>((r / Wo) % Ho);
-  const int n = static_cast<int>(r / (static_cast<long long>(Wo) * Ho));
-  const T* img = y + (static_cast<long long>(n) * (cls + H * W) + cls) * C;
-  float acc[NOUT][V];
-#pragma unroll
-  for (int t = 0; t < NOUT; ++t)
-#pragma unroll
-    for (int j = 0; j < V; ++j) acc[t][j] = 0.f;
-#pragma unroll
-  for (int ky = 0; ky < 3; ++ky) {
-    const int iy = oy * stride - 1 + ky;
-    if (iy < 0 || iy >= H) continue;
-#pragma unroll
-    for (int kx = 0; kx < 3; ++kx) {
-      const int ix = ox * stride - 1 + kx;
-      if (ix < 0 || ix >= W) continue;
-      Vec16<T> xv;
-      xv.load(img + (static_cast<long long>(iy) * W + ix) * C + c);
-      float xf[V];
-      xv.unpack(xf);
-#pragma unroll
-      for (int t = 0; t < NOUT; ++t) {
-        const float* wt = w + (static_cast<long long>(which0 + t) * 9 + ky * 3 + kx) * C + c;
-#pragma unroll
-        for (int j = 0; j < V; ++j) acc[t][j] = fmaf(xf[j], wt[j], acc[t][j]);
-      }
-    }
-  }
-  const long long orow = static_cast<long long>(n) * (cls + Ho * Wo) + cls + static_cast<long long>(oy) * Wo + ox;
-#pragma unroll
-  for (int t = 0; t < NOUT; ++t) {
-    const float* sc = scale + static_cast<long long>(which0 + t) * C + c;
-    const float* sh = shift + static_cast<long long>(which0 + t) * C + c;
-    float of[V];
-#pragma unroll
-    for (int j = 0; j < V; ++j) of[j] = fmaf(acc[t][j], sc[j], sh[j]);
-    Vec16<T> ov;
-    ov.pack(of);
-    ov.store((t == 0 ? o0 : o1) + orow * C + c);
-  }
-}
-
-// copy the cls row of y into row 0 of q, k, v
-template <typename T>
-__global__ void copy_cls_kernel(const T* __restrict__ y, T* __restrict__ q, T* __restrict__ k, T* __restrict__ v,
-                                int n_img, int HWq, int HWk, int C) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_img * C) return;
-  const int n = i / C, c = i % C;
-  const T val = y[static_cast<long long>(n) * (1 + HWq) * C + c];
-  q[static_cast<long long>(n) * (1 + HWq) * C + c] = val;
-  k[static_cast<long long>(n) * (1 + HWk) * C + c] = val;
-  v[static_cast<long long>(n) * (1 + HWk) * C + c] = val;
-}
-
 template <typename T>
 __global__ void cat_cls_kernel(const T* __restrict__ tokens, const float* __restrict__ cls_token, T* __restrict__ out,
                                int n_img, int HW, int C) {
@@ -610,32 +538,6 @@ void im2col_tokens(const T* in, T* out, int n_img, int H, int W, int C, int ksz,
 }
 
 template <typename T>
-void dwconv_bn_qkv(const T* y, T* q, T* k, T* v, const float* w, const float* scale, const float* shift, int n_img,
-                   int H, int W, int C, int cls, cudaStream_t stream) {
-  if (n_img <= 0) return;
-  constexpr int V = Vec16<T>::N;
-  CXRM_CHECK(C % V == 0, "dwconv needs C multiple of the vector width");
-  const int Hk = (H + 2 - 3) / 2 + 1, Wk = (W + 2 - 3) / 2 + 1;
-  {
-    const long long total = static_cast<long long>(n_img) * H * W * (C / V);
-    dwconv_bn_kernel<T, 1><<<static_cast<unsigned>(ceil_div_ll(total, 256)), 256, 0, stream>>>(
-        y, q, nullptr, w, scale, shift, n_img, H, W, C, cls, 1, H, W, 0);
-    check_launch("dwconv_q");
-  }
-  {
-    const long long total = static_cast<long long>(n_img) * Hk * Wk * (C / V);
-    dwconv_bn_kernel<T, 2><<<static_cast<unsigned>(ceil_div_ll(total, 256)), 256, 0, stream>>>(
-        y, k, v, w, scale, shift, n_img, H, W, C, cls, 2, Hk, Wk, 1);
-    check_launch("dwconv_kv");
-  }
-  if (cls) {
-    copy_cls_kernel<T><<<ceil_div(n_img * C, 256), 256, 0, stream>>>(y, q, k, v, n_img, H * W, Hk * Wk, C);
-    check_launch("copy_cls");
-  }
-}
-
-
-template <typename T>
 void ln_dwconv_qkv(const T* x, T* q, T* k, T* v, float* stats, const float* gamma, const float* beta, float eps,
                    const float* w, const float* scale, const float* shift, int n_img, int H, int W, int C, int cls,
                    cudaStream_t stream) {
@@ -740,8 +642,6 @@ void pack_dw(const float* src, float* dst, int C, cudaStream_t stream) {
                             const float*, T*, long long, int, float, cudaStream_t);                                   \
   template void im2col_pixels<T>(const float*, const int*, T*, int, int, int, int, int, int, int, cudaStream_t);      \
   template void im2col_tokens<T>(const T*, T*, int, int, int, int, int, int, int, cudaStream_t);                      \
-  template void dwconv_bn_qkv<T>(const T*, T*, T*, T*, const float*, const float*, const float*, int, int, int, int,  \
-                                 int, cudaStream_t);                                                                  \
   template void ln_dwconv_qkv<T>(const T*, T*, T*, T*, float*, const float*, const float*, float, const float*,        \
                                  const float*, const float*, int, int, int, int, int, cudaStream_t);                  \
   template void cat_cls<T>(const T*, const float*, T*, int, int, int, cudaStream_t);                                  \

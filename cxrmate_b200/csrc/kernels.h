@@ -117,13 +117,9 @@ void im2col_pixels(const float* pixels, const int* img_idx, T* out, int n_img, i
 template <typename T>
 void im2col_tokens(const T* in, T* out, int n_img, int H, int W, int C, int ksz, int stride, int pad,
                    cudaStream_t stream);
-// depth-wise 3x3 (pad 1) + folded BatchNorm for the CvT q/k/v convolutional projections.
-// y [n_img, cls+H*W, C]; q [n_img, cls+H*W, C] (stride 1); k,v [n_img, cls+Hk*Wk, C] (stride 2).
-// w [3][9][C] fp32 (q,k,v; tap-major), scale/shift [3][C] fp32.  cls rows are copied through.
-template <typename T>
-void dwconv_bn_qkv(const T* y, T* q, T* k, T* v, const float* w, const float* scale, const float* shift, int n_img,
-                   int H, int W, int C, int cls, cudaStream_t stream);
-// The same front end fused with the preceding LayerNorm (gamma/beta/eps): x [n_img, cls+H*W, C] -> q, k, v as above.
+// CvT attention front end: LayerNorm (gamma/beta/eps) -> depth-wise 3x3 (pad 1) + folded BatchNorm for the q/k/v
+// convolutional projections, fused.  x [n_img, cls+H*W, C] -> q [n_img, cls+H*W, C] (stride 1); k,v [n_img, cls+Hk*Wk, C]
+// (stride 2).  w [3][9][C] fp32 (q,k,v; tap-major), scale/shift [3][C] fp32.  cls rows bypass the convolution.
 // stats: scratch of 2 floats per token (mean, rstd).
 template <typename T>
 void ln_dwconv_qkv(const T* x, T* q, T* k, T* v, float* stats, const float* gamma, const float* beta, float eps,
