@@ -624,16 +624,23 @@ __device__ __forceinline__ void flush_group(const WarpAcc& acc, float* wpart, co
     }
   }
   if (n_parts > 1) {
-    __threadfence();
+    // release / acquire through ONE thread: the partial stores of all 128 consumers are ordered before thread 0's
+    // fence by the barrier, the fence makes them visible before the ticket; the last arriver fences again before the
+    // barrier that lets the others read the partials (through L2: __ldcg in merge_partials).  128 threads fencing
+    // (MEMBAR + L1 invalidate each) showed up as the membar stalls of this kernel in ncu.
     cons_sync();
     if (tid == 0) {
+      __threadfence();
       const unsigned prev = atomicAdd(ticket, 1u);
-      *sh_last = (prev == static_cast<unsigned>(n_parts) - 1) ? 1 : 0;
-      if (*sh_last) *ticket = 0;   // ready for the next launch
+      const int last = (prev == static_cast<unsigned>(n_parts) - 1) ? 1 : 0;
+      if (last) {
+        *ticket = 0;   // ready for the next launch
+        __threadfence();
+      }
+      *sh_last = last;
     }
     cons_sync();
     if (*sh_last) {
-      __threadfence();
       if (tid < NQ * HD) {
         const int i = tid / HD, d = tid % HD;
         merge_partials<bf16>(ws + (static_cast<long long>(rows[i]) * NH + h) * maxp * (HD + 2), n_parts,
