@@ -241,18 +241,19 @@ __global__ void __launch_bounds__(SNT) sample_step_kernel(RolloutState st, Rollo
     // ---- pass 1: stage the row as sortable keys; per-thread and block maximum ---------------------
     ValIdx best{-INFINITY, 0x7fffffff};
     if ((V % 4) == 0 && (ldl % 4) == 0 && (reinterpret_cast<uintptr_t>(logits) % 16) == 0) {
-      // 128-bit streaming loads, four in flight per thread (a scalar loop serialises ~60 L2 round trips)
+      // 128-bit streaming loads, eight in flight per thread (a scalar loop serialises ~60 L2 round trips)
       const float4* l4 = reinterpret_cast<const float4*>(lrow);
       const int nv4 = V / 4;
-      for (int base = tid; base < nv4; base += 4 * SNT) {
-        float4 v[4];
+      constexpr int U = 8;   // 16-byte loads in flight per thread: the 120 KB row arrives in two L2 round trips
+      for (int base = tid; base < nv4; base += U * SNT) {
+        float4 v[U];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < U; ++u) {
           const int idx = base + u * SNT;
           v[u] = (idx < nv4) ? __ldcs(l4 + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < U; ++u) {
           const int idx = base + u * SNT;
           if (idx >= nv4) continue;
           float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};

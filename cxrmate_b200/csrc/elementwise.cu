@@ -88,6 +88,63 @@ __global__ void embed_ln_kernel(const int* __restrict__ ids, const int* __restri
   }
 }
 
+// Vectorised version (16-byte gathers, NV vectors per lane, C == 32 * NV * Vec16<T>::N): the decode step opens with
+// this kernel, one warp per rollout row, so its latency is on every token's critical path.
+template <typename T, int NV>
+__global__ void __launch_bounds__(128) embed_ln_vec_kernel(const int* __restrict__ ids, const int* __restrict__ types,
+                                                           const int* __restrict__ pos, const T* __restrict__ word,
+                                                           const T* __restrict__ type_emb, const T* __restrict__ pos_emb,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                           T* __restrict__ out, long long rows, int C, float eps) {
+  constexpr int V = Vec16<T>::N;
+  const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) / kWarp;
+  const int lane = threadIdx.x % kWarp;
+  pdl_launch_dependents();
+  if (row >= rows) return;
+  const T* w = word + static_cast<long long>(ids[row]) * C;
+  const T* t = type_emb + static_cast<long long>(types ? types[row] : 0) * C;
+  const T* p = pos_emb + static_cast<long long>(pos[row]) * C;
+  Vec16<T> wv[NV], tv[NV], pv[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (lane + i * kWarp) * V;
+    wv[i].load(w + c);
+    tv[i].load(t + c);
+    pv[i].load(p + c);
+  }
+  float v[NV][V];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    float a[V], b[V], c3[V];
+    wv[i].unpack(a);
+    tv[i].unpack(b);
+    pv[i].unpack(c3);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      v[i][j] = (a[j] + b[j]) + c3[j];   // (word + type) + position, as BertEmbeddings.forward associates it
+      s += v[i][j];
+    }
+  }
+  const float mean = warp_sum(s) / C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int j = 0; j < V; ++j) q += (v[i][j] - mean) * (v[i][j] - mean);
+  const float rstd = rsqrtf(warp_sum(q) / C + eps);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (lane + i * kWarp) * V;
+    float o[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) o[j] = (v[i][j] - mean) * rstd * gamma[c + j] + beta[c + j];
+    Vec16<T> ov;
+    ov.pack(o);
+    ov.store(out + row * C + c);
+  }
+}
+
 // ---- im2col ------------------------------------------------------------------
 template <typename T>
 __global__ void im2col_pixels_kernel(const float* __restrict__ pixels, const int* __restrict__ img_idx,
@@ -508,6 +565,14 @@ void embed_ln(const int* ids, const int* types, const int* pos, const T* word, c
               const float* gamma, const float* beta, T* out, long long rows, int C, float eps, cudaStream_t stream) {
   if (rows <= 0) return;
   CXRM_CHECK(C <= kMaxPerLane * kWarp, "embed_ln supports C <= 768");
+  constexpr int NV = 768 / (kWarp * Vec16<T>::N);   // the BERT width: 3 (bf16) / 6 (fp32) vectors per lane
+  auto al16 = [](const void* q) { return reinterpret_cast<uintptr_t>(q) % 16 == 0; };
+  if (C == 768 && al16(word) && al16(type_emb) && al16(pos_emb) && al16(out)) {
+    embed_ln_vec_kernel<T, NV><<<static_cast<unsigned>(ceil_div_ll(rows * kWarp, 128)), 128, 0, stream>>>(
+        ids, types, pos, word, type_emb, pos_emb, gamma, beta, out, rows, C, eps);
+    check_launch("embed_ln");
+    return;
+  }
   const int block = 256;
   const long long grid = ceil_div_ll(rows * kWarp, block);
   embed_ln_kernel<T><<<static_cast<unsigned>(grid), block, 0, stream>>>(ids, types, pos, word, type_emb, pos_emb, gamma,
