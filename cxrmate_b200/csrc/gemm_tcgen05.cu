@@ -387,6 +387,202 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const __grid_constant
 
 
 // =====================================================================================================
+// Persistent variant for the big-M GEMMs of the encoder / prefill / reward model (TMA-store epilogues only).
+// One CTA per SM walks the output tiles (M fastest, so the CTAs running together share a weight slice in L2):
+//   warp 0      TMA producer: runs AHEAD through the shared-memory ring across tile boundaries
+//   warp 1      MMA issuer: accumulates tile i into TMEM buffer i % 2
+//   warps 2..5  epilogue of tile i (TMEM -> registers -> bias / GELU / residual -> swizzled panels -> TMA store)
+//               while the MMAs of tile i + 1 fill the other TMEM buffer.
+// The per-tile kernel above gives every CTA one tile: its loads start cold and its epilogue has nothing to hide
+// behind, which is why the K = 192 / 384 contractions of CvT ran at 180-330 TF/s.
+// =====================================================================================================
+constexpr int P_MAX_STAGES = 8;
+__device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int BN>
+struct PCfg {
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGING = (BN / 32) * (BM * 64);                       // one 64B-swizzled panel per 32 columns
+  static constexpr int TMEM_COLS = BN <= 16 ? 32 : BN <= 32 ? 64 : BN <= 64 ? 128 : BN <= 128 ? 256 : 512;   // 2 accumulators
+  static constexpr int ACC_STRIDE = TMEM_COLS / 2;
+  static constexpr int stages() {
+    int s = (220 * 1024 - STAGING - 2048 - BN * 4) / STAGE_BYTES;
+    return s > P_MAX_STAGES ? P_MAX_STAGES : s;
+  }
+  static constexpr int smem() { return stages() * STAGE_BYTES + STAGING + 1024 /*alignment*/ + 512 /*barriers*/ + BN * 4; }
+};
+
+template <int BN, int EPI>   // EPI 1: bias (+ residual) -> bf16;  2: bias -> GELU (+ residual) -> bf16
+__global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                      const __grid_constant__ CUtensorMap tmB,
+                                                                      const __grid_constant__ CUtensorMap tmC, GemmArgs g,
+                                                                      int vec_ok, int tiles_m, int n_tiles) {
+  using C_ = PCfg<BN>;
+  constexpr int STAGES = C_::stages();
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* staging = tiles + STAGES * C_::STAGE_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(staging + C_::STAGING);
+  uint64_t* empty = full + P_MAX_STAGES;
+  uint64_t* tfull = empty + P_MAX_STAGES;      // [2] accumulator complete
+  uint64_t* tempty = tfull + 2;                // [2] accumulator drained by the epilogue
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* sbias = reinterpret_cast<float*>(tmem_slot + 2);   // [BN]
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int num_kb = (g.K + BK - 1) / BK;
+
+  if (threadIdx.x == 0) {
+#pragma unroll 1
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull[b], 1);
+      mbar_init(&tempty[b], 4);   // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(C_::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+      int it = 0;   // k-blocks issued so far, across tiles
+#pragma unroll 1
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
+#pragma unroll 1
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_expect_tx(&full[s], C_::STAGE_BYTES);
+          uint8_t* a_dst = tiles + s * C_::STAGE_BYTES;
+          tma_load_2d(a_dst, &tmA, kb * BK, m0, &full[s]);
+          tma_load_2d(a_dst + A_BYTES, &tmB, kb * BK, n0, &full[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BN);
+      int it = 0, t = 0;
+#pragma unroll 1
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+        const int buf = t & 1;
+        mbar_wait(&tempty[buf], ((t >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator (first use: passes)
+        tc_fence_after();
+        const uint32_t acc = tmem_base + static_cast<uint32_t>(buf * C_::ACC_STRIDE);
+#pragma unroll 1
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(tiles + s * C_::STAGE_BYTES);
+          const uint64_t da = make_desc(a_addr), db = make_desc(a_addr + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma(acc, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&tfull[buf]);
+      }
+    }
+  } else {
+    const int quarter = warp % 4;
+    const int et = threadIdx.x - 64;   // 0..127
+    const bf16* __restrict__ R = static_cast<const bf16*>(g.residual);
+    int t = 0;
+#pragma unroll 1
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+      const int buf = t & 1;
+      const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
+      const long long m = static_cast<long long>(m0) + quarter * 32 + lane;
+      const bool row_ok = m < g.M;
+      // the panels still belong to the TMA stores of the previous tile until they have been read out
+      if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // (also: every thread is done with the previous tile's sbias)
+      for (int j = et; j < BN; j += 128) sbias[j] = (g.bias && n0 + j < g.N) ? g.bias[n0 + j] : 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(&tfull[buf], (t >> 1) & 1);
+      tc_fence_after();
+      const uint32_t acc = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(buf * C_::ACC_STRIDE);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        if (n0 + c0 >= g.N) break;   // warp-uniform
+        uint32_t r[32];
+        tmem_ld32(acc + static_cast<uint32_t>(c0), r);
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + sbias[c0 + j];
+        if (EPI == 2) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+        }
+        if (R && row_ok) {
+          const bf16* rp = R + m * g.ldr + n0 + c0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            Vec16<bf16> rv;
+            rv.load(rp + 8 * q);
+            float rf[8];
+            rv.unpack(rf);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[8 * q + j] += rf[j];
+          }
+        }
+        const int row = quarter * 32 + lane;
+        uint8_t* panel = staging + (c0 / 32) * (BM * 64);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          Vec16<bf16> ov;
+          ov.pack(v + 8 * q);
+          *reinterpret_cast<uint4*>(panel + row * 64 + ((q ^ ((row >> 1) & 3)) << 4)) = ov.raw;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (et == 0) {
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                           reinterpret_cast<uint64_t>(&tmC)),
+                       "r"(smem_u32(panel)), "r"(n0 + c0), "r"(m0)
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+      // every tcgen05.ld of this tile has completed (tmem_ld32 waits): hand the accumulator back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cta(&tempty[buf]);
+    }
+    if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem read out before exit
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C_::TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// =====================================================================================================
 // Skinny GEMM for the decode steps: M <= 64 rows (2B rollout rows), weights streamed from HBM once.
 // Such a GEMM is bound by the latency of its TMA round trips, not by the MMAs: the generic kernel's
 // 4-stage ring needs K/64/4 serial round trips (9.7 us for K = 768, 19.4 us for K = 3072 measured by ncu).
@@ -1173,6 +1369,16 @@ void pick_tile(int M, int N, int K, int* bn_out, int* stages_out) {
   *stages_out = std::max(stages, 1);
 }
 
+int persist_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    CXRM_CUDA_CHECK(cudaGetDevice(&dev));
+    CXRM_CUDA_CHECK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+  }
+  return n;
+}
+
 template <int BN>
 void launch(const GemmArgs& g, int stages, cudaStream_t stream) {
   static bool configured = false;
@@ -1194,6 +1400,28 @@ void launch(const GemmArgs& g, int stages, cudaStream_t stream) {
                          stages * Cfg<BN>::STAGE_BYTES >= BM * BN * 2 && (!g.residual || g.N % 32 == 0)) ? 1 : 0;
   const CUtensorMap tc = tma_store ? make_map_out(g.C, g.M, g.N, g.ldc) : ta;
   dim3 grid(ceil_div(g.M, BM), ceil_div(g.N, BN));
+  // enough tiles for every SM to overlap epilogues with mainloops: the persistent kernel (residual rows must be
+  // 16-byte loadable there: guaranteed by vec_ok, which tma_store implies)
+  static const bool persist_ok = std::getenv("CXRM_NO_PERSIST_GEMM") == nullptr;
+  const int n_tiles = static_cast<int>(grid.x * grid.y);
+  // ... and a mainloop long enough to hide an epilogue behind: with K < 384 and narrow N the tile is all epilogue, and
+  // one persistent CTA per SM has only 4 epilogue warps where 2-3 co-resident one-tile CTAs have 8-12 (measured:
+  // [256x64] 82 -> 121 us, [192x192] 17 -> 19.5 us persistent; [1536x384] 62 -> 57, [3072x768] 194 -> 160 us)
+  if (persist_ok && tma_store && n_tiles >= 2 * persist_sms() && (g.N % 32 == 0) && (g.K >= 384 || g.N >= 512)) {
+    static bool pconf = false;
+    if (!pconf) {
+      CXRM_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_persist_kernel<BN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg<BN>::smem()));
+      CXRM_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_persist_kernel<BN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg<BN>::smem()));
+      pconf = true;
+    }
+    const int ctas = std::min(n_tiles, persist_sms());
+    if (g.act == ACT_GELU)
+      gemm_tc_persist_kernel<BN, 2><<<ctas, NTHREADS, PCfg<BN>::smem(), stream>>>(ta, tb, tc, g, vec_ok, static_cast<int>(grid.x), n_tiles);
+    else
+      gemm_tc_persist_kernel<BN, 1><<<ctas, NTHREADS, PCfg<BN>::smem(), stream>>>(ta, tb, tc, g, vec_ok, static_cast<int>(grid.x), n_tiles);
+    check_launch("gemm_tcgen05_persist");
+    return;
+  }
   const size_t smem = Cfg<BN>::smem(stages);
   if (tma_store && g.act == ACT_GELU)
     gemm_tc_kernel<BN, 2><<<grid, NTHREADS, smem, stream>>>(ta, tb, tc, g, vec_ok, stages, tma_store);

@@ -20,6 +20,8 @@ def _ref_gemm(A, W, bias, act, residual):
 SHAPES = [
     (128, 64, 64), (300, 192, 576), (1000, 384, 1728), (577, 1536, 384), (64, 2304, 768), (64, 768, 3072),
     (33, 30000, 768), (4096, 256, 64), (129, 100, 152), (2, 128, 768), (700, 768, 768),
+    # >= 2 tiles per SM: the persistent kernel (double-buffered TMEM accumulators), tile widths 128 / 64 / 256 / 96
+    (20000, 384, 384), (38000, 64, 64), (19000, 768, 1536), (37900, 96, 192),
 ]
 
 

@@ -455,3 +455,23 @@ def test_scst_step_host_equals_device(sd, rsd, dtype):
         assert torch.allclose(d["advantage"], d["reward"] - d["baseline"])
     finally:
         e.close()
+
+
+# ------------------------------------------------------------------------------ encoder at benchmark-like size (persistent GEMMs)
+def test_encoder_many_images_bf16_vs_oracle(sd):
+    """20 valid 384x384 images in one encoder chunk: every GEMM has >= 2 tiles per SM and runs the persistent tcgen05
+    kernel (as in the benchmark); compared with the CPU oracle.  Tolerance: relative L2 < 3e-2 (bf16, 21 layers)."""
+    from oracle import cvt
+    e = _engine(sd, None, "bf16", max_studies=4, max_images=5, enc_chunk=32)
+    try:
+        g = torch.Generator().manual_seed(77)
+        px = torch.randn(4, 5, 3, 384, 384, generator=g)
+        mem_o, mask_o = cvt.encode_multi(sd, px)
+        mem, mask = e.encode(px.cuda())
+        torch.cuda.synchronize()
+        assert torch.equal(mask.cpu(), mask_o)
+        err = rel_l2(mem.cpu().float(), mem_o)
+        print("20-image encoder rel L2 vs oracle:", err)
+        assert err < 3e-2
+    finally:
+        e.close()
