@@ -214,7 +214,10 @@ CXRM_API int cxrm_reward(cxrm_engine* e, const int32_t* pred_ids, const int32_t*
  *   pixels host fp32 [B,N,3,H,W]; prompt_ids host int32 [B,P]; label_ids host int32 [B,L_label];
  *   label_lens host int32 [B]; id_map dev int32 [vocab] (set once with cxrm_set_id_map)
  *   outputs host: sequences int32 [2B, P+T], logprobs fp32 [2B, T], reward/baseline/advantage fp32 [B]
- * Synchronous.
+ * Padding images (pixels[b, n, 0, 0, 0] == 0, modelling_longitudinal.py:83) are detected on the host and never
+ * copied: only the valid images cross PCIe, compacted, one encoder chunk at a time on the engine's copy stream, so
+ * chunk c + 1 is in flight while chunk c is encoded.  Pinned host memory makes those copies asynchronous; pageable
+ * memory works but serialises them.  Synchronous: returns when the outputs are in the host buffers.
  */
 CXRM_API int cxrm_set_id_map(cxrm_engine* e, const int32_t* id_map_host, int n, int cls_id, int sep_id, int bos_id,
                     int sep_dec_id);
