@@ -1,5 +1,6 @@
 // extern "C" boundary (include/cxrm.h): exception -> status translation only.
 #include <cstring>
+#include <memory>
 #include <string>
 
 #include "engine.cuh"
@@ -17,11 +18,14 @@ static thread_local std::string g_create_error;
   try {                                                       \
     body;                                                     \
     return CXRM_OK;                                           \
+  } catch (const cxrm::WeightError& ex) {                     \
+    (e)->impl->last_error = ex.what();                        \
+    return CXRM_ERR_WEIGHT;                                   \
+  } catch (const cxrm::CudaError& ex) {                       \
+    (e)->impl->last_error = ex.what();                        \
+    return CXRM_ERR_CUDA;                                     \
   } catch (const std::exception& ex) {                        \
     (e)->impl->last_error = ex.what();                        \
-    const std::string m = ex.what();                          \
-    if (m.find("weight") != std::string::npos) return CXRM_ERR_WEIGHT; \
-    if (m.find("cuda") != std::string::npos || m.find("CUDA") != std::string::npos) return CXRM_ERR_CUDA; \
     return CXRM_ERR_INVALID;                                  \
   } catch (...) {                                             \
     (e)->impl->last_error = "unknown exception";              \
@@ -57,13 +61,19 @@ int cxrm_create(const cxrm_config* cfg, int device, cxrm_engine** out) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0)
       throw std::runtime_error("no CUDA device: the engine has no CPU fallback");
-    cxrm_engine* e = new cxrm_engine();
-    e->impl = make_engine(*cfg, device);
-    *out = e;
+    std::unique_ptr<cxrm_engine> e(new cxrm_engine());
+    e->impl = make_engine(*cfg, device);     // throws: the wrapper is released by the unique_ptr
+    *out = e.release();
     return CXRM_OK;
-  } catch (const std::exception& ex) {
+  } catch (const cxrm::CudaError& ex) {
     g_create_error = ex.what();
     return CXRM_ERR_CUDA;
+  } catch (const std::exception& ex) {
+    g_create_error = ex.what();
+    return CXRM_ERR_INVALID;
+  } catch (...) {
+    g_create_error = "unknown exception";
+    return CXRM_ERR_INTERNAL;
   }
 }
 
@@ -121,15 +131,34 @@ int cxrm_reward(cxrm_engine* e, const int32_t* pred_ids, const int32_t* pred_len
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     float* emb = nullptr;
     CXRM_CUDA_CHECK(cudaMallocAsync(&emb, static_cast<size_t>(2) * n * 128 * sizeof(float), s));
-    e->impl->reward_embed(pred_ids, pred_lens, n, L_pred, emb, s);
-    e->impl->reward_embed(label_ids, label_lens, n, L_label, emb + static_cast<size_t>(n) * 128, s);
-    cosine_rows(emb, emb + static_cast<size_t>(n) * 128, reward_out, n, 128, s);
+    try {
+      e->impl->reward_embed(pred_ids, pred_lens, n, L_pred, emb, s);
+      e->impl->reward_embed(label_ids, label_lens, n, L_label, emb + static_cast<size_t>(n) * 128, s);
+      cosine_rows(emb, emb + static_cast<size_t>(n) * 128, reward_out, n, 128, s);
+    } catch (...) {
+      cudaFreeAsync(emb, s);
+      throw;
+    }
     CXRM_CUDA_CHECK(cudaFreeAsync(emb, s));
   });
 }
 int cxrm_set_id_map(cxrm_engine* e, const int32_t* id_map_host, int n, int cls_id, int sep_id, int bos_id,
-                    int sep_dec_id) {
-  CXRM_GUARD(e, e->impl->set_id_map(id_map_host, n, cls_id, sep_id, bos_id, sep_dec_id));
+                    int sep_dec_id, int n_special) {
+  CXRM_GUARD(e, e->impl->set_id_map(id_map_host, n, cls_id, sep_id, bos_id, sep_dec_id, n_special));
+}
+int cxrm_bridge_ids(cxrm_engine* e, const int32_t* sequences, int R, int L, int eos_token_id, int32_t* out_ids,
+                    int32_t* out_lens, int L_out, void* stream) {
+  CXRM_GUARD(e, e->impl->bridge_ids(sequences, R, L, eos_token_id, out_ids, out_lens, L_out, static_cast<cudaStream_t>(stream)));
+}
+int cxrm_test_sample(const float* logits, int R, int V, int top_k, float temperature, uint64_t seed, int step, int Tmax,
+                     int32_t* out_tokens, float* out_logprob, void* stream) {
+  try {
+    sample_rows_test(logits, R, V, top_k, temperature, seed, step, Tmax, out_tokens, out_logprob, static_cast<cudaStream_t>(stream));
+    return CXRM_OK;
+  } catch (const std::exception& ex) {
+    g_create_error = ex.what();
+    return CXRM_ERR_INVALID;
+  }
 }
 int cxrm_scst_step_host(cxrm_engine* e, const float* pixels, int B, int N, const int32_t* prompt_ids, int P,
                         const cxrm_rollout_args* tmpl, const int32_t* label_ids, const int32_t* label_lens,

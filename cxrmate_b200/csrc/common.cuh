@@ -14,11 +14,15 @@ namespace cxrm {
 
 using bf16 = __nv_bfloat16;
 
+// typed failures, mapped to cxrm_status by the C ABI (capi.cu)
+struct WeightError : std::runtime_error { using std::runtime_error::runtime_error; };   // CXRM_ERR_WEIGHT
+struct CudaError : std::runtime_error { using std::runtime_error::runtime_error; };     // CXRM_ERR_CUDA
+
 #define CXRM_CUDA_CHECK(expr)                                                                      \
   do {                                                                                             \
     cudaError_t _e = (expr);                                                                       \
     if (_e != cudaSuccess) {                                                                       \
-      throw std::runtime_error(std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " at " + \
+      throw ::cxrm::CudaError(std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " at " +    \
                                __FILE__ + ":" + std::to_string(__LINE__));                         \
     }                                                                                              \
   } while (0)
@@ -36,7 +40,7 @@ extern unsigned long long g_launch_count;   // kernels launched by this library 
 inline void check_launch(const char* what) {
   ++g_launch_count;
   cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) throw std::runtime_error(std::string(what) + " launch failed: " + cudaGetErrorString(e));
+  if (e != cudaSuccess) throw CudaError(std::string(what) + " launch failed: " + cudaGetErrorString(e));
 }
 
 // Programmatic dependent launch (PDL) for the decode-step kernel chain: while g_pdl is set, the chain's kernels are
@@ -64,7 +68,7 @@ inline void launch_chain(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t s
   cfg.attrs = at;
   cfg.numAttrs = g_pdl ? 1 : 0;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
-  if (e != cudaSuccess) throw std::runtime_error(std::string("cudaLaunchKernelEx failed: ") + cudaGetErrorString(e));
+  if (e != cudaSuccess) throw CudaError(std::string("cudaLaunchKernelEx failed: ") + cudaGetErrorString(e));
 }
 #endif
 

@@ -491,6 +491,50 @@ void sample_step(const RolloutState& st, const RolloutParams& p, const float* lo
   check_launch("sample_step");
 }
 
+// Test hook (cxrm_test_sample): one call of the sampling head on caller-provided logits, every row a SAMPLE row of a
+// fresh rollout whose step counter is `step` - the in-kernel Philox stream is (seed, step * R + row), the draw for
+// vocabulary entry i is counter i of that stream (cxrm.h).
+void sample_rows_test(const float* logits, int R, int V, int top_k, float temperature, unsigned long long seed, int step,
+                      int Tmax, int* out_tokens, float* out_logprob, cudaStream_t stream) {
+  CXRM_CHECK(R >= 1 && V >= 1 && step >= 0 && step < Tmax, "sample_rows_test shape");
+  const int Lmax = Tmax + 16;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~static_cast<size_t>(255); return o; };
+  const size_t o_tok = take(sizeof(int) * R), o_len = take(sizeof(int) * R), o_type = take(sizeof(int) * R),
+               o_pos = take(sizeof(int) * R), o_nv = take(sizeof(int) * R), o_seen = take(sizeof(unsigned) * R),
+               o_fin = take(R), o_kv = take(static_cast<size_t>(R) * Lmax), o_seq = take(sizeof(int) * R * Lmax),
+               o_lp = take(sizeof(float) * R * Tmax), o_mg = take(sizeof(float) * R * Tmax),
+               o_ti = take(sizeof(int) * R * Tmax * kTopKCap), o_tv = take(sizeof(float) * R * Tmax * kTopKCap),
+               o_tc = take(sizeof(int) * R * Tmax), o_sc = take(256);
+  char* base = nullptr;
+  CXRM_CUDA_CHECK(cudaMallocAsync(&base, off, stream));
+  CXRM_CUDA_CHECK(cudaMemsetAsync(base, 0, off, stream));
+  RolloutState st{};
+  st.cur_token = reinterpret_cast<int*>(base + o_tok); st.cur_len = reinterpret_cast<int*>(base + o_len);
+  st.cur_type = reinterpret_cast<int*>(base + o_type); st.cur_pos = reinterpret_cast<int*>(base + o_pos);
+  st.n_valid = reinterpret_cast<int*>(base + o_nv); st.seen = reinterpret_cast<unsigned*>(base + o_seen);
+  st.finished = reinterpret_cast<uint8_t*>(base + o_fin); st.key_valid = reinterpret_cast<uint8_t*>(base + o_kv);
+  st.seq = reinterpret_cast<int*>(base + o_seq); st.logprob = reinterpret_cast<float*>(base + o_lp);
+  st.margin = reinterpret_cast<float*>(base + o_mg); st.topk_idx = reinterpret_cast<int*>(base + o_ti);
+  st.topk_val = reinterpret_cast<float*>(base + o_tv); st.topk_cnt = reinterpret_cast<int*>(base + o_tc);
+  st.step = reinterpret_cast<int*>(base + o_sc); st.done = st.step + 1;
+  st.arrive = reinterpret_cast<unsigned*>(st.step + 2);
+  st.seed = reinterpret_cast<unsigned long long*>(base + o_sc + 64);
+  CXRM_CUDA_CHECK(cudaMemcpyAsync(st.step, &step, sizeof(int), cudaMemcpyHostToDevice, stream));
+  CXRM_CUDA_CHECK(cudaMemcpyAsync(st.seed, &seed, sizeof(seed), cudaMemcpyHostToDevice, stream));
+  RolloutParams p{};
+  p.R = R; p.B = R; p.P = 1; p.Lmax = Lmax; p.Tmax = Tmax; p.V = V;
+  p.mode_of_block[0] = 0; p.mode_of_block[1] = 0;
+  p.mask_token_id = -1; p.eos = -1; p.pad = -2; p.top_k = top_k; p.temperature = temperature; p.seed = seed;
+  sample_step(st, p, logits, V, nullptr, stream);
+  CXRM_CUDA_CHECK(cudaMemcpy2DAsync(out_tokens, sizeof(int), st.seq + 1 + step, sizeof(int) * Lmax, sizeof(int), R,
+                                    cudaMemcpyDeviceToDevice, stream));
+  if (out_logprob)
+    CXRM_CUDA_CHECK(cudaMemcpy2DAsync(out_logprob, sizeof(float), st.logprob + step, sizeof(float) * Tmax, sizeof(float), R,
+                                      cudaMemcpyDeviceToDevice, stream));
+  CXRM_CUDA_CHECK(cudaFreeAsync(base, stream));
+}
+
 // Pull the described segments into L2 without keeping anything in the SM.  MODE 0: one prefetch.global.L2 hint per
 // 128-byte line; MODE 1: cp.async.bulk.prefetch.L2 (TMA prefetch engine), one 4 KiB request per thread-iteration;
 // MODE 2: real 16-byte loads (L1 no-allocate) whose results are discarded.  Runs on a parallel branch of the

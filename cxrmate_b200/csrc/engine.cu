@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <set>
 #include <type_traits>
 
 namespace cxrm {
@@ -161,16 +162,31 @@ class Engine : public EngineBase {
 
   const RawTensor& need(const std::string& name, std::initializer_list<int64_t> shape) {
     auto it = raw.find(name);
-    if (it == raw.end()) throw std::runtime_error("missing weight: " + name);
+    if (it == raw.end()) throw WeightError("missing weight: " + name);
+    consumed.insert(name);
     std::vector<int64_t> want(shape);
     if (it->second.shape != want) {
       std::string got;
       for (auto s : it->second.shape) got += std::to_string(s) + ",";
-      throw std::runtime_error("weight " + name + " has shape [" + got + "]");
+      throw WeightError("weight " + name + " has shape [" + got + "]");
     }
     return it->second;
   }
   bool has(const std::string& name) const { return raw.count(name) != 0; }
+  // W[n_out, n_in] (fp32 staging) += (alpha / r) . B . A when the LoRA pair of `prefix` was loaded (both or neither)
+  void merge_lora(const std::string& prefix, float* W, int n_out, int n_in) {
+    const bool hasA = has(prefix + ".lora_A.weight"), hasB = has(prefix + ".lora_B.weight");
+    if (!hasA && !hasB) return;
+    if (hasA != hasB) throw WeightError("weight " + prefix + ": lora_A / lora_B must be loaded as a pair");
+    const RawTensor& A = raw.at(prefix + ".lora_A.weight");
+    const RawTensor& Bm = raw.at(prefix + ".lora_B.weight");
+    consumed.insert(prefix + ".lora_A.weight");
+    consumed.insert(prefix + ".lora_B.weight");
+    if (!(A.shape.size() == 2 && A.shape[1] == n_in && Bm.shape.size() == 2 && Bm.shape[0] == n_out &&
+          Bm.shape[1] == A.shape[0]))
+      throw WeightError("weight " + prefix + ": LoRA shapes do not match [r, n_in] / [n_out, r]");
+    lora_merge(W, A.data, Bm.data, n_out, n_in, static_cast<int>(A.shape[0]), LORA_SCALE, 0);
+  }
 
   template <typename U> U* dalloc(long long n) {
     void* p = nullptr;
@@ -212,13 +228,7 @@ class Engine : public EngineBase {
       const RawTensor& w = need(p + ".weight", {n_each, n_in});
       const RawTensor& b = need(p + ".bias", {n_each});
       CXRM_CUDA_CHECK(cudaMemcpyAsync(tmp, w.data, static_cast<size_t>(n_each) * n_in * sizeof(float), cudaMemcpyDeviceToDevice, 0));
-      if (has(p + ".lora_A.weight")) {
-        const RawTensor& A = raw.at(p + ".lora_A.weight");
-        const RawTensor& Bm = raw.at(p + ".lora_B.weight");
-        CXRM_CHECK(A.shape.size() == 2 && A.shape[1] == n_in && Bm.shape.size() == 2 && Bm.shape[0] == n_each &&
-                       Bm.shape[1] == A.shape[0], "LoRA shapes");
-        lora_merge(tmp, A.data, Bm.data, n_each, n_in, static_cast<int>(A.shape[0]), LORA_SCALE, 0);
-      }
+      merge_lora(p, tmp, n_each, n_in);
       pack_matrix<T>(tmp, L.w + static_cast<long long>(i) * n_each * n_in, n_each, n_in, n_in, 0);
       CXRM_CUDA_CHECK(cudaMemcpyAsync(L.b + i * n_each, b.data, n_each * sizeof(float), cudaMemcpyDeviceToDevice, 0));
     }
@@ -247,11 +257,7 @@ class Engine : public EngineBase {
         const RawTensor& w = need(p + ".weight", {n_each, n_in});
         const float* bias = has(p + ".bias") ? need(p + ".bias", {n_each}).data : nullptr;
         CXRM_CUDA_CHECK(cudaMemcpyAsync(tmp, w.data, static_cast<size_t>(n_each) * n_in * sizeof(float), cudaMemcpyDeviceToDevice, 0));
-        if (has(p + ".lora_A.weight")) {
-          const RawTensor& A = raw.at(p + ".lora_A.weight");
-          const RawTensor& Bm = raw.at(p + ".lora_B.weight");
-          lora_merge(tmp, A.data, Bm.data, n_each, n_in, static_cast<int>(A.shape[0]), LORA_SCALE, 0);
-        }
+        merge_lora(p, tmp, n_each, n_in);
         fold_ln_weights(tmp, n_each, n_in, gamma, beta, bias, L.w + static_cast<long long>(i) * n_each * n_in,
                         L.s + i * n_each, L.b + i * n_each, 0);
       }
@@ -381,8 +387,25 @@ class Engine : public EngineBase {
       have_reward = true;
     }
     CXRM_CUDA_CHECK(cudaDeviceSynchronize());
+    // Every loaded tensor must have been used (cxrm.h: unknown weights are CXRM_ERR_WEIGHT).  A state_dict whose keys
+    // were renamed only in part (peft's base_layer / lora_A.default naming) would otherwise lose its LoRA update
+    // silently.  Tied / alias tensors of the reference's state_dict are accepted.
+    std::string leftover;
+    int n_left = 0;
+    for (auto& kv : raw) {
+      if (consumed.count(kv.first)) continue;
+      const std::string& k = kv.first;
+      if (k == "decoder.cls.predictions.decoder.weight" || k == "decoder.cls.predictions.decoder.bias" ||
+          k.find("position_ids") != std::string::npos || k.find("num_batches_tracked") != std::string::npos ||
+          (k.rfind("reward.", 0) == 0 && (cfg.rwd_layers == 0 || k.rfind("reward.cls.", 0) == 0 ||
+                                         k.find("pooler") != std::string::npos)))
+        continue;
+      if (n_left++ < 4) leftover += (leftover.empty() ? "" : ", ") + k;
+    }
     for (auto& kv : raw) cudaFree(kv.second.data);
     raw.clear();
+    consumed.clear();
+    if (n_left) throw WeightError("unknown weight: " + std::to_string(n_left) + " loaded tensor(s) match no parameter of the engine: " + leftover);
     finalized = true;
   }
 
@@ -395,6 +418,7 @@ class Engine : public EngineBase {
                                      std::to_string(prop.major) + std::to_string(prop.minor));
     CXRM_CHECK(cfg.image_h % 16 == 0 && cfg.image_w % 16 == 0, "image size must be a multiple of 16");
     CXRM_CHECK(cfg.max_prompt + cfg.max_new_tokens <= 512, "prompt + new tokens must fit 512 positions");
+    CXRM_CHECK(cfg.rwd_layers == 0 || (cfg.rwd_max_len >= 1 && cfg.rwd_max_len <= 512), "rwd_max_len must fit the 512 learned positions");
     if (cfg.enc_chunk <= 0) cfg.enc_chunk = 32;
     T2 = (cfg.image_h / 16) * (cfg.image_w / 16);
     Smax = cfg.max_images * T2;
@@ -1109,7 +1133,14 @@ class Engine : public EngineBase {
     rp.mask_token_id = a.mask_token_id; rp.eos = a.eos_token_id; rp.pad = a.pad_token_id;
     rp.top_k = a.top_k; rp.temperature = a.temperature; rp.seed = a.seed;
     rp.want_margin = a.margins ? 1 : 0;
-    // the kernels index logprob/topk buffers with Tmax = Tn
+    // the kernels index logprob/topk buffers with Tmax = Tn.  Steps after every row finished are skipped inside the
+    // kernels (`*done`), so the [R,Tn] outputs are cleared first: log-prob 0 where PAD (cxrm.h), no stale columns.
+    {
+      const size_t rt0 = static_cast<size_t>(R) * Tn;
+      CXRM_CUDA_CHECK(cudaMemsetAsync(st.logprob, 0, rt0 * sizeof(float), s));
+      CXRM_CUDA_CHECK(cudaMemsetAsync(st.margin, 0, rt0 * sizeof(float), s));
+      CXRM_CUDA_CHECK(cudaMemsetAsync(st.topk_cnt, 0, rt0 * sizeof(int), s));
+    }
     PF("init", s, [&] { rollout_init(st, rp, a.prompt_ids, pre_ids, pre_types, pre_pos, s); });
 
     arena.reset();
@@ -1263,14 +1294,30 @@ class Engine : public EngineBase {
   }
 
   // =========================================================================== host-buffer SCST step
-  void set_id_map(const int* id_map_host, int n, int cls_id, int sep_id, int bos_id, int sep_dec_id) override {
+  void set_id_map(const int* id_map_host, int n, int cls_id, int sep_id, int bos_id, int sep_dec_id,
+                  int n_special) override {
     CXRM_CHECK(n == cfg.vocab, "id map must cover the decoder vocabulary");
+    CXRM_CHECK(n_special >= 0 && n_special <= n, "n_special outside the decoder vocabulary");
+    auto in_rwd = [&](int v) { return v >= 0 && v < cfg.rwd_vocab; };
+    CXRM_CHECK(in_rwd(cls_id) && in_rwd(sep_id), "[CLS] / [SEP] id outside the reward vocabulary");
+    for (int i = n_special; i < n; ++i)   // the embedding gather of the reward model does not bounds-check
+      CXRM_CHECK(in_rwd(id_map_host[i]), "id_map[" + std::to_string(i) + "] outside the reward vocabulary");
+    bridge_n_special = n_special;
     if (!id_map) id_map = dalloc<int>(n);
     CXRM_CUDA_CHECK(cudaMemcpy(id_map, id_map_host, n * sizeof(int), cudaMemcpyHostToDevice));
     bridge_cls = cls_id;
     bridge_sep = sep_id;
     bridge_bos = bos_id;
     bridge_sep_dec = sep_dec_id;
+  }
+
+  // generated ids [R, L] -> reward-model ids [R, Lout] ([CLS] findings impression [SEP], specials dropped) + lengths
+  void bridge_ids(const int* seq, int R, int L, int eos, int* out_ids, int* out_lens, int Lout, cudaStream_t s) override {
+    CXRM_CHECK(id_map != nullptr, "cxrm_bridge_ids needs cxrm_set_id_map");
+    CXRM_CHECK(R >= 1 && L >= 1 && Lout >= 2, "bridge_ids shape");
+    bridge_ids_kernel<<<ceil_div(R, 64), 64, 0, s>>>(seq, L, L, R, bridge_bos, bridge_sep_dec, eos, bridge_n_special, id_map,
+                                                      bridge_cls, bridge_sep, out_ids, out_lens, Lout);
+    check_launch("bridge_ids");
   }
 
   void scst_step_host(const float* pixels, int B, int N, const int* prompt_ids, int P, const cxrm_rollout_args& tmpl,
@@ -1301,7 +1348,6 @@ class Engine : public EngineBase {
       h_rlens = dalloc<int>(3LL * cfg.max_studies);
       h_emb = dalloc<float>(3LL * cfg.max_studies * 128);
       h_out = dalloc<float>(3LL * cfg.max_studies);
-      h_labels = dalloc<int>(static_cast<long long>(cfg.max_studies) * cfg.rwd_max_len);
     }
     // cudaMemcpyDefault: the direction is inferred from the (unified) addresses, host or device
     CXRM_CUDA_CHECK(cudaMemcpyAsync(prompt_dev, prompt_ids, static_cast<size_t>(B) * P * sizeof(int), cudaMemcpyDefault, s));
@@ -1361,7 +1407,7 @@ class Engine : public EngineBase {
     mark();
     // text bridge: sample rows [0,B), greedy rows [B,2B) -> reward ids rows [0,2B); labels -> rows [2B,3B)
     bridge_ids_kernel<<<ceil_div(R, 64), 64, 0, s>>>(h_seq, Lseq, Lseq, R, bridge_bos, bridge_sep_dec, a.eos_token_id,
-                                                      12, id_map, bridge_cls, bridge_sep, h_rids, h_rlens, Lr);
+                                                      bridge_n_special, id_map, bridge_cls, bridge_sep, h_rids, h_rlens, Lr);
     check_launch("bridge_ids");
     // labels are already reward-model ids, padded to L_label: copy into the [*, Lr] layout
     CXRM_CUDA_CHECK(cudaMemsetAsync(h_rids + static_cast<long long>(R) * Lr, 0, static_cast<size_t>(B) * Lr * sizeof(int), s));
@@ -1398,6 +1444,7 @@ class Engine : public EngineBase {
   cxrm_config cfg;
   int device;
   std::map<std::string, RawTensor> raw;
+  std::set<std::string> consumed;          // raw keys finalize_weights has used
   std::vector<void*> owned;
   long long persistent_bytes = 0;
   bool finalized = false, have_reward = false;
@@ -1445,8 +1492,8 @@ class Engine : public EngineBase {
   int* pre_ids = nullptr; int* pre_types = nullptr; int* pre_pos = nullptr; int* prompt_dev = nullptr;
   // host-step staging
   float* h_pixels = nullptr; int* h_seq = nullptr; float* h_lp = nullptr; int* h_rids = nullptr; int* h_rlens = nullptr;
-  float* h_emb = nullptr; float* h_out = nullptr; int* h_labels = nullptr;
-  int* id_map = nullptr; int bridge_cls = 0, bridge_sep = 0, bridge_bos = 1, bridge_sep_dec = 3;
+  float* h_emb = nullptr; float* h_out = nullptr;
+  int* id_map = nullptr; int bridge_cls = 0, bridge_sep = 0, bridge_bos = 1, bridge_sep_dec = 3, bridge_n_special = 12;
   // CUDA graph of one decode step
   struct GraphKey {
     int R, B, P, Tmax, top_k; float temperature; const float* noise; const void* buf;

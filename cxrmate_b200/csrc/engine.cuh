@@ -48,11 +48,13 @@ class EngineBase {
   virtual void decoder_forward(const int* ids, const int* tt, const int* pos, const uint8_t* key_mask, int R, int L,
                                int B, bool last_only, float* logits_out, cudaStream_t s) = 0;
   virtual void reward_embed(const int* ids, const int* lens, int n, int L, float* emb_out, cudaStream_t s) = 0;
-  virtual void set_id_map(const int* id_map_host, int n, int cls_id, int sep_id, int bos_id, int sep_dec_id) = 0;
+  virtual void set_id_map(const int* id_map_host, int n, int cls_id, int sep_id, int bos_id, int sep_dec_id,
+                          int n_special) = 0;
   virtual void scst_step_host(const float* pixels, int B, int N, const int* prompt_ids, int P,
                               const cxrm_rollout_args& tmpl, const int* label_ids, const int* label_lens, int L_label,
                               int* sequences, float* logprobs, float* reward, float* baseline, float* advantage,
                               int* steps_out, bool on_device, cudaStream_t s) = 0;
+  virtual void bridge_ids(const int* seq, int R, int L, int eos, int* out_ids, int* out_lens, int Lout, cudaStream_t s) = 0;
   virtual size_t workspace_bytes() const = 0;
   virtual void set_profile(bool on) = 0;
   virtual std::string profile_report() = 0;

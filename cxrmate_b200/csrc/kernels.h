@@ -239,6 +239,10 @@ void rollout_init(const RolloutState& st, const RolloutParams& p, const int* pro
 void sample_step(const RolloutState& st, const RolloutParams& p, const float* logits, int ldl, const float* exp_noise,
                  cudaStream_t stream);
 
+// test hook: the sampling head on caller logits [R,V], all rows sample rows, Philox draws of (seed, step) -> tokens [R]
+void sample_rows_test(const float* logits, int R, int V, int top_k, float temperature, unsigned long long seed, int step,
+                      int Tmax, int* out_tokens, float* out_logprob, cudaStream_t stream);
+
 // ---- one-token attention over the head-major K/V caches (decode_attn.cu) ----------------------------------
 // Work units of the cross-attention: (study, chunk of <= CH encoder tokens); built on the host at
 // cxrm_prefill_cross_kv, read by every decode step.  The grid is sized for max_units so that the captured

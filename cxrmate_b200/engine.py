@@ -31,6 +31,17 @@ class RolloutOutput:
     last_logits: torch.Tensor     # [R, V] fp32
 
 
+def normalise_weight_name(name: str) -> str:
+    """state_dict key of a real `peft`-wrapped decoder -> the plain key the engine knows (last
+    row: `decoder.base_model.model.<...>.base_layer.weight`, `<...>.lora_A.default.weight`).  Keys that peft did not
+    touch pass through unchanged; cxrm_finalize_weights rejects anything it cannot place (CXRM_ERR_WEIGHT)."""
+    name = name.replace("decoder.base_model.model.", "decoder.")
+    name = name.replace(".base_layer.", ".")
+    for ab in ("lora_A", "lora_B"):
+        name = name.replace(f".{ab}.default.", f".{ab}.")
+    return name
+
+
 class Engine:
     """One engine per process / GPU."""
 
@@ -86,6 +97,7 @@ class Engine:
         for name, t in sd.items():
             if not torch.is_floating_point(t):
                 continue                       # num_batches_tracked
+            name = normalise_weight_name(name)
             t = t.detach().to(torch.float32).contiguous()
             shape = (C.c_int64 * max(t.dim(), 1))(*t.shape)
             rc = self.lib.cxrm_load_weight(self.h, (prefix + name).encode(), C.c_void_p(t.data_ptr()), shape, t.dim(),
@@ -230,10 +242,23 @@ class Engine:
         return out
 
     # ------------------------------------------------------------------ host-buffer SCST step
-    def set_id_map(self, id_map: torch.Tensor, cls_id: int, sep_id: int, bos_id: int, sep_dec_id: int):
+    def set_id_map(self, id_map: torch.Tensor, cls_id: int, sep_id: int, bos_id: int, sep_dec_id: int,
+                   n_special: int = 12):
+        """id_map[i] = reward-model id of decoder id i; decoder ids < n_special are special tokens (skipped, like
+        tokenizer.decode(skip_special_tokens=True))."""
         m = id_map.to(torch.int32).cpu().contiguous()
-        self._check(self.lib.cxrm_set_id_map(self.h, _ptr(m), m.numel(), cls_id, sep_id, bos_id, sep_dec_id),
+        self._check(self.lib.cxrm_set_id_map(self.h, _ptr(m), m.numel(), cls_id, sep_id, bos_id, sep_dec_id, n_special),
                     "cxrm_set_id_map")
+
+    def bridge_ids(self, sequences: torch.Tensor, eos_token_id: int, out_len: int):
+        """Device-side text bridge (cxrm_bridge_ids): generated ids [R, L] -> (reward ids [R, out_len], lens [R])."""
+        seq = sequences.to(torch.int32).contiguous()
+        R, L = seq.shape
+        ids = torch.empty(R, out_len, dtype=torch.int32, device=seq.device)
+        lens = torch.empty(R, dtype=torch.int32, device=seq.device)
+        self._check(self.lib.cxrm_bridge_ids(self.h, _ptr(seq), R, L, int(eos_token_id), _ptr(ids), _ptr(lens), out_len,
+                                             _stream()), "cxrm_bridge_ids")
+        return ids, lens
 
     def set_profile(self, on: bool):
         self._check(self.lib.cxrm_set_profile(self.h, int(on)), "cxrm_set_profile")
@@ -247,7 +272,8 @@ class Engine:
     def scst_step(self, pixels: torch.Tensor, prompt_ids: torch.Tensor, label_ids: torch.Tensor,
                   label_lens: torch.Tensor, *, max_new_tokens: int, eos_token_id: int, pad_token_id: int,
                   mask_token_id: int, special_sample, sections_sample, special_greedy, sections_greedy,
-                  top_k: int = 50, temperature: float = 1.0, seed: int = 0, out=None):
+                  top_k: int = 50, temperature: float = 1.0, seed: int = 0, out=None,
+                  exp_noise: Optional[torch.Tensor] = None):
         """Whole SCST rollout step.  Either every tensor is a HOST tensor (pinned for speed; the timed end-to-end
         call: H2D inside, D2H inside, synchronous) or every tensor is a CUDA tensor (device-resident variant).
         prompt_ids / label_ids / label_lens must be int32."""
@@ -280,6 +306,10 @@ class Engine:
             a.sections_greedy[i] = int(v)
         a.max_new_tokens, a.eos_token_id, a.pad_token_id = T, int(eos_token_id), int(pad_token_id)
         a.top_k, a.temperature, a.seed = int(top_k), float(temperature), int(seed)
+        if exp_noise is not None:      # validation: the sample rows consume this Exp(1) tensor instead of Philox draws
+            assert exp_noise.shape == (T, B, self.cfg.vocab) and exp_noise.dtype == torch.float32 and exp_noise.is_cuda
+            exp_noise = exp_noise.contiguous()
+            a.exp_noise = exp_noise.data_ptr()
         fn = self.lib.cxrm_scst_step_device if on_dev else self.lib.cxrm_scst_step_host
         rc = fn(
             self.h, _ptr(pixels), B, N, _ptr(p32), P, C.byref(a), _ptr(l32), _ptr(ll), l32.shape[1],
@@ -301,6 +331,20 @@ def gemm_hook(impl: str, A, W, bias=None, act: int = 0, residual=None, out_f32: 
     if rc != 0:
         raise RuntimeError(f"cxrm_test_gemm failed ({rc}): {lib.cxrm_last_error(None).decode()}")
     return out
+
+
+def sample_hook(logits: torch.Tensor, top_k: int, temperature: float, seed: int, step: int, tmax: int = 256):
+    """The sampling head on caller logits [R, V] fp32 (cxrm_test_sample): tokens [R] int32, log-probs [R]."""
+    lib = _lib.load()
+    logits = logits.contiguous().float()
+    R, V = logits.shape
+    tok = torch.empty(R, dtype=torch.int32, device=logits.device)
+    lp = torch.empty(R, dtype=torch.float32, device=logits.device)
+    rc = lib.cxrm_test_sample(_ptr(logits), R, V, int(top_k), float(temperature), int(seed), int(step), int(tmax), _ptr(tok),
+                              _ptr(lp), _stream())
+    if rc != 0:
+        raise RuntimeError(f"cxrm_test_sample failed ({rc}): {lib.cxrm_last_error(None).decode()}")
+    return tok, lp
 
 
 def gemm_ln_hook(A, W, bias, act, residual, gamma, beta, eps=1e-12, cluster=False):

@@ -19,6 +19,29 @@ import torch
 from .engine import Engine, RolloutOutput
 
 
+TOPK_CAP = 64   # survivors recorded per (row, step): include/cxrm.h cxrm_rollout_args.topk_idx
+
+
+class DecoderPast:
+    """`past_key_values` of CXRMateEngineModel.forward: ids / token types / positions of the cached tokens."""
+
+    def __init__(self, ids, tt, pos):
+        self.ids, self.tt, self.pos = ids, tt, pos
+
+    @property
+    def length(self) -> int:
+        return int(self.ids.shape[1])
+
+    def get_seq_length(self, layer_idx: int = 0) -> int:     # transformers.Cache surface used by callers
+        return self.length
+
+    def __len__(self):
+        return self.length
+
+    def __bool__(self):
+        return self.length > 0
+
+
 class ModelOutput(dict):
     """dict with attribute access, like transformers.modeling_outputs.ModelOutput."""
 
@@ -180,7 +203,7 @@ class CXRMateEngineModel:
             self._kv_token = None
         return memory.shape[0]
 
-    def generate(self, pixel_values=None, encoder_outputs=None, decoder_input_ids=None, input_ids=None,
+    def _generate(self, pixel_values=None, encoder_outputs=None, decoder_input_ids=None, input_ids=None,
                  special_token_ids=None, mask_token_id=None, max_length=None, max_new_tokens=None, bos_token_id=None,
                  eos_token_id=None, pad_token_id=None, num_beams=1, do_sample=False, top_k=50, top_p=1.0,
                  temperature=1.0, output_scores=False, return_dict_in_generate=False, use_cache=True,
@@ -195,6 +218,8 @@ class CXRMateEngineModel:
         """
         if num_beams != 1:
             raise NotImplementedError("beam search is outside the SCST rollout path (SURVEY.md section 8f rank 3)")
+        if do_sample and top_k is not None and top_k > TOPK_CAP and output_scores:
+            raise ValueError(f"output_scores with top_k > {TOPK_CAP}: the engine records at most {TOPK_CAP} survivors per step")
         if top_p != 1.0:
             raise NotImplementedError("top_p != 1.0 is not used by the reference's SCST recipe")
         cfg = self.config
@@ -250,39 +275,72 @@ class CXRMateEngineModel:
         res["rollout"] = out
         return res
 
+    # The reference's SCST sampler calls `generate.__wrapped__(model, ...)` to step around HF's @torch.no_grad()
+    # (scst/gen_prompt.py:279, scst/gt_prompt.py:162).  The engine's rollout is grad-free by construction (the log-probs
+    # the REINFORCE loss needs are recorded by the sampling head), so the wrapped and the unwrapped call are the same
+    # function; `generate.__wrapped__` exists so that the reference's call site works unchanged.
+    generate = torch.no_grad()(_generate)
+
     def _dense_scores(self, out: RolloutOutput, sampled: bool):
-        """HF's `scores`: one [B,V] fp32 tensor per executed step, -inf outside the top-k survivors."""
+        """HF's `scores`: one [B,V] fp32 tensor per executed step, -inf outside the top-k survivors.  One scatter for
+        all steps (a [steps, B, V] tensor), returned as a tuple of its per-step views.  Raises when a step had more
+        survivors than the engine records (ties at the k-th value beyond TOPK_CAP slots): the dense scores would
+        silently miss entries otherwise."""
         if not sampled:
             raise NotImplementedError("dense greedy scores are not kept (only the last step's logits are)")
         V = self.engine.cfg.vocab
-        scores = []
-        for t in range(out.steps):
-            s = torch.full((out.topk_idx.shape[0], V), float("-inf"), device=out.topk_idx.device)
-            cnt = out.topk_cnt[:, t].clamp(max=out.topk_idx.shape[-1])
-            valid = torch.arange(out.topk_idx.shape[-1], device=s.device)[None] < cnt[:, None]
-            idx = out.topk_idx[:, t].long()
-            rows = torch.arange(idx.shape[0], device=s.device)[:, None].expand_as(idx)
-            s[rows[valid], idx[valid]] = out.topk_val[:, t][valid]
-            scores.append(s)
-        return tuple(scores)
+        T = out.steps
+        cap = out.topk_idx.shape[-1]
+        cnt = out.topk_cnt[:, :T]
+        if T and int(cnt.max()) > cap:
+            r, t = divmod(int(cnt.argmax()), T)
+            raise RuntimeError(f"step {t} of row {r} kept {int(cnt.max())} top-k survivors (ties at the k-th value); only "
+                               f"{cap} are recorded, so `scores` cannot be rebuilt exactly - use `logprobs`")
+        Bn = out.topk_idx.shape[0]
+        dense = torch.full((T, Bn, V), float("-inf"), device=out.topk_idx.device)
+        valid = torch.arange(cap, device=dense.device)[None, None] < cnt.t()[:, :, None]          # [T, B, cap]
+        idx = out.topk_idx[:, :T].permute(1, 0, 2).long()
+        val = out.topk_val[:, :T].permute(1, 0, 2)
+        tb = torch.nonzero(valid, as_tuple=True)
+        dense[tb[0], tb[1], idx[valid]] = val[valid]
+        return tuple(dense.unbind(0))
 
     # ---- teacher-forced forward --------------------------------------------------------------------
     def forward(self, pixel_values=None, decoder_input_ids=None, decoder_attention_mask=None, encoder_outputs=None,
                 decoder_token_type_ids=None, decoder_position_ids=None, past_key_values=None, use_cache=None,
                 labels=None, return_dict=True, **kwargs):
-        """Full-sequence decoder forward (modelling_longitudinal.py:173-249) -> ModelOutput(logits [B,L,V] fp32)."""
-        if past_key_values is not None:
-            raise NotImplementedError("incremental forward() is internal to generate(); pass the full sequence")
+        """Decoder forward (modelling_longitudinal.py:173-249; multi: modelling_multi.py:150-227; single:
+        modelling_single.py:138-215) -> ModelOutput(logits [B,q,V] fp32, past_key_values).
+
+        `past_key_values` is a `DecoderPast`: the inputs of the tokens seen so far.  An incremental call returns the
+        logits of the NEW tokens only, computed by one causal pass over cached + new tokens (identical values to a
+        K/V-cached step: SURVEY.md finding 4, and the engine's own test_cached_decode_equals_teacher_forced_long);
+        the per-token K/V cache that makes decoding O(L) lives inside `generate()` / `cxrm_rollout`."""
         B = self._ensure_cross_kv(pixel_values, encoder_outputs)
         ids = decoder_input_ids.to(self.device)
-        mask = torch.ones_like(ids) if decoder_attention_mask is None else decoder_attention_mask.to(self.device)
+        q = ids.shape[1]
+        past = past_key_values if isinstance(past_key_values, DecoderPast) and past_key_values.length else None
+        n_past = past.length if past is not None else 0
         tt = torch.zeros_like(ids) if decoder_token_type_ids is None else decoder_token_type_ids.to(self.device)
-        pos = (torch.arange(ids.shape[1], device=self.device)[None].expand_as(ids)
+        pos = (torch.arange(n_past, n_past + q, device=self.device)[None].expand_as(ids)      # BERT's default positions
                if decoder_position_ids is None else decoder_position_ids.to(self.device))
-        logits = self.engine.decoder_forward(ids, tt, pos, mask, n_studies=B)
+        # decoder_attention_mask covers past + new tokens (HF semantics, modelling_longitudinal.py:274)
+        mask = (torch.ones(ids.shape[0], n_past + q, dtype=torch.int64, device=self.device)
+                if decoder_attention_mask is None else decoder_attention_mask.to(self.device))
+        if mask.shape[1] != n_past + q:
+            raise ValueError(f"decoder_attention_mask has {mask.shape[1]} columns for {n_past} cached + {q} new tokens")
+        if past is not None:
+            ids_all, tt_all, pos_all = (torch.cat((a, b), dim=1) for a, b in ((past.ids, ids), (past.tt, tt), (past.pos, pos)))
+        else:
+            ids_all, tt_all, pos_all = ids, tt, pos
+        logits = self.engine.decoder_forward(ids_all, tt_all, pos_all, mask, n_studies=B)
+        logits = logits[:, n_past:]
         loss = None
         if labels is not None:
             loss = torch.nn.functional.cross_entropy(logits.reshape(-1, logits.shape[-1]), labels.reshape(-1).to(self.device))
-        return ModelOutput(loss=loss, logits=logits)
+        out = ModelOutput(loss=loss, logits=logits)
+        if use_cache or past_key_values is not None:
+            out["past_key_values"] = DecoderPast(ids_all, tt_all, pos_all)
+        return out
 
     __call__ = forward

@@ -14,7 +14,7 @@ divides evenly, and rank r takes indices r, r + world, r + 2*world, ...
 from __future__ import annotations
 
 import math
-from typing import List, Tuple
+from typing import List, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
@@ -58,6 +58,28 @@ def gather_rewards(reward: torch.Tensor, baseline: torch.Tensor, group=None) -> 
     return out[:, 0], out[:, 1]
 
 
+def balance_by_images(n_images: Sequence[int], world: int) -> List[List[int]]:
+    """Study indices per rank for one global SCST batch, balanced by WORK rather than by count.
+
+    Encoder and cross-attention cost grow with the number of valid images of a study (1..5 in MIMIC-CXR), so
+    `DistributedSampler` order gives ranks 80..102 images for the same 32 studies and the step time is the slowest
+    rank's.  Every rank still gets exactly len(n_images) / world studies (the rollout batch shape is fixed); studies
+    are dealt largest-first to the rank with the fewest images among those that still have room (LPT with a
+    cardinality constraint).  Deterministic; ties go to the lower rank, equal studies keep dataset order.
+    Independent studies only: the generated-prompt schedule keeps subjects on their lane (allocate_subjects)."""
+    n = len(n_images)
+    if world < 1 or n % world != 0:
+        raise ValueError("the global batch must divide evenly over the ranks")
+    per = n // world
+    order = sorted(range(n), key=lambda i: (-int(n_images[i]), i))
+    load, out = [0] * world, [[] for _ in range(world)]
+    for i in order:
+        r = min((r for r in range(world) if len(out[r]) < per), key=lambda r: (load[r], r))
+        out[r].append(i)
+        load[r] += int(n_images[i])
+    return [sorted(x) for x in out]
+
+
 def unshard(per_rank: torch.Tensor, n_studies: int) -> torch.Tensor:
     """Inverse of shard_studies for gathered values: per_rank [world, per_rank_count] -> [n_studies] in dataset
     order (wrap-around duplicates dropped)."""
@@ -99,11 +121,13 @@ def allocate_subjects(subject_lists: List[List[int]], world: int, mbatch: int, s
     """Order in which the dataset serves study ids so that, with DistributedSampler(shuffle=False) and
     batch_size=mbatch, every subject stays on one (rank, batch slot) lane with its studies in consecutive batches.
 
-    Same algorithm as the reference: subjects sorted by number of studies (stable, largest first) are packed
-    greedily onto the currently shortest of world*mbatch lanes (numpy argmin: first minimum), lanes are optionally
-    shuffled per lane with `random.seed(seed); random.sample(...)`, flattened, and interleaved element-wise.
-    The reference interleaves with zip(), which silently requires equally long lanes; here an unequal packing raises
-    (the reference's final assert fails in that case)."""
+    Same algorithm as the reference (data/prompt.py:164-213): subjects sorted by number of studies (stable, largest
+    first) are packed greedily onto the currently shortest of world*mbatch lanes (numpy argmin: first minimum); when
+    the study count does not divide by world*mbatch the LAST (shortest) subject is appended again - oversampled - to
+    the lane that was shortest after packing until it does (the reference tests a length list it never updates, so
+    every copy lands on that one lane: reproduced); lanes are optionally shuffled per lane with
+    `random.seed(seed); random.sample(...)`, flattened, and interleaved element-wise with zip(), which truncates to
+    the shortest lane.  Like the reference, the result must still serve every study: AssertionError otherwise."""
     import itertools
     import random
 
@@ -117,15 +141,24 @@ def allocate_subjects(subject_lists: List[List[int]], world: int, mbatch: int, s
         i = total.index(min(total))                                # np.argmin: first occurrence of the minimum
         lanes[i].append(studies)
         total[i] += len(studies)
-    if len(set(total)) != 1:
-        raise ValueError(f"lanes are not equally long after packing ({min(total)}..{max(total)} studies): the reference "
-                         "pads by oversampling single-study subjects before interleaving")
+    n_served = sum(total)
+    if n_served % lanes_n != 0:
+        if not lists or not lists[-1]:
+            raise ValueError("nothing to oversample")
+        i = total.index(min(total))                                # stale in the reference's loop: one fixed lane
+        while n_served % lanes_n != 0:
+            lanes[i].append(lists[-1])
+            n_served += len(lists[-1])
     if shuffle_subjects:
         random.seed(seed)
         flat = [list(itertools.chain(*random.sample(lane, k=len(lane)))) for lane in lanes]
     else:
         flat = [list(itertools.chain(*lane)) for lane in lanes]
-    return [study for row in zip(*flat) for study in row]
+    order = [study for row in zip(*flat) for study in row]
+    every = {st for studies in subject_lists for st in studies}
+    assert set(order) == every, ("interleaving dropped studies: the lanes are not equally long "
+                                 f"({min(map(len, flat))}..{max(map(len, flat))}); the reference's final assert fails too")
+    return order
 
 
 def lane_of_position(pos: int, world: int, mbatch: int) -> Tuple[int, int, int]:

@@ -86,7 +86,8 @@ CXRM_API void cxrm_destroy(cxrm_engine* e);
 CXRM_API const char* cxrm_last_error(const cxrm_engine* e);
 /* Bytes of device memory the engine allocated for scratch + caches (informational). */
 CXRM_API size_t cxrm_workspace_bytes(const cxrm_engine* e);
-/* Number of kernels launched by the engine since creation (for bench.py's gpu_launches). */
+/* Number of kernels launched by this library since it was loaded (for bench.py's gpu_launches).  The counter is
+ * process-wide: the contract is one engine per process / GPU. */
 CXRM_API uint64_t cxrm_launch_count(const cxrm_engine* e);
 
 /*
@@ -219,8 +220,16 @@ CXRM_API int cxrm_reward(cxrm_engine* e, const int32_t* pred_ids, const int32_t*
  * chunk c + 1 is in flight while chunk c is encoded.  Pinned host memory makes those copies asynchronous; pageable
  * memory works but serialises them.  Synchronous: returns when the outputs are in the host buffers.
  */
+/* n = decoder vocabulary; decoder ids < n_special are special tokens and are dropped (skip_special_tokens=True);
+ * every id_map[i >= n_special], cls_id and sep_id must lie in [0, rwd_vocab): CXRM_ERR_INVALID otherwise. */
 CXRM_API int cxrm_set_id_map(cxrm_engine* e, const int32_t* id_map_host, int n, int cls_id, int sep_id, int bos_id,
-                    int sep_dec_id);
+                    int sep_dec_id, int n_special);
+/* The device-side text bridge on its own: generated rows [R, L] (prompt included or not) -> reward-model ids
+ * out_ids dev int32 [R, L_out] = [CLS] map(findings) map(impression) [SEP], zero padded; out_lens dev int32 [R].
+ * Sections as split_and_decode_sections (modelling_longitudinal.py:413-457) with specials [BOS, SEP, EOS]: section j is
+ * ids[first col of special j-1 : first col of special j] (absent or at column 0 -> to the end); ids < n_special dropped. */
+CXRM_API int cxrm_bridge_ids(cxrm_engine* e, const int32_t* sequences, int R, int L, int eos_token_id, int32_t* out_ids,
+                    int32_t* out_lens, int L_out, void* stream);
 CXRM_API int cxrm_scst_step_host(cxrm_engine* e, const float* pixels, int B, int N, const int32_t* prompt_ids, int P,
                         const cxrm_rollout_args* rollout_template, const int32_t* label_ids,
                         const int32_t* label_lens, int L_label, int32_t* sequences, float* logprobs, float* reward,
@@ -259,6 +268,12 @@ CXRM_API void cxrm_test_set_gemm_trace(unsigned long long* dev_buf);
 CXRM_API int cxrm_test_attention(int dtype, const void* q, const void* k, const void* v, void* o, int batch, int heads,
                         int Lq, int Lk, const uint8_t* key_mask, int causal, float scale, void* stream);
 
+/* Sampling head on caller-provided logits dev fp32 [R, V]: every row is a sample row of a fresh rollout at decode step
+ * `step` (< Tmax).  Philox4x32-10 contract of the in-kernel draw (exp_noise == NULL): stream = (seed, subsequence
+ * step * R + row), the Exp(1) variate of vocabulary entry i is -log(curand_uniform) at offset i of that stream, and the
+ * token is argmax_i softmax(top-k-masked scores)_i / q_i.  out_tokens dev int32 [R]; out_logprob dev fp32 [R] or NULL. */
+CXRM_API int cxrm_test_sample(const float* logits, int R, int V, int top_k, float temperature, uint64_t seed, int step, int Tmax,
+                     int32_t* out_tokens, float* out_logprob, void* stream);
 /* LayerNorm of rows [rows, C] (eps as given), dtype = cxrm_dtype of x / y. */
 CXRM_API int cxrm_test_layernorm(int dtype, const void* x, void* y, const float* gamma, const float* beta, long long rows,
                         int C, float eps, void* stream);

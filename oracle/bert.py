@@ -89,13 +89,13 @@ def decoder_hidden(sd, ids, token_type_ids, position_ids, key_mask, memory, memo
     past = cache.length() if cache is not None else 0
     neg = torch.finfo(torch.float32).min
     # causal AND key-padding (create_causal_mask + padding, modeling_bert.py:628-691)
-    kpos = torch.arange(past + q)
-    qpos = torch.arange(past, past + q)
+    kpos = torch.arange(past + q, device=ids.device)
+    qpos = torch.arange(past, past + q, device=ids.device)
     allowed = (kpos[None, :] <= qpos[:, None])[None, None] & key_mask.bool()[:, None, None, :]
-    self_mask = torch.zeros(B, 1, q, past + q).masked_fill(~allowed, neg)
+    self_mask = torch.zeros(B, 1, q, past + q, device=ids.device).masked_fill(~allowed, neg)
     cross_mask = None
     if memory_mask is not None:
-        cross_mask = torch.zeros(B, 1, 1, memory.shape[1]).masked_fill(~memory_mask.bool()[:, None, None, :], neg)
+        cross_mask = torch.zeros(B, 1, 1, memory.shape[1], device=ids.device).masked_fill(~memory_mask.bool()[:, None, None, :], neg)
 
     x = embeddings(sd, "decoder.bert.", ids, token_type_ids, position_ids)
     for l in range(layers):
@@ -154,8 +154,8 @@ def decoder_logits(sd, ids, token_type_ids, position_ids, key_mask, memory, memo
 def cxrbert_hidden(sd, ids, attention_mask, layers=12):
     B, T = ids.shape
     neg = torch.finfo(torch.float32).min
-    add_mask = torch.zeros(B, 1, 1, T).masked_fill(~attention_mask.bool()[:, None, None, :], neg)
-    pos = torch.arange(T)[None].expand(B, T)
+    add_mask = torch.zeros(B, 1, 1, T, device=ids.device).masked_fill(~attention_mask.bool()[:, None, None, :], neg)
+    pos = torch.arange(T, device=ids.device)[None].expand(B, T)
     x = embeddings(sd, "bert.", ids, torch.zeros_like(ids), pos)
     for l in range(layers):
         p = f"bert.encoder.layer.{l}."

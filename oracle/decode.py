@@ -34,7 +34,7 @@ def token_type_ids_full(ids: torch.Tensor, special_token_ids, sections=None) -> 
     sections = sections if sections is not None else list(range(len(special_token_ids) + 1))
     B, L = ids.shape
     tt = torch.full_like(ids, sections[0])
-    col_idx = torch.arange(L)[None]
+    col_idx = torch.arange(L, device=ids.device)[None]
     for i, tok in enumerate(special_token_ids):
         cols = (ids == tok).int().argmax(dim=1) + 1
         ok = (cols != 1) & (cols < L)
@@ -47,7 +47,7 @@ def token_type_ids_past(ids: torch.Tensor, special_token_ids, sections=None) -> 
     """(:340-364) type of the LAST token of `ids`: sections[i+1] of the last
     listed special token that occurs anywhere in ids[:, :-1]."""
     sections = sections if sections is not None else list(range(len(special_token_ids) + 1))
-    tt = torch.full((ids.shape[0], 1), sections[0], dtype=torch.long)
+    tt = torch.full((ids.shape[0], 1), sections[0], dtype=torch.long, device=ids.device)
     prev = ids[:, :-1]
     for i, tok in enumerate(special_token_ids):
         exists = torch.any(prev == tok, dim=1, keepdim=True)
@@ -90,7 +90,7 @@ def rollout(sd, memory, memory_mask, prompt_ids, *, special_token_ids, sections,
     """
     ids = prompt_ids.clone()
     B = ids.shape[0]
-    unfinished = torch.ones(B, dtype=torch.bool)
+    unfinished = torch.ones(B, dtype=torch.bool, device=ids.device)
     cache = bert.DecoderCache() if use_cache else None
     scores, lps, margins = [], [], []
     steps = 0

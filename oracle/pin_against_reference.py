@@ -19,6 +19,10 @@ What is compared (every check asserts; the script exits non-zero on failure):
    vectorised restatement, on random id matrices with edge cases;
 4. a greedy and a sampled rollout driven through the REFERENCE forward() and
    REFERENCE token-type helpers by the Appendix-B loop vs `oracle.decode.rollout`;
+6. `MultiCXREncoderDecoderModel` (modelling_multi.py:90-261) and
+   `SingleCXREncoderDecoderModel` (modelling_single.py:81-249): encoder, greedy
+   rollout from [BOS] through the reference forward(), teacher-forced logits
+   -> tests/golden/cxrmate_ref_variants.npz;
 5. structural pins from the reference notebooks: decoder parameter count
    80,769,072 + 147,456 LoRA = 80,916,528 (examples/cxrmate.ipynb:89), tied LM head,
    no-history prompt ids [8,10,9,11,1] (examples/cxrmate.ipynb:307-311).
@@ -225,9 +229,74 @@ def main():
         gold[f"{name}_last_logits_0"] = r_scores[-1][0].numpy()
         gold[f"{name}_first_logits_1"] = r_scores[0][1].numpy()
 
+    # -- 6. the prompt-free variants: MultiCXREncoderDecoderModel (modelling_multi.py:90-261) and
+    #       SingleCXREncoderDecoderModel (modelling_single.py:81-249): no LoRA, prompt = [[BOS]], default sections
+    #       list(range(len(special)+1)) with special_token_ids=[SEP] (multi.py:218-228, single.py:483-493), default BERT
+    #       positions (arange), cross-attention mask from the encoder (multi) / none (single)
+    import transformers
+    from modules.transformers.multi_model import modelling_multi as mm
+    sd_plain = {k: v for k, v in sd.items() if "lora_" not in k}
+    var = {}
+    for vname, mod, cls_name, enc_cfg_cls in (("multi", mm, "MultiCXREncoderDecoderModel", "CvtWithProjectionHeadConfig"),
+                                               ("single", ms, "SingleCXREncoderDecoderModel", "CvtWithProjectionHeadConfig")):
+        enc_cfg = getattr(mod, enc_cfg_cls)(depth=[1, 4, 16], projection_size=768)
+        dec_cfg = transformers.BertConfig(vocab_size=30000, num_hidden_layers=6, type_vocab_size=2, is_decoder=True,
+                                          add_cross_attention=True)
+        cfg = transformers.VisionEncoderDecoderConfig.from_encoder_decoder_configs(enc_cfg, dec_cfg)
+        vm = getattr(mod, cls_name)(config=cfg)
+        missing, unexpected = vm.load_state_dict(sd_plain, strict=False)
+        missing = [m for m in missing if "position_ids" not in m and "token_type_ids" not in m]
+        assert not missing and not unexpected, (vname, missing[:5], unexpected[:5])
+        vm.eval()
+        vpx = pixels if vname == "multi" else pixels[:, 0]
+        venc = vm.encoder(vpx)
+        if vname == "multi":
+            vmem, vmask = cvt.encode_multi(sd_plain, vpx)
+            assert torch.equal(venc.attention_mask, vmask)
+        else:
+            vmem, vmask = cvt.encode_single(sd_plain, vpx), None
+        assert (venc.last_hidden_state - vmem).abs().max().item() < 2e-4
+        Tv = 8
+        ids = torch.full((2, 1), BOS)
+        unfinished = torch.ones(2, dtype=torch.bool)
+        past, v_scores = None, []
+        for t in range(Tv):                                  # Appendix-B loop over the REFERENCE forward()
+            if past is None:
+                tt, feed = vm.token_ids_to_token_type_ids(ids, [SEP]), ids
+            else:
+                tt, feed = vm.token_ids_to_token_type_ids_past(ids, [SEP]), ids[:, -1:]
+            out = vm(encoder_outputs=venc, decoder_input_ids=feed, decoder_attention_mask=torch.ones_like(ids),
+                     decoder_token_type_ids=tt, past_key_values=past, use_cache=True, return_dict=True)
+            past = out.past_key_values
+            lg = out.logits[:, -1].float()
+            nxt = torch.argmax(lg, dim=-1)
+            nxt = nxt * unfinished + PAD * (~unfinished)
+            ids = torch.cat((ids, nxt[:, None]), dim=1)
+            v_scores.append(lg)
+            unfinished = unfinished & (nxt != EOS)
+            if not unfinished.any():
+                break
+        o = decode.rollout(sd_plain, vmem, vmask, torch.full((2, 1), BOS), special_token_ids=[SEP], sections=None,
+                           mask_token_id=None, max_new_tokens=Tv, eos_token_id=EOS, pad_token_id=PAD)
+        assert torch.equal(ids, o.sequences), (vname, ids, o.sequences)
+        d = (v_scores[-1] - o.scores[-1]).abs().max().item()
+        assert d < 5e-4, (vname, d)
+        report[f"{vname}_last_score_maxabs"] = d
+        # teacher-forced forward of the variant on the generated ids (what model.forward returns)
+        tt_full = vm.token_ids_to_token_type_ids(ids, [SEP])
+        tf = vm(encoder_outputs=venc, decoder_input_ids=ids, decoder_attention_mask=torch.ones_like(ids),
+                decoder_token_type_ids=tt_full, return_dict=True).logits
+        var[f"{vname}_sequences"] = ids.numpy()
+        var[f"{vname}_last_logits_0"] = v_scores[-1][0].numpy()
+        var[f"{vname}_tf_logits_slice"] = tf[:, :, ::101].numpy()
+        var[f"{vname}_tf_argmax"] = tf.argmax(-1).numpy()
+        var[f"{vname}_memory_slice"] = venc.last_hidden_state[:, ::37, ::29].numpy()
+
     print("pin report:", report)
     if args.check:
         return
+    np.savez_compressed(os.path.join(GOLDEN, "cxrmate_ref_variants.npz"), T=Tv, **var)
+    print("wrote", os.path.join(GOLDEN, "cxrmate_ref_variants.npz"))
     os.makedirs(GOLDEN, exist_ok=True)
     np.savez_compressed(
         os.path.join(GOLDEN, "cxrmate_ref_small.npz"),

@@ -70,6 +70,26 @@ def main():
                 ex = reference_schedule(subj, stud, world, mbatch, seed, shuffle)
                 cases.append(dict(world=world, mbatch=mbatch, seed=seed, shuffle=shuffle, subject_ids=subj, study_ids=stud,
                                   examples=ex))
+    # non-divisible study counts: the reference oversamples its last (single-study) subject into one lane.  Only
+    # tables the reference itself accepts are kept (its zip() truncates unequal lanes and its final assert then fails).
+    n_odd = 0
+    for world, mbatch in [(1, 4), (2, 2), (2, 3), (8, 4)]:
+        for attempt in range(200):
+            subj, stud = make_table(3 * world * mbatch + 1, rng, divisible_by=world * mbatch)
+            extra = rng.randint(1, world * mbatch - 1)
+            s0, sid0 = max(subj) + 1, max(stud) + 1
+            for k in range(extra):
+                subj.append(s0 + k); stud.append(sid0 + k)
+            assert len(set(stud)) % (world * mbatch) != 0
+            try:
+                ex = reference_schedule(subj, stud, world, mbatch, 7, True)
+            except AssertionError:
+                continue
+            cases.append(dict(world=world, mbatch=mbatch, seed=7, shuffle=True, subject_ids=subj, study_ids=stud,
+                              examples=ex, oversampled=True))
+            n_odd += 1
+            break
+    print("non-divisible cases accepted by the reference:", n_odd)
     out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "subject_schedule.json")
     json.dump(cases, open(out, "w"))
     print(len(cases), "cases ->", out, os.path.getsize(out), "bytes")
