@@ -251,7 +251,10 @@ def test_prompt_free_variants_vs_reference_fixtures(sd, variant):
         enc = m.encoder(px.cuda())
         assert ("attention_mask" in enc) == (variant == "multi")
         ms = torch.from_numpy(gold[f"{variant}_memory_slice"])
-        assert (enc["last_hidden_state"][:, ::37, ::29].cpu() - ms).abs().max().item() < 2e-3
+        d = (enc["last_hidden_state"][:, ::37, ::29].cpu() - ms).abs()
+        if variant == "multi":     # padded images: the reference encodes and masks them, the engine leaves zeros (cxrm.h)
+            d = d * enc["attention_mask"][:, ::37, None].cpu()
+        assert d.max().item() < 2e-3
         T = int(gold["T"])
         seq = m.generate(encoder_outputs=enc, special_token_ids=[SEP], max_length=T + 1, bos_token_id=BOS, eos_token_id=EOS,
                          pad_token_id=PAD, num_beams=1, return_dict_in_generate=True, use_cache=True)["sequences"]
