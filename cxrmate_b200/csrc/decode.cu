@@ -26,7 +26,7 @@ constexpr int H = 768, HD = 64, NH = 12;
 // rollout_init
 // =============================================================================
 __global__ void rollout_init_kernel(RolloutState st, RolloutParams p, const int* __restrict__ prompt, int* pre_ids,
-                                    int* pre_types, int* pre_pos) {
+                                    int* pre_types, int* pre_pos, uint8_t* pre_valid) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r == 0) {
     *st.step = 0;
@@ -64,18 +64,19 @@ __global__ void rollout_init_kernel(RolloutState st, RolloutParams p, const int*
     for (int i = 0; i < ns; ++i)
       if (ok[i] && c >= cols[i]) tt = p.sections[blk][i + 1];
     st.seq[static_cast<long long>(r) * p.Lmax + c] = id;
-    st.key_valid[static_cast<long long>(r) * p.Lmax + c] = valid ? 1 : 0;
+    pre_valid[static_cast<long long>(r) * p.P + c] = valid ? 1 : 0;   // key mask of the prompt pass (column layout)
     pre_ids[static_cast<long long>(r) * p.P + c] = id;
     pre_types[static_cast<long long>(r) * p.P + c] = tt;
     pre_pos[static_cast<long long>(r) * p.P + c] = max(cum - 1, 0);
   }
-  for (int c = p.P; c < p.Lmax; ++c) {
-    st.seq[static_cast<long long>(r) * p.Lmax + c] = p.pad;
-    st.key_valid[static_cast<long long>(r) * p.Lmax + c] = 0;
-  }
+  // The self-attention cache holds only the VISIBLE prompt tokens, compacted: token (r, c) sits at slot pos = cum - 1
+  // (a masked key has softmax weight exactly 0 in the reference - additive finfo.min - so dropping it changes
+  // nothing, and right-padded prompts stop costing K/V reads on every decode step); generated tokens follow.
+  for (int c = 0; c < p.Lmax; ++c) st.key_valid[static_cast<long long>(r) * p.Lmax + c] = c < cum ? 1 : 0;
+  for (int c = p.P; c < p.Lmax; ++c) st.seq[static_cast<long long>(r) * p.Lmax + c] = p.pad;
   st.n_valid[r] = cum;
   st.seen[r] = seen;
-  st.cur_len[r] = p.P;
+  st.cur_len[r] = cum - 1;   // last occupied cache slot; the sampling head advances it per emitted token
   st.cur_token[r] = p.pad;
   st.cur_type[r] = 0;
   st.cur_pos[r] = 0;
@@ -410,7 +411,8 @@ __global__ void __launch_bounds__(SNT) sample_step_kernel(RolloutState st, Rollo
     st.topk_cnt[ro * p.Tmax + t] = n_surv;
     if (!was_finished) {
       const bool valid = p.mask_token_id < 0 || next != p.mask_token_id;
-      st.key_valid[ro * p.Lmax + slot] = valid ? 1 : 0;
+      const int cslot = st.cur_len[r] + 1;     // cache slot of the emitted token (visible prompt tokens + emitted so far)
+      st.key_valid[ro * p.Lmax + cslot] = valid ? 1 : 0;
       const int nv = st.n_valid[r] + (valid ? 1 : 0);
       st.n_valid[r] = nv;
       st.cur_pos[r] = max(nv - 1, 0);
@@ -425,7 +427,7 @@ __global__ void __launch_bounds__(SNT) sample_step_kernel(RolloutState st, Rollo
         if (next == p.special_ids[blk][i]) add |= 1u << i;
       st.seen[r] = seen | add;
       st.cur_token[r] = next;
-      st.cur_len[r] = slot;
+      st.cur_len[r] = cslot;
       if (next == p.eos) st.finished[r] = 1;
     }
     __threadfence();
@@ -472,8 +474,8 @@ __global__ void cosine_rows_kernel(const float* __restrict__ a, const float* __r
 }  // namespace
 
 void rollout_init(const RolloutState& st, const RolloutParams& p, const int* prompt_ids, int* pre_ids, int* pre_types,
-                  int* pre_pos, cudaStream_t stream) {
-  rollout_init_kernel<<<ceil_div(p.R, 64), 64, 0, stream>>>(st, p, prompt_ids, pre_ids, pre_types, pre_pos);
+                  int* pre_pos, uint8_t* pre_valid, cudaStream_t stream) {
+  rollout_init_kernel<<<ceil_div(p.R, 64), 64, 0, stream>>>(st, p, prompt_ids, pre_ids, pre_types, pre_pos, pre_valid);
   check_launch("rollout_init");
 }
 

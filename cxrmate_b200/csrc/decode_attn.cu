@@ -821,7 +821,7 @@ __global__ void __launch_bounds__(PNT, 2) decode_self_persist_kernel(const __gri
   // step, and a step opens with a plain (fully serialised) launch: it is readable ahead of the dependency wait, and
   // so are all cache rows except the slot of the token being fed.  Only q/k/v of the QKV projection wait.
   const bool done = *st.done != 0;
-  // live rows sit at slot P + step (rollout_init / sample_step keep cur_len uniform); chunks of the longest row
+  // a live row's token sits at slot (visible prompt tokens) + step <= P + step: chunks of the longest possible row
   const int mc = ceil_div(P + *st.step + 1, CHB);
   const int n_items = NH * R * mc;
   // whole (row, head) groups per CTA (a multiple of mc items): no group straddles two CTAs, so the cross-CTA ticket
@@ -969,7 +969,8 @@ __global__ void __launch_bounds__(PNT, 2) decode_self_persist_kernel(const __gri
 // qkv [R*P, 3*768] -> head-major caches [R][12][Lmax][64], columns [0,P)
 template <typename T>
 __global__ void prefill_store_kv_kernel(const T* __restrict__ qkv, T* __restrict__ kcache, T* __restrict__ vcache,
-                                        int R, int P, int Lmax) {
+                                        const int* __restrict__ slot, const uint8_t* __restrict__ valid, int R, int P,
+                                        int Lmax) {
   constexpr int VN = Vec16<T>::N;
   const int cv = H / VN;
   const long long total = static_cast<long long>(R) * P * cv * 2;
@@ -981,10 +982,11 @@ __global__ void prefill_store_kv_kernel(const T* __restrict__ qkv, T* __restrict
     t /= 2;
     const int pcol = static_cast<int>(t % P);
     const long long r = t / P;
+    if (!valid[r * P + pcol]) continue;
     Vec16<T> v;
     v.load(qkv + (r * P + pcol) * 3 * H + (1 + which) * H + c);
     const int h = c / HD, d = c % HD;
-    v.store((which ? vcache : kcache) + ((r * NH + h) * Lmax + pcol) * HD + d);
+    v.store((which ? vcache : kcache) + ((r * NH + h) * Lmax + slot[r * P + pcol]) * HD + d);
   }
 }
 
@@ -1089,12 +1091,13 @@ void decode_cross_attention(const T* q, int ldq, const T* kc, const T* vc, long 
 }
 
 template <typename T>
-void prefill_store_kv(const T* qkv, T* kcache, T* vcache, int R, int P, int Lmax, cudaStream_t stream) {
+void prefill_store_kv(const T* qkv, T* kcache, T* vcache, const int* slot, const uint8_t* valid, int R, int P, int Lmax,
+                      cudaStream_t stream) {
   const long long total = static_cast<long long>(R) * P * (H / Vec16<T>::N) * 2;
   if (total <= 0) return;
   long long grid = ceil_div_ll(total, 256);
   if (grid > 148 * 32) grid = 148 * 32;
-  prefill_store_kv_kernel<T><<<static_cast<unsigned>(grid), 256, 0, stream>>>(qkv, kcache, vcache, R, P, Lmax);
+  prefill_store_kv_kernel<T><<<static_cast<unsigned>(grid), 256, 0, stream>>>(qkv, kcache, vcache, slot, valid, R, P, Lmax);
   check_launch("prefill_store_kv");
 }
 
@@ -1104,7 +1107,7 @@ void prefill_store_kv(const T* qkv, T* kcache, T* vcache, int R, int P, int Lmax
   template void decode_cross_attention<T>(const T*, int, const T*, const T*, long long, T*, const CrossUnits&,        \
                                           const RolloutState&, int, int, float*, unsigned*, const AttnMaps*, int,     \
                                           cudaStream_t);                                                              \
-  template void prefill_store_kv<T>(const T*, T*, T*, int, int, int, cudaStream_t);
+  template void prefill_store_kv<T>(const T*, T*, T*, const int*, const uint8_t*, int, int, int, cudaStream_t);
 INST(float)
 INST(bf16)
 #undef INST

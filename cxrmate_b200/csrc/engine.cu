@@ -460,6 +460,7 @@ class Engine : public EngineBase {
     pre_ids = dalloc<int>(static_cast<long long>(Rmax) * cfg.max_prompt);
     pre_types = dalloc<int>(static_cast<long long>(Rmax) * cfg.max_prompt);
     pre_pos = dalloc<int>(static_cast<long long>(Rmax) * cfg.max_prompt);
+    pre_valid = dalloc<uint8_t>(static_cast<long long>(Rmax) * cfg.max_prompt);
     prompt_dev = dalloc<int>(B * cfg.max_prompt);
     // decode-attention work units (decode_attn.cu): partials + arrival tickets, zeroed once
     attn_ch = decode_attn_chunk(sizeof(T));
@@ -479,6 +480,10 @@ class Engine : public EngineBase {
     CXRM_CUDA_CHECK(cudaMemset(self_v, 0, sizeof(T) * cfg.dec_layers * self_layer_stride()));
     setup_attn_maps();
     skinny_ws = dalloc<float>(static_cast<long long>(gemm_skinny_partial_floats(DH)));
+    chain_bar = dalloc<unsigned>(kChainBarWords);
+    CXRM_CUDA_CHECK(cudaMemset(chain_bar, 0, kChainBarWords * sizeof(unsigned)));
+    chain_xf = dalloc<float>(static_cast<long long>(Rmax) * DH);
+    chain_x1f = dalloc<float>(static_cast<long long>(Rmax) * DH);
 
     // scratch arena: max over the phases
     const long long e = sizeof(T);
@@ -905,7 +910,8 @@ class Engine : public EngineBase {
       const BertLayerW& w = dec.layers[l];
       gemm(b.x, DH, w.qkv, b.qkv, 3 * DH, M, ACT_NONE, nullptr, 0, false, nullptr, s);
       if (store_cache)
-        PF("store_kv", s, [&] { prefill_store_kv<T>(b.qkv, self_k + l * self_layer_stride(), self_v + l * self_layer_stride(), R, q, Lmax, s); });
+        PF("store_kv", s, [&] { prefill_store_kv<T>(b.qkv, self_k + l * self_layer_stride(), self_v + l * self_layer_stride(), pre_pos, pre_valid,
+                                                    R, q, Lmax, s); });
       AttnArgs a{};
       a.q = b.qkv; a.k = b.qkv + DH; a.v = b.qkv + 2 * DH; a.o = b.ctx;
       a.q_bs = static_cast<long long>(q) * 3 * DH; a.q_hs = 64; a.q_ts = 3 * DH;
@@ -1035,7 +1041,118 @@ class Engine : public EngineBase {
     PF("sample", s, [&] { sample_step(st, rp, logits, cfg.vocab, noise, s); });
   }
 
+  // ---- decode step with the GEMM / LayerNorm work between the attention kernels as persistent multi-phase launches
+  // (decode_chain.cu): per step 1 + 6 x (self-attention, chain A, cross-attention, chain B) + LM head + sample = 27
+  // launches instead of 71.  Phase lists are built once per (buffers, R) and kept in device memory.
+  bool use_chain(int R) const {
+    return std::is_same<T, bf16>::value && cfg.use_tensor_cores && R <= 64 && ablate_mask() == 0 && !use_lnfold() &&
+           decode_chain_available();
+  }
+  void ensure_chain(const DecBufs& b, T* head_tmp, int R) {
+    if constexpr (std::is_same<T, bf16>::value) {
+      if (chain_key_buf == b.x && chain_key_R == R && chain_key_head == head_tmp && !chain_launch.empty()) return;
+      // fp32 residual stream beside the bf16 activations (CXRM_CHAIN_BF16_RES=1: bf16 residuals, pre-LN sum rounded to
+      // bf16 as the round-1 kernels and bf16 autocast do)
+      static const bool f32res = std::getenv("CXRM_CHAIN_BF16_RES") == nullptr;
+      std::vector<ChainPhase> ph;
+      chain_launch.clear();
+      const int ctas = decode_chain_ctas();
+      auto gemm_phase = [&](const T* A, int Ktot, const Lin& L, int bn, int epi, void* out, int ldo) {
+        ChainPhase p;
+        std::memset(&p, 0, sizeof(p));
+        p.type = CH_GEMM;
+        p.tmA = make_tensor_map_bf16_kblocks(A, R, Ktot, Ktot, 64, DH / 64);
+        p.tmB = make_tensor_map_bf16(L.w, L.n_out, L.n_in, L.n_in, bn, 64);
+        p.bn = bn; p.n_tiles = L.n_out / bn; p.nsplit = Ktot / DH; p.epi = epi; p.N = L.n_out; p.ldo = ldo;
+        p.bias = L.b; p.out = out; p.partial = skinny_ws;
+        CXRM_CHECK(L.n_in == Ktot && L.n_out % bn == 0 && Ktot % DH == 0 && p.n_tiles * p.nsplit <= ctas &&
+                       (epi != CE_PARTIAL || (L.n_out == DH && p.nsplit <= 4)), "decode chain: GEMM phase shape");
+        ph.push_back(p);
+      };
+      auto ln_phase = [&](int type, int nsplit, const float* bias, int act, const T* res, const float* res32, const LNp& ln,
+                          T* out, float* out32) {
+        ChainPhase p;
+        std::memset(&p, 0, sizeof(p));
+        p.type = type; p.nsplit = nsplit; p.bias = bias; p.act = act; p.partial = skinny_ws;
+        p.residual = f32res ? nullptr : res; p.residual_f32 = f32res ? res32 : nullptr;
+        p.round_pre = f32res ? 0 : 1;
+        p.gamma = ln.g; p.beta = ln.b; p.eps = LN_EPS_BERT; p.out = out; p.ldo = DH; p.out_f32 = f32res ? out32 : nullptr;
+        p.word = dec.word; p.type_emb = dec.type; p.pos_emb = dec.pos;
+        ph.push_back(p);
+      };
+      auto close = [&](size_t first) { chain_launch.push_back({static_cast<int>(first), static_cast<int>(ph.size() - first)}); };
+      float* xf = chain_xf; float* x1f = chain_x1f;
+      size_t f0 = ph.size();
+      ln_phase(CH_EMBED, 0, nullptr, ACT_NONE, nullptr, nullptr, dec.emb_ln, b.x, xf);
+      gemm_phase(b.x, DH, dec.layers[0].qkv, 16, CE_BF16, b.qkv, 3 * DH);
+      close(f0);
+      for (int l = 0; l < cfg.dec_layers; ++l) {
+        const BertLayerW& w = dec.layers[l];
+        f0 = ph.size();                                                             // chain A: after self-attention
+        gemm_phase(b.ctx, DH, w.o, 16, CE_PARTIAL, nullptr, 0);
+        ln_phase(CH_LN, 1, w.o.b, ACT_NONE, b.x, xf, w.ln1, b.x1, x1f);
+        gemm_phase(b.x1, DH, w.cq, 16, CE_BF16, b.qkv, DH);
+        close(f0);
+        f0 = ph.size();                                                             // chain B: after cross-attention
+        gemm_phase(b.ctx, DH, w.co, 16, CE_PARTIAL, nullptr, 0);
+        ln_phase(CH_LN, 1, w.co.b, ACT_NONE, b.x1, x1f, w.ln2, b.x, xf);
+        gemm_phase(b.x, DH, w.fc1, 32, CE_BF16_GELU, b.hid, DFF);
+        gemm_phase(b.hid, DFF, w.fc2, 32, CE_PARTIAL, nullptr, 0);
+        ln_phase(CH_LN, DFF / DH, w.fc2.b, ACT_NONE, b.x, xf, w.ln3, b.x, xf);
+        if (l + 1 < cfg.dec_layers) {
+          gemm_phase(b.x, DH, dec.layers[l + 1].qkv, 16, CE_BF16, b.qkv, 3 * DH);
+        } else {                                                                    // LM-head transform: dense -> GELU -> LN
+          gemm_phase(b.x, DH, dec_head_t, 16, CE_PARTIAL, nullptr, 0);
+          ln_phase(CH_LN, 1, dec_head_t.b, ACT_GELU, nullptr, nullptr, dec_head_ln, head_tmp, nullptr);
+        }
+        close(f0);
+      }
+      static const bool want_trace = std::getenv("CXRM_CHAIN_TRACE") != nullptr;
+      if (want_trace && !chain_trace)
+      {
+        const long long nt = static_cast<long long>(chain_launch.size()) * decode_chain_ctas() * kChainTraceSlots;
+        chain_trace = dalloc<unsigned long long>(nt);
+        CXRM_CUDA_CHECK(cudaMemset(chain_trace, 0, nt * sizeof(unsigned long long)));
+      }
+      chain_host = std::move(ph);
+      chain_key_buf = b.x; chain_key_R = R; chain_key_head = head_tmp;
+    }
+  }
+  void decode_step_chain(DecBufs& b, T* head_tmp, const RolloutParams& rp, const float* noise, cudaStream_t s) {
+    phase = "decode";
+    const int R = rp.R, B = rp.B;
+    const int* skip = st.done;
+    size_t k = 0;
+    auto chain = [&]() {
+      const auto fc = chain_launch[k];
+      unsigned long long* tr = chain_trace ? chain_trace + k * static_cast<size_t>(decode_chain_ctas()) * kChainTraceSlots : nullptr;
+      ++k;
+      PF("chain", s, [&] { decode_chain(chain_host.data() + fc.first, fc.second, R, st, chain_bar, s, tr); });
+    };
+    chain();                                   // embedding + LayerNorm, QKV of layer 0 (plain launch: opens the step)
+    struct PdlScope {
+      explicit PdlScope(bool on) { g_pdl = on; }
+      ~PdlScope() { g_pdl = false; }
+    } pdl_scope(chain_pdl() && !profiling);
+    for (int l = 0; l < cfg.dec_layers; ++l) {
+      PF("self_attn", s, [&] { decode_self_attention<T>(b.qkv, self_k + l * self_layer_stride(), self_v + l * self_layer_stride(), b.ctx, st, R,
+                               rp.P, Lmax, self_ws, self_tickets, attn_maps_ptr, l, s); });
+      chain();                                 // O projection, LayerNorm, cross-attention query
+      const T* kvl = cross_kv + static_cast<long long>(l) * cross_layer_stride();
+      PF("cross_attn", s, [&] { decode_cross_attention<T>(b.qkv, DH, kvl, kvl + NHEAD * cross_head_stride(), cross_head_stride(), b.ctx,
+                                cross_units(), st, R, B, cross_ws, cross_tickets, attn_maps_ptr, l, s); });
+      chain();                                 // cross output, LayerNorm, FFN, LayerNorm, next layer's QKV / head transform
+    }
+    gemm(head_tmp, DH, dec_lm, logits, cfg.vocab, R, ACT_NONE, nullptr, 0, true, skip, s);
+    PF("sample", s, [&] { sample_step(st, rp, logits, cfg.vocab, noise, s); });
+  }
+
   void decode_step(DecBufs& b, T* head_tmp, const RolloutParams& rp, const float* noise, cudaStream_t s) {
+    if (use_chain(rp.R)) {
+      ensure_chain(b, head_tmp, rp.R);
+      decode_step_chain(b, head_tmp, rp, noise, s);
+      return;
+    }
     if (use_lnfold()) {
       decode_step_folded(b, head_tmp, rp, noise, s);
       return;
@@ -1141,7 +1258,7 @@ class Engine : public EngineBase {
       CXRM_CUDA_CHECK(cudaMemsetAsync(st.margin, 0, rt0 * sizeof(float), s));
       CXRM_CUDA_CHECK(cudaMemsetAsync(st.topk_cnt, 0, rt0 * sizeof(int), s));
     }
-    PF("init", s, [&] { rollout_init(st, rp, a.prompt_ids, pre_ids, pre_types, pre_pos, s); });
+    PF("init", s, [&] { rollout_init(st, rp, a.prompt_ids, pre_ids, pre_types, pre_pos, pre_valid, s); });
 
     arena.reset();
     const long long M = static_cast<long long>(R) * P;
@@ -1152,7 +1269,7 @@ class Engine : public EngineBase {
     DecBufs pb = dec_bufs(M);
     PF("embed_ln", s, [&] { embed_ln<T>(pre_ids, pre_types, pre_pos, dec.word, dec.type, dec.pos, dec.emb_ln.g, dec.emb_ln.b, pb.x, M, DH,
                 LN_EPS_BERT, s); });
-    T* hid = decoder_full(pb, R, P, a.B, st.key_valid, Lmax, /*store_cache=*/true, s);
+    T* hid = decoder_full(pb, R, P, a.B, pre_valid, P, /*store_cache=*/true, s);
     PF("take_last", s, [&] { take_last_token<T>(hid, last, R, P, DH, s); });
     lm_head(last, R, head_tmp, logits, cfg.vocab, nullptr, s);
     PF("sample", s, [&] { sample_step(st, rp, logits, cfg.vocab, a.exp_noise, s); });
@@ -1176,6 +1293,10 @@ class Engine : public EngineBase {
     if (a.topk_cnt) CXRM_CUDA_CHECK(cudaMemcpyAsync(a.topk_cnt, st.topk_cnt, rt * sizeof(int), cudaMemcpyDeviceToDevice, s));
     if (a.last_logits)
       CXRM_CUDA_CHECK(cudaMemcpyAsync(a.last_logits, logits, static_cast<size_t>(R) * cfg.vocab * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    if (chain_trace) {
+      static int dumped = 0;
+      if (dumped++ == 2) dump_chain_trace(s);   // third rollout of the process: warm
+    }
     if (hop) {
       CXRM_CUDA_CHECK(cudaEventRecord(ev_b, s));
       CXRM_CUDA_CHECK(cudaStreamWaitEvent(s_user, ev_b, 0));
@@ -1490,10 +1611,59 @@ class Engine : public EngineBase {
   size_t h2d_pixel_bytes = 0;             // pixel bytes copied by the last host-buffer step
   RolloutState st{};
   int* pre_ids = nullptr; int* pre_types = nullptr; int* pre_pos = nullptr; int* prompt_dev = nullptr;
+  uint8_t* pre_valid = nullptr;           // [R, P] key mask of the prompt pass
   // host-step staging
   float* h_pixels = nullptr; int* h_seq = nullptr; float* h_lp = nullptr; int* h_rids = nullptr; int* h_rlens = nullptr;
   float* h_emb = nullptr; float* h_out = nullptr;
   int* id_map = nullptr; int bridge_cls = 0, bridge_sep = 0, bridge_bos = 1, bridge_sep_dec = 3, bridge_n_special = 12;
+  // persistent decode chain (decode_chain.cu): phase lists, (first, count) per launch of a step
+  std::vector<ChainPhase> chain_host;
+  unsigned* chain_bar = nullptr;
+  unsigned long long* chain_trace = nullptr;                  // CXRM_CHAIN_TRACE: stamps of the last executed decode step
+  // timeline of the last traced decode step: per launch and phase, when the slowest CTA started / ended it
+  void dump_chain_trace(cudaStream_t s) {
+    if (!chain_trace || chain_launch.empty()) return;
+    CXRM_CUDA_CHECK(cudaStreamSynchronize(s));
+    const int nc = decode_chain_ctas();
+    std::vector<unsigned long long> h(chain_launch.size() * nc * kChainTraceSlots);
+    CXRM_CUDA_CHECK(cudaMemcpy(h.data(), chain_trace, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    auto at = [&](size_t k, int c, int slot) { return h[(k * nc + c) * kChainTraceSlots + slot]; };
+    unsigned long long t00 = ~0ull;
+    for (int c = 0; c < nc; ++c) t00 = std::min(t00, at(0, c, 0));
+    fprintf(stderr, "[cxrm chain trace] one decode step, us since the first chain CTA started (min..max over %d CTAs)\n", nc);
+    for (size_t k = 0; k < chain_launch.size(); ++k) {
+      auto mm = [&](int slot, double& lo, double& hi) {
+        unsigned long long a = ~0ull, b = 0;
+        for (int c = 0; c < nc; ++c) {
+          a = std::min(a, at(k, c, slot));
+          b = std::max(b, at(k, c, slot));
+        }
+        lo = (a - t00) * 1e-3;
+        hi = (b - t00) * 1e-3;
+      };
+      double lo, hi, lo1, hi1;
+      mm(0, lo, hi);
+      mm(1, lo1, hi1);
+      fprintf(stderr, "  launch %2zu: entry %.1f..%.1f  dep-wait done %.1f..%.1f |", k, lo, hi, lo1, hi1);
+      for (int i = 0; i < chain_launch[k].second; ++i) {
+        double s0, s1, e0, e1;
+        mm(2 + 8 * i, s0, s1);
+        mm(2 + 8 * i + 7, e0, e1);
+        fprintf(stderr, " p%d start %.1f..%.1f", i, s0, s1);
+        if (at(k, 0, 2 + 8 * i + 3)) {   // GEMM sub-stamps of CTA 0 (it takes part in every GEMM phase), relative to its phase start
+          const unsigned long long b = at(k, 0, 2 + 8 * i);
+          auto rel = [&](int sub) { return (static_cast<double>(at(k, 0, 2 + 8 * i + sub)) - static_cast<double>(b)) * 1e-3; };
+          fprintf(stderr, " [cta0 +: A-issued %.2f A-in %.2f mma-issued %.2f acc %.2f]", rel(5), rel(2), rel(3), rel(4));
+        }
+        fprintf(stderr, " end %.1f..%.1f |", e0, e1);
+      }
+      fprintf(stderr, "\n");
+    }
+  }
+  float* chain_xf = nullptr; float* chain_x1f = nullptr;      // fp32 residual stream [Rmax, 768] x 2
+  struct ChainSpan { int first, second; };
+  std::vector<ChainSpan> chain_launch;
+  const void* chain_key_buf = nullptr; const void* chain_key_head = nullptr; int chain_key_R = 0;
   // CUDA graph of one decode step
   struct GraphKey {
     int R, B, P, Tmax, top_k; float temperature; const float* noise; const void* buf;

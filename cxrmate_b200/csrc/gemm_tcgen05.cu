@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(kFull, *tmem_slot, 0);   // provably warp-uniform: no R2UR waterfall around each tcgen05.mma
   if (threadIdx.x == 0) TRACE(1);
 
   if (warp == 0) {
@@ -457,7 +457,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_persist_kernel(const __gr
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(kFull, *tmem_slot, 0);   // provably warp-uniform: no R2UR waterfall around each tcgen05.mma
 
   if (warp == 0) {
     if (lane == 0) {
@@ -644,7 +644,7 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_skinny_kernel(const __grid_c
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(kFull, *tmem_slot, 0);   // provably warp-uniform: no R2UR waterfall around each tcgen05.mma
   // After a skip (every rollout row finished) only the loads already requested are drained; no MMA, no stores.
   const int npre = min(nkb, stages);
 
@@ -1030,7 +1030,7 @@ __global__ void __cluster_dims__(CL_SIZE, 1, 1) __launch_bounds__(NTHREADS)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(kFull, *tmem_slot, 0);   // provably warp-uniform: no R2UR waterfall around each tcgen05.mma
   const int npre = min(nkb, stages);
   cluster_sync_all();   // every CTA of the cluster is running before anyone writes into a peer's shared memory
 
@@ -1501,6 +1501,24 @@ CUtensorMap make_tensor_map_bf16(const void* ptr, long long rows, long long cols
   return m;
 }
 
+
+// A row-major bf16 matrix [rows, cols] (row pitch ld) seen as [cols / 64 k-blocks][rows][64]: one TMA box
+// {64, box_rows, box_kblocks} lands in shared memory as box_kblocks consecutive K-major 128-byte-swizzled tiles of
+// box_rows x 64 - the operand layout of tcgen05.mma - with ONE instruction instead of one per k-block.
+CUtensorMap make_tensor_map_bf16_kblocks(const void* ptr, long long rows, long long cols, long long ld, int box_rows,
+                                         int box_kblocks) {
+  CUtensorMap m;
+  const cuuint64_t dims[3] = {64, static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(cols / 64)};
+  const cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 2, 128};
+  const cuuint32_t box[3] = {64, static_cast<cuuint32_t>(box_rows), static_cast<cuuint32_t>(box_kblocks)};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    throw std::runtime_error("cuTensorMapEncodeTiled (k-block view) failed (CUresult " + std::to_string(static_cast<int>(r)) + ")");
+  return m;
+}
 
 int gemm_ln_cluster_supported(const GemmArgs& g) {
   if (gemm_tcgen05_supported(g) != 0) return 1;

@@ -231,8 +231,10 @@ struct RolloutParams {
 
 // state from the prompt (reference modelling_longitudinal.py:274-282): types (full rule), positions,
 // key validity, `seen` bitmask; copies the prompt into seq; also emits the [R,P] prefill inputs.
+// pre_valid [R,P]: key mask of the prompt pass.  The self-attention cache is COMPACT: only visible prompt tokens are
+// stored (token (r, c) at slot pre_pos[r, c]), st.key_valid / st.cur_len are in cache-slot coordinates.
 void rollout_init(const RolloutState& st, const RolloutParams& p, const int* prompt_ids, int* pre_ids, int* pre_types,
-                  int* pre_pos, cudaStream_t stream);
+                  int* pre_pos, uint8_t* pre_valid, cudaStream_t stream);
 
 // logits [R,V] fp32 (row stride ldl) -> next token per row (greedy argmax or top-k multinomial),
 // log-prob, survivors, and the state for the next decoder step.  exp_noise: nullable [Tmax, B, V].
@@ -265,6 +267,9 @@ struct AttnMaps {
 };
 // 2-D bf16 tensor map [rows, cols] (row pitch ld elements), box [box_cols, box_rows], 128-byte swizzle (gemm_tcgen05.cu)
 CUtensorMap make_tensor_map_bf16(const void* ptr, long long rows, long long cols, long long ld, int box_rows, int box_cols);
+// the same matrix as [cols / 64][rows][64]: box {64, box_rows, box_kblocks} = consecutive K-major swizzled k-block tiles
+CUtensorMap make_tensor_map_bf16_kblocks(const void* ptr, long long rows, long long cols, long long ld, int box_rows,
+                                         int box_kblocks);
 int decode_attn_chunk(size_t elem_size);                   // CH: keys per unit (192 bf16 / 96 fp32)
 size_t decode_attn_ws_floats(int rows, int max_chunks);    // fp32 partials (max, sum, out[64]) per (row, head, chunk)
 
@@ -281,12 +286,51 @@ void decode_cross_attention(const T* q, int ldq, const T* kc, const T* vc, long 
                             const CrossUnits& cu, const RolloutState& st, int R, int B, float* ws, unsigned* tickets,
                             const AttnMaps* maps, int layer, cudaStream_t stream);
 
-// qkv [R*P, 3*768] -> head-major kcache/vcache [R][12][Lmax][64] columns [0,P)
+// qkv [R*P, 3*768] -> head-major kcache/vcache [R][12][Lmax][64]: token (r, c) goes to slot[r*P + c] when valid[r*P + c]
+// (masked prompt tokens are not cached)
 template <typename T>
-void prefill_store_kv(const T* qkv, T* kcache, T* vcache, int R, int P, int Lmax, cudaStream_t stream);
+void prefill_store_kv(const T* qkv, T* kcache, T* vcache, const int* slot, const uint8_t* valid, int R, int P, int Lmax,
+                      cudaStream_t stream);
 
 // issue the prefetch described by p (plain launch: belongs on a side stream / parallel graph branch)
 void l2_prefetch(const L2Prefetch& p, cudaStream_t stream);
+
+// ---- persistent GEMM / LayerNorm chain of the decode step (decode_chain.cu) ---------------------------------------
+enum ChainPhaseType : int { CH_GEMM = 0, CH_LN = 1, CH_EMBED = 2 };
+enum ChainEpi : int { CE_PARTIAL = 0, CE_BF16 = 1, CE_BF16_GELU = 2 };
+// One phase of a chain launch; a launch's list (<= 7 phases) travels in the kernel's parameter block.
+struct alignas(128) ChainPhase {
+  CUtensorMap tmA;           // GEMM: activations [R, K_total] bf16 as k-blocks: box {64, 64 rows, 12 k-blocks}
+  CUtensorMap tmB;           // GEMM: weights [N, K_total] bf16, box bn rows x 64 columns
+  int type;                  // ChainPhaseType
+  int n_tiles, nsplit, bn;   // GEMM: column tiles, 768-deep K splits, tile width (16 | 32); n_tiles * nsplit <= CTAs
+  int epi;                   // ChainEpi
+  int N;                     // GEMM: output columns (row pitch of the partials)
+  int ldo;                   // row pitch of `out` (bf16 elements)
+  int act;                   // LN: activation applied to partial sum + bias (ACT_GELU: LM-head transform)
+  int round_pre;             // LN: round the pre-LayerNorm sum to bf16 first (what bf16 autocast does)
+  float eps;
+  const float* bias;         // GEMM epilogue (CE_BF16*) or LN
+  void* out;                 // bf16 output (GEMM CE_BF16*, LN, EMBED)
+  float* partial;            // GEMM CE_PARTIAL: destination [nsplit][64][N]; LN: source (N == 768)
+  const void* residual;      // LN: bf16 [R, 768] or nullptr
+  const float* residual_f32; // LN: fp32 residual stream (takes precedence over `residual`)
+  float* out_f32;            // LN / EMBED: optional fp32 copy of the output (residual stream)
+  const float* gamma;
+  const float* beta;
+  const bf16* word;          // EMBED tables
+  const bf16* type_emb;
+  const bf16* pos_emb;
+};
+bool decode_chain_available();   // false: CXRM_NO_CHAIN set, or the device cannot hold one CTA per phase item
+int decode_chain_ctas();
+// one launch interpreting phases[0 .. count): bar = kChainBarWords zeroed unsigned counters owned by the caller
+// trace (nullable, debug): kChainTraceSlots %globaltimer stamps per CTA: [0] entry, [1] after the dependency wait,
+// [2 + 8i] start of phase i, [+1..+6] GEMM sub-stamps (decode_chain.cu GTRACE), [+7] end of phase i
+constexpr int kChainTraceSlots = 64;
+constexpr int kChainBarWords = 64 + 32 * 16;   // grid-barrier counters of decode_chain (zeroed once by the caller)
+void decode_chain(const ChainPhase* host_phases, int count, int R, const RolloutState& st, unsigned* bar, cudaStream_t stream,
+                  unsigned long long* trace = nullptr);
 
 // copy rows [r, P-1] of x [R*P, C] into out [R, C]
 template <typename T>
