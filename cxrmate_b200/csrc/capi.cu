@@ -178,6 +178,10 @@ int cxrm_scst_step_device(cxrm_engine* e, const float* pixels, int B, int N, con
                                         logprobs, reward, baseline, advantage, steps_out, /*on_device=*/true,
                                         static_cast<cudaStream_t>(stream)));
 }
+int cxrm_last_phase_ms(cxrm_engine* e, float* out5) {
+  if (!out5) return CXRM_ERR_INVALID;
+  CXRM_GUARD(e, e->impl->last_phase_ms(out5));
+}
 int cxrm_set_profile(cxrm_engine* e, int on) { CXRM_GUARD(e, e->impl->set_profile(on != 0)); }
 int cxrm_profile_report(cxrm_engine* e, char* buf, size_t len) {
   CXRM_GUARD(e, {

@@ -141,6 +141,9 @@ class Engine : public EngineBase {
       if (e) cudaEventDestroy(e);
     if (ev_pf_join) cudaEventDestroy(ev_pf_join);
     for (cudaEvent_t e : ev_chunk) cudaEventDestroy(e);
+    for (cudaEvent_t e : phase_ev)
+      if (e) cudaEventDestroy(e);
+    if (prefill_done_ev) cudaEventDestroy(prefill_done_ev);
   }
 
   // =========================================================================== weights
@@ -509,6 +512,9 @@ class Engine : public EngineBase {
   }
   void setup_attn_maps();
   size_t workspace_bytes() const override { return arena.capacity() + static_cast<size_t>(persistent_bytes); }
+  void last_phase_ms(float* out5) const override {
+    for (int i = 0; i < 5; ++i) out5[i] = phase_ms[i];
+  }
 
   // =========================================================================== per-kernel-class profiler
   // When enabled (cxrm_set_profile), every kernel launch of the engine is bracketed by a CUDA event pair on
@@ -1274,6 +1280,9 @@ class Engine : public EngineBase {
     lm_head(last, R, head_tmp, logits, cfg.vocab, nullptr, s);
     PF("sample", s, [&] { sample_step(st, rp, logits, cfg.vocab, a.exp_noise, s); });
 
+    if (!prefill_done_ev) CXRM_CUDA_CHECK(cudaEventCreate(&prefill_done_ev));
+    CXRM_CUDA_CHECK(cudaEventRecord(prefill_done_ev, s));   // prompt pass + first token done; decode steps follow
+    prefill_recorded = true;
     if (Tn > 1) {
       if (cfg.use_cuda_graph && !profiling) {
         run_decode_graph(db, head_tmp, rp, a.exp_noise, Tn - 1, s);
@@ -1450,13 +1459,12 @@ class Engine : public EngineBase {
     CXRM_CHECK(3 * B <= cfg.rwd_max_seqs && L_label <= cfg.rwd_max_len, "reward batch exceeds rwd_max_seqs");
     // timing aid: CXRM_PHASE_TIMES=1 prints the device time of each phase of the step (events on the step's stream)
     static const bool phase_times = std::getenv("CXRM_PHASE_TIMES") != nullptr;
-    cudaEvent_t pe[6] = {};
+    // device time of each phase of the step: five event records per step, read back by cxrm_last_phase_ms
+    if (!phase_ev[0])
+      for (cudaEvent_t& e : phase_ev) CXRM_CUDA_CHECK(cudaEventCreate(&e));
+    cudaEvent_t* pe = phase_ev;
     int n_pe = 0;
-    auto mark = [&]() {
-      if (!phase_times) return;
-      CXRM_CUDA_CHECK(cudaEventCreate(&pe[n_pe]));
-      CXRM_CUDA_CHECK(cudaEventRecord(pe[n_pe++], s));
-    };
+    auto mark = [&]() { CXRM_CUDA_CHECK(cudaEventRecord(pe[n_pe++], s)); };
     mark();
     const int Tn = tmpl.max_new_tokens, R = 2 * B, Lseq = P + Tn;
     // longest possible reward input: [CLS] + generated words + [SEP], or the longest label
@@ -1548,16 +1556,17 @@ class Engine : public EngineBase {
     if (steps_out) CXRM_CUDA_CHECK(cudaMemcpyAsync(steps_out, st.step, sizeof(int), cudaMemcpyDefault, s));
     mark();
     CXRM_CUDA_CHECK(cudaStreamSynchronize(s));
-    if (phase_times) {
+    {
       const char* names[4] = {"encode", "cross_kv", "rollout", "reward+copy"};
       std::string line = "[cxrm phases ms]";
       for (int i = 0; i + 1 < n_pe; ++i) {
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, pe[i], pe[i + 1]);
-        line += std::string(" ") + names[i] + " " + std::to_string(ms);
+        cudaEventElapsedTime(&phase_ms[i], pe[i], pe[i + 1]);
+        line += std::string(" ") + names[i] + " " + std::to_string(phase_ms[i]);
       }
-      fprintf(stderr, "%s\n", line.c_str());
-      for (int i = 0; i < n_pe; ++i) cudaEventDestroy(pe[i]);
+      // prompt pass (prefill + first token) inside the rollout: its end was recorded by rollout()
+      phase_ms[4] = 0.f;
+      if (prefill_done_ev && prefill_recorded) cudaEventElapsedTime(&phase_ms[4], pe[2], prefill_done_ev);
+      if (phase_times) fprintf(stderr, "%s (prompt pass %.3f)\n", line.c_str(), phase_ms[4]);
     }
   }
 
@@ -1607,6 +1616,10 @@ class Engine : public EngineBase {
   cudaEvent_t ev_pf[kMaxForks] = {};
   cudaEvent_t ev_pf_join = nullptr;
   int pf_forks = 0;
+  cudaEvent_t phase_ev[5] = {};           // scst step: start, encoded, cross K/V, rollout, reward
+  cudaEvent_t prefill_done_ev = nullptr;
+  bool prefill_recorded = false;
+  float phase_ms[5] = {0.f, 0.f, 0.f, 0.f, 0.f};   // encode, cross_kv, rollout, reward+copy, (prompt pass inside rollout)
   std::vector<cudaEvent_t> ev_chunk;      // host-buffer step: pixels of encoder chunk c have arrived
   size_t h2d_pixel_bytes = 0;             // pixel bytes copied by the last host-buffer step
   RolloutState st{};

@@ -56,6 +56,7 @@ class EngineBase {
                               int* steps_out, bool on_device, cudaStream_t s) = 0;
   virtual void bridge_ids(const int* seq, int R, int L, int eos, int* out_ids, int* out_lens, int Lout, cudaStream_t s) = 0;
   virtual size_t workspace_bytes() const = 0;
+  virtual void last_phase_ms(float* out5) const = 0;
   virtual void set_profile(bool on) = 0;
   virtual std::string profile_report() = 0;
   std::string last_error;

@@ -260,6 +260,12 @@ class Engine:
                                              _stream()), "cxrm_bridge_ids")
         return ids, lens
 
+    def last_phase_ms(self) -> dict:
+        """device ms of the phases of the last scst_step: encode, cross_kv, rollout, reward, prompt pass (inside rollout)"""
+        buf = (C.c_float * 5)()
+        self._check(self.lib.cxrm_last_phase_ms(self.h, buf), "cxrm_last_phase_ms")
+        return dict(zip(("encode", "cross_kv", "rollout", "reward", "prompt_pass"), (float(x) for x in buf)))
+
     def set_profile(self, on: bool):
         self._check(self.lib.cxrm_set_profile(self.h, int(on)), "cxrm_set_profile")
 

@@ -71,6 +71,7 @@ SYMBOLS = {
     "cxrm_scst_step_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int,
                                         C.POINTER(CxrmRolloutArgs), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cxrm_last_phase_ms": (C.c_int, [C.c_void_p, C.c_void_p]),
     "cxrm_set_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "cxrm_profile_report": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t]),
     "cxrm_test_gemm": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,

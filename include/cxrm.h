@@ -241,6 +241,10 @@ CXRM_API int cxrm_scst_step_device(cxrm_engine* e, const float* pixels, int B, i
                           const int32_t* label_lens, int L_label, int32_t* sequences, float* logprobs, float* reward,
                           float* baseline, float* advantage, int32_t* steps_out, void* stream);
 
+/* Device time (ms, CUDA events on the step's stream) of the phases of the LAST cxrm_scst_step_* call:
+ * out5 = {encode, cross K/V, rollout, reward + result copies, prompt pass (prefill + first token; part of rollout)}. */
+CXRM_API int cxrm_last_phase_ms(cxrm_engine* e, float* out5);
+
 /*
  * Per-kernel-class timing: while enabled every kernel launch is bracketed by a CUDA event pair on its stream
  * (CUDA-graph replay is bypassed so each launch is visible).  cxrm_profile_report synchronises, writes a JSON
