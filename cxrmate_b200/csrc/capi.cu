@@ -52,6 +52,7 @@ void cxrm_default_config(cxrm_config* c) {
   c->enc_chunk = 32;
   c->use_tensor_cores = 1;
   c->use_cuda_graph = 1;
+  c->max_train_tokens = 0;
 }
 
 int cxrm_create(const cxrm_config* cfg, int device, cxrm_engine** out) {
@@ -177,6 +178,27 @@ int cxrm_scst_step_device(cxrm_engine* e, const float* pixels, int B, int N, con
   CXRM_GUARD(e, e->impl->scst_step_host(pixels, B, N, prompt_ids, P, *tmpl, label_ids, label_lens, L_label, sequences,
                                         logprobs, reward, baseline, advantage, steps_out, /*on_device=*/true,
                                         static_cast<cudaStream_t>(stream)));
+}
+int cxrm_train_step(cxrm_engine* e, const cxrm_train_args* a, int stage, void* stream) {
+  if (!a) return CXRM_ERR_INVALID;
+  CXRM_GUARD(e, e->impl->train_step(*a, stage, static_cast<cudaStream_t>(stream)));
+}
+int cxrm_train_stages(const cxrm_engine* e) { return (e && e->impl) ? e->impl->train_stages() : 0; }
+int cxrm_grad_count(const cxrm_engine* e, int lora_only) { return (e && e->impl) ? e->impl->grad_count(lora_only != 0) : 0; }
+int64_t cxrm_grad_total(const cxrm_engine* e, int lora_only) { return (e && e->impl) ? e->impl->grad_total(lora_only != 0) : 0; }
+int cxrm_grad_info(const cxrm_engine* e, int lora_only, int i, char* name, size_t name_len, int64_t* offset, int64_t* numel,
+                   int* stage) {
+  if (!e || !e->impl || !name || name_len == 0) return CXRM_ERR_INVALID;
+  std::string n;
+  long long off = 0, ne = 0;
+  int st = 0;
+  if (!e->impl->grad_info(lora_only != 0, i, &n, &off, &ne, &st)) return CXRM_ERR_INVALID;
+  std::strncpy(name, n.c_str(), name_len - 1);
+  name[name_len - 1] = 0;
+  if (offset) *offset = off;
+  if (numel) *numel = ne;
+  if (stage) *stage = st;
+  return CXRM_OK;
 }
 int cxrm_last_phase_ms(cxrm_engine* e, float* out5) {
   if (!out5) return CXRM_ERR_INVALID;

@@ -5,6 +5,7 @@
 #include "engine.cuh"
 
 #include <algorithm>
+#include <array>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -381,6 +382,32 @@ class Engine : public EngineBase {
       dec_stats = dalloc<float2>(2LL * kStatTiles * 64);
       CXRM_CUDA_CHECK(cudaMemset(dec_stats, 0, sizeof(float2) * 2 * kStatTiles * 64));
     }
+    // ---- training: the LoRA factors themselves (the merged weights above serve the forward pass) ----
+    lora_r.assign(cfg.dec_layers, 0);
+    lora_A.assign(cfg.dec_layers, {nullptr, nullptr});
+    lora_Bt.assign(cfg.dec_layers, {nullptr, nullptr});
+    if (cfg.max_train_tokens > 0) {
+      for (int l = 0; l < cfg.dec_layers; ++l) {
+        const char* names[2] = {"query", "key"};
+        for (int j = 0; j < 2; ++j) {
+          const std::string p = "decoder.bert.encoder.layer." + std::to_string(l) + ".attention.self." + names[j];
+          if (!has(p + ".lora_A.weight")) continue;
+          const RawTensor& A = raw.at(p + ".lora_A.weight");
+          const RawTensor& Bm = raw.at(p + ".lora_B.weight");
+          const int r = static_cast<int>(A.shape[0]);
+          CXRM_CHECK(r % 8 == 0 && r <= 64 && (lora_r[l] == 0 || lora_r[l] == r), "LoRA rank must be a multiple of 8 (<= 64), equal for query and key");
+          lora_r[l] = r;
+          lora_A[l][j] = dalloc<T>(1LL * r * DH);
+          pack_matrix<T>(A.data, lora_A[l][j], r, DH, DH, 0);
+          T* Bt = dalloc<T>(1LL * DH * r);
+          pack_matrix<T>(Bm.data, Bt, DH, r, r, 0);                  // B [768, r]
+          lora_Bt[l][j] = dalloc<T>(1LL * r * DH);
+          transpose<T>(Bt, r, lora_Bt[l][j], DH, DH, r, 0);          // B^T [r, 768]
+        }
+      }
+    }
+    build_grad_layout();
+    wt_cache.clear();
     // ---- reward model ----
     if (cfg.rwd_layers > 0 && has("reward.bert.embeddings.word_embeddings.weight")) {
       load_bert(rwd, "reward.bert.", cfg.rwd_layers, cfg.rwd_vocab, false);
@@ -501,7 +528,15 @@ class Engine : public EngineBase {
     const long long dec_bytes = (dec_tok + 4LL * Rmax) * per_tok + (1 << 20);
     const long long rwd_tok = static_cast<long long>(std::max(cfg.rwd_max_seqs, 1)) * cfg.rwd_max_len;
     const long long rwd_bytes = cfg.rwd_layers > 0 ? rwd_tok * (per_tok + 16) + (1 << 22) : 0;
-    arena.init(static_cast<size_t>(std::max({enc_bytes, dec_bytes, rwd_bytes})) + (8 << 20));
+    long long train_bytes = 0;
+    if (cfg.max_train_tokens > 0) {     // mirrors train_stage(stage 0)
+      const long long Mx = cfg.max_train_tokens, V = cfg.vocab, NLd = cfg.dec_layers;
+      const long long kvx = B * Smax;
+      const long long elems = Mx * (2LL * DH + 15360LL * NLd + 7LL * DH + DFF + 3LL * DH + 2LL * V + DH) +
+                              2 * std::max<long long>(Mx * DFF, kvx * 2 * DH) + kvx * 2 * DH;
+      train_bytes = elems * e + Mx * (V * 4 + 2LL * NHEAD * 4 + 16) + (64 << 20);
+    }
+    arena.init(static_cast<size_t>(std::max({enc_bytes, dec_bytes, rwd_bytes, train_bytes})) + (8 << 20));
     CXRM_CUDA_CHECK(cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking));
     CXRM_CUDA_CHECK(cudaEventCreateWithFlags(&ev_a, cudaEventDisableTiming));
     CXRM_CUDA_CHECK(cudaEventCreateWithFlags(&ev_b, cudaEventDisableTiming));
@@ -1382,6 +1417,354 @@ class Engine : public EngineBase {
     }
   }
 
+
+  // =========================================================================== teacher-forced forward + backward
+  // (train.cu has the non-GEMM kernels and the derivation; include/cxrm.h cxrm_train_step the contract)
+  struct GradSlot { std::string name; long long offset, numel; int stage; };
+  int train_stages() const override { return cfg.dec_layers + 2; }
+  const std::vector<GradSlot>& slots(bool lora_only) const { return grad_slots[lora_only ? 1 : 0]; }
+  int grad_count(bool lora_only) const override { return static_cast<int>(slots(lora_only).size()); }
+  long long grad_total(bool lora_only) const override {
+    const auto& v = slots(lora_only);
+    return v.empty() ? 0 : v.back().offset + v.back().numel;
+  }
+  bool grad_info(bool lora_only, int i, std::string* name, long long* offset, long long* numel, int* stage) const override {
+    const auto& v = slots(lora_only);
+    if (i < 0 || i >= static_cast<int>(v.size())) return false;
+    *name = v[i].name; *offset = v[i].offset; *numel = v[i].numel; *stage = v[i].stage;
+    return true;
+  }
+  void build_grad_layout() {
+    for (int lo = 0; lo < 2; ++lo) {
+      auto& v = grad_slots[lo];
+      v.clear();
+      long long off = 0;
+      auto add = [&](const std::string& n, long long ne, int stage) {
+        v.push_back({n, off, ne, stage});
+        off += ne;
+      };
+      const int NL = cfg.dec_layers;
+      if (!lo) {
+        const std::string t = "decoder.cls.predictions.";
+        add(t + "transform.dense.weight", 1LL * DH * DH, 0);
+        add(t + "transform.dense.bias", DH, 0);
+        add(t + "transform.LayerNorm.weight", DH, 0);
+        add(t + "transform.LayerNorm.bias", DH, 0);
+        add(t + "bias", cfg.vocab, 0);
+      }
+      for (int l = NL - 1; l >= 0; --l) {
+        const int st = 1 + (NL - 1 - l);
+        const std::string p = "decoder.bert.encoder.layer." + std::to_string(l) + ".";
+        if (lo) {
+          for (const char* nm : {"query", "key"}) {
+            if (lora_r[l] <= 0) continue;
+            add(p + "attention.self." + nm + ".lora_A.weight", 1LL * lora_r[l] * DH, st);
+            add(p + "attention.self." + nm + ".lora_B.weight", 1LL * DH * lora_r[l], st);
+          }
+          continue;
+        }
+        for (const char* nm : {"query", "key", "value"}) add(p + "attention.self." + nm + ".weight", 1LL * DH * DH, st);   // contiguous = fused q|k|v
+        for (const char* nm : {"query", "key", "value"}) add(p + "attention.self." + nm + ".bias", DH, st);
+        add(p + "attention.output.dense.weight", 1LL * DH * DH, st);
+        add(p + "attention.output.dense.bias", DH, st);
+        add(p + "attention.output.LayerNorm.weight", DH, st);
+        add(p + "attention.output.LayerNorm.bias", DH, st);
+        add(p + "crossattention.self.query.weight", 1LL * DH * DH, st);
+        add(p + "crossattention.self.query.bias", DH, st);
+        for (const char* nm : {"key", "value"}) add(p + "crossattention.self." + nm + ".weight", 1LL * DH * DH, st);     // contiguous = fused k|v
+        for (const char* nm : {"key", "value"}) add(p + "crossattention.self." + nm + ".bias", DH, st);
+        add(p + "crossattention.output.dense.weight", 1LL * DH * DH, st);
+        add(p + "crossattention.output.dense.bias", DH, st);
+        add(p + "crossattention.output.LayerNorm.weight", DH, st);
+        add(p + "crossattention.output.LayerNorm.bias", DH, st);
+        add(p + "intermediate.dense.weight", 1LL * DFF * DH, st);
+        add(p + "intermediate.dense.bias", DFF, st);
+        add(p + "output.dense.weight", 1LL * DH * DFF, st);
+        add(p + "output.dense.bias", DH, st);
+        add(p + "output.LayerNorm.weight", DH, st);
+        add(p + "output.LayerNorm.bias", DH, st);
+      }
+      if (!lo) {
+        const std::string e = "decoder.bert.embeddings.";
+        const int st = NL + 1;
+        add(e + "position_embeddings.weight", 512LL * DH, st);
+        add(e + "token_type_embeddings.weight", 2LL * DH, st);
+        add(e + "LayerNorm.weight", DH, st);
+        add(e + "LayerNorm.bias", DH, st);
+        add(e + "word_embeddings.weight", 1LL * cfg.vocab * DH, st);   // tied: LM-head gradient + embedding gradient
+      }
+    }
+  }
+  long long slot_off(bool lo, const std::string& name) const {
+    for (const auto& s : slots(lo))
+      if (s.name == name) return s.offset;
+    throw std::runtime_error("no gradient slot " + name);
+  }
+  T* transposed(const Lin& L) {     // W [n_out, n_in] -> W^T [n_in, n_out], cached (weights are constants between loads)
+    auto it = wt_cache.find(L.w);
+    if (it != wt_cache.end()) return it->second;
+    T* t = dalloc<T>(1LL * L.n_out * L.n_in);
+    transpose<T>(L.w, L.n_in, t, L.n_out, L.n_out, L.n_in, 0);
+    CXRM_CUDA_CHECK(cudaStreamSynchronize(0));
+    wt_cache[L.w] = t;
+    return t;
+  }
+
+  struct Tape { T *x, *qkv, *ctx, *x1_pre, *x1, *cq, *cctx, *x2_pre, *x2, *h_pre, *hid, *x3_pre; };
+  struct TrainState {
+    cxrm_train_args a{};
+    long long M = 0;
+    int next_stage = 0;
+    std::vector<Tape> tp;
+    T *emb_pre = nullptr, *x0 = nullptr, *xL = nullptr, *t_pre = nullptr, *t_act = nullptr, *t_ln = nullptr;
+    T *dx = nullptr, *d1 = nullptr, *d2 = nullptr, *dbig = nullptr, *dqkv = nullptr, *tA = nullptr, *tB = nullptr;
+    T *dkv = nullptr;
+    float *lse = nullptr, *Dd = nullptr, *row_loss = nullptr;
+    float2* lnstats = nullptr;
+    int* n_counted = nullptr;
+  } tr;
+
+  AttnArgs self_attn_args(const T* qkv, T* ctx, int R, int L, const uint8_t* key_mask) const {
+    AttnArgs a{};
+    a.q = qkv; a.k = qkv + DH; a.v = qkv + 2 * DH; a.o = ctx;
+    a.q_bs = static_cast<long long>(L) * 3 * DH; a.q_hs = 64; a.q_ts = 3 * DH;
+    a.k_bs = a.q_bs; a.k_hs = 64; a.k_ts = 3 * DH;
+    a.v_bs = a.q_bs; a.v_hs = 64; a.v_ts = 3 * DH;
+    a.o_bs = static_cast<long long>(L) * DH; a.o_hs = 64; a.o_ts = DH;
+    a.batch = R; a.heads = NHEAD; a.Lq = L; a.Lk = L;
+    a.key_mask = key_mask; a.key_mask_ld = L; a.key_mask_per_q_batch = 1;
+    a.causal = 1; a.q_pos_offset = 0; a.scale = 0.125f;
+    return a;
+  }
+  AttnArgs cross_attn_args(const T* q, T* ctx, const T* kvl, int R, int L, int B) const {
+    AttnArgs c{};
+    c.q = q; c.k = kvl; c.v = kvl + NHEAD * cross_head_stride(); c.o = ctx;
+    c.q_bs = static_cast<long long>(L) * DH; c.q_hs = 64; c.q_ts = DH;
+    c.k_bs = 0; c.k_hs = cross_head_stride(); c.k_ts = 64;
+    c.v_bs = 0; c.v_hs = cross_head_stride(); c.v_ts = 64;
+    c.o_bs = c.q_bs; c.o_hs = 64; c.o_ts = DH;
+    c.batch = R; c.heads = NHEAD; c.Lq = L; c.Lk = kv_maxlen;
+    c.Lk_per_batch = kv_len; c.kv_offset = kv_off; c.kv_batch_mod = B;
+    c.scale = 0.125f;
+    return c;
+  }
+
+  void train_step(const cxrm_train_args& a, int stage, cudaStream_t s) override {
+    CXRM_CHECK(finalized, "weights not finalized");
+    CXRM_CHECK(cfg.max_train_tokens > 0, "the engine was created without a training workspace (cxrm_config.max_train_tokens)");
+    const int NL = cfg.dec_layers, NS = train_stages();
+    CXRM_CHECK(stage >= -1 && stage < NS, "stage");
+    if (stage == -1) {
+      for (int st = 0; st < NS; ++st) train_stage(a, st, s);
+      return;
+    }
+    train_stage(a, stage, s);
+    (void)NL;
+  }
+
+  // rank-r LoRA contractions (N or M = r = 8): strict-FMA kernel in both modes, the shapes are far below a tensor-core tile
+  void gemm_small(const T* A, int lda, const T* W, int n_out, int n_in, void* C, int ldc, long long M, bool out_f32, cudaStream_t s) {
+    GemmArgs g;
+    g.c_head_stride = 0; g.trace = nullptr;
+    g.A = A; g.lda = lda; g.W = W; g.ldw = n_in; g.C = C; g.ldc = ldc; g.M = static_cast<int>(M); g.N = n_out; g.K = n_in;
+    g.bias = nullptr; g.act = ACT_NONE; g.residual = nullptr; g.ldr = 0; g.out_f32 = out_f32 ? 1 : 0; g.skip_flag = nullptr;
+    PF("lora", s, [&] { gemm_simt<T>(g, s); });
+  }
+  // dX[M, K] = dY[M, N] . W  (W [N, K]; wt = W^T [K, N])
+  void dgrad(const T* dY, int ldy, const Lin& L, T* dX, long long M, const T* add_res, cudaStream_t s) {
+    Lin t;
+    t.w = transposed(L); t.b = nullptr; t.n_out = L.n_in; t.n_in = L.n_out;
+    gemm(dY, ldy, t, dX, L.n_in, M, ACT_NONE, add_res, L.n_in, false, nullptr, s, "dgrad");
+  }
+  // dW[N, K] (fp32) = dY^T . X; db[N] = column sums of dY
+  void wgrad(const T* dY, int ldy, int N, const T* X, int ldx, int K, long long M, float* dW, float* db, cudaStream_t s) {
+    transpose<T>(dY, ldy, tr.tA, M, M, N, s);          // [N, M]
+    transpose<T>(X, ldx, tr.tB, M, M, K, s);           // [K, M]
+    Lin t;
+    t.w = tr.tB; t.b = nullptr; t.n_out = K; t.n_in = static_cast<int>(M);
+    gemm(tr.tA, static_cast<int>(M), t, dW, K, N, ACT_NONE, nullptr, 0, true, nullptr, s, "wgrad");
+    if (db) colsum<T>(dY, ldy, M, N, db, false, s);
+  }
+
+  void train_stage(const cxrm_train_args& a, int stage, cudaStream_t s) {
+    const int NL = cfg.dec_layers;
+    const int R = a.R, L = a.L, B = kv_B;
+    const long long M = static_cast<long long>(R) * L;
+    const bool lo = a.lora_only != 0;
+    float* G = a.grads;
+    if (stage == 0) {
+      CXRM_CHECK(kv_B > 0 && kv_total > 0 && R >= 1 && R % B == 0, "cxrm_train_step needs cxrm_prefill_cross_kv; rows must be a multiple of the studies");
+      CXRM_CHECK(L >= 1 && L <= 512 && M % 8 == 0 && M <= cfg.max_train_tokens, "train batch: R * L must be a multiple of 8 and fit max_train_tokens");
+      CXRM_CHECK(a.ids && a.token_type_ids && a.position_ids && a.key_mask && a.targets && a.loss_out && G, "train_step: null argument");
+      CXRM_CHECK(a.loss_kind == 0 || (a.loss_kind == 1 && a.advantage), "loss_kind");
+      phase = "train";
+      tr = TrainState{};
+      tr.a = a;
+      tr.M = M;
+      arena.reset();
+      auto get = [&](long long n) { return arena.get<T>(n); };
+      tr.emb_pre = get(M * DH); tr.x0 = get(M * DH);
+      tr.tp.resize(NL);
+      for (int l = 0; l < NL; ++l) {
+        Tape& t = tr.tp[l];
+        t.x = l == 0 ? tr.x0 : get(M * DH);
+        t.qkv = get(M * 3 * DH); t.ctx = get(M * DH); t.x1_pre = get(M * DH); t.x1 = get(M * DH); t.cq = get(M * DH);
+        t.cctx = get(M * DH); t.x2_pre = get(M * DH); t.x2 = get(M * DH); t.h_pre = get(M * DFF); t.hid = get(M * DFF);
+        t.x3_pre = get(M * DH);
+      }
+      tr.xL = get(M * DH); tr.t_pre = get(M * DH); tr.t_act = get(M * DH); tr.t_ln = get(M * DH);
+      tr.dx = get(M * DH); tr.d1 = get(M * DH); tr.d2 = get(M * DH); tr.dbig = get(M * DFF); tr.dqkv = get(M * 3 * DH);
+      const long long tmax = std::max<long long>(M * DFF, lo ? 0 : static_cast<long long>(kv_total) * 2 * DH);
+      tr.tA = get(tmax); tr.tB = get(tmax);
+      tr.lse = arena.get<float>(static_cast<long long>(R) * NHEAD * L);
+      tr.Dd = arena.get<float>(static_cast<long long>(R) * NHEAD * L);
+      tr.row_loss = arena.get<float>(M);
+      tr.lnstats = arena.get<float2>(M);
+      tr.n_counted = arena.get<int>(1);
+      if (!lo) tr.dkv = get(static_cast<long long>(kv_total) * 2 * DH);
+
+      // ---------------- forward, keeping what the backward needs ----------------
+      embed_sum<T>(a.ids, a.token_type_ids, a.position_ids, dec.word, dec.type, dec.pos, tr.emb_pre, M, DH, s);
+      layernorm<T>(tr.emb_pre, DH, tr.x0, DH, dec.emb_ln.g, dec.emb_ln.b, M, DH, LN_EPS_BERT, s);
+      for (int l = 0; l < NL; ++l) {
+        const BertLayerW& w = dec.layers[l];
+        Tape& t = tr.tp[l];
+        T* x_next = l + 1 < NL ? tr.tp[l + 1].x : tr.xL;
+        gemm(t.x, DH, w.qkv, t.qkv, 3 * DH, M, ACT_NONE, nullptr, 0, false, nullptr, s);
+        attention(self_attn_args(t.qkv, t.ctx, R, L, a.key_mask), s);
+        gemm(t.ctx, DH, w.o, t.x1_pre, DH, M, ACT_NONE, t.x, DH, false, nullptr, s);
+        layernorm<T>(t.x1_pre, DH, t.x1, DH, w.ln1.g, w.ln1.b, M, DH, LN_EPS_BERT, s);
+        gemm(t.x1, DH, w.cq, t.cq, DH, M, ACT_NONE, nullptr, 0, false, nullptr, s);
+        const T* kvl = cross_kv + static_cast<long long>(l) * cross_layer_stride();
+        attention(cross_attn_args(t.cq, t.cctx, kvl, R, L, B), s);
+        gemm(t.cctx, DH, w.co, t.x2_pre, DH, M, ACT_NONE, t.x1, DH, false, nullptr, s);
+        layernorm<T>(t.x2_pre, DH, t.x2, DH, w.ln2.g, w.ln2.b, M, DH, LN_EPS_BERT, s);
+        gemm(t.x2, DH, w.fc1, t.h_pre, DFF, M, ACT_NONE, nullptr, 0, false, nullptr, s);
+        gelu_fwd<T>(t.h_pre, t.hid, M * DFF, s);
+        gemm(t.hid, DFF, w.fc2, t.x3_pre, DH, M, ACT_NONE, t.x2, DH, false, nullptr, s);
+        layernorm<T>(t.x3_pre, DH, x_next, DH, w.ln3.g, w.ln3.b, M, DH, LN_EPS_BERT, s);
+      }
+      gemm(tr.xL, DH, dec_head_t, tr.t_pre, DH, M, ACT_NONE, nullptr, 0, false, nullptr, s);
+      gelu_fwd<T>(tr.t_pre, tr.t_act, M * DH, s);
+      layernorm<T>(tr.t_act, DH, tr.t_ln, DH, dec_head_ln.g, dec_head_ln.b, M, DH, LN_EPS_BERT, s);
+      // logits, loss and dlogits (the [M, V] buffers live only inside this stage: they reuse the arena tail)
+      const long long V = cfg.vocab;
+      float* lg = arena.get<float>(M * V);
+      T* dz = arena.get<T>(M * V);
+      gemm(tr.t_ln, DH, dec_lm, lg, static_cast<int>(V), M, ACT_NONE, nullptr, 0, true, nullptr, s);
+      loss_head<T>(lg, M, static_cast<int>(V), a.targets, a.ignore_index, a.loss_kind, a.advantage, L, R, a.top_k,
+                   a.temperature == 0.f ? 1.0f : a.temperature, dz, tr.row_loss, tr.n_counted, a.loss_out, s);
+      // ---------------- LM head backward ----------------
+      dgrad(dz, static_cast<int>(V), dec_lm, tr.d1, M, nullptr, s);                        // d t_ln = dz . E
+      if (!lo) {
+        T* dzt = arena.get<T>(M * V);                                                       // dE = dz^T . t_ln
+        T* tlt = arena.get<T>(M * DH);
+        transpose<T>(dz, V, dzt, M, M, static_cast<int>(V), s);
+        transpose<T>(tr.t_ln, DH, tlt, M, M, DH, s);
+        Lin t;
+        t.w = tlt; t.b = nullptr; t.n_out = DH; t.n_in = static_cast<int>(M);
+        gemm(dzt, static_cast<int>(M), t, G + slot_off(false, "decoder.bert.embeddings.word_embeddings.weight"), DH, V, ACT_NONE,
+             nullptr, 0, true, nullptr, s, "wgrad");
+        colsum<T>(dz, V, M, static_cast<int>(V), G + slot_off(false, "decoder.cls.predictions.bias"), false, s);
+      }
+      float* gG = lo ? nullptr : G + slot_off(false, "decoder.cls.predictions.transform.LayerNorm.weight");
+      layernorm_bwd<T>(tr.t_act, tr.d1, dec_head_ln.g, LN_EPS_BERT, tr.d2, tr.lnstats, gG, gG ? gG + DH : nullptr, false, M, DH, s);
+      gelu_bwd<T>(tr.t_pre, tr.d2, tr.d1, M * DH, s);                                       // d t_pre
+      if (!lo)
+        wgrad(tr.d1, DH, DH, tr.xL, DH, DH, M, G + slot_off(false, "decoder.cls.predictions.transform.dense.weight"),
+              G + slot_off(false, "decoder.cls.predictions.transform.dense.bias"), s);
+      dgrad(tr.d1, DH, dec_head_t, tr.dx, M, nullptr, s);                                   // dx = gradient of the trunk output
+      tr.next_stage = 1;
+      return;
+    }
+    CXRM_CHECK(stage == tr.next_stage && tr.M == M && tr.a.grads == a.grads, "cxrm_train_step stages must be called in order with the same arguments");
+    if (stage <= NL) {
+      const int l = NL - stage;
+      const BertLayerW& w = dec.layers[l];
+      Tape& t = tr.tp[l];
+      const std::string p = "decoder.bert.encoder.layer." + std::to_string(l) + ".";
+      auto g = [&](const std::string& n) { return lo ? nullptr : G + slot_off(false, p + n); };
+      // LN3: x_{l+1} = LN(x3_pre)
+      layernorm_bwd<T>(t.x3_pre, tr.dx, w.ln3.g, LN_EPS_BERT, tr.d1, tr.lnstats, g("output.LayerNorm.weight"), g("output.LayerNorm.bias"),
+                       false, M, DH, s);                                                     // d1 = d x3_pre (also the residual branch to x2)
+      if (!lo) wgrad(tr.d1, DH, DH, t.hid, DFF, DFF, M, g("output.dense.weight"), g("output.dense.bias"), s);
+      dgrad(tr.d1, DH, w.fc2, tr.dbig, M, nullptr, s);                                      // d hid
+      gelu_bwd<T>(t.h_pre, tr.dbig, tr.dbig, M * DFF, s);                                   // d h_pre
+      if (!lo) wgrad(tr.dbig, DFF, DFF, t.x2, DH, DH, M, g("intermediate.dense.weight"), g("intermediate.dense.bias"), s);
+      dgrad(tr.dbig, DFF, w.fc1, tr.d2, M, tr.d1, s);                                       // d x2 = d h_pre . W1 + d x3_pre
+      // LN2: x2 = LN(x2_pre)
+      layernorm_bwd<T>(t.x2_pre, tr.d2, w.ln2.g, LN_EPS_BERT, tr.d1, tr.lnstats, g("crossattention.output.LayerNorm.weight"),
+                       g("crossattention.output.LayerNorm.bias"), false, M, DH, s);         // d1 = d x2_pre (residual branch to x1)
+      if (!lo) wgrad(tr.d1, DH, DH, t.cctx, DH, DH, M, g("crossattention.output.dense.weight"), g("crossattention.output.dense.bias"), s);
+      dgrad(tr.d1, DH, w.co, tr.d2, M, nullptr, s);                                         // d cctx
+      const T* kvl = cross_kv + static_cast<long long>(l) * cross_layer_stride();
+      AttnArgs ca = cross_attn_args(t.cq, t.cctx, kvl, R, L, B);
+      if (!lo) {
+        // d cq (packed [M, 768] in dqkv) and d(k | v) of the compact encoder tokens, token-major [kv_total, 1536], which
+        // is the dY of the fused cross K|V projection: dW = d(k|v)^T . memory
+        CXRM_CHECK(kv_total % 8 == 0, "cxrm_train_step (all parameters): the visible encoder-token count must be a multiple of 8");
+        attention_bwd<T>(ca, tr.d2, tr.dqkv, tr.dkv, tr.dkv + DH, 0, 64, 2 * DH, tr.lse, tr.Dd, s);
+        wgrad(tr.dkv, 2 * DH, 2 * DH, mem_compact, DH, DH, kv_total, g("crossattention.self.key.weight"),
+              g("crossattention.self.key.bias"), s);
+      } else {
+        attention_bwd<T>(ca, tr.d2, tr.dqkv, nullptr, nullptr, 0, 0, 0, tr.lse, tr.Dd, s);
+      }
+      if (!lo) wgrad(tr.dqkv, DH, DH, t.x1, DH, DH, M, g("crossattention.self.query.weight"), g("crossattention.self.query.bias"), s);
+      dgrad(tr.dqkv, DH, w.cq, tr.d2, M, tr.d1, s);                                         // d x1 = d cq . Wcq + d x2_pre
+      // LN1: x1 = LN(x1_pre)
+      layernorm_bwd<T>(t.x1_pre, tr.d2, w.ln1.g, LN_EPS_BERT, tr.d1, tr.lnstats, g("attention.output.LayerNorm.weight"),
+                       g("attention.output.LayerNorm.bias"), false, M, DH, s);              // d1 = d x1_pre (residual branch to x)
+      if (!lo) wgrad(tr.d1, DH, DH, t.ctx, DH, DH, M, g("attention.output.dense.weight"), g("attention.output.dense.bias"), s);
+      dgrad(tr.d1, DH, w.o, tr.d2, M, nullptr, s);                                          // d ctx
+      AttnArgs sa = self_attn_args(t.qkv, t.ctx, R, L, a.key_mask);
+      attention_bwd<T>(sa, tr.d2, tr.dqkv, tr.dqkv + DH, tr.dqkv + 2 * DH, sa.k_bs, sa.k_hs, sa.k_ts, tr.lse, tr.Dd,
+                       s);                                                                   // dq | dk | dv, token-major like qkv
+      if (!lo) {
+        wgrad(tr.dqkv, 3 * DH, 3 * DH, t.x, DH, DH, M, g("attention.self.query.weight"), g("attention.self.query.bias"), s);
+      } else if (lora_r[l] > 0) {
+        const int r = lora_r[l];
+        const char* names[2] = {"query", "key"};
+        for (int j = 0; j < 2; ++j) {
+          const T* dY = tr.dqkv + j * DH;                      // [M, 768] slice, row pitch 2304
+          const std::string lp = p + "attention.self." + names[j] + ".";
+          float* dA = G + slot_off(true, lp + "lora_A.weight");
+          float* dB = G + slot_off(true, lp + "lora_B.weight");
+          T* P = tr.tB;                                        // X . A^T  [M, r]
+          gemm_small(t.x, DH, lora_A[l][j], r, DH, P, r, M, false, s);
+          T* Pt = tr.tB + M * r;                               // [r, M]
+          transpose<T>(P, r, Pt, M, M, r, s);
+          transpose<T>(dY, 3 * DH, tr.tA, M, M, DH, s);        // dY^T [768, M]
+          gemm_small(tr.tA, static_cast<int>(M), Pt, r, static_cast<int>(M), dB, r, DH, true, s);            // dB = dY^T . P
+          scale_f32(dB, LORA_SCALE, 1LL * DH * r, s);
+          T* Q = tr.tB + 2 * M * r;                            // dY . B  [M, r]
+          gemm_small(dY, 3 * DH, lora_Bt[l][j], r, DH, Q, r, M, false, s);
+          T* Qt = tr.tB + 3 * M * r;                           // [r, M]
+          transpose<T>(Q, r, Qt, M, M, r, s);
+          transpose<T>(t.x, DH, tr.tA, M, M, DH, s);           // X^T [768, M]
+          gemm_small(Qt, static_cast<int>(M), tr.tA, DH, static_cast<int>(M), dA, DH, r, true, s);           // dA = Q^T . X
+          scale_f32(dA, LORA_SCALE, 1LL * r * DH, s);
+        }
+      }
+      dgrad(tr.dqkv, 3 * DH, w.qkv, tr.dx, M, tr.d1, s);                                   // dx = dqkv . Wqkv + d x1_pre
+      tr.next_stage = stage + 1;
+      return;
+    }
+    // ---------------- embeddings ----------------
+    if (!lo) {
+      const std::string e = "decoder.bert.embeddings.";
+      float* gG = G + slot_off(false, e + "LayerNorm.weight");
+      layernorm_bwd<T>(tr.emb_pre, tr.dx, dec.emb_ln.g, LN_EPS_BERT, tr.d1, tr.lnstats, gG, gG + DH, false, M, DH, s);
+      float* dpos = G + slot_off(false, e + "position_embeddings.weight");
+      float* dtyp = G + slot_off(false, e + "token_type_embeddings.weight");
+      CXRM_CUDA_CHECK(cudaMemsetAsync(dpos, 0, (512LL + 2) * DH * sizeof(float), s));      // position | token type are adjacent
+      (void)dtyp;
+      scatter_add_rows<T>(tr.d1, a.position_ids, dpos, M, DH, s);
+      scatter_add_rows<T>(tr.d1, a.token_type_ids, G + slot_off(false, e + "token_type_embeddings.weight"), M, DH, s);
+      scatter_add_rows<T>(tr.d1, a.ids, G + slot_off(false, e + "word_embeddings.weight"), M, DH, s);   // onto the LM-head part
+    }
+    tr.next_stage = 0;
+  }
+
   // =========================================================================== reward model
   void reward_embed(const int* ids, const int* lens, int n, int L, float* emb_out, cudaStream_t s) override {
     CXRM_CHECK(finalized && have_reward, "reward model weights not loaded");
@@ -1629,6 +2012,11 @@ class Engine : public EngineBase {
   float* h_pixels = nullptr; int* h_seq = nullptr; float* h_lp = nullptr; int* h_rids = nullptr; int* h_rlens = nullptr;
   float* h_emb = nullptr; float* h_out = nullptr;
   int* id_map = nullptr; int bridge_cls = 0, bridge_sep = 0, bridge_bos = 1, bridge_sep_dec = 3, bridge_n_special = 12;
+  // training
+  std::vector<GradSlot> grad_slots[2];            // [0] every decoder parameter, [1] LoRA only
+  std::map<const void*, T*> wt_cache;             // transposed weight copies for the dX GEMMs
+  std::vector<int> lora_r;                        // LoRA rank per decoder layer (0: none)
+  std::vector<std::array<T*, 2>> lora_A, lora_Bt; // per layer, (query, key): A [r, 768], B^T [r, 768]
   // persistent decode chain (decode_chain.cu): phase lists, (first, count) per launch of a step
   std::vector<ChainPhase> chain_host;
   unsigned* chain_bar = nullptr;

@@ -57,6 +57,11 @@ class EngineBase {
   virtual void bridge_ids(const int* seq, int R, int L, int eos, int* out_ids, int* out_lens, int Lout, cudaStream_t s) = 0;
   virtual size_t workspace_bytes() const = 0;
   virtual void last_phase_ms(float* out5) const = 0;
+  virtual void train_step(const cxrm_train_args& a, int stage, cudaStream_t s) = 0;
+  virtual int train_stages() const = 0;
+  virtual int grad_count(bool lora_only) const = 0;
+  virtual long long grad_total(bool lora_only) const = 0;
+  virtual bool grad_info(bool lora_only, int i, std::string* name, long long* offset, long long* numel, int* stage) const = 0;
   virtual void set_profile(bool on) = 0;
   virtual std::string profile_report() = 0;
   std::string last_error;

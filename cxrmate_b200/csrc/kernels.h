@@ -339,6 +339,40 @@ void take_last_token(const T* x, T* out, int R, int P, int C, cudaStream_t strea
 // loss[0] = mean_b( -sum_t logprob[b * ld + t] * advantage[b] )  (reinforce_loss, scst/gen_prompt.py:350-364)
 void reinforce_loss(const float* logprob, int ld, const float* advantage, int B, int T, float* loss, cudaStream_t stream);
 
+// ---- backward-pass kernels of the teacher-forced step (train.cu) ----------------------------------------------------
+template <typename T>
+void transpose(const T* in, long long ld_in, T* out, long long ld_out, long long rows, int cols, cudaStream_t stream);
+// out[n] (+)= sum_m x[m, n]
+template <typename T>
+void colsum(const T* x, long long ldx, long long rows, int cols, float* out, bool accumulate, cudaStream_t stream);
+// dx of y = LayerNorm(x) (stats: scratch [rows] (mean, rstd)); dgamma / dbeta (nullable) fp32, optionally accumulated
+template <typename T>
+void layernorm_bwd(const T* x, const T* dy, const float* gamma, float eps, T* dx, float2* stats, float* dgamma, float* dbeta,
+                   bool accumulate, long long rows, int C, cudaStream_t stream);
+template <typename T> void gelu_fwd(const T* x, T* y, long long n, cudaStream_t stream);
+template <typename T> void gelu_bwd(const T* x, const T* dy, T* dx, long long n, cudaStream_t stream);
+template <typename T> void add_inplace(T* a, const T* b, long long n, cudaStream_t stream);
+void scale_f32(float* a, float s, long long n, cudaStream_t stream);
+// logits [rows, V] fp32 -> loss (sum of row losses) and dz [rows, V] (T).  kind 0: cross-entropy, mean over targets !=
+// ignore_index; kind 1: REINFORCE, -adv[row / L] / R * log_softmax(top-k-masked z / temperature)[target].
+template <typename T>
+void loss_head(const float* logits, long long rows, int V, const int* targets, int ignore_index, int kind, const float* adv,
+               int L, int R, int top_k, float temperature, T* dz, float* row_loss, int* n_counted, float* loss_out,
+               cudaStream_t stream);
+// backward of the attention described by f (f.o = the forward output); dQ is laid out like q; dK == nullptr: dQ only,
+// else element (kv batch b', head h, key j) of dK / dV sits at b' * g_bs + h * g_hs + (kv_offset[b'] + j) * g_ts.
+// lse / D: scratch [batch, heads, Lq]
+template <typename T>
+void attention_bwd(const AttnArgs& f, const void* dO, void* dQ, void* dK, void* dV, long long g_bs, long long g_hs,
+                   long long g_ts, float* lse, float* D, cudaStream_t stream);
+// table[idx[r], :] += dx[r, :]
+template <typename T>
+void scatter_add_rows(const T* dx, const int* idx, float* table, long long rows, int C, cudaStream_t stream);
+
+template <typename T>
+void embed_sum(const int* ids, const int* types, const int* pos, const T* word, const T* type_emb, const T* pos_emb, T* out,
+               long long rows, int C, cudaStream_t stream);
+
 // cosine similarity of rows: out[i] = <a_i, b_i> / (max(|a_i|, eps) * max(|b_i|, eps))  (torch eps 1e-8)
 void cosine_rows(const float* a, const float* b, float* out, int n, int C, cudaStream_t stream);
 

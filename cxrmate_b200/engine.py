@@ -49,7 +49,8 @@ class Engine:
                  max_images: int = 5, max_prompt: int = 256, max_new_tokens: int = 255, vocab: int = 30000,
                  cvt_depth: Sequence[int] = (1, 4, 16), dec_layers: int = 6, rwd_layers: int = 12,
                  rwd_vocab: int = 30522, rwd_max_len: int = 512, rwd_max_seqs: Optional[int] = None,
-                 enc_chunk: int = 32, use_tensor_cores: bool = True, use_cuda_graph: bool = True):
+                 enc_chunk: int = 32, use_tensor_cores: bool = True, use_cuda_graph: bool = True,
+                 max_train_tokens: int = 0):
         if not torch.cuda.is_available():
             raise RuntimeError("cxrmate_b200.Engine needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
@@ -65,6 +66,7 @@ class Engine:
         cfg.enc_chunk = enc_chunk
         cfg.use_tensor_cores = int(use_tensor_cores)
         cfg.use_cuda_graph = int(use_cuda_graph)
+        cfg.max_train_tokens = int(max_train_tokens)
         self.cfg = cfg
         self.dtype = dtype
         self.torch_dtype = torch.float32 if dtype == "fp32" else torch.bfloat16
@@ -259,6 +261,53 @@ class Engine:
         self._check(self.lib.cxrm_bridge_ids(self.h, _ptr(seq), R, L, int(eos_token_id), _ptr(ids), _ptr(lens), out_len,
                                              _stream()), "cxrm_bridge_ids")
         return ids, lens
+
+    # ------------------------------------------------------------------ training (teacher-forced forward + backward)
+    def grad_layout(self, lora_only: bool):
+        """[(name, offset, numel, stage)] of the flat fp32 gradient buffer (cxrm_grad_info)."""
+        out = []
+        name = C.create_string_buffer(256)
+        off, ne, st = C.c_int64(), C.c_int64(), C.c_int()
+        for i in range(self.lib.cxrm_grad_count(self.h, int(lora_only))):
+            self._check(self.lib.cxrm_grad_info(self.h, int(lora_only), i, name, len(name), C.byref(off), C.byref(ne),
+                                                C.byref(st)), "cxrm_grad_info")
+            out.append((name.value.decode(), int(off.value), int(ne.value), int(st.value)))
+        return out
+
+    @property
+    def train_stages(self) -> int:
+        return int(self.lib.cxrm_train_stages(self.h))
+
+    def train_step(self, ids, token_type_ids, position_ids, key_mask, targets, *, loss_kind: str, ignore_index: int,
+                   advantage: Optional[torch.Tensor] = None, top_k: int = 0, temperature: float = 1.0,
+                   lora_only: bool = False, grads: Optional[torch.Tensor] = None, stage: int = -1, _keep=None):
+        """Teacher-forced decoder forward + backward (cxrm_train_step).  ids / token_type_ids / position_ids / targets
+        [R, L] int, key_mask [R, L]; loss_kind 'ce' | 'reinforce'.  Returns (loss 0-dim tensor, flat fp32 gradients).
+        stage -1 runs everything; otherwise the caller runs stages 0 .. train_stages-1 in order with the same tensors
+        (`_keep` carries the int32 copies between stage calls)."""
+        R, L = ids.shape
+        if _keep is None:
+            i32 = lambda t: t.to(torch.int32).contiguous()
+            _keep = dict(ids=i32(ids), tt=i32(token_type_ids), pos=i32(position_ids), km=key_mask.to(torch.uint8).contiguous(),
+                         tgt=i32(targets), adv=None if advantage is None else advantage.contiguous().float(),
+                         loss=torch.zeros(1, dtype=torch.float32, device=ids.device))
+        if grads is None:
+            grads = torch.zeros(int(self.lib.cxrm_grad_total(self.h, int(lora_only))), dtype=torch.float32, device=ids.device)
+        a = _lib.CxrmTrainArgs()
+        a.R, a.L = R, L
+        a.ids, a.token_type_ids, a.position_ids = _keep["ids"].data_ptr(), _keep["tt"].data_ptr(), _keep["pos"].data_ptr()
+        a.key_mask, a.targets = _keep["km"].data_ptr(), _keep["tgt"].data_ptr()
+        a.ignore_index = int(ignore_index)
+        a.loss_kind = {"ce": 0, "reinforce": 1}[loss_kind]
+        a.advantage = None if _keep["adv"] is None else _keep["adv"].data_ptr()
+        a.top_k, a.temperature, a.lora_only = int(top_k), float(temperature), int(lora_only)
+        a.loss_out, a.grads = _keep["loss"].data_ptr(), grads.data_ptr()
+        self._check(self.lib.cxrm_train_step(self.h, C.byref(a), int(stage), _stream()), "cxrm_train_step")
+        self._train_keep = _keep
+        return _keep["loss"][0], grads
+
+    def grads_by_name(self, flat: torch.Tensor, lora_only: bool) -> dict:
+        return {n: flat[o:o + ne] for n, o, ne, _ in self.grad_layout(lora_only)}
 
     def last_phase_ms(self) -> dict:
         """device ms of the phases of the last scst_step: encode, cross_kv, rollout, reward, prompt pass (inside rollout)"""

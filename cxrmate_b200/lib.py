@@ -23,7 +23,7 @@ class CxrmConfig(C.Structure):
         ("max_images", C.c_int), ("max_prompt", C.c_int), ("max_new_tokens", C.c_int), ("vocab", C.c_int),
         ("cvt_depth", C.c_int * 3), ("dec_layers", C.c_int), ("rwd_layers", C.c_int), ("rwd_vocab", C.c_int),
         ("rwd_max_len", C.c_int), ("rwd_max_seqs", C.c_int), ("enc_chunk", C.c_int),
-        ("use_tensor_cores", C.c_int), ("use_cuda_graph", C.c_int),
+        ("use_tensor_cores", C.c_int), ("use_cuda_graph", C.c_int), ("max_train_tokens", C.c_int),
     ]
 
 
@@ -36,6 +36,15 @@ class CxrmRolloutArgs(C.Structure):
         ("temperature", C.c_float), ("exp_noise", C.c_void_p), ("seed", C.c_uint64),
         ("sequences", C.c_void_p), ("logprobs", C.c_void_p), ("margins", C.c_void_p), ("topk_idx", C.c_void_p),
         ("topk_val", C.c_void_p), ("topk_cnt", C.c_void_p), ("last_logits", C.c_void_p), ("steps_out", C.c_void_p),
+    ]
+
+
+class CxrmTrainArgs(C.Structure):
+    _fields_ = [
+        ("R", C.c_int), ("L", C.c_int), ("ids", C.c_void_p), ("token_type_ids", C.c_void_p), ("position_ids", C.c_void_p),
+        ("key_mask", C.c_void_p), ("targets", C.c_void_p), ("ignore_index", C.c_int), ("loss_kind", C.c_int),
+        ("advantage", C.c_void_p), ("top_k", C.c_int), ("temperature", C.c_float), ("lora_only", C.c_int),
+        ("loss_out", C.c_void_p), ("grads", C.c_void_p),
     ]
 
 
@@ -72,6 +81,12 @@ SYMBOLS = {
                                         C.POINTER(CxrmRolloutArgs), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cxrm_last_phase_ms": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "cxrm_train_step": (C.c_int, [C.c_void_p, C.POINTER(CxrmTrainArgs), C.c_int, C.c_void_p]),
+    "cxrm_train_stages": (C.c_int, [C.c_void_p]),
+    "cxrm_grad_count": (C.c_int, [C.c_void_p, C.c_int]),
+    "cxrm_grad_total": (C.c_int64, [C.c_void_p, C.c_int]),
+    "cxrm_grad_info": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.c_size_t, C.POINTER(C.c_int64),
+                                 C.POINTER(C.c_int64), C.POINTER(C.c_int)]),
     "cxrm_set_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "cxrm_profile_report": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t]),
     "cxrm_test_gemm": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,

@@ -75,6 +75,7 @@ typedef struct cxrm_config {
   int enc_chunk;           /* images encoded per pass (0 = default 32) */
   int use_tensor_cores;    /* bf16 only: 1 = tcgen05 GEMMs (default), 0 = SIMT debug path */
   int use_cuda_graph;      /* 1 = replay the decode step as a CUDA graph */
+  int max_train_tokens;    /* rows x tokens of the largest cxrm_train_step batch; 0 = no training workspace (default) */
 } cxrm_config;
 
 /* Fills `cfg` with the named architecture (cxrmate, config 4 of BASELINE.json). */
@@ -240,6 +241,51 @@ CXRM_API int cxrm_scst_step_device(cxrm_engine* e, const float* pixels, int B, i
                           const cxrm_rollout_args* rollout_template, const int32_t* label_ids,
                           const int32_t* label_lens, int L_label, int32_t* sequences, float* logprobs, float* reward,
                           float* baseline, float* advantage, int32_t* steps_out, void* stream);
+
+/*
+ * Teacher-forced decoder forward + backward: the training half of the SCST step and the plain teacher-forced step.
+ * Replaces, for the decoder, `loss.backward()` of
+ *   - longitudinal/gt_prompt.py:186-249 (cross-entropy on the radiologist report, loss_kind 0), and
+ *   - scst/gen_prompt.py:331-366 (`reinforce_loss`, loss_kind 1): the reference backpropagates through the autograd
+ *     graph of the 255 cached decode steps of the sampled rollout; here the sampled sequence is run ONCE teacher-forced
+ *     (identical arithmetic in eval mode: SURVEY.md finding 9) and the gradient of
+ *     mean_b( -sum_t log_softmax(top-k-masked scores)[b, t, id] * advantage[b] ) flows back through that pass.
+ * Requires cxrm_prefill_cross_kv for the same studies (row r attends study r % B); the encoder is frozen.
+ * Gradients are written, fp32, into ONE flat buffer (`grads`) laid out by cxrm_grad_info; with lora_only = 1 only the
+ * LoRA A / B matrices of the self-attention query / key projections (modelling_longitudinal.py:163-170) get gradients,
+ * otherwise every decoder parameter does (the LoRA update is then part of the merged weight).  Eval-mode arithmetic:
+ * no dropout.
+ *
+ * Stages (for overlapping the gradient all-reduce with the backward pass): stage -1 runs everything;
+ * otherwise call stages 0 .. cxrm_train_stages() - 1 in order with the same arguments: stage 0 = forward + loss + LM-head
+ * backward, stage 1 + i = decoder layer (last - i), the last stage = embeddings.  When stage s returns, the slice of
+ * `grads` belonging to the slots with stage == s is final.
+ */
+typedef struct cxrm_train_args {
+  int R, L;                        /* rows, tokens per row (R * L a multiple of 8, <= max_train_tokens) */
+  const int32_t* ids;              /* dev [R, L] decoder input ids */
+  const int32_t* token_type_ids;   /* dev [R, L] */
+  const int32_t* position_ids;     /* dev [R, L] */
+  const uint8_t* key_mask;         /* dev [R, L] decoder_attention_mask */
+  const int32_t* targets;          /* dev [R, L] id to predict at each position; ignore_index where nothing is counted */
+  int ignore_index;
+  int loss_kind;                   /* 0 cross-entropy (mean over counted targets), 1 REINFORCE */
+  const float* advantage;          /* dev [R] (loss_kind 1) */
+  int top_k;                       /* loss_kind 1: the sampling head's top-k (0 = none) */
+  float temperature;               /* loss_kind 1 */
+  int lora_only;
+  float* loss_out;                 /* dev [1] */
+  float* grads;                    /* dev fp32 [cxrm_grad_total(e, lora_only)] */
+} cxrm_train_args;
+CXRM_API int cxrm_train_step(cxrm_engine* e, const cxrm_train_args* a, int stage, void* stream);
+CXRM_API int cxrm_train_stages(const cxrm_engine* e);
+/* layout of the flat gradient buffer: slot i has the reference's state_dict name (e.g.
+ * "decoder.bert.encoder.layer.3.attention.self.query.lora_A.weight"), an element offset, a size and the stage that
+ * finishes it; slots are ordered by stage, so every stage owns one contiguous range. */
+CXRM_API int cxrm_grad_count(const cxrm_engine* e, int lora_only);
+CXRM_API int64_t cxrm_grad_total(const cxrm_engine* e, int lora_only);
+CXRM_API int cxrm_grad_info(const cxrm_engine* e, int lora_only, int i, char* name, size_t name_len, int64_t* offset,
+                   int64_t* numel, int* stage);
 
 /* Device time (ms, CUDA events on the step's stream) of the phases of the LAST cxrm_scst_step_* call:
  * out5 = {encode, cross K/V, rollout, reward + result copies, prompt pass (prefill + first token; part of rollout)}. */

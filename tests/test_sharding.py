@@ -160,3 +160,54 @@ def test_balance_by_images_levels_the_ranks():
     assert max(loads) < max(naive)
     with pytest.raises(ValueError):
         S.balance_by_images([1, 2, 3], 2)
+
+
+def _allreduce_worker(rank, world, port, q):
+    import os
+
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from cxrmate_b200 import training
+
+        class FakeEngine:
+            """stands in for the CUDA engine: stage s writes (rank + 1) * (s + 1) into the slots of stage s"""
+            train_stages = 4
+
+            def grad_layout(self, lora_only):
+                return [("a", 0, 3, 0), ("b", 3, 2, 1), ("c", 5, 4, 1), ("d", 9, 1, 3)]     # stage 2 owns nothing
+
+            def train_step(self, *tensors, grads=None, stage=-1, _keep=None, **kw):
+                if grads is None:
+                    grads = torch.zeros(10)
+                for _, o, ne, s_ in self.grad_layout(False):
+                    if stage in (-1, s_):
+                        grads[o:o + ne] = (rank + 1) * (s_ + 1)
+                self._train_keep = {"loss": torch.tensor([float(rank)])}
+                return self._train_keep["loss"][0], grads
+
+        t = torch.zeros(2, 8, dtype=torch.int64)
+        _, g = training._staged(FakeEngine(), (t, t, t, t, t), dict(loss_kind="ce", ignore_index=4, lora_only=False), None, True)
+        q.put((rank, g.tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_staged_gradient_all_reduce_gloo_world2():
+    """the bucket-by-bucket gradient all-reduce of cxrmate_b200.training (NCCL on the GPUs; gloo here): every stage's
+    slice is averaged over the ranks, stages without slots are skipped"""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29671
+    procs = [ctx.Process(target=_allreduce_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    mean = 1.5                                                           # mean of (rank + 1) over ranks 0, 1
+    want = [mean * 1] * 3 + [mean * 2] * 6 + [mean * 4]
+    assert res[0] == pytest.approx(want) and res[1] == pytest.approx(want)
