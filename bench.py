@@ -25,6 +25,7 @@ Synthetic data and random-init weights of the named architecture (no network, no
 Other BASELINE.json configs (each prints its own JSON line; not the driver's default):
     python bench.py --config 1     # single-tf, 1 image, batch 1, greedy 255 tokens
     python bench.py --config 2     # multi-tf, <= 5 images, batch 32, greedy 255 tokens
+    python bench.py --config 3 [--all-params]   # longitudinal teacher-forced forward/backward, batch 64 (+ gradient all-reduce, N > 1)
     python bench.py --config 5     # generation sweep: 1 -> 512 studies per GPU, greedy 255 tokens
 """
 from __future__ import annotations
@@ -60,7 +61,8 @@ def parse():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-profile", action="store_true", help="skip the per-kernel-class event profile (no roofline)")
     ap.add_argument("--profile-out", default="")
-    ap.add_argument("--config", type=int, default=4, choices=[1, 2, 4, 5], help="BASELINE.json configs[] index + 1")
+    ap.add_argument("--config", type=int, default=4, choices=[1, 2, 3, 4, 5], help="BASELINE.json configs[] index + 1")
+    ap.add_argument("--all-params", action="store_true", help="config 3: gradients of every decoder parameter (default: LoRA only)")
     ap.add_argument("--no-balance", action="store_true", help="N > 1: DistributedSampler order instead of image-balanced shards")
     ap.add_argument("--no-gpu-eager", action="store_true", help="skip the eager-PyTorch-on-GPU baseline")
     ap.add_argument("--sweep-max", type=int, default=512)
@@ -591,10 +593,102 @@ def run_generation(a):
         print(json.dumps(line), flush=True)
 
 
+# ----------------------------------------------------------------------------------------- config 3: teacher-forced fwd/bwd
+def run_teacher_forced(a):
+    """BASELINE.json configs[2]: longitudinal teacher-forced forward/backward, batch 64 studies per GPU, prompt <= 256 +
+    report 256 tokens (512 decoder positions): frozen CvT encode -> cross K/V -> decoder forward -> cross-entropy ->
+    backward (cxrm_train_step; LoRA-only or every decoder parameter) -> gradient all-reduce over the ranks (NCCL),
+    bucketed per decoder layer and overlapped with the backward pass."""
+    import torch
+    import torch.distributed as dist
+
+    from cxrmate_b200 import synthetic as S
+    from cxrmate_b200 import synthetic_weights as W
+    from cxrmate_b200 import training
+    from cxrmate_b200.engine import Engine
+    from cxrmate_b200.modelling import position_ids_from_mask, token_ids_to_token_type_ids
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = 64 if a.studies == 32 else a.studies
+    N, L = a.images, 512
+    eng = Engine(dtype=a.dtype, device=local, max_studies=B, max_images=N, max_prompt=8, max_new_tokens=8, rwd_layers=0,
+                 enc_chunk=32, max_train_tokens=B * L)
+    eng.load_state_dict(W.make_cxrmate_weights(seed=0))
+    eng.finalize()
+    counts = global_image_counts(world * B, N)
+    px = torch.stack([S.make_images(1, N, seed=5000 + g, n_per_study=[counts[g]])[0] for g in range(rank * B, (rank + 1) * B)])
+    px_h = px.pin_memory()
+    g = torch.Generator().manual_seed(77 + rank)
+    ids = torch.randint(S.N_SPECIAL, S.DEC_VOCAB, (B, L), generator=g)
+    plen = torch.randint(8, 257, (B,), generator=g)            # prompt tokens, then [BOS] findings [SEP] impression [EOS]
+    rlen = torch.randint(64, 257, (B,), generator=g)
+    for b in range(B):
+        p_, r_ = int(plen[b]), int(rlen[b])
+        ids[b, 0], ids[b, p_ // 2], ids[b, p_ - 1] = S.PMT, S.PMT_SEP, S.BOS
+        ids[b, p_ - 1 + r_ // 2] = S.SEP
+        ids[b, p_ + r_ - 1:] = S.PAD
+    labels = torch.roll(ids, -1, 1)
+    labels[:, -1] = S.PAD
+    for b in range(B):
+        labels[b, : int(plen[b]) - 1] = S.PAD                  # the prompt is not a target
+    mask = (ids != S.PAD).long()
+    tt = token_ids_to_token_type_ids(ids, S.SPECIAL_GREEDY, S.SECTIONS)
+    pos = position_ids_from_mask(mask)
+    t_dev = [x.to(dev) for x in (ids, tt, pos, mask, labels)]
+    lora = not a.all_params
+    grads = torch.zeros(sum(ne for _, _, ne, _ in eng.grad_layout(lora)), dtype=torch.float32, device=dev)
+
+    def step():
+        eng.encode(px_h.to(dev, non_blocking=True))
+        eng.prefill_cross_kv()
+        return training.cross_entropy_backward(eng, *t_dev, pad_token_id=S.PAD, lora_only=lora, grads=grads, all_reduce=world > 1)
+
+    for _ in range(a.warmup):
+        loss, _ = step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    l0 = eng.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        loss, _ = step()
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / a.steps
+    if rank == 0:
+        n_tok = int((labels != S.PAD).sum())
+        print(json.dumps({
+            "metric": "teacher_forced_samples_per_sec", "value": world * B / (ms / 1000.0), "unit": "samples/s", "n_gpus": world,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
+            "config": {"workload": "BASELINE.json configs[2] 'cxrmate-tf longitudinal': batch 64/GPU, 512 decoder positions (prompt <= 256 + "
+                                   "report <= 256), frozen encoder, teacher-forced forward + backward, " +
+                                   ("LoRA-only gradients" if lora else "gradients of every decoder parameter"),
+                       "counted_target_tokens_rank0": n_tok, "valid_images_rank0": int(sum(counts[rank * B:(rank + 1) * B])),
+                       "gradient_bytes_all_reduced": int(grads.numel() * 4) if world > 1 else 0,
+                       "all_reduce": "NCCL, one bucket per decoder layer, async on the NCCL stream under the backward" if world > 1 else "none"},
+            "loss": float(loss.item()), "gpu_launches": int(eng.launch_count - l0),
+        }), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    eng.close()
+
+
 def main():
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.config == 3:
+        run_teacher_forced(a)
     elif a.config != 4:
         run_generation(a)
     else:
