@@ -402,6 +402,37 @@ def run_b200(a):
             e2e = {"value": world * B * a.steps / (float(t2.item()) / 1000.0), "unit": UNIT,
                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}
 
+        # ---- the same step with the REAL text bridge in the loop (BPE decode + WordPiece encode on the host) ---------
+        e2e_text = None
+        if not a.no_e2e and rank == 0:
+            try:
+                from cxrmate_b200.scst import scst_step_text
+                from cxrmate_b200.text_bridge import TextBridge
+                dec_tok, rwd_tok = S.train_tokenizers()
+                br = TextBridge(dec_tok, rwd_tok, S.BOS, S.SEP, S.EOS)
+                lab_txt = [[rwd_tok.decode(s_[2].tolist(), skip_special_tokens=True)] for s_ in studies]
+                tkw = dict(max_new_tokens=T, eos_token_id=S.EOS, pad_token_id=S.PAD, mask_token_id=S.PAD,
+                           special_sample=S.SPECIAL_SAMPLE, sections_sample=S.SECTIONS[:3], special_greedy=S.SPECIAL_GREEDY,
+                           sections_greedy=S.SECTIONS, top_k=50)
+                scst_step_text(eng, br, px_h, prompt_h, lab_txt, seed=300, **tkw)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                bms = []
+                for i in range(a.steps):
+                    o_ = scst_step_text(eng, br, px_h, prompt_h, lab_txt, seed=301 + i, **tkw)
+                    _ = o_["advantage"].cpu()
+                    bms.append(o_["bridge_ms"])
+                torch.cuda.synchronize()
+                wall = (time.perf_counter() - t0) / a.steps
+                e2e_text = {"value": B / wall, "unit": UNIT, "ms_per_step": wall * 1000.0, "bridge_ms": sum(bms) / len(bms),
+                            "n_gpus": 1,
+                            "what": "cxrmate_b200.scst.scst_step_text on rank 0: pinned host pixels in, engine encode + rollouts, "
+                                    "sequences to the host, split + byte-level BPE decode + WordPiece encode (30k / 30.5k "
+                                    "vocabularies trained offline) on the host, engine CXR-BERT reward, advantage to the "
+                                    "host; wall clock"}
+            except Exception as ex:
+                e2e_text = {"unavailable": f"{type(ex).__name__}: {ex}"[:300]}
+
         # ---- per-kernel-class profile of one more step (event pairs around every launch, no graph) ------
         roofline, breakdown = None, None
         if rank == 0 and not a.no_profile:
@@ -491,7 +522,7 @@ def run_b200(a):
                        "cuda_graph": not a.no_graph},
             "decode_tokens_per_s": world * 2 * B * steps_exec * a.steps / (ms / 1000.0),
             "phase_ms": {k: round(v, 3) for k, v in phases.items()},
-            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": e2e, "e2e_text": e2e_text, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "gpu_eager_baseline": eager, "breakdown": breakdown,
         }
         print(json.dumps(line), flush=True)

@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(CT, 1) decode_chain_kernel(const __grid_consta
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(128) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(256) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -248,12 +248,12 @@ __global__ void __launch_bounds__(CT, 1) decode_chain_kernel(const __grid_consta
     for (; pf_phase < a.count; ++pf_phase) {
       const ChainPhase& q = a.phases[pf_phase];
       if (q.type != CH_GEMM || cta >= q.n_tiles * q.nsplit) continue;
-      const int n0 = (cta % q.n_tiles) * q.bn, k0 = (cta / q.n_tiles) * C_K;
+      const int n0 = (cta % q.n_tiles) * q.bn, k0 = (cta / q.n_tiles) * q.kslice, nkb = q.kslice / C_BK;
       uint8_t* dst = sW + (pf_ord & 1) * C_WBYTES;
       uint64_t* bar = &wfull[pf_ord & 1];
-      mbar_expect_tx(bar, static_cast<uint32_t>(q.bn) * C_K * 2);
+      mbar_expect_tx(bar, static_cast<uint32_t>(q.bn) * q.kslice * 2);
 #pragma unroll 1
-      for (int kb = 0; kb < C_KB; ++kb) tma_load_2d(dst + kb * q.bn * 128, &q.tmB, k0 + kb * C_BK, n0, bar);
+      for (int kb = 0; kb < nkb; ++kb) tma_load_2d(dst + kb * q.bn * 128, &q.tmB, k0 + kb * C_BK, n0, bar);
       ++pf_ord;
       ++pf_phase;
       return;
@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(CT, 1) decode_chain_kernel(const __grid_consta
       CTRACE(2 + 8 * i);               // start of phase i
       if (p.type == CH_GEMM) {
         if (cta >= p.n_tiles * p.nsplit) continue;
-        const int n0 = (cta % p.n_tiles) * p.bn, split = cta / p.n_tiles, k0 = split * C_K;
+        const int n0 = (cta % p.n_tiles) * p.bn, split = cta / p.n_tiles, k0 = split * p.kslice, nkb = p.kslice / C_BK;
         const int buf = ord & 1;
         const uint32_t par = ord & 1, wpar = (ord >> 1) & 1;
         if (warp == 0) {
@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(CT, 1) decode_chain_kernel(const __grid_consta
             // SLOWER than these 12 TMA boxes: 5.7 vs 3.5 us until the operands are in)
             // ONE 3-D box: 12 k-block tiles of 64 x 64 (twelve 2-D boxes arrived one L2 round trip after the other:
             // 3.4 us for the 96 KiB; CXRM_CHAIN_TRACE)
-            mbar_expect_tx(&afull[0], C_ABYTES);
+            mbar_expect_tx(&afull[0], static_cast<uint32_t>(nkb) * C_AKB);
             tma_load_3d(sA, &p.tmA, 0, 0, k0 / C_BK, &afull[0]);
             GTRACE(5);
             mbar_wait(tfull, par);       // the MMAs have read this phase's weight buffer: refill it two GEMMs ahead
@@ -314,14 +314,14 @@ __global__ void __launch_bounds__(CT, 1) decode_chain_kernel(const __grid_consta
           const uint32_t ab = smem_u32(sA);
           const uint32_t wstep = static_cast<uint32_t>(p.bn) * 128u;
 #pragma unroll 1
-          for (int kb = 0; kb < C_KB; ++kb) {
+          for (int kb = 0; kb < nkb; ++kb) {
             const uint64_t da = make_desc(ab + static_cast<uint32_t>(kb * C_AKB)), db = make_desc(wb + static_cast<uint32_t>(kb) * wstep);
             // FOUR accumulators (TMEM columns 32j ..): the k-steps of a k-block go to different ones, so consecutive
             // MMAs are independent; the epilogue adds the four
 #pragma unroll
             for (int k = 0; k < C_BK / 16; ++k)
               if (leader)
-                umma(tmem + static_cast<uint32_t>(32 * k), da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
+                umma(tmem + static_cast<uint32_t>(64 * k), da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
                      kb != 0 ? 1u : 0u);
           }
           if (leader) {
@@ -348,14 +348,14 @@ __global__ void __launch_bounds__(CT, 1) decode_chain_kernel(const __grid_consta
           tc_fence_after();
           if (threadIdx.x == 64) GTRACE(4);
 #pragma unroll
-          for (int ch = 0; ch < 2; ++ch) {
+          for (int ch = 0; ch < 4; ++ch) {
             if (ch >= nchunk) break;     // warp-uniform
             uint32_t r[16];
             tmem_ld16(taddr + static_cast<uint32_t>(ch * 16), r);
 #pragma unroll
             for (int acc = 1; acc < 4; ++acc) {
               uint32_t r2[16];
-              tmem_ld16(taddr + static_cast<uint32_t>(32 * acc + ch * 16), r2);
+              tmem_ld16(taddr + static_cast<uint32_t>(64 * acc + ch * 16), r2);
 #pragma unroll
               for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
             }
@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(CT, 1) decode_chain_kernel(const __grid_consta
                 float v[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                  v[j] = __uint_as_float(r[8 * q8 + j]) + bs[ch * 16 + 8 * q8 + j];
+                  v[j] = __uint_as_float(r[8 * q8 + j]) + bs[(ch & 1) * 16 + 8 * q8 + j];   // (bias epilogues: bn <= 32)
                   if (p.epi == CE_BF16_GELU) v[j] = gelu_fast(v[j]);
                 }
                 Vec16<bf16> ov;
@@ -391,10 +391,20 @@ __global__ void __launch_bounds__(CT, 1) decode_chain_kernel(const __grid_consta
         float v[4];
         if (p.type == CH_LN) {
           float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-          float4 part[4];
+          // split-K partials, four loads in flight, summed in split order (reproducible)
+#pragma unroll 1
+          for (int s0 = 0; s0 < p.nsplit; s0 += 4) {
+            float4 part[4];
 #pragma unroll
-          for (int s = 0; s < 4; ++s)
-            if (s < p.nsplit) part[s] = __ldcg(reinterpret_cast<const float4*>(p.partial + (static_cast<long long>(s) * C_ROWS + m) * C_H + c));
+            for (int s = 0; s < 4; ++s)
+              if (s0 + s < p.nsplit)
+                part[s] = __ldcg(reinterpret_cast<const float4*>(p.partial + (static_cast<long long>(s0 + s) * C_ROWS + m) * C_H + c));
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+              if (s0 + s < p.nsplit) {
+                acc.x += part[s].x; acc.y += part[s].y; acc.z += part[s].z; acc.w += part[s].w;
+              }
+          }
           float rs[4] = {0.f, 0.f, 0.f, 0.f};
           if (p.residual_f32) {
             const float4 r4 = __ldcg(reinterpret_cast<const float4*>(p.residual_f32 + static_cast<long long>(m) * C_H + c));
@@ -405,11 +415,6 @@ __global__ void __launch_bounds__(CT, 1) decode_chain_kernel(const __grid_consta
             rs[2] = __uint_as_float(rr.y << 16); rs[3] = __uint_as_float(rr.y & 0xffff0000u);
           }
           const float4 b4 = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-          for (int s = 0; s < 4; ++s)
-            if (s < p.nsplit) {
-              acc.x += part[s].x; acc.y += part[s].y; acc.z += part[s].z; acc.w += part[s].w;
-            }
           v[0] = acc.x + b4.x; v[1] = acc.y + b4.y; v[2] = acc.z + b4.z; v[3] = acc.w + b4.w;
           if (p.act == ACT_GELU) {
 #pragma unroll
@@ -452,7 +457,7 @@ __global__ void __launch_bounds__(CT, 1) decode_chain_kernel(const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(128) : "memory");
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(256) : "memory");
 }
 
 }  // namespace
@@ -463,8 +468,11 @@ bool decode_chain_available() {
   static int ok = -1;
   if (ok < 0) {
     ok = 0;
-    // opt-in (CXRM_CHAIN=1): measured on B200 the persistent chain is SLOWER than the PDL-chained kernels it was
-    // meant to replace (rollout 152.8 vs 142.7 ms at the benchmark shape; DESIGN.md section 4e has the phase trace)
+    // OPT-IN (CXRM_CHAIN=1).  Measured on B200 at the benchmark shape: both the full chain (all
+    // GEMM / LayerNorm work between two attention kernels in one launch: rollout 152.8 ms) and the pair form used now
+    // (one launch per split-K GEMM + LayerNorm pair: 160.0 ms) are SLOWER than the PDL-chained stand-alone kernels
+    // (147.4 ms): a resident 198 KB CTA per SM keeps the NEXT kernel from becoming resident early, so its weight / K/V
+    // prefetch ahead of the dependency wait - what the PDL chain lives on - is lost.
     if (std::getenv("CXRM_CHAIN") != nullptr) {
       int dev = 0, sms = 0, per_sm = 0;
       if (cudaGetDevice(&dev) == cudaSuccess &&
@@ -478,8 +486,9 @@ bool decode_chain_available() {
   return ok == 1;
 }
 
-void decode_chain(const ChainPhase* phases, int count, int R, const RolloutState& st, unsigned* bar, cudaStream_t stream,
-                  unsigned long long* trace) {
+void decode_chain(const ChainPhase* phases, int count, int R, const RolloutState& st, unsigned* bar, int n_ctas,
+                  cudaStream_t stream, unsigned long long* trace) {
+  CXRM_CHECK(n_ctas >= 1 && n_ctas <= decode_chain_ctas(), "decode_chain grid");
   CXRM_CHECK(decode_chain_available(), "decode chain kernel unavailable on this device");
   CXRM_CHECK(count >= 1 && count <= kMaxPhases && R >= 1 && R <= C_ROWS && 2 + 8 * count <= kChainTraceSlots, "decode_chain shape");
   static_assert(sizeof(ChainArgs) <= 4000, "kernel parameter block");
@@ -489,7 +498,7 @@ void decode_chain(const ChainPhase* phases, int count, int R, const RolloutState
   for (int i = 0; i < count; ++i) a.phases[i] = phases[i];
   a.count = count; a.R = R; a.done = st.done; a.bar = bar;
   a.cur_token = st.cur_token; a.cur_type = st.cur_type; a.cur_pos = st.cur_pos;
-  launch_chain(decode_chain_kernel, dim3(decode_chain_ctas()), dim3(CT), C_SMEM, stream, a);
+  launch_chain(decode_chain_kernel, dim3(n_ctas), dim3(CT), C_SMEM, stream, a);
   check_launch("decode_chain");
 }
 

@@ -512,6 +512,7 @@ class Engine : public EngineBase {
     skinny_ws = dalloc<float>(static_cast<long long>(gemm_skinny_partial_floats(DH)));
     chain_bar = dalloc<unsigned>(kChainBarWords);
     CXRM_CUDA_CHECK(cudaMemset(chain_bar, 0, kChainBarWords * sizeof(unsigned)));
+    chain_ws = dalloc<float>(static_cast<long long>(kChainMaxSplit) * 64 * DH);
     chain_xf = dalloc<float>(static_cast<long long>(Rmax) * DH);
     chain_x1f = dalloc<float>(static_cast<long long>(Rmax) * DH);
 
@@ -1082,9 +1083,12 @@ class Engine : public EngineBase {
     PF("sample", s, [&] { sample_step(st, rp, logits, cfg.vocab, noise, s); });
   }
 
-  // ---- decode step with the GEMM / LayerNorm work between the attention kernels as persistent multi-phase launches
-  // (decode_chain.cu): per step 1 + 6 x (self-attention, chain A, cross-attention, chain B) + LM head + sample = 27
-  // launches instead of 71.  Phase lists are built once per (buffers, R) and kept in device memory.
+  // ---- decode step with every (split-K GEMM, reduce + LayerNorm) pair as ONE persistent two-phase launch
+  // (decode_chain.cu): the GEMM phase leaves fp32 partials, a grid barrier replaces the kernel boundary, the second
+  // phase reduces + normalises one row per CTA.  The projections that feed an attention kernel (QKV, cross-Q) and FFN-up
+  // stay on the PDL-chained skinny kernels, so the attention kernels keep prefetching K/V under their predecessor.
+  // A version that ran ALL GEMM / LayerNorm work between two attention kernels as one launch measured slower than the
+  // PDL chain.  Per step 58 launches instead of 71.
   bool use_chain(int R) const {
     return std::is_same<T, bf16>::value && cfg.use_tensor_cores && R <= 64 && ablate_mask() == 0 && !use_lnfold() &&
            decode_chain_available();
@@ -1093,64 +1097,45 @@ class Engine : public EngineBase {
     if constexpr (std::is_same<T, bf16>::value) {
       if (chain_key_buf == b.x && chain_key_R == R && chain_key_head == head_tmp && !chain_launch.empty()) return;
       // fp32 residual stream beside the bf16 activations (CXRM_CHAIN_BF16_RES=1: bf16 residuals, pre-LN sum rounded to
-      // bf16 as the round-1 kernels and bf16 autocast do)
+      // bf16 as the stand-alone reduce + LayerNorm kernel and bf16 autocast do)
       static const bool f32res = std::getenv("CXRM_CHAIN_BF16_RES") == nullptr;
       std::vector<ChainPhase> ph;
       chain_launch.clear();
-      const int ctas = decode_chain_ctas();
-      auto gemm_phase = [&](const T* A, int Ktot, const Lin& L, int bn, int epi, void* out, int ldo) {
+      auto pair = [&](const T* A, int Ktot, const Lin& L, int kslice, int act, const T* res, const float* res32, const LNp& ln,
+                      T* out, float* out32) {
+        const size_t first = ph.size();
         ChainPhase p;
         std::memset(&p, 0, sizeof(p));
         p.type = CH_GEMM;
-        p.tmA = make_tensor_map_bf16_kblocks(A, R, Ktot, Ktot, 64, DH / 64);
-        p.tmB = make_tensor_map_bf16(L.w, L.n_out, L.n_in, L.n_in, bn, 64);
-        p.bn = bn; p.n_tiles = L.n_out / bn; p.nsplit = Ktot / DH; p.epi = epi; p.N = L.n_out; p.ldo = ldo;
-        p.bias = L.b; p.out = out; p.partial = skinny_ws;
-        CXRM_CHECK(L.n_in == Ktot && L.n_out % bn == 0 && Ktot % DH == 0 && p.n_tiles * p.nsplit <= ctas &&
-                       (epi != CE_PARTIAL || (L.n_out == DH && p.nsplit <= 4)), "decode chain: GEMM phase shape");
+        p.bn = 64; p.kslice = kslice; p.n_tiles = L.n_out / p.bn; p.nsplit = Ktot / kslice; p.epi = CE_PARTIAL; p.N = L.n_out;
+        p.tmA = make_tensor_map_bf16_kblocks(A, R, Ktot, Ktot, 64, kslice / 64);
+        p.tmB = make_tensor_map_bf16(L.w, L.n_out, L.n_in, L.n_in, p.bn, 64);
+        p.partial = chain_ws;
+        CXRM_CHECK(L.n_in == Ktot && L.n_out == DH && Ktot % kslice == 0 && kslice % 64 == 0 && p.nsplit <= kChainMaxSplit &&
+                       p.bn * kslice * 2 <= 48 * 1024, "decode chain: GEMM phase shape");
         ph.push_back(p);
+        ChainPhase q;
+        std::memset(&q, 0, sizeof(q));
+        q.type = CH_LN; q.nsplit = p.nsplit; q.bias = L.b; q.act = act; q.partial = chain_ws;
+        const bool use32 = f32res && res32 != nullptr;
+        q.residual = use32 ? nullptr : res; q.residual_f32 = use32 ? res32 : nullptr;
+        q.round_pre = f32res ? 0 : 1;
+        q.gamma = ln.g; q.beta = ln.b; q.eps = LN_EPS_BERT; q.out = out; q.ldo = DH; q.out_f32 = f32res ? out32 : nullptr;
+        ph.push_back(q);
+        const int ctas = std::max(p.n_tiles * p.nsplit, R);
+        chain_launch.push_back({static_cast<int>(first), 2, ctas});
       };
-      auto ln_phase = [&](int type, int nsplit, const float* bias, int act, const T* res, const float* res32, const LNp& ln,
-                          T* out, float* out32) {
-        ChainPhase p;
-        std::memset(&p, 0, sizeof(p));
-        p.type = type; p.nsplit = nsplit; p.bias = bias; p.act = act; p.partial = skinny_ws;
-        p.residual = f32res ? nullptr : res; p.residual_f32 = f32res ? res32 : nullptr;
-        p.round_pre = f32res ? 0 : 1;
-        p.gamma = ln.g; p.beta = ln.b; p.eps = LN_EPS_BERT; p.out = out; p.ldo = DH; p.out_f32 = f32res ? out32 : nullptr;
-        p.word = dec.word; p.type_emb = dec.type; p.pos_emb = dec.pos;
-        ph.push_back(p);
-      };
-      auto close = [&](size_t first) { chain_launch.push_back({static_cast<int>(first), static_cast<int>(ph.size() - first)}); };
       float* xf = chain_xf; float* x1f = chain_x1f;
-      size_t f0 = ph.size();
-      ln_phase(CH_EMBED, 0, nullptr, ACT_NONE, nullptr, nullptr, dec.emb_ln, b.x, xf);
-      gemm_phase(b.x, DH, dec.layers[0].qkv, 16, CE_BF16, b.qkv, 3 * DH);
-      close(f0);
       for (int l = 0; l < cfg.dec_layers; ++l) {
         const BertLayerW& w = dec.layers[l];
-        f0 = ph.size();                                                             // chain A: after self-attention
-        gemm_phase(b.ctx, DH, w.o, 16, CE_PARTIAL, nullptr, 0);
-        ln_phase(CH_LN, 1, w.o.b, ACT_NONE, b.x, xf, w.ln1, b.x1, x1f);
-        gemm_phase(b.x1, DH, w.cq, 16, CE_BF16, b.qkv, DH);
-        close(f0);
-        f0 = ph.size();                                                             // chain B: after cross-attention
-        gemm_phase(b.ctx, DH, w.co, 16, CE_PARTIAL, nullptr, 0);
-        ln_phase(CH_LN, 1, w.co.b, ACT_NONE, b.x1, x1f, w.ln2, b.x, xf);
-        gemm_phase(b.x, DH, w.fc1, 32, CE_BF16_GELU, b.hid, DFF);
-        gemm_phase(b.hid, DFF, w.fc2, 32, CE_PARTIAL, nullptr, 0);
-        ln_phase(CH_LN, DFF / DH, w.fc2.b, ACT_NONE, b.x, xf, w.ln3, b.x, xf);
-        if (l + 1 < cfg.dec_layers) {
-          gemm_phase(b.x, DH, dec.layers[l + 1].qkv, 16, CE_BF16, b.qkv, 3 * DH);
-        } else {                                                                    // LM-head transform: dense -> GELU -> LN
-          gemm_phase(b.x, DH, dec_head_t, 16, CE_PARTIAL, nullptr, 0);
-          ln_phase(CH_LN, 1, dec_head_t.b, ACT_GELU, nullptr, nullptr, dec_head_ln, head_tmp, nullptr);
-        }
-        close(f0);
+        // layer 0's input comes from the embedding kernel (bf16 only); later layers carry the fp32 copy written by LN3
+        pair(b.ctx, DH, w.o, 192, ACT_NONE, b.x, l == 0 ? nullptr : xf, w.ln1, b.x1, x1f);
+        pair(b.ctx, DH, w.co, 192, ACT_NONE, b.x1, x1f, w.ln2, b.x, xf);
+        pair(b.hid, DFF, w.fc2, 256, ACT_NONE, b.x, xf, w.ln3, b.x, xf);
       }
+      pair(b.x, DH, dec_head_t, 192, ACT_GELU, nullptr, nullptr, dec_head_ln, head_tmp, nullptr);
       static const bool want_trace = std::getenv("CXRM_CHAIN_TRACE") != nullptr;
-      if (want_trace && !chain_trace)
-      {
+      if (want_trace && !chain_trace) {
         const long long nt = static_cast<long long>(chain_launch.size()) * decode_chain_ctas() * kChainTraceSlots;
         chain_trace = dalloc<unsigned long long>(nt);
         CXRM_CUDA_CHECK(cudaMemset(chain_trace, 0, nt * sizeof(unsigned long long)));
@@ -1168,22 +1153,29 @@ class Engine : public EngineBase {
       const auto fc = chain_launch[k];
       unsigned long long* tr = chain_trace ? chain_trace + k * static_cast<size_t>(decode_chain_ctas()) * kChainTraceSlots : nullptr;
       ++k;
-      PF("chain", s, [&] { decode_chain(chain_host.data() + fc.first, fc.second, R, st, chain_bar, s, tr); });
+      PF("gemm_ln", s, [&] { decode_chain(chain_host.data() + fc.first, fc.second, R, st, chain_bar, fc.ctas, s, tr); });
     };
-    chain();                                   // embedding + LayerNorm, QKV of layer 0 (plain launch: opens the step)
+    PF("embed_ln", s, [&] { embed_ln<T>(st.cur_token, st.cur_type, st.cur_pos, dec.word, dec.type, dec.pos, dec.emb_ln.g, dec.emb_ln.b, b.x, R,
+                DH, LN_EPS_BERT, s); });
     struct PdlScope {
       explicit PdlScope(bool on) { g_pdl = on; }
       ~PdlScope() { g_pdl = false; }
     } pdl_scope(chain_pdl() && !profiling);
     for (int l = 0; l < cfg.dec_layers; ++l) {
+      const BertLayerW& w = dec.layers[l];
+      gemm(b.x, DH, w.qkv, b.qkv, 3 * DH, R, ACT_NONE, nullptr, 0, false, skip, s);
       PF("self_attn", s, [&] { decode_self_attention<T>(b.qkv, self_k + l * self_layer_stride(), self_v + l * self_layer_stride(), b.ctx, st, R,
                                rp.P, Lmax, self_ws, self_tickets, attn_maps_ptr, l, s); });
-      chain();                                 // O projection, LayerNorm, cross-attention query
+      chain();                                 // x1 = LN1(ctx . Wo + b + x)
+      gemm(b.x1, DH, w.cq, b.qkv, DH, R, ACT_NONE, nullptr, 0, false, skip, s);
       const T* kvl = cross_kv + static_cast<long long>(l) * cross_layer_stride();
       PF("cross_attn", s, [&] { decode_cross_attention<T>(b.qkv, DH, kvl, kvl + NHEAD * cross_head_stride(), cross_head_stride(), b.ctx,
                                 cross_units(), st, R, B, cross_ws, cross_tickets, attn_maps_ptr, l, s); });
-      chain();                                 // cross output, LayerNorm, FFN, LayerNorm, next layer's QKV / head transform
+      chain();                                 // x = LN2(ctx . Wco + b + x1)
+      gemm(b.x, DH, w.fc1, b.hid, DFF, R, ACT_GELU, nullptr, 0, false, skip, s);
+      chain();                                 // x = LN3(hid . W2 + b + x)
     }
+    chain();                                   // LM-head transform: LN(GELU(x . Wt + b))
     gemm(head_tmp, DH, dec_lm, logits, cfg.vocab, R, ACT_NONE, nullptr, 0, true, skip, s);
     PF("sample", s, [&] { sample_step(st, rp, logits, cfg.vocab, noise, s); });
   }
@@ -2030,12 +2022,12 @@ class Engine : public EngineBase {
     CXRM_CUDA_CHECK(cudaMemcpy(h.data(), chain_trace, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     auto at = [&](size_t k, int c, int slot) { return h[(k * nc + c) * kChainTraceSlots + slot]; };
     unsigned long long t00 = ~0ull;
-    for (int c = 0; c < nc; ++c) t00 = std::min(t00, at(0, c, 0));
+    for (int c = 0; c < chain_launch[0].ctas; ++c) t00 = std::min(t00, at(0, c, 0));
     fprintf(stderr, "[cxrm chain trace] one decode step, us since the first chain CTA started (min..max over %d CTAs)\n", nc);
     for (size_t k = 0; k < chain_launch.size(); ++k) {
       auto mm = [&](int slot, double& lo, double& hi) {
         unsigned long long a = ~0ull, b = 0;
-        for (int c = 0; c < nc; ++c) {
+        for (int c = 0; c < chain_launch[k].ctas; ++c) {
           a = std::min(a, at(k, c, slot));
           b = std::max(b, at(k, c, slot));
         }
@@ -2062,7 +2054,8 @@ class Engine : public EngineBase {
     }
   }
   float* chain_xf = nullptr; float* chain_x1f = nullptr;      // fp32 residual stream [Rmax, 768] x 2
-  struct ChainSpan { int first, second; };
+  struct ChainSpan { int first, second, ctas; };
+  float* chain_ws = nullptr;                                  // split-K partials [kChainMaxSplit][64][768]
   std::vector<ChainSpan> chain_launch;
   const void* chain_key_buf = nullptr; const void* chain_key_head = nullptr; int chain_key_R = 0;
   // CUDA graph of one decode step

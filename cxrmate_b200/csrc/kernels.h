@@ -300,10 +300,11 @@ enum ChainPhaseType : int { CH_GEMM = 0, CH_LN = 1, CH_EMBED = 2 };
 enum ChainEpi : int { CE_PARTIAL = 0, CE_BF16 = 1, CE_BF16_GELU = 2 };
 // One phase of a chain launch; a launch's list (<= 7 phases) travels in the kernel's parameter block.
 struct alignas(128) ChainPhase {
-  CUtensorMap tmA;           // GEMM: activations [R, K_total] bf16 as k-blocks: box {64, 64 rows, 12 k-blocks}
+  CUtensorMap tmA;           // GEMM: activations [R, K_total] bf16 as k-blocks: box {64, 64 rows, kslice / 64 k-blocks}
   CUtensorMap tmB;           // GEMM: weights [N, K_total] bf16, box bn rows x 64 columns
   int type;                  // ChainPhaseType
-  int n_tiles, nsplit, bn;   // GEMM: column tiles, 768-deep K splits, tile width (16 | 32); n_tiles * nsplit <= CTAs
+  int n_tiles, nsplit, bn;   // GEMM: column tiles, K splits, tile width (16 | 32 | 64); n_tiles * nsplit <= CTAs
+  int kslice;                // GEMM: K elements per split (multiple of 64, <= 768; bn * kslice * 2 <= 48 KiB)
   int epi;                   // ChainEpi
   int N;                     // GEMM: output columns (row pitch of the partials)
   int ldo;                   // row pitch of `out` (bf16 elements)
@@ -329,8 +330,9 @@ int decode_chain_ctas();
 // [2 + 8i] start of phase i, [+1..+6] GEMM sub-stamps (decode_chain.cu GTRACE), [+7] end of phase i
 constexpr int kChainTraceSlots = 64;
 constexpr int kChainBarWords = 64 + 32 * 16;   // grid-barrier counters of decode_chain (zeroed once by the caller)
-void decode_chain(const ChainPhase* host_phases, int count, int R, const RolloutState& st, unsigned* bar, cudaStream_t stream,
-                  unsigned long long* trace = nullptr);
+constexpr int kChainMaxSplit = 12;
+void decode_chain(const ChainPhase* host_phases, int count, int R, const RolloutState& st, unsigned* bar, int n_ctas,
+                  cudaStream_t stream, unsigned long long* trace = nullptr);
 
 // copy rows [r, P-1] of x [R*P, C] into out [R, C]
 template <typename T>

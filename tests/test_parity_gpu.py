@@ -475,3 +475,15 @@ def test_encoder_many_images_bf16_vs_oracle(sd):
         assert err < 3e-2
     finally:
         e.close()
+
+
+def test_persistent_chain_kernel_opt_in_path():
+    """the persistent GEMM + LayerNorm chain kernel (decode_chain.cu, CXRM_CHAIN=1; opt-in because it measured slower than the
+    PDL chain) keeps its parity coverage: the cached-decode == teacher-forced property in a subprocess with the switch set"""
+    import subprocess
+    import sys
+    env = dict(os.environ, CXRM_CHAIN="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-k",
+                        "test_cached_decode_equals_teacher_forced_long and bf16"], env=env, capture_output=True, text=True,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))), timeout=600)
+    assert r.returncode == 0 and "1 passed" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

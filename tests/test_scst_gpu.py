@@ -355,3 +355,44 @@ def test_unknown_and_peft_named_weights(sd):
             c.finalize()
     finally:
         c.close()
+
+
+def test_scst_step_with_real_text_bridge_vs_oracle_fp32(sd, rsd):
+    """scst_step with STRINGS in the loop (cxrmate_b200.scst.scst_step_text: engine rollout -> CPU split / byte-level BPE
+    decode / WordPiece encode -> engine reward) against oracle.scst.scst_step driven with the same subword tokenizers and
+    the oracle's CXRBERTReward: ids and strings exact, rewards / baseline / advantage 1e-3"""
+    from cxrmate_b200 import synthetic as S
+    from cxrmate_b200.scst import scst_step_text
+    from cxrmate_b200.text_bridge import TextBridge
+    from oracle import reward as oreward
+    from oracle import scst
+    dec_tok, rwd_tok = S.train_tokenizers()
+    B, N, T = 4, 2, 10
+    px = S.make_images(B, N, size=64, seed=60)
+    prompt = S.make_prompts(B, 10, seed=61)
+    P = prompt.shape[1]
+    labels = [["Moderate right pleural effusion has increased. No pneumothorax."], ["Heart size is normal."],
+              ["Lines and tubes unchanged. Mild bibasilar atelectasis."], ["No acute osseous abnormality."]]
+    noise = torch.empty(T, B, S.DEC_VOCAB).exponential_(1, generator=torch.Generator().manual_seed(62))
+    e = _engine(sd, rsd, "fp32", image_size=64, max_studies=B, max_images=N, max_prompt=P, max_new_tokens=T, rwd_max_len=512,
+                rwd_max_seqs=3 * B, enc_chunk=8)
+    try:
+        br = TextBridge(dec_tok, rwd_tok, S.BOS, S.SEP, S.EOS)
+        out = scst_step_text(e, br, px.pin_memory(), prompt.pin_memory(), labels, max_new_tokens=T, eos_token_id=S.EOS,
+                             pad_token_id=S.PAD, mask_token_id=S.PAD, special_sample=S.SPECIAL_SAMPLE,
+                             sections_sample=S.SECTIONS[:3], special_greedy=S.SPECIAL_GREEDY, sections_greedy=S.SECTIONS,
+                             top_k=50, exp_noise=noise.cuda())
+        torch.cuda.synchronize()
+        with torch.no_grad():
+            o = scst.scst_step(sd, oreward.CXRBERTReward(rsd, rwd_tok), dec_tok, px, prompt, labels, decoder_max_len=T + 1,
+                               top_k=50, exp_noise=noise)
+        assert torch.equal(out["sequences"][:B].cpu(), o.sample.sequences)
+        assert torch.equal(out["sequences"][B:].cpu(), o.greedy.sequences)
+        assert out["sample_str"] == o.sample_str and out["baseline_str"] == o.baseline_str
+        for k, ref in (("reward", o.sample_reward), ("baseline", o.baseline), ("advantage", o.reward)):
+            err = (out[k].cpu() - ref).abs().max().item()
+            print(f"scst_step_text fp32 {k} max abs err vs oracle: {err:.2e}")
+            assert err < 1e-3, (k, err)
+        print("bridge ms", round(out["bridge_ms"], 2), "sample report:", out["sample_str"][0][:60])
+    finally:
+        e.close()
