@@ -37,7 +37,7 @@ def test_struct_layouts_match_the_header():
     assert cfg.use_cuda_graph == 1 and cfg.use_tensor_cores == 1   # last fields: the whole struct lines up
     # pointer members are 8-byte aligned exactly like the C struct
     assert lib.CxrmRolloutArgs.prompt_ids.offset == 16
-    assert ctypes.sizeof(lib.CxrmConfig) == 19 * 4
+    assert ctypes.sizeof(lib.CxrmConfig) == 20 * 4   # 17 scalar ints + cvt_depth[3]
 
 
 def test_no_cpu_fallback():
