@@ -997,6 +997,16 @@ int dbg_nocompute() {
   return v;
 }
 
+// experiment knob (tools/exp_two_stream.py): persistent decode-attention CTAs per SM (default 2)
+int attn_ctas_per_sm() {
+  static int v = 0;
+  if (v == 0) {
+    const char* e = std::getenv("CXRM_ATTN_CPS");
+    v = e ? std::max(1, std::atoi(e)) : 2;
+  }
+  return v;
+}
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -1031,7 +1041,7 @@ void decode_self_attention(const T* qkv, T* kcache, T* vcache, T* ctx, const Rol
     const int layer_row0 = layer * maps->self_rows_per_layer;
     // the kernel rounds its per-CTA item count up to whole (row, head) groups: leave max_chunks of head room in MAXI
     CXRM_CHECK(max_chunks < MAXI / 2, "self-attention cache too long for the per-CTA work list");
-    const int grid = std::max(2 * num_sms(), ceil_div(NH * R * max_chunks, MAXI - max_chunks));
+    const int grid = std::max(attn_ctas_per_sm() * num_sms(), ceil_div(NH * R * max_chunks, MAXI - max_chunks));
     launch_chain(decode_self_persist_kernel, dim3(grid), dim3(PNT), kPersistSmem, stream, maps->self_k, maps->self_v,
                  layer_row0, qkv, kcache, vcache, ctx, st, R, P, Lmax, max_chunks, ws, tickets, dbg_nocompute());
   } else {
@@ -1069,7 +1079,7 @@ void decode_cross_attention(const T* q, int ldq, const T* kc, const T* vc, long 
       configured = true;
     }
     auto launch = [&](auto kern) {
-      const int grid = std::max(2 * num_sms(), ceil_div(NH * cu.max_units, MAXI));
+      const int grid = std::max(attn_ctas_per_sm() * num_sms(), ceil_div(NH * cu.max_units, MAXI));
       launch_chain(kern, dim3(grid), dim3(PNT), kPersistSmem, stream, maps->cross, row_k, row_v, tok_cap, q, ldq, ctx, cu,
                    st, B, ws, tickets, dbg_nocompute());
     };

@@ -1577,6 +1577,10 @@ void gemm_tcgen05_skinny(const GemmArgs& g, float* partial, int* nsplit_out, cud
   const int kb_per_split = ceil_div(num_kb, nsplit);
   nsplit = ceil_div(num_kb, kb_per_split);
   stages = std::min(stages, kb_per_split);
+  {   // experiment knob (tools/exp_two_stream.py): cap the ring depth so that the CTA fits beside an attention CTA
+    static const int cap = std::getenv("CXRM_SK_STAGES") ? std::max(2, std::atoi(std::getenv("CXRM_SK_STAGES"))) : SK_MAX_STAGES;
+    stages = std::min(stages, cap);
+  }
   if (nsplit_out) *nsplit_out = partial ? nsplit : 0;
   switch (bn) {
     case 16: launch_skinny<16>(g, stages, nsplit, kb_per_split, partial, stream, fold); break;
