@@ -108,6 +108,10 @@ int cxrm_rollout(cxrm_engine* e, const cxrm_rollout_args* a, void* stream) {
   if (!a) return CXRM_ERR_INVALID;
   CXRM_GUARD(e, e->impl->rollout(*a, static_cast<cudaStream_t>(stream)));
 }
+int cxrm_rollout_beam(cxrm_engine* e, const cxrm_beam_args* a, void* stream) {
+  if (!a) return CXRM_ERR_INVALID;
+  CXRM_GUARD(e, e->impl->rollout_beam(*a, static_cast<cudaStream_t>(stream)));
+}
 int cxrm_decoder_forward(cxrm_engine* e, const int32_t* ids, const int32_t* tt, const int32_t* pos,
                          const uint8_t* key_mask, int R, int L, int B, int last_only, float* logits_out, void* stream) {
   CXRM_GUARD(e, e->impl->decoder_forward(ids, tt, pos, key_mask, R, L, B, last_only != 0, logits_out,

@@ -133,6 +133,7 @@ class Engine : public EngineBase {
   Engine(const cxrm_config& c, int dev) : cfg(c), device(dev) { setup(); }
   ~Engine() override {
     for (void* p : owned) cudaFree(p);
+    if (beam_scratch) cudaFree(beam_scratch);
     for (auto& kv : raw) cudaFree(kv.second.data);
     arena.release();
     if (graph_exec) cudaGraphExecDestroy(graph_exec);
@@ -877,6 +878,8 @@ class Engine : public EngineBase {
     kv_total = total;
     kv_maxlen = mx;
     kv_B = B;
+    h_kv_len = len;
+    h_kv_off = off;
     CXRM_CUDA_CHECK(cudaMemcpyAsync(kv_off, off.data(), B * sizeof(int), cudaMemcpyHostToDevice, s));
     compact_rows_kernel<<<ceil_div(B, 64), 64, 0, s>>>(mask, kv_off, compact_idx, B, S);
     check_launch("compact_rows");
@@ -911,7 +914,8 @@ class Engine : public EngineBase {
     CXRM_CUDA_CHECK(cudaMemcpyAsync(unit_tab, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice, s));
     CXRM_CUDA_CHECK(cudaStreamSynchronize(s));   // `tab` is pageable host memory going out of scope
   }
-  CrossUnits cross_units() const {
+  CrossUnits cross_units() const { return units_of(unit_tab); }
+  CrossUnits units_of(const int* unit_tab) const {
     CrossUnits cu;
     cu.study = unit_tab;
     cu.j0 = unit_tab + cross_max_units;
@@ -1181,17 +1185,19 @@ class Engine : public EngineBase {
   }
 
   void decode_step(DecBufs& b, T* head_tmp, const RolloutParams& rp, const float* noise, cudaStream_t s) {
-    if (use_chain(rp.R)) {
+    if (rp.beams == 0 && use_chain(rp.R)) {
       ensure_chain(b, head_tmp, rp.R);
       decode_step_chain(b, head_tmp, rp, noise, s);
       return;
     }
-    if (use_lnfold()) {
+    if (rp.beams == 0 && use_lnfold()) {
       decode_step_folded(b, head_tmp, rp, noise, s);
       return;
     }
     phase = "decode";
+    // beam search: every running beam is a virtual study (B == R) whose units point at its real study's encoder K/V
     const int R = rp.R, B = rp.B;
+    const CrossUnits cunits = rp.beams ? units_of(unit_tab_beam) : cross_units();
     const int* skip = st.done;
     const unsigned abl = ablate_mask();
     const bool no_gemm = abl & 1, no_ln = abl & 2, no_self = abl & 4, no_cross = abl & 8, no_sample = abl & 16, no_embed = abl & 32;
@@ -1228,7 +1234,7 @@ class Engine : public EngineBase {
       // the grid covers cross_max_units so that the captured graph does not depend on the batch's image counts
       if (!no_cross)
         PF("cross_attn", s, [&] { decode_cross_attention<T>(b.qkv, DH, kvl, kvl + NHEAD * cross_head_stride(), cross_head_stride(), b.ctx,
-                                  cross_units(), st, R, B, cross_ws, cross_tickets, attn_maps_ptr, l, s); });
+                                  cunits, st, R, B, cross_ws, cross_tickets, attn_maps_ptr, l, s); });
       // ... and the next self-attention's K/V (layer 0 of the NEXT step after the last layer) beside cross-out / FFN
       fork_prefetch(l + 1 < cfg.dec_layers ? pf_self(l + 1, R, rp.P, 0) : pf_self(0, R, rp.P, 1), s);
       GL(b.ctx, DH, w.co, ACT_NONE, b.x1, w.ln2, b.x);
@@ -1246,7 +1252,13 @@ class Engine : public EngineBase {
         lm_head(b.x, R, head_tmp, logits, cfg.vocab, skip, s);
       }
     }
-    if (!no_sample) PF("sample", s, [&] { sample_step(st, rp, logits, cfg.vocab, noise, s); });
+    if (rp.beams) {
+      PF("beam_step", s, [&] { beam_step(st, rp, bs, logits, cfg.vocab, s); });
+      PF("beam_reorder", s, [&] { beam_reorder_kv<T>(self_k, self_v, beam_scratch, st, bs, R, Lmax, rp.Tmax, cfg.dec_layers,
+                                                      self_layer_stride(), s); });
+    } else if (!no_sample) {
+      PF("sample", s, [&] { sample_step(st, rp, logits, cfg.vocab, noise, s); });
+    }
     join_prefetch(s);
   }
 
@@ -1354,6 +1366,7 @@ class Engine : public EngineBase {
     key.R = rp.R; key.B = rp.B; key.P = rp.P; key.Tmax = rp.Tmax; key.top_k = rp.top_k;
     key.temperature = rp.temperature; key.noise = noise; key.buf = db.x;
     key.mask_id = rp.mask_token_id; key.eos = rp.eos; key.pad = rp.pad; key.want_margin = rp.want_margin;
+    key.beams = rp.beams; key.length_penalty = rp.length_penalty; key.beam_scratch = rp.beams ? beam_scratch : nullptr;
     std::memcpy(key.special, rp.special_ids, sizeof(key.special));
     std::memcpy(key.sections, rp.sections, sizeof(key.sections));
     std::memcpy(key.nspecial, rp.n_special, sizeof(key.nspecial));
@@ -1386,6 +1399,127 @@ class Engine : public EngineBase {
     }
     for (int t = 0; t < n_steps; ++t) CXRM_CUDA_CHECK(cudaGraphLaunch(graph_exec, s));
     g_launch_count += graph_nodes * static_cast<unsigned long long>(n_steps);
+  }
+
+  // =========================================================================== beam search
+  // HF _beam_search over the KV-cached rollout (include/cxrm.h cxrm_rollout_beam; kernels and bookkeeping: beam.cu).
+  void ensure_beam_buffers(int R, int Tn) {
+    if (!unit_tab_beam) {
+      unit_tab_beam = dalloc<int>(4LL * cross_max_units + 2LL * cfg.max_studies + 1);
+      const long long nbm = static_cast<long long>(cfg.max_studies);
+      bs.run_score = dalloc<float>(nbm);
+      bs.fin_score = dalloc<float>(nbm);
+      bs.fin_len = dalloc<int>(nbm);
+      bs.is_fin = dalloc<uint8_t>(nbm);
+      bs.can_improve = dalloc<uint8_t>(nbm);
+      bs.fin_seq = dalloc<int>(nbm * kBeamMaxT);
+      bs.src_row = dalloc<int>(nbm);
+      bs.n_slots = dalloc<int>(4);
+      bs.arrive = reinterpret_cast<unsigned*>(bs.n_slots + 1);
+      bs.cnt_can = bs.n_slots + 2;
+      bs.cnt_hit = bs.n_slots + 3;
+    }
+    const size_t need = beam_scratch_elems(R, Tn, cfg.dec_layers);
+    if (need > beam_scratch_cap) {
+      if (beam_scratch) CXRM_CUDA_CHECK(cudaFree(beam_scratch));
+      beam_scratch = nullptr;
+      CXRM_CUDA_CHECK(cudaMalloc(&beam_scratch, need * sizeof(T)));
+      beam_scratch_cap = need;
+      graph_valid = false;
+    }
+  }
+  void rollout_beam(const cxrm_beam_args& a, cudaStream_t s_user) override {
+    CXRM_CHECK(finalized, "weights not finalized");
+    cudaStream_t s = s_user;
+    const bool hop = cfg.use_cuda_graph && (s_user == nullptr || s_user == cudaStreamLegacy);
+    if (hop) {
+      s = side_stream;
+      CXRM_CUDA_CHECK(cudaEventRecord(ev_a, s_user));
+      CXRM_CUDA_CHECK(cudaStreamWaitEvent(s, ev_a, 0));
+    }
+    const int nb = a.num_beams, B = a.B, P = a.P, Tn = a.max_new_tokens;
+    CXRM_CHECK(nb >= 2 && nb <= kMaxBeams, "num_beams must be 2..8 (num_beams == 1 is cxrm_rollout's greedy mode)");
+    CXRM_CHECK(kv_B == B && kv_total > 0, "cxrm_rollout_beam needs cxrm_prefill_cross_kv for the same B");
+    const int R = B * nb;
+    CXRM_CHECK(R <= cfg.max_studies, "beam search: B * num_beams must not exceed the engine's max_studies");
+    CXRM_CHECK(P >= 1 && P <= cfg.max_prompt && Tn >= 1 && Tn <= cfg.max_new_tokens && Tn <= kBeamMaxT, "rollout shape");
+    CXRM_CHECK(a.n_special <= kMaxSpecial, "too many special tokens");
+    CXRM_CHECK(a.sequences != nullptr && a.prompt_ids != nullptr, "sequences / prompt_ids");
+    ensure_beam_buffers(R, Tn);
+    RolloutParams rp{};
+    rp.R = R; rp.B = R; rp.P = P; rp.Lmax = Lmax; rp.Tmax = Tn; rp.V = cfg.vocab;
+    rp.mode_of_block[0] = 1;
+    rp.n_special[0] = a.n_special;
+    for (int i = 0; i < a.n_special; ++i) rp.special_ids[0][i] = a.special[i];
+    for (int i = 0; i <= a.n_special; ++i) rp.sections[0][i] = a.sections[i];
+    rp.mask_token_id = a.mask_token_id; rp.eos = a.eos_token_id; rp.pad = a.pad_token_id;
+    rp.top_k = 0; rp.temperature = 1.0f; rp.seed = 0; rp.want_margin = 0;
+    rp.beams = nb; rp.length_penalty = a.length_penalty;
+    // virtual studies: beam j of study b is row j * B + b; its cross-attention units are those of study b
+    {
+      std::vector<int> tab(4 * static_cast<size_t>(cross_max_units) + 2 * cfg.max_studies + 1, 0);
+      int* u_study = tab.data();
+      int* u_j0 = u_study + cross_max_units;
+      int* u_n = u_j0 + cross_max_units;
+      int* u_chunk = u_n + cross_max_units;
+      int* n_chunks = u_chunk + cross_max_units;
+      int* first_unit = n_chunks + cfg.max_studies;
+      int nu = 0;
+      for (int v = 0; v < R; ++v) {
+        const int b = v % B;
+        const int nc = ceil_div(h_kv_len[b], attn_ch);
+        n_chunks[v] = nc;
+        first_unit[v] = nu;
+        for (int c = 0; c < nc; ++c, ++nu) {
+          CXRM_CHECK(nu < cross_max_units, "beam search: too many cross-attention units");
+          u_study[nu] = v;
+          u_j0[nu] = h_kv_off[b] + c * attn_ch;
+          u_n[nu] = std::min(attn_ch, h_kv_len[b] - c * attn_ch);
+          u_chunk[nu] = c;
+        }
+      }
+      first_unit[cfg.max_studies] = nu;
+      CXRM_CUDA_CHECK(cudaMemcpyAsync(unit_tab_beam, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+      CXRM_CUDA_CHECK(cudaStreamSynchronize(s));
+    }
+    for (int j = 0; j < nb; ++j)
+      CXRM_CUDA_CHECK(cudaMemcpyAsync(prompt_dev + static_cast<long long>(j) * B * P, a.prompt_ids, sizeof(int) * B * P,
+                                      cudaMemcpyDeviceToDevice, s));
+    PF("init", s, [&] { rollout_init(st, rp, prompt_dev, pre_ids, pre_types, pre_pos, pre_valid, s); });
+    beam_init(bs, B, nb, Tn, a.pad_token_id ? a.pad_token_id : a.eos_token_id, s);
+
+    arena.reset();
+    const long long M = static_cast<long long>(R) * P;
+    DecBufs db = dec_bufs(R);
+    T* last = arena.get<T>(static_cast<long long>(R) * DH);
+    T* head_tmp = arena.get<T>(static_cast<long long>(R) * DH);
+    for (T*& fb : fold_buf) fb = arena.get<T>(static_cast<long long>(R) * DH);
+    DecBufs pb = dec_bufs(M);
+    phase = "prefill";
+    PF("embed_ln", s, [&] { embed_ln<T>(pre_ids, pre_types, pre_pos, dec.word, dec.type, dec.pos, dec.emb_ln.g, dec.emb_ln.b, pb.x, M, DH,
+                LN_EPS_BERT, s); });
+    T* hid = decoder_full(pb, R, P, B, pre_valid, P, /*store_cache=*/true, s);   // row r attends the encoder K/V of study r % B
+    PF("take_last", s, [&] { take_last_token<T>(hid, last, R, P, DH, s); });
+    lm_head(last, R, head_tmp, logits, cfg.vocab, nullptr, s);
+    PF("beam_step", s, [&] { beam_step(st, rp, bs, logits, cfg.vocab, s); });   // step 0: no generated cache slot to move yet
+    if (Tn > 1) {
+      if (cfg.use_cuda_graph && !profiling) {
+        run_decode_graph(db, head_tmp, rp, nullptr, Tn - 1, s);
+      } else {
+        for (int t = 1; t < Tn; ++t) decode_step(db, head_tmp, rp, nullptr, s);
+      }
+    }
+    beam_finalize(st, bs, B, nb, P, Lmax, Tn, a.sequences, a.scores, a.lengths, s);
+    if (hop) {
+      CXRM_CUDA_CHECK(cudaEventRecord(ev_b, s));
+      CXRM_CUDA_CHECK(cudaStreamWaitEvent(s_user, ev_b, 0));
+    }
+    if (a.steps_out) {
+      int steps = 0;
+      CXRM_CUDA_CHECK(cudaMemcpyAsync(&steps, st.step, sizeof(int), cudaMemcpyDeviceToHost, s));
+      CXRM_CUDA_CHECK(cudaStreamSynchronize(s));
+      *a.steps_out = steps;
+    }
   }
 
   // =========================================================================== teacher-forced forward
@@ -1983,6 +2117,12 @@ class Engine : public EngineBase {
   float* cross_ws = nullptr; float* self_ws = nullptr;
   unsigned* cross_tickets = nullptr; unsigned* self_tickets = nullptr;
   int* unit_tab = nullptr;
+  // beam search (beam.cu): virtual-study unit table, bookkeeping state, scratch of the cache reorder (allocated on first use)
+  int* unit_tab_beam = nullptr;
+  BeamState bs{};
+  T* beam_scratch = nullptr;
+  size_t beam_scratch_cap = 0;
+  std::vector<int> h_kv_len, h_kv_off;    // host copies of kv_len / kv_off (cxrm_prefill_cross_kv)
   AttnMaps attn_maps{};
   const AttnMaps* attn_maps_ptr = nullptr;
   float* skinny_ws = nullptr;
@@ -2062,6 +2202,7 @@ class Engine : public EngineBase {
   struct GraphKey {
     int R, B, P, Tmax, top_k; float temperature; const float* noise; const void* buf;
     int mask_id, eos, pad, want_margin;
+    int beams; float length_penalty; const void* beam_scratch;
     int special[2][kMaxSpecial]; int sections[2][kMaxSpecial + 1]; int nspecial[2]; int modes[2];
   };
   GraphKey graph_key;

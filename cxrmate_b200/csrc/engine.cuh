@@ -45,6 +45,7 @@ class EngineBase {
   virtual void encode(const float* pixels, int B, int N, void* memory_out, uint8_t* mask_out, cudaStream_t s) = 0;
   virtual void prefill_cross_kv(const void* memory, const uint8_t* mask, int B, int S, cudaStream_t s) = 0;
   virtual void rollout(const cxrm_rollout_args& a, cudaStream_t s) = 0;
+  virtual void rollout_beam(const cxrm_beam_args& a, cudaStream_t s) = 0;
   virtual void decoder_forward(const int* ids, const int* tt, const int* pos, const uint8_t* key_mask, int R, int L,
                                int B, bool last_only, float* logits_out, cudaStream_t s) = 0;
   virtual void reward_embed(const int* ids, const int* lens, int n, int L, float* emb_out, cudaStream_t s) = 0;

@@ -227,6 +227,8 @@ struct RolloutParams {
   float temperature;
   unsigned long long seed;
   int want_margin;       // 1: also compute the decision margins (two more passes over the row; diagnostics)
+  int beams;             // 0: greedy / sampling heads; nb >= 2: beam search, rows = beam * (R / nb) + study (beam.cu)
+  float length_penalty;  // beam search: finished score = sum_logprob / generated_len ** length_penalty
 };
 
 // state from the prompt (reference modelling_longitudinal.py:274-282): types (full rule), positions,
@@ -240,6 +242,34 @@ void rollout_init(const RolloutState& st, const RolloutParams& p, const int* pro
 // log-prob, survivors, and the state for the next decoder step.  exp_noise: nullable [Tmax, B, V].
 void sample_step(const RolloutState& st, const RolloutParams& p, const float* logits, int ldl, const float* exp_noise,
                  cudaStream_t stream);
+
+// ---- beam search (beam.cu): HF `_beam_search` bookkeeping on the device ------------------------------------------
+constexpr int kMaxBeams = 8, kBeamMaxT = 256;
+struct BeamState {
+  float* run_score;      // [B, nb] accumulated log-prob of the running beams
+  float* fin_score;      // [B, nb] length-penalised scores of the finished set, best first (-1e9: empty slot)
+  int* fin_len;          // [B, nb] generated length of each finished hypothesis
+  uint8_t* is_fin;       // [B, nb]
+  uint8_t* can_improve;  // [B] early-stop heuristic still unsatisfied
+  int* fin_seq;          // [B, nb, Tmax] generated tokens of the finished set
+  int* src_row;          // [R] row whose self K/V (generated slots) this row continues from
+  int* n_slots;          // scalar: generated cache slots to move in this step's reorder (0: none)
+  unsigned* arrive;      // scalar
+  int* cnt_can;          // scalar: studies that can still improve (this step)
+  int* cnt_hit;          // scalar: studies whose every continuation hit a stopping criterion (this step)
+};
+size_t beam_scratch_elems(int R, int Tmax, int layers);
+void beam_init(const BeamState& bs, int B, int nb, int Tmax, int fill, cudaStream_t stream);
+// logits [R, V] fp32 of the running beams -> next running beams (st: tokens, sequences, decode state), finished set
+void beam_step(const RolloutState& st, const RolloutParams& p, const BeamState& bs, const float* logits, int ldl,
+               cudaStream_t stream);
+// Cache.reorder_cache(beam_idx) for the generated slots of the self-attention caches [layers][R][12][Lmax][64]
+template <typename T>
+void beam_reorder_kv(T* kcache, T* vcache, T* scratch, const RolloutState& st, const BeamState& bs, int R, int Lmax, int Tmax,
+                     int layers, long long layer_stride, cudaStream_t stream);
+// best finished hypothesis per study -> out_seq [B, P + Tmax] (prompt + generated, fill = pad or eos), score, length
+void beam_finalize(const RolloutState& st, const BeamState& bs, int B, int nb, int P, int Lmax, int Tmax, int* out_seq,
+                   float* out_score, int* out_len, cudaStream_t stream);
 
 // test hook: the sampling head on caller logits [R,V], all rows sample rows, Philox draws of (seed, step) -> tokens [R]
 void sample_rows_test(const float* logits, int R, int V, int top_k, float temperature, unsigned long long seed, int step,

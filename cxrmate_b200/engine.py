@@ -31,6 +31,14 @@ class RolloutOutput:
     last_logits: torch.Tensor     # [R, V] fp32
 
 
+@dataclass
+class BeamOutput:
+    sequences: torch.Tensor       # [B, P + longest hypothesis] int64, PAD filled
+    scores: torch.Tensor          # [B] fp32 (HF sequences_scores)
+    lengths: torch.Tensor         # [B] int32 generated length of each hypothesis
+    steps: int                    # decode steps executed
+
+
 def normalise_weight_name(name: str) -> str:
     """state_dict key of a real `peft`-wrapped decoder -> the plain key the engine knows (last
     row: `decoder.base_model.model.<...>.base_layer.weight`, `<...>.lora_A.default.weight`).  Keys that peft did not
@@ -192,6 +200,36 @@ class Engine:
         out.steps = int(steps.value)
         out.sequences = out.sequences.to(torch.int64)
         return out
+
+    def rollout_beam(self, prompt_ids: torch.Tensor, *, num_beams: int, max_new_tokens: int, eos_token_id: int,
+                     pad_token_id: int, mask_token_id: Optional[int], special=(), sections=(0,),
+                     length_penalty: float = 1.0) -> "BeamOutput":
+        """Beam search (cxrm_rollout_beam): prompt [B, P] -> best finished hypothesis per study, trimmed to the longest
+        one like HF's `generate(num_beams=...)['sequences']` (without the auto-prepended BOS)."""
+        dev = prompt_ids.device
+        B, P = prompt_ids.shape
+        p32 = prompt_ids.to(torch.int32).contiguous()
+        T = max_new_tokens
+        seq = torch.empty(B, P + T, dtype=torch.int32, device=dev)
+        scores = torch.empty(B, dtype=torch.float32, device=dev)
+        lens = torch.empty(B, dtype=torch.int32, device=dev)
+        a = _lib.CxrmBeamArgs()
+        a.B, a.P, a.prompt_ids = B, P, p32.data_ptr()
+        a.mask_token_id = -1 if mask_token_id is None else int(mask_token_id)
+        assert len(sections) == len(special) + 1
+        a.n_special = len(special)
+        for i, v in enumerate(special):
+            a.special[i] = int(v)
+        for i, v in enumerate(sections):
+            a.sections[i] = int(v)
+        a.num_beams, a.max_new_tokens = int(num_beams), T
+        a.eos_token_id, a.pad_token_id, a.length_penalty = int(eos_token_id), int(pad_token_id), float(length_penalty)
+        a.sequences, a.scores, a.lengths = seq.data_ptr(), scores.data_ptr(), lens.data_ptr()
+        steps = C.c_int32(0)
+        a.steps_out = C.addressof(steps)
+        self._check(self.lib.cxrm_rollout_beam(self.h, C.byref(a), _stream()), "cxrm_rollout_beam")
+        n = int(lens.max())
+        return BeamOutput(sequences=seq[:, : P + n].to(torch.int64), scores=scores, lengths=lens, steps=int(steps.value))
 
     # ------------------------------------------------------------------ teacher-forced forward
     def decoder_forward(self, ids, token_type_ids, position_ids, key_mask, n_studies: int, last_only: bool = False):

@@ -39,6 +39,16 @@ class CxrmRolloutArgs(C.Structure):
     ]
 
 
+class CxrmBeamArgs(C.Structure):
+    _fields_ = [
+        ("B", C.c_int), ("P", C.c_int), ("prompt_ids", C.c_void_p), ("mask_token_id", C.c_int),
+        ("n_special", C.c_int), ("special", C.c_int * 8), ("sections", C.c_int * 9),
+        ("num_beams", C.c_int), ("max_new_tokens", C.c_int), ("eos_token_id", C.c_int), ("pad_token_id", C.c_int),
+        ("length_penalty", C.c_float), ("sequences", C.c_void_p), ("scores", C.c_void_p), ("lengths", C.c_void_p),
+        ("steps_out", C.c_void_p),
+    ]
+
+
 class CxrmTrainArgs(C.Structure):
     _fields_ = [
         ("R", C.c_int), ("L", C.c_int), ("ids", C.c_void_p), ("token_type_ids", C.c_void_p), ("position_ids", C.c_void_p),
@@ -61,6 +71,7 @@ SYMBOLS = {
     "cxrm_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cxrm_prefill_cross_kv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "cxrm_rollout": (C.c_int, [C.c_void_p, C.POINTER(CxrmRolloutArgs), C.c_void_p]),
+    "cxrm_rollout_beam": (C.c_int, [C.c_void_p, C.POINTER(CxrmBeamArgs), C.c_void_p]),
     "cxrm_decoder_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                        C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "cxrm_reward_embed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),

@@ -216,8 +216,8 @@ class CXRMateEngineModel:
         prompt-free variants; with return_dict_in_generate a mapping that also holds `scores` (tuple of t fp32
         [B,V] tensors, top-k-masked for sampling) when output_scores is set.
         """
-        if num_beams != 1:
-            raise NotImplementedError("beam search is outside the SCST rollout path (SURVEY.md section 8f rank 3)")
+        if num_beams != 1 and do_sample:
+            raise NotImplementedError("beam-sample is not used by the reference (test_step: num_beams > 1, do_sample False)")
         if do_sample and top_k is not None and top_k > TOPK_CAP and output_scores:
             raise ValueError(f"output_scores with top_k > {TOPK_CAP}: the engine records at most {TOPK_CAP} survivors per step")
         if top_p != 1.0:
@@ -255,6 +255,17 @@ class CXRMateEngineModel:
             prompt_dec = prompt
         if self.variant != "longitudinal":
             prompt_dec = prompt                                       # [BOS] is the real first decoder token
+        if num_beams != 1:
+            # test_step of the reference (gt_prompt.py:344-362, single.py:552-562): HF beam search, default flags
+            bo = self.engine.rollout_beam(prompt_dec, num_beams=num_beams, max_new_tokens=max_new_tokens, eos_token_id=eos,
+                                          pad_token_id=pad, mask_token_id=mask_token_id, special=special_token_ids,
+                                          sections=sections, length_penalty=kwargs.get("length_penalty", 1.0))
+            seq = bo.sequences
+            if auto_bos or (self.variant == "longitudinal" and prompt_dec.shape[1] != P):
+                seq = torch.cat((torch.full((B, 1), bos, dtype=seq.dtype, device=seq.device), seq), dim=1)
+            if not return_dict_in_generate:
+                return seq
+            return ModelOutput(sequences=seq, sequences_scores=bo.scores, steps=bo.steps)
         mode = "sample" if do_sample else "greedy"
         kw = dict(special_sample=special_token_ids, sections_sample=sections) if do_sample else \
             dict(special_greedy=special_token_ids, sections_greedy=sections)

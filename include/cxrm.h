@@ -172,6 +172,32 @@ typedef struct cxrm_rollout_args {
 CXRM_API int cxrm_rollout(cxrm_engine* e, const cxrm_rollout_args* a, void* stream);
 
 /*
+ * Beam search.  Replaces generate(num_beams = num_test_beams) of the reference's test_step
+ * (modules/lightning_modules/longitudinal/gt_prompt.py:344-362, gen_prompt.py:184-200, single.py:552-562,
+ * multi.py:265-275), i.e. HF GenerationMixin._beam_search (SP/generation/utils.py:3076-3385) with the default flags
+ * (early_stopping False, num_return_sequences 1, no logits processors) driven by the reference's
+ * prepare_inputs_for_generation.  The running beams are rows of the KV-cached rollout (the encoder K/V of a study is
+ * shared by its beams, the generated part of the self-attention cache is reordered every step), so
+ * B * num_beams <= max_studies of the engine.  Requires cxrm_prefill_cross_kv for the same B.
+ */
+typedef struct cxrm_beam_args {
+  int B, P;                        /* studies, prompt columns */
+  const int32_t* prompt_ids;       /* dev [B, P] right-padded prompt (no auto-prepended BOS) */
+  int mask_token_id;               /* as cxrm_rollout_args; -1 = none */
+  int n_special;  int special[8];  int sections[9];
+  int num_beams;                   /* 2..8 */
+  int max_new_tokens;              /* T <= 255 */
+  int eos_token_id, pad_token_id;
+  float length_penalty;            /* HF default 1.0: score = sum_logprob / generated_len ** length_penalty */
+  /* outputs, all dev */
+  int32_t* sequences;              /* [B, P + T] prompt + best finished hypothesis, filled with pad (eos when pad == 0, as HF) */
+  float* scores;                   /* [B] its score (HF sequences_scores); may be NULL */
+  int32_t* lengths;                /* [B] its generated length (tokens up to and including EOS); may be NULL */
+  int32_t* steps_out;              /* host int: decode steps executed; synchronises if non-NULL */
+} cxrm_beam_args;
+CXRM_API int cxrm_rollout_beam(cxrm_engine* e, const cxrm_beam_args* a, void* stream);
+
+/*
  * Teacher-forced decoder forward.  Replaces
  * LongitudinalPromptMultiCXREncoderDecoderModel.forward with encoder_outputs
  * given (modelling_longitudinal.py:173-249).

@@ -131,6 +131,7 @@ def ref_rollout(model, enc, prompt_ids, special_token_ids, sections, mask_token_
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--beam-only", action="store_true", help="write only tests/golden/cxrmate_ref_beam.npz")
     args = ap.parse_args()
     torch.manual_seed(0)
     torch.set_grad_enabled(False)
@@ -229,6 +230,50 @@ def main():
         gold[f"{name}_last_logits_0"] = r_scores[-1][0].numpy()
         gold[f"{name}_first_logits_1"] = r_scores[0][1].numpy()
 
+    # -- 4b. beam search (test_step: generate(num_beams=4), gt_prompt.py:344-362): HF's _beam_search loop as restated
+    #        in oracle/beam.py (pinned against transformers' generate in tests/test_beam_oracle.py) driven through the
+    #        REFERENCE forward() with `past_key_values.reorder_cache(beam_idx)`, vs the same loop over the oracle decoder.
+    #        EOS is biased so that hypotheses finish early and the early-stop heuristic is exercised.
+    from oracle import beam as obeam
+    beam_gold = {}
+    dm_bias = dm.cls.predictions.bias
+    for tag, eos_bias, nbeams in (("a", 8.0, 4), ("b", 10.0, 4), ("c", 9.0, 3)):
+        dm_bias.data[EOS] += eos_bias
+        sd_b = dict(sd)
+        sd_b["decoder.cls.predictions.bias"] = sd["decoder.cls.predictions.bias"].clone()
+        sd_b["decoder.cls.predictions.bias"][EOS] += eos_bias
+        enc_rep = type(enc)(last_hidden_state=enc.last_hidden_state.repeat_interleave(nbeams, 0),
+                            attention_mask=enc.attention_mask.repeat_interleave(nbeams, 0))
+        state = {"past": None}
+
+        def ref_step(ids, beam_idx):
+            m_ = (ids != PAD).int()
+            pos_ = torch.nn.functional.relu(torch.cumsum(m_, dim=1, dtype=torch.int64) - 1)
+            if state["past"] is None:
+                tt_, feed_ = model.token_ids_to_token_type_ids(ids, [9, 1, 3], [0, 1, 0, 1]), ids
+            else:
+                state["past"].reorder_cache(beam_idx)
+                tt_ = model.token_ids_to_token_type_ids_past(ids, [9, 1, 3], [0, 1, 0, 1])
+                feed_, pos_ = ids[:, -1:], pos_[:, -1:]
+            out_ = model(encoder_outputs=enc_rep, decoder_input_ids=feed_, decoder_attention_mask=m_,
+                         decoder_token_type_ids=tt_, decoder_position_ids=pos_, past_key_values=state["past"],
+                         use_cache=True, return_dict=True)
+            state["past"] = out_.past_key_values
+            return out_.logits[:, -1].float()
+
+        Tb = 10
+        r_b = obeam.beam_search(ref_step, prompt, num_beams=nbeams, max_new_tokens=Tb, eos_token_id=EOS, pad_token_id=PAD)
+        o_b = obeam.beam_rollout(sd_b, mem_o, mask_o, prompt, num_beams=nbeams, special_token_ids=[9, 1, 3],
+                                 sections=[0, 1, 0, 1], mask_token_id=PAD, max_new_tokens=Tb, eos_token_id=EOS,
+                                 pad_token_id=PAD)
+        dm_bias.data[EOS] -= eos_bias
+        assert torch.equal(r_b.sequences, o_b.sequences), (tag, r_b.sequences[:, P:], o_b.sequences[:, P:])
+        assert torch.allclose(r_b.scores, o_b.scores, atol=1e-4), (tag, r_b.scores, o_b.scores)
+        report[f"beam_{tag}_lengths"] = [int((row[P:] != PAD).sum()) for row in r_b.sequences]
+        beam_gold[f"beam_{tag}_sequences"] = r_b.sequences.numpy()
+        beam_gold[f"beam_{tag}_scores"] = r_b.scores.numpy()
+        beam_gold[f"beam_{tag}_cfg"] = np.array([eos_bias, nbeams, Tb], dtype=np.float64)
+
     # -- 6. the prompt-free variants: MultiCXREncoderDecoderModel (modelling_multi.py:90-261) and
     #       SingleCXREncoderDecoderModel (modelling_single.py:81-249): no LoRA, prompt = [[BOS]], default sections
     #       list(range(len(special)+1)) with special_token_ids=[SEP] (multi.py:218-228, single.py:483-493), default BERT
@@ -294,6 +339,10 @@ def main():
 
     print("pin report:", report)
     if args.check:
+        return
+    np.savez_compressed(os.path.join(GOLDEN, "cxrmate_ref_beam.npz"), **beam_gold)
+    print("wrote", os.path.join(GOLDEN, "cxrmate_ref_beam.npz"))
+    if args.beam_only:
         return
     np.savez_compressed(os.path.join(GOLDEN, "cxrmate_ref_variants.npz"), T=Tv, **var)
     print("wrote", os.path.join(GOLDEN, "cxrmate_ref_variants.npz"))

@@ -1,0 +1,140 @@
+"""Beam search of the engine (cxrm_rollout_beam) against the oracle's restated HF beam search (oracle/beam.py, itself
+pinned against transformers' generate in tests/test_beam_oracle.py), through the C ABI.
+
+fp32 validation mode: the returned hypotheses are bit-exact, scores within 1e-3; EOS is biased so that hypotheses
+finish at different lengths and the early-stop heuristic ends the search before max length for some studies.
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _weights(eos_bias):
+    from cxrmate_b200 import synthetic as S
+    from oracle import weights
+    sd = dict(weights.make_cxrmate_weights(seed=0))
+    b = sd["decoder.cls.predictions.bias"].clone()
+    b[S.EOS] += eos_bias
+    sd["decoder.cls.predictions.bias"] = b
+    return sd
+
+
+def _engine(sd, dtype, graph=True):
+    from cxrmate_b200.engine import Engine
+    e = Engine(dtype=dtype, image_size=64, max_studies=12, max_images=2, max_prompt=16, max_new_tokens=16, rwd_layers=0,
+               enc_chunk=4, use_cuda_graph=graph)
+    e.load_state_dict(sd)
+    e.finalize()
+    return e
+
+
+def _inputs():
+    from cxrmate_b200 import synthetic as S
+    px = S.make_images(3, 2, size=64, seed=5, n_per_study=[2, 1, 2])
+    prompt = S.make_prompts(3, 10, seed=11)
+    return px, prompt
+
+
+@pytest.mark.parametrize("eos_bias,nb,T,lp", [(8.0, 4, 12, 1.0), (10.0, 4, 12, 1.0), (6.0, 3, 8, 1.0), (10.0, 4, 12, 2.0),
+                                              (9.0, 2, 16, 1.0)])
+def test_beam_search_fp32_vs_oracle(eos_bias, nb, T, lp):
+    from cxrmate_b200 import synthetic as S
+    from oracle import cvt
+    from oracle.beam import beam_rollout
+    sd = _weights(eos_bias)
+    px, prompt = _inputs()
+    with torch.no_grad():
+        mem, mask = cvt.encode_multi(sd, px)
+    ref = beam_rollout(sd, mem, mask, prompt, num_beams=nb, special_token_ids=S.SPECIAL_GREEDY, sections=S.SECTIONS,
+                       mask_token_id=S.PAD, max_new_tokens=T, eos_token_id=S.EOS, pad_token_id=S.PAD, length_penalty=lp)
+    for graph in (True, False):
+        e = _engine(sd, "fp32", graph)
+        try:
+            e.encode(px.cuda())
+            e.prefill_cross_kv()
+            for rep in range(2):      # the second call replays the captured step graph
+                out = e.rollout_beam(prompt.cuda(), num_beams=nb, max_new_tokens=T, eos_token_id=S.EOS, pad_token_id=S.PAD,
+                                     mask_token_id=S.PAD, special=S.SPECIAL_GREEDY, sections=S.SECTIONS, length_penalty=lp)
+                torch.cuda.synchronize()
+                print(f"bias {eos_bias} nb {nb} graph {graph}: steps {out.steps} (oracle {ref.steps}), lengths {out.lengths.tolist()}, "
+                      f"scores {out.scores.tolist()}")
+                assert out.steps == ref.steps
+                assert out.sequences.shape == ref.sequences.shape
+                assert torch.equal(out.sequences.cpu(), ref.sequences)
+                assert torch.allclose(out.scores.cpu(), ref.scores, atol=1e-3)
+            # a plain rollout afterwards still sees its own unit table and state
+            g = e.rollout(prompt.cuda(), mode="greedy", max_new_tokens=4, eos_token_id=S.EOS, pad_token_id=S.PAD,
+                          mask_token_id=S.PAD, special_greedy=S.SPECIAL_GREEDY, sections_greedy=S.SECTIONS)
+            assert g.sequences.shape == (3, prompt.shape[1] + 4)
+        finally:
+            e.close()
+
+
+def test_beam_search_bf16_and_generate_surface():
+    """bf16 mode runs the tensor-core / persistent-attention decode step under the beam bookkeeping; the reference-facing
+    call `generate(num_beams=4)` returns HF's shape (leading auto-BOS, trimmed to the longest hypothesis)."""
+    from cxrmate_b200 import synthetic as S
+    from cxrmate_b200.modelling import CXRMateEngineModel
+    from oracle import cvt
+    from oracle.beam import beam_rollout
+    sd = _weights(8.0)
+    px, prompt = _inputs()
+    with torch.no_grad():
+        mem, mask = cvt.encode_multi(sd, px)
+    T = 12
+    ref = beam_rollout(sd, mem, mask, prompt, num_beams=4, special_token_ids=S.SPECIAL_GREEDY, sections=S.SECTIONS,
+                       mask_token_id=S.PAD, max_new_tokens=T, eos_token_id=S.EOS, pad_token_id=S.PAD)
+    e = _engine(sd, "bf16")
+    try:
+        m = CXRMateEngineModel(e, variant="longitudinal")
+        out = m.generate(pixel_values=px.cuda(), decoder_input_ids=prompt.cuda(), special_token_ids=S.SPECIAL_GREEDY,
+                         mask_token_id=S.PAD, max_length=T + 1 + prompt.shape[1], bos_token_id=S.BOS, eos_token_id=S.EOS,
+                         pad_token_id=S.PAD, num_beams=4, return_dict_in_generate=True, use_cache=True)
+        seq = out["sequences"]
+        torch.cuda.synchronize()
+        assert torch.all(seq[:, 0] == S.BOS)                              # HF's auto-prepended BOS
+        assert torch.equal(seq[:, 1:1 + prompt.shape[1]].cpu(), prompt)
+        gen, gref = seq[:, 1 + prompt.shape[1]:].cpu(), ref.sequences[:, prompt.shape[1]:]
+        n = min(gen.shape[1], gref.shape[1])
+        agree = (gen[:, :n] == gref[:, :n]).float().mean().item()
+        print("bf16 beam search vs fp32 oracle: token agreement", agree, "scores", out["sequences_scores"].tolist(),
+              "oracle", ref.scores.tolist())
+        assert torch.allclose(out["sequences_scores"].cpu(), ref.scores, atol=0.15)
+    finally:
+        e.close()
+
+
+def test_beam_search_fp32_vs_reference_fixture():
+    """tests/golden/cxrmate_ref_beam.npz: beam search driven through the REFERENCE model's forward() with HF cache
+    reordering (oracle/pin_against_reference.py section 4b), 384x384 images, right-padded prompt batch."""
+    import os
+
+    import numpy as np
+    from cxrmate_b200.engine import Engine
+    here = os.path.dirname(__file__)
+    gb = np.load(os.path.join(here, "golden", "cxrmate_ref_beam.npz"))
+    gs = np.load(os.path.join(here, "golden", "cxrmate_ref_small.npz"))
+    prompt = torch.from_numpy(gs["prompt"])
+    g = torch.Generator().manual_seed(1234)
+    px = torch.randn(2, 2, 3, 384, 384, generator=g)
+    px[1, 1] = 0.0
+    for tag in ("a", "b", "c"):
+        eos_bias, nb, T = gb[f"beam_{tag}_cfg"]
+        nb, T = int(nb), int(T)
+        sd = _weights(float(eos_bias))
+        e = Engine(dtype="fp32", max_studies=8, max_images=2, max_prompt=32, max_new_tokens=16, rwd_layers=0, enc_chunk=4)
+        try:
+            e.load_state_dict(sd)
+            e.finalize()
+            e.encode(px.cuda())
+            e.prefill_cross_kv()
+            out = e.rollout_beam(prompt.cuda(), num_beams=nb, max_new_tokens=T, eos_token_id=2, pad_token_id=4,
+                                 mask_token_id=4, special=[9, 1, 3], sections=[0, 1, 0, 1])
+            torch.cuda.synchronize()
+            ref = torch.from_numpy(gb[f"beam_{tag}_sequences"])
+            assert out.sequences.shape == ref.shape, (tag, out.sequences.shape, ref.shape)
+            assert torch.equal(out.sequences.cpu(), ref), (tag, out.sequences[:, prompt.shape[1]:], ref[:, prompt.shape[1]:])
+            assert np.allclose(out.scores.cpu().numpy(), gb[f"beam_{tag}_scores"], atol=1e-3)
+        finally:
+            e.close()
