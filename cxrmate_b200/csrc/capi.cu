@@ -108,6 +108,28 @@ int cxrm_rollout(cxrm_engine* e, const cxrm_rollout_args* a, void* stream) {
   if (!a) return CXRM_ERR_INVALID;
   CXRM_GUARD(e, e->impl->rollout(*a, static_cast<cudaStream_t>(stream)));
 }
+int cxrm_preprocess_image(cxrm_engine* e, const uint8_t* img, int H, int W, int channels, long long row_pitch, int img_on_device,
+                          int size, const float* mean3, const float* std3, float* out, void* stream) {
+  CXRM_GUARD(e, {
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (!img || !mean3 || !std3 || H < 1 || W < 1) throw std::runtime_error("cxrm_preprocess_image: bad arguments");
+    const uint8_t* dev = img;
+    uint8_t* staged = nullptr;
+    if (!img_on_device) {
+      const size_t bytes = static_cast<size_t>(H) * row_pitch;
+      CXRM_CUDA_CHECK(cudaMallocAsync(&staged, bytes, s));
+      CXRM_CUDA_CHECK(cudaMemcpyAsync(staged, img, bytes, cudaMemcpyHostToDevice, s));
+      dev = staged;
+    }
+    try {
+      preprocess_image(dev, H, W, channels, row_pitch, size, mean3, std3, out, s);
+    } catch (...) {
+      if (staged) cudaFreeAsync(staged, s);
+      throw;
+    }
+    if (staged) CXRM_CUDA_CHECK(cudaFreeAsync(staged, s));
+  });
+}
 int cxrm_rollout_beam(cxrm_engine* e, const cxrm_beam_args* a, void* stream) {
   if (!a) return CXRM_ERR_INVALID;
   CXRM_GUARD(e, e->impl->rollout_beam(*a, static_cast<cudaStream_t>(stream)));

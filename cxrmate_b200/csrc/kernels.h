@@ -405,6 +405,11 @@ template <typename T>
 void embed_sum(const int* ids, const int* types, const int* pos, const T* word, const T* type_emb, const T* pos_emb, T* out,
                long long rows, int C, cudaStream_t stream);
 
+// Resize(size) + CenterCrop(size) + ToTensor + Normalize of one uint8 image [H, W, channels] (device, row pitch in
+// bytes) -> out [3, size, size] fp32, bit-exact with the reference's torchvision / Pillow pipeline (preprocess.cu)
+void preprocess_image(const uint8_t* img_dev, int H, int W, int channels, long long pitch, int size, const float* mean,
+                      const float* stdv, float* out, cudaStream_t stream);
+
 // cosine similarity of rows: out[i] = <a_i, b_i> / (max(|a_i|, eps) * max(|b_i|, eps))  (torch eps 1e-8)
 void cosine_rows(const float* a, const float* b, float* out, int n, int C, cudaStream_t stream);
 

@@ -71,6 +71,8 @@ SYMBOLS = {
     "cxrm_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cxrm_prefill_cross_kv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "cxrm_rollout": (C.c_int, [C.c_void_p, C.POINTER(CxrmRolloutArgs), C.c_void_p]),
+    "cxrm_preprocess_image": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_int, C.c_int,
+                                        C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_void_p, C.c_void_p]),
     "cxrm_rollout_beam": (C.c_int, [C.c_void_p, C.POINTER(CxrmBeamArgs), C.c_void_p]),
     "cxrm_decoder_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                        C.c_int, C.c_int, C.c_void_p, C.c_void_p]),

@@ -198,6 +198,19 @@ typedef struct cxrm_beam_args {
 CXRM_API int cxrm_rollout_beam(cxrm_engine* e, const cxrm_beam_args* a, void* stream);
 
 /*
+ * Image preprocessing on the GPU.  Replaces the reference's test_transforms
+ * (modules/lightning_modules/single.py:248-262, multi.py:89-103: Resize(size) -> CenterCrop([size, size]) -> ToTensor ->
+ * Normalize(mean, std)) applied to the decoded image of data/dicom_id.py:91-92 (`convert('RGB')`; a grey image,
+ * channels == 1, fills the three output channels).  Pillow's antialiased bilinear resampler is reproduced bit for bit
+ * (22-bit fixed point, uint8 intermediate).  img: uint8 [H, W, channels] with `row_pitch` bytes per row, on the device
+ * (img_on_device != 0) or on the host (copied inside the call); out: dev fp32 [3, size, size], e.g. slot (b, n) of the
+ * pixel tensor cxrm_encode takes.  JPEG decoding stays with the caller.
+ */
+CXRM_API int cxrm_preprocess_image(cxrm_engine* e, const uint8_t* img, int H, int W, int channels, long long row_pitch,
+                                   int img_on_device, int size, const float* mean3, const float* std3, float* out,
+                                   void* stream);
+
+/*
  * Teacher-forced decoder forward.  Replaces
  * LongitudinalPromptMultiCXREncoderDecoderModel.forward with encoder_outputs
  * given (modelling_longitudinal.py:173-249).
