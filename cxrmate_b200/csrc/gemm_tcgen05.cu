@@ -63,6 +63,20 @@ __device__ __forceinline__ unsigned long long gtimer() {
   do {                                                                                                   \
     if (g.trace) g.trace[(static_cast<long long>(blockIdx.y) * gridDim.x + blockIdx.x) * 8 + (i)] = gtimer(); \
   } while (0)
+// one lane of a converged warp (the loops around it stay warp-uniform, so descriptors / TMEM addresses live in uniform
+// registers: a loop run by `if (lane == 0)` makes every operand of UTCHMMA / UTMALDG divergent and ptxas wraps each
+// instruction in an ELECT + R2UR.BROADCAST waterfall loop)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -582,6 +596,281 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_persist_kernel(const __gr
   }
 }
 
+
+// =====================================================================================================
+// Weight-resident persistent GEMM for the short-K, huge-M contractions of CvT (K <= 384: q/k/v/o projections, MLP-up,
+// conv embeddings of stage 1; M = 4.6 k .. 295 k rows).  With a ring that streams A AND B, a 128 x BN tile of such a GEMM
+// loads as many bytes from L2 as it has time to compute on (K = 384, BN = 128: 196 KB per 12.6 MFLOP = 64 FLOP/B, an
+// L2 ceiling of ~390 TF/s; measured 215-330 TF/s).  Here a CTA owns ONE column slice of the output for its whole life:
+//   * the slice's weights [BN, K] are loaded ONCE into shared memory (<= 147 KB) and stay there;
+//   * warp 0 streams only A tiles (128 x 64, 16 KB stages) through a 4-8 deep ring, running ahead across tiles;
+//   * warp 1 issues the MMAs into two alternating TMEM accumulators;
+//   * 8 epilogue warps in two groups (group g takes the 32-column chunks g, g + 2, ...): TMEM -> registers -> bias /
+//     GELU / residual (the next chunk's residual row is requested before the current chunk is processed) -> one of two
+//     64B-swizzled staging panels per group -> TMA store.
+// CTA c works on slice c % n_slices and on the M tiles c / n_slices, + grid / n_slices, ...: the CTAs of one M tile run
+// at the same time, so A comes from HBM once and from L2 n_slices times.
+// =====================================================================================================
+constexpr int W_GROUPS = 2, W_THREADS = 64 + 128 * W_GROUPS, W_MAX_STAGES = 8, W_PANEL = BM * 64;
+
+template <int BN>
+struct WCfg {
+  static constexpr int TMEM_COLS = BN <= 16 ? 32 : BN <= 32 ? 64 : BN <= 64 ? 128 : BN <= 128 ? 256 : 512;   // 2 accumulators
+  static constexpr int ACC_STRIDE = TMEM_COLS / 2;
+};
+inline size_t wres_smem(int bn, int nkb, int stages) {
+  return static_cast<size_t>(nkb) * bn * 128 + static_cast<size_t>(stages) * A_BYTES + W_GROUPS * 2 * W_PANEL + 1024 + 512 + bn * 4;
+}
+
+template <int BN, int EPI>   // EPI 1: bias (+ residual) -> bf16;  2: bias -> GELU (+ residual) -> bf16
+__global__ void __launch_bounds__(W_THREADS, 1) gemm_tc_wres_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                    const __grid_constant__ CUtensorMap tmB,
+                                                                    const __grid_constant__ CUtensorMap tmC, GemmArgs g,
+                                                                    int tiles_m, int n_slices, int STAGES) {
+  using C_ = WCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  // debug stamps (cxrm_test_set_gemm_trace): 16 slots per CTA - 0 entry, 1 set-up done, 2 weights resident, 3 first A
+  // tile arrived, 4 last MMA issued, 5 first accumulator seen by the epilogue, 6 first tile stored, 7 last tile
+  // stored, 8 exit, 9 / 10 ns the MMA warp waited for A data / for a drained accumulator, 11 ns epilogue group 0
+  // waited for accumulators, 12 tiles of this CTA
+#define WTRACE(i) do { if (g.trace) g.trace[static_cast<long long>(blockIdx.x) * 16 + (i)] = gtimer(); } while (0)
+#define WTRACE_ADD(i, v) do { if (g.trace) g.trace[static_cast<long long>(blockIdx.x) * 16 + (i)] += (v); } while (0)
+  const int num_kb = (g.K + BK - 1) / BK;
+  if (threadIdx.x == 0) WTRACE(0);
+  uint8_t* wres = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* ring = wres + num_kb * (BN * 128);
+  uint8_t* staging = ring + STAGES * A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(staging + W_GROUPS * 2 * W_PANEL);
+  uint64_t* empty = full + W_MAX_STAGES;
+  uint64_t* tfull = empty + W_MAX_STAGES;      // [2] accumulator complete
+  uint64_t* tempty = tfull + 2;                // [2] accumulator drained by the epilogue
+  uint64_t* wfull = tempty + 2;                // weights resident
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
+  float* sbias = reinterpret_cast<float*>(tmem_slot + 2);   // [BN]
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int slice = blockIdx.x % n_slices, mt0 = blockIdx.x / n_slices, mstride = gridDim.x / n_slices;
+  const int n0 = slice * BN;
+
+  if (threadIdx.x == 0) {
+#pragma unroll 1
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull[b], 1);
+      mbar_init(&tempty[b], 4 * W_GROUPS);   // one arrival per epilogue warp
+    }
+    mbar_init(wfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(C_::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int j = threadIdx.x; j < BN; j += W_THREADS) sbias[j] = g.bias ? g.bias[n0 + j] : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(kFull, *tmem_slot, 0);
+  if (threadIdx.x == 0) WTRACE(1);
+
+  if (warp == 0) {
+    // TMA producer: the whole warp walks the loops (uniform control flow), one elected lane issues
+    if (elect_one()) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+      mbar_expect_tx(wfull, static_cast<uint32_t>(num_kb * BN * 128));
+#pragma unroll 1
+      for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(wres + kb * (BN * 128), &tmB, kb * BK, n0, wfull);
+    }
+    __syncwarp();
+    int it = 0;
+#pragma unroll 1
+    for (int mt = mt0; mt < tiles_m; mt += mstride) {
+#pragma unroll 1
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const int s = it % STAGES;
+        mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(&full[s], A_BYTES);
+          tma_load_2d(ring + s * A_BYTES, &tmA, kb * BK, mt * BM, &full[s]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // MMA issuer: uniform loops, one elected lane issues the MMAs and their commits
+    constexpr uint32_t idesc = make_idesc(BN);
+    mbar_wait(wfull, 0);
+    tc_fence_after();
+    if (lane == 0) WTRACE(2);
+    const uint32_t w_addr = smem_u32(wres);
+    const uint32_t ring_addr = smem_u32(ring);
+    int it = 0, t = 0;
+    unsigned long long wait_data = 0, wait_acc = 0, t_first = 0;   // trace only: kept in registers, stored once
+#pragma unroll 1
+    for (int mt = mt0; mt < tiles_m; mt += mstride, ++t) {
+      const int buf = t & 1;
+      unsigned long long w0 = g.trace ? gtimer() : 0;
+      mbar_wait(&tempty[buf], ((t >> 1) & 1) ^ 1);
+      tc_fence_after();
+      if (g.trace) wait_acc += gtimer() - w0;
+      const uint32_t acc = tmem_base + static_cast<uint32_t>(buf * C_::ACC_STRIDE);
+#pragma unroll 1
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const int s = it % STAGES;
+        w0 = g.trace ? gtimer() : 0;
+        mbar_wait(&full[s], (it / STAGES) & 1);
+        tc_fence_after();
+        if (g.trace) {
+          const unsigned long long now = gtimer();
+          wait_data += now - w0;
+          if (it == 0) t_first = now;
+        }
+        const uint64_t da = make_desc(ring_addr + static_cast<uint32_t>(s * A_BYTES));
+        const uint64_t db = make_desc(w_addr + static_cast<uint32_t>(kb * (BN * 128)));
+#ifdef CXRM_WRES_KBTRACE
+        const long long c0 = clock64();
+#endif
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma(acc, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+#ifdef CXRM_WRES_KBTRACE
+          const long long c1 = clock64();
+#endif
+          umma_commit(&empty[s]);
+          if (kb == num_kb - 1) umma_commit(&tfull[buf]);
+#ifdef CXRM_WRES_KBTRACE
+          if (g.trace && t == 1 && kb < 6) {   // debug build only: clocks of tile 1 (k-block start, MMAs issued, commits issued)
+            unsigned long long* q = g.trace + 148 * 16 + static_cast<long long>(blockIdx.x) * 32 + kb * 4;
+            q[0] = static_cast<unsigned long long>(c0);
+            q[1] = static_cast<unsigned long long>(c1);
+            q[2] = static_cast<unsigned long long>(clock64());
+          }
+#endif
+        }
+        __syncwarp();
+      }
+    }
+    if (lane == 0 && g.trace) {
+      WTRACE(4);
+      g.trace[static_cast<long long>(blockIdx.x) * 16 + 3] = t_first;
+      WTRACE_ADD(9, wait_data);
+      WTRACE_ADD(10, wait_acc);
+      WTRACE_ADD(12, static_cast<unsigned long long>(t));
+    }
+  } else {
+    const int quarter = warp % 4;                 // TMEM lane quarter this warp may read
+    const int grp = (warp - 2) / 4;               // epilogue group
+    const int et = threadIdx.x - 64 - grp * 128;  // 0..127 within the group
+    const int bar_id = 1 + grp;
+    uint8_t* panels = staging + grp * 2 * W_PANEL;
+    const bf16* __restrict__ R = static_cast<const bf16*>(g.residual);
+    constexpr int NCH = BN / 32;
+    int t = 0, pi = 0;
+    unsigned long long wait_epi = 0;
+#pragma unroll 1
+    for (int mt = mt0; mt < tiles_m; mt += mstride, ++t) {
+      const int buf = t & 1;
+      const int m0 = mt * BM;
+      const long long m = static_cast<long long>(m0) + quarter * 32 + lane;
+      const bool row_ok = m < g.M;
+      const bf16* rrow = (R && row_ok) ? R + m * g.ldr + n0 : nullptr;
+      uint4 rnext[4];
+      if (rrow && grp < NCH) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) rnext[q] = __ldg(reinterpret_cast<const uint4*>(rrow + grp * 32 + 8 * q));
+      }
+      const bool tr = g.trace && grp == 0 && et == 0;
+      const unsigned long long w1 = tr ? gtimer() : 0;
+      mbar_wait(&tfull[buf], (t >> 1) & 1);
+      tc_fence_after();
+      if (tr) {
+        wait_epi += gtimer() - w1;
+        if (t == 0) WTRACE(5);
+      }
+      const uint32_t acc = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(buf * C_::ACC_STRIDE);
+#pragma unroll 1
+      for (int ci = grp; ci < NCH; ci += W_GROUPS) {
+        const int c0 = ci * 32;
+        uint32_t r[32];
+        tmem_ld32(acc + static_cast<uint32_t>(c0), r);
+        uint4 rcur[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) rcur[q] = rnext[q];
+        if (rrow && ci + W_GROUPS < NCH) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) rnext[q] = __ldg(reinterpret_cast<const uint4*>(rrow + (ci + W_GROUPS) * 32 + 8 * q));
+        }
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + sbias[c0 + j];
+        if (EPI == 2) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+        }
+        if (rrow) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            Vec16<bf16> rv;
+            rv.raw = rcur[q];
+            float rf[8];
+            rv.unpack(rf);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[8 * q + j] += rf[j];
+          }
+        }
+        // the panel about to be written was handed to the TMA unit two chunks ago: its read must have finished
+        if (et == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        const int row = quarter * 32 + lane;
+        uint8_t* panel = panels + pi * W_PANEL;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          Vec16<bf16> ov;
+          ov.pack(v + 8 * q);
+          *reinterpret_cast<uint4*>(panel + row * 64 + ((q ^ ((row >> 1) & 3)) << 4)) = ov.raw;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        if (et == 0) {
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                           reinterpret_cast<uint64_t>(&tmC)),
+                       "r"(smem_u32(panel)), "r"(n0 + c0), "r"(m0)
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        pi ^= 1;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cta(&tempty[buf]);
+      if (tr && t == 0) WTRACE(6);
+    }
+    if (g.trace && grp == 0 && et == 0) {
+      WTRACE(7);
+      WTRACE_ADD(11, wait_epi);
+    }
+    if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem read out before exit
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C_::TMEM_COLS)
+                 : "memory");
+  }
+  if (threadIdx.x == 0) WTRACE(8);
+#undef WTRACE
+#undef WTRACE_ADD
+}
+
 // =====================================================================================================
 // Skinny GEMM for the decode steps: M <= 64 rows (2B rollout rows), weights streamed from HBM once.
 // Such a GEMM is bound by the latency of its TMA round trips, not by the MMAs: the generic kernel's
@@ -592,6 +881,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_persist_kernel(const __gr
 // fp32 partial tiles go to `partial[split][64][N]`; splitk_ln_kernel below reduces them and applies
 // bias / GELU / residual / LayerNorm in the same pass (every split GEMM of the decoder is followed by one).
 // =====================================================================================================
+constexpr int kSkMaxSplit = 8;   // split-K partials of the skinny GEMM (workspace: gemm_skinny_partial_floats)
 constexpr int SK_ROWS = 64, SK_A_BYTES = SK_ROWS * BK * 2, SK_MAX_STAGES = 16, SK_SLACK = A_BYTES - SK_A_BYTES;
 
 struct NoFold {};
@@ -649,53 +939,63 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_skinny_kernel(const __grid_c
   const int npre = min(nkb, stages);
 
   if (warp == 0) {
-    if (lane == 0) {
-      // weight tiles do not depend on the previous kernel: request the first ring-full BEFORE the dependency wait
+    // (uniform control flow + one elected lane per issue: operands stay in uniform registers, see elect_one())
+    // weight tiles do not depend on the previous kernel: request the first ring-full BEFORE the dependency wait
+    if (elect_one()) {
 #pragma unroll 1
       for (int i = 0; i < npre; ++i) {
         mbar_expect_tx(&full[i], STAGE_BYTES);
         tma_load_2d(tiles + i * STAGE_BYTES + SK_A_BYTES, &tmB, (kb0 + i) * BK, n0, &full[i]);
       }
-      pdl_wait();
-      const bool skip = g.skip_flag && *g.skip_flag;
+    }
+    __syncwarp();
+    pdl_wait();
+    const bool skip = g.skip_flag && *g.skip_flag;
+    if (elect_one()) {
 #pragma unroll 1
       for (int i = 0; i < npre; ++i) tma_load_2d(tiles + i * STAGE_BYTES, &tmA, (kb0 + i) * BK, 0, &full[i]);
-      if (!skip) {
+    }
+    __syncwarp();
+    if (!skip) {
 #pragma unroll 1
-        for (int i = npre; i < nkb; ++i) {
-          const int s = i % stages;
-          const uint32_t ph = (i / stages) & 1;
-          mbar_wait(&empty[s], ph ^ 1);
+      for (int i = npre; i < nkb; ++i) {
+        const int s = i % stages;
+        const uint32_t ph = (i / stages) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        if (elect_one()) {
           mbar_expect_tx(&full[s], STAGE_BYTES);
           uint8_t* a_dst = tiles + s * STAGE_BYTES;
           tma_load_2d(a_dst, &tmA, (kb0 + i) * BK, 0, &full[s]);
           tma_load_2d(a_dst + SK_A_BYTES, &tmB, (kb0 + i) * BK, n0, &full[s]);
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      pdl_wait();
-      const bool skip = g.skip_flag && *g.skip_flag;
-      const int n_do = skip ? npre : nkb;
-      constexpr uint32_t idesc = make_idesc(BN);
+    pdl_wait();
+    const bool skip = g.skip_flag && *g.skip_flag;
+    const int n_do = skip ? npre : nkb;
+    constexpr uint32_t idesc = make_idesc(BN);
+    const uint32_t tiles_addr = smem_u32(tiles);
 #pragma unroll 1
-      for (int i = 0; i < n_do; ++i) {
-        const int s = i % stages;
-        const uint32_t ph = (i / stages) & 1;
-        mbar_wait(&full[s], ph);
-        tc_fence_after();
+    for (int i = 0; i < n_do; ++i) {
+      const int s = i % stages;
+      const uint32_t ph = (i / stages) & 1;
+      mbar_wait(&full[s], ph);
+      tc_fence_after();
+      const uint32_t a_addr = tiles_addr + static_cast<uint32_t>(s * STAGE_BYTES);
+      const uint64_t da = make_desc(a_addr), db = make_desc(a_addr + SK_A_BYTES);
+      if (elect_one()) {
         if (!skip) {
-          const uint32_t a_addr = smem_u32(tiles + s * STAGE_BYTES);
-          const uint64_t da = make_desc(a_addr), db = make_desc(a_addr + SK_A_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
             umma(tmem_base, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
                  (i | k) != 0 ? 1u : 0u);
         }
         umma_commit(&empty[s]);
+        if (i == n_do - 1) umma_commit(tmem_full);
       }
-      umma_commit(tmem_full);
+      __syncwarp();
     }
   } else if (FOLD && warp % 4 < 2) {
    if constexpr (FOLD) {
@@ -1234,15 +1534,15 @@ __global__ void __launch_bounds__(256) splitk_ln_kernel(const float* __restrict_
   }
   if (on) {
     // all loads first (one L2 round trip instead of a dependent chain), then the arithmetic
-    float4 p[4];
+    float4 p[kSkMaxSplit];
     uint2 rr = make_uint2(0u, 0u);
 #pragma unroll
-    for (int s = 0; s < 4; ++s)
+    for (int s = 0; s < kSkMaxSplit; ++s)
       p[s] = (s < nsplit) ? __ldcg(reinterpret_cast<const float4*>(partial + (static_cast<long long>(s) * SK_ROWS + m) * N + c))
                           : make_float4(0.f, 0.f, 0.f, 0.f);
     if (residual && !res_gamma) rr = *reinterpret_cast<const uint2*>(residual + static_cast<long long>(m) * ldr + c);
 #pragma unroll
-    for (int s = 0; s < 4; ++s) {
+    for (int s = 0; s < kSkMaxSplit; ++s) {
       v[0] += p[s].x; v[1] += p[s].y; v[2] += p[s].z; v[3] += p[s].w;
     }
     v[0] += bs.x; v[1] += bs.y; v[2] += bs.z; v[3] += bs.w;
@@ -1432,6 +1732,54 @@ void launch(const GemmArgs& g, int stages, cudaStream_t stream) {
   check_launch("gemm_tcgen05");
 }
 
+
+// ---- weight-resident path -----------------------------------------------------------------------------
+// Picks the widest column slice whose weights fit beside a >= 4-stage A ring; 0: not eligible.
+int wres_pick(const GemmArgs& g, int* stages_out, int* n_slices_out, int* grid_out) {
+  static const bool off = std::getenv("CXRM_NO_WRES_GEMM") != nullptr;
+  if (off || g.out_f32 || g.c_head_stride != 0 || g.K > 384 || g.N % 32 != 0 || g.skip_flag) return 0;
+  const int esz = 2;
+  bool vec_ok = (reinterpret_cast<uintptr_t>(g.C) % 16 == 0) && ((static_cast<long long>(g.ldc) * esz) % 16 == 0);
+  if (g.residual) vec_ok = vec_ok && (reinterpret_cast<uintptr_t>(g.residual) % 16 == 0) && (g.ldr % 8 == 0);
+  if (!vec_ok) return 0;
+  const int nkb = ceil_div(g.K, BK), tiles_m = ceil_div(g.M, BM);
+  const int cand[6] = {256, 192, 128, 96, 64, 32};
+  for (int bn : cand) {
+    if (g.N % bn != 0) continue;
+    const int n_slices = g.N / bn;
+    if (n_slices > persist_sms()) continue;
+    int stages = W_MAX_STAGES;
+    while (stages >= 4 && wres_smem(bn, nkb, stages) > 227 * 1024) --stages;
+    if (stages < 4) continue;
+    const int grid = (persist_sms() / n_slices) * n_slices;
+    if (tiles_m < 2 * (grid / n_slices)) return 0;     // too few row tiles to amortise the resident weights
+    *stages_out = stages; *n_slices_out = n_slices; *grid_out = grid;
+    return bn;
+  }
+  return 0;
+}
+
+template <int BN>
+void launch_wres(const GemmArgs& g, int stages, int n_slices, int grid, cudaStream_t stream) {
+  const int nkb = ceil_div(g.K, BK);
+  const size_t smem = wres_smem(BN, nkb, stages);
+  static size_t configured = 0;
+  if (smem > configured) {
+    CXRM_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_wres_kernel<BN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    CXRM_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_wres_kernel<BN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    configured = smem;
+  }
+  const CUtensorMap ta = make_map(g.A, g.M, g.K, g.lda, BM);
+  const CUtensorMap tb = make_map(g.W, g.N, g.K, g.ldw, BN);
+  const CUtensorMap tc = make_map_out(g.C, g.M, g.N, g.ldc);
+  const int tiles_m = ceil_div(g.M, BM);
+  if (g.act == ACT_GELU)
+    gemm_tc_wres_kernel<BN, 2><<<grid, W_THREADS, smem, stream>>>(ta, tb, tc, g, tiles_m, n_slices, stages);
+  else
+    gemm_tc_wres_kernel<BN, 1><<<grid, W_THREADS, smem, stream>>>(ta, tb, tc, g, tiles_m, n_slices, stages);
+  check_launch("gemm_tcgen05_wres");
+}
+
 // ---- skinny path (M <= 64) -------------------------------------------------------------------------
 template <int BN>
 void launch_skinny(const GemmArgs& g, int stages, int nsplit, int kb_per_split, float* partial, cudaStream_t stream,
@@ -1572,8 +1920,13 @@ void gemm_tcgen05_skinny(const GemmArgs& g, float* partial, int* nsplit_out, cud
     CXRM_CHECK(fold->ln_in.tiles <= 48 && fold->ln_res.tiles <= 48 && fold->ln_in.tiles % 2 == 0 && fold->ln_res.tiles % 2 == 0,
                "LN-folded epilogue: at most 48 (even) statistics tiles per row");
   }
+  // split-K: every tcgen05.mma of this kernel costs ~93 clocks whatever its width (the 128 x 16 A slice is read from shared
+  // memory per instruction: tools/mb_mma.cu), so a CTA's floor is 4 * k-blocks * 93 clocks - 2.3 us for K = 768 unsplit.
+  // The GEMMs that feed the reduce + LayerNorm kernel split as far as kSkMaxSplit partials of >= kb_min k-blocks.
+  static const int max_split = std::getenv("CXRM_SK_MAXSPLIT") ? std::max(1, std::min(kSkMaxSplit, std::atoi(std::getenv("CXRM_SK_MAXSPLIT")))) : kSkMaxSplit;
+  static const int kb_min = std::getenv("CXRM_SK_KBMIN") ? std::max(1, std::atoi(std::getenv("CXRM_SK_KBMIN"))) : 3;   // measured: 8 x >= 3 k-blocks, -3.2 ms per SCST step vs 4 x >= 6
   int nsplit = 1;
-  if (partial && ceil_div(g.N, bn) < 64) nsplit = std::max(1, std::min(4, num_kb / 6));
+  if (partial && ceil_div(g.N, bn) < 64) nsplit = std::max(1, std::min(max_split, num_kb / kb_min));
   const int kb_per_split = ceil_div(num_kb, nsplit);
   nsplit = ceil_div(num_kb, kb_per_split);
   stages = std::min(stages, kb_per_split);
@@ -1609,7 +1962,7 @@ void fold_ln_weights(const float* W, int n_out, int n_in, const float* gamma, co
   check_launch("fold_ln_weights");
 }
 
-size_t gemm_skinny_partial_floats(int N) { return static_cast<size_t>(4) * SK_ROWS * N; }
+size_t gemm_skinny_partial_floats(int N) { return static_cast<size_t>(kSkMaxSplit) * SK_ROWS * N; }
 
 namespace {
 }  // namespace
@@ -1628,6 +1981,18 @@ int gemm_tcgen05_supported(const GemmArgs& g) {
 void gemm_tcgen05(const GemmArgs& g, cudaStream_t stream) {
   CXRM_CHECK(gemm_tcgen05_supported(g) == 0, "shape/alignment not supported by the tcgen05 GEMM");
   int bn = 128, stages = 3;
+  {
+    int wst = 0, wsl = 0, wgrid = 0;
+    switch (wres_pick(g, &wst, &wsl, &wgrid)) {
+      case 32: launch_wres<32>(g, wst, wsl, wgrid, stream); return;
+      case 64: launch_wres<64>(g, wst, wsl, wgrid, stream); return;
+      case 96: launch_wres<96>(g, wst, wsl, wgrid, stream); return;
+      case 128: launch_wres<128>(g, wst, wsl, wgrid, stream); return;
+      case 192: launch_wres<192>(g, wst, wsl, wgrid, stream); return;
+      case 256: launch_wres<256>(g, wst, wsl, wgrid, stream); return;
+      default: break;
+    }
+  }
   pick_tile(g.M, g.N, g.K, &bn, &stages);
   switch (bn) {
     case 32: launch<32>(g, stages, stream); break;

@@ -22,6 +22,8 @@ SHAPES = [
     (33, 30000, 768), (4096, 256, 64), (129, 100, 152), (2, 128, 768), (700, 768, 768),
     # >= 2 tiles per SM: the persistent kernel (double-buffered TMEM accumulators), tile widths 128 / 64 / 256 / 96
     (20000, 384, 384), (38000, 64, 64), (19000, 768, 1536), (37900, 96, 192),
+    # short K, huge M: the weight-resident persistent kernel (column slices of 128 / 192 / 256 / 64 / 128, ragged last row tile)
+    (18464, 1536, 384), (40000, 192, 192), (40010, 768, 192), (60000, 64, 152), (40000, 256, 64), (18432, 768, 384),
 ]
 
 
