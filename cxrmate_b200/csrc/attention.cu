@@ -252,6 +252,8 @@ __device__ __forceinline__ void load_tile(uint32_t dst, const bf16* src, long lo
 
 __global__ void __launch_bounds__(TNT) attention_mma_kernel(AttnArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
+  pdl_launch_dependents();   // programmatic dependent launch (encoder chain)
+  pdl_wait();
   unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~static_cast<uintptr_t>(127));
   const uint32_t sQ = smem_u32(sm), sK = sQ + TILE_B, sV = sK + 2 * TILE_B;   // K, V double-buffered
   const int tid = threadIdx.x, warp = tid / kWarp, lane = tid % kWarp;
@@ -443,7 +445,7 @@ void attention_mma(const AttnArgs& a, cudaStream_t stream) {
   }
   dim3 grid(ceil_div(a.Lq, tc::TBQ), a.heads, a.batch);
   CXRM_CHECK(grid.z <= 65535 && grid.y <= 65535, "attention batch too large for grid.z");
-  tc::attention_mma_kernel<<<grid, tc::TNT, smem, stream>>>(a);
+  launch_chain(tc::attention_mma_kernel, grid, dim3(tc::TNT), smem, stream, a);
   check_launch("attention_mma");
 }
 

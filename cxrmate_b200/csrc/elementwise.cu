@@ -19,6 +19,8 @@ template <typename T>
 __global__ void layernorm_kernel(const T* __restrict__ x, int ldx, T* __restrict__ y, int ldy,
                                  const float* __restrict__ gamma, const float* __restrict__ beta, long long rows, int C,
                                  float eps) {
+  pdl_launch_dependents();   // programmatic dependent launch (encoder chain): the next kernel may start its prologue
+  pdl_wait();                // ... and nothing below touches global memory before the previous kernel has completed
   const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) / kWarp;
   const int lane = threadIdx.x % kWarp;
   if (row >= rows) return;
@@ -150,6 +152,8 @@ template <typename T>
 __global__ void im2col_pixels_kernel(const float* __restrict__ pixels, const int* __restrict__ img_idx,
                                      T* __restrict__ out, int n_img, int H, int W, int Ho, int Wo, int ksz, int stride,
                                      int pad, int Kpad) {
+  pdl_launch_dependents();   // programmatic dependent launch (encoder chain): the next kernel may start its prologue
+  pdl_wait();                // ... and nothing below touches global memory before the previous kernel has completed
   const long long total = static_cast<long long>(n_img) * Ho * Wo * Kpad;
   const int K = 3 * ksz * ksz;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -176,6 +180,8 @@ __global__ void im2col_pixels_kernel(const float* __restrict__ pixels, const int
 template <typename T>
 __global__ void im2col_tokens_kernel(const T* __restrict__ in, T* __restrict__ out, int n_img, int H, int W, int C,
                                      int Ho, int Wo, int ksz, int stride, int pad) {
+  pdl_launch_dependents();   // programmatic dependent launch (encoder chain): the next kernel may start its prologue
+  pdl_wait();                // ... and nothing below touches global memory before the previous kernel has completed
   constexpr int V = Vec16<T>::N;
   const int cv = C / V;
   const long long total = static_cast<long long>(n_img) * Ho * Wo * ksz * ksz * cv;
@@ -212,6 +218,8 @@ template <typename T, int LPR, bool STATS>
 __global__ void __launch_bounds__(256) ln_rows_kernel(const T* __restrict__ x, int ldx, T* __restrict__ y, int ldy,
                                                       float2* __restrict__ stats, const float* __restrict__ gamma,
                                                       const float* __restrict__ beta, long long rows, int C, float eps) {
+  pdl_launch_dependents();   // programmatic dependent launch (encoder chain): the next kernel may start its prologue
+  pdl_wait();                // ... and nothing below touches global memory before the previous kernel has completed
   constexpr int V = Vec16<T>::N;
   const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) / LPR;
   const int sub = threadIdx.x % LPR;
@@ -298,6 +306,8 @@ __global__ void __launch_bounds__(256, 3) ln_dwconv_qkv_kernel(const T* __restri
                                                             const float* __restrict__ scale,
                                                             const float* __restrict__ shift, int H, int W, int C, int cls,
                                                             int Hk, int Wk, int cols) {
+  pdl_launch_dependents();   // programmatic dependent launch (encoder chain): the next kernel may start its prologue
+  pdl_wait();                // ... and nothing below touches global memory before the previous kernel has completed
   const int cv = C / V;
   const int tc = threadIdx.x % cv, tcol = threadIdx.x / cv;
   const int ox = blockIdx.x * cols + tcol;
@@ -390,6 +400,8 @@ template <typename T>
 __global__ void ln_cls_kernel(const T* __restrict__ x, const float2* __restrict__ stats, const float* __restrict__ gamma,
                               const float* __restrict__ beta, T* __restrict__ q, T* __restrict__ k, T* __restrict__ v,
                               int n_img, int HWq, int HWk, int C) {
+  pdl_launch_dependents();   // programmatic dependent launch (encoder chain): the next kernel may start its prologue
+  pdl_wait();                // ... and nothing below touches global memory before the previous kernel has completed
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_img * C) return;
   const int n = i / C, c = i % C;
@@ -404,6 +416,8 @@ __global__ void ln_cls_kernel(const T* __restrict__ x, const float2* __restrict_
 template <typename T>
 __global__ void cat_cls_kernel(const T* __restrict__ tokens, const float* __restrict__ cls_token, T* __restrict__ out,
                                int n_img, int HW, int C) {
+  pdl_launch_dependents();   // programmatic dependent launch (encoder chain): the next kernel may start its prologue
+  pdl_wait();                // ... and nothing below touches global memory before the previous kernel has completed
   const long long total = static_cast<long long>(n_img) * (1 + HW) * C;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -417,6 +431,8 @@ __global__ void cat_cls_kernel(const T* __restrict__ tokens, const float* __rest
 
 template <typename T>
 __global__ void drop_cls_kernel(const T* __restrict__ in, T* __restrict__ out, int n_img, int HW, int C) {
+  pdl_launch_dependents();   // programmatic dependent launch (encoder chain): the next kernel may start its prologue
+  pdl_wait();                // ... and nothing below touches global memory before the previous kernel has completed
   const long long total = static_cast<long long>(n_img) * HW * C;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -538,11 +554,11 @@ bool ln_rows_launch(const T* x, int ldx, T* y, int ldy, float2* stats, const flo
   while (lpr * kLnMaxVec < cv) lpr *= 2;
   const unsigned grid = static_cast<unsigned>(ceil_div_ll(rows * lpr, 256));
   switch (lpr) {
-    case 2: ln_rows_kernel<T, 2, STATS><<<grid, 256, 0, stream>>>(x, ldx, y, ldy, stats, gamma, beta, rows, C, eps); break;
-    case 4: ln_rows_kernel<T, 4, STATS><<<grid, 256, 0, stream>>>(x, ldx, y, ldy, stats, gamma, beta, rows, C, eps); break;
-    case 8: ln_rows_kernel<T, 8, STATS><<<grid, 256, 0, stream>>>(x, ldx, y, ldy, stats, gamma, beta, rows, C, eps); break;
-    case 16: ln_rows_kernel<T, 16, STATS><<<grid, 256, 0, stream>>>(x, ldx, y, ldy, stats, gamma, beta, rows, C, eps); break;
-    default: ln_rows_kernel<T, 32, STATS><<<grid, 256, 0, stream>>>(x, ldx, y, ldy, stats, gamma, beta, rows, C, eps); break;
+    case 2: launch_chain(ln_rows_kernel<T, 2, STATS>, dim3(grid), dim3(256), 0, stream, x, ldx, y, ldy, stats, gamma, beta, rows, C, eps); break;
+    case 4: launch_chain(ln_rows_kernel<T, 4, STATS>, dim3(grid), dim3(256), 0, stream, x, ldx, y, ldy, stats, gamma, beta, rows, C, eps); break;
+    case 8: launch_chain(ln_rows_kernel<T, 8, STATS>, dim3(grid), dim3(256), 0, stream, x, ldx, y, ldy, stats, gamma, beta, rows, C, eps); break;
+    case 16: launch_chain(ln_rows_kernel<T, 16, STATS>, dim3(grid), dim3(256), 0, stream, x, ldx, y, ldy, stats, gamma, beta, rows, C, eps); break;
+    default: launch_chain(ln_rows_kernel<T, 32, STATS>, dim3(grid), dim3(256), 0, stream, x, ldx, y, ldy, stats, gamma, beta, rows, C, eps); break;
   }
   check_launch(STATS ? "ln_stats" : "layernorm_vec");
   return true;
@@ -556,7 +572,7 @@ void layernorm(const T* x, int ldx, T* y, int ldy, const float* gamma, const flo
   if (ln_rows_launch<T, false>(x, ldx, y, ldy, nullptr, gamma, beta, rows, C, eps, stream)) return;
   const int block = 256;
   const long long grid = ceil_div_ll(rows * kWarp, block);
-  layernorm_kernel<T><<<static_cast<unsigned>(grid), block, 0, stream>>>(x, ldx, y, ldy, gamma, beta, rows, C, eps);
+  launch_chain(layernorm_kernel<T>, dim3(static_cast<unsigned>(grid)), dim3(block), 0, stream, x, ldx, y, ldy, gamma, beta, rows, C, eps);
   check_launch("layernorm");
 }
 
@@ -586,8 +602,8 @@ void im2col_pixels(const float* pixels, const int* img_idx, T* out, int n_img, i
   const int Ho = (H + 2 * pad - ksz) / stride + 1, Wo = (W + 2 * pad - ksz) / stride + 1;
   const long long total = static_cast<long long>(n_img) * Ho * Wo * Kpad;
   if (total <= 0) return;
-  im2col_pixels_kernel<T><<<grid_for(total, 256), 256, 0, stream>>>(pixels, img_idx, out, n_img, H, W, Ho, Wo, ksz,
-                                                                    stride, pad, Kpad);
+  launch_chain(im2col_pixels_kernel<T>, dim3(grid_for(total, 256)), dim3(256), 0, stream, pixels, img_idx, out, n_img, H, W, Ho, Wo, ksz,
+               stride, pad, Kpad);
   check_launch("im2col_pixels");
 }
 
@@ -598,7 +614,7 @@ void im2col_tokens(const T* in, T* out, int n_img, int H, int W, int C, int ksz,
   CXRM_CHECK(C % Vec16<T>::N == 0, "im2col_tokens needs C multiple of the vector width");
   const long long total = static_cast<long long>(n_img) * Ho * Wo * ksz * ksz * (C / Vec16<T>::N);
   if (total <= 0) return;
-  im2col_tokens_kernel<T><<<grid_for(total, 256), 256, 0, stream>>>(in, out, n_img, H, W, C, Ho, Wo, ksz, stride, pad);
+  launch_chain(im2col_tokens_kernel<T>, dim3(grid_for(total, 256)), dim3(256), 0, stream, in, out, n_img, H, W, C, Ho, Wo, ksz, stride, pad);
   check_launch("im2col_tokens");
 }
 
@@ -618,11 +634,11 @@ void ln_dwconv_qkv(const T* x, T* q, T* k, T* v, float* stats, const float* gamm
   const int cols = std::min(W, 256 / cv);
   dim3 grid(ceil_div(W, cols), ceil_div(H, TY), n_img);
   CXRM_CHECK(grid.z <= 65535, "ln_dwconv_qkv: too many images per chunk");
-  ln_dwconv_qkv_kernel<T, TY, V><<<grid, cols * cv, 0, stream>>>(x, q, k, v, st, gamma, beta, w, scale, shift, H, W, C, cls,
-                                                              Hk, Wk, cols);
+  launch_chain(ln_dwconv_qkv_kernel<T, TY, V>, grid, dim3(cols * cv), 0, stream, x, q, k, v, st, gamma, beta, w, scale, shift, H, W, C, cls,
+               Hk, Wk, cols);
   check_launch("ln_dwconv_qkv");
   if (cls) {
-    ln_cls_kernel<T><<<ceil_div(n_img * C, 256), 256, 0, stream>>>(x, st, gamma, beta, q, k, v, n_img, H * W, Hk * Wk, C);
+    launch_chain(ln_cls_kernel<T>, dim3(ceil_div(n_img * C, 256)), dim3(256), 0, stream, x, st, gamma, beta, q, k, v, n_img, H * W, Hk * Wk, C);
     check_launch("ln_cls");
   }
 }
@@ -631,7 +647,7 @@ template <typename T>
 void cat_cls(const T* tokens, const float* cls_token, T* out, int n_img, int HW, int C, cudaStream_t stream) {
   const long long total = static_cast<long long>(n_img) * (1 + HW) * C;
   if (total <= 0) return;
-  cat_cls_kernel<T><<<grid_for(total, 256), 256, 0, stream>>>(tokens, cls_token, out, n_img, HW, C);
+  launch_chain(cat_cls_kernel<T>, dim3(grid_for(total, 256)), dim3(256), 0, stream, tokens, cls_token, out, n_img, HW, C);
   check_launch("cat_cls");
 }
 
@@ -639,7 +655,7 @@ template <typename T>
 void drop_cls(const T* in, T* out, int n_img, int HW, int C, cudaStream_t stream) {
   const long long total = static_cast<long long>(n_img) * HW * C;
   if (total <= 0) return;
-  drop_cls_kernel<T><<<grid_for(total, 256), 256, 0, stream>>>(in, out, n_img, HW, C);
+  launch_chain(drop_cls_kernel<T>, dim3(grid_for(total, 256)), dim3(256), 0, stream, in, out, n_img, HW, C);
   check_launch("drop_cls");
 }
 

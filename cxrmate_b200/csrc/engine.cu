@@ -719,6 +719,12 @@ class Engine : public EngineBase {
   T* encode_chunk(const float* pixels, const int* idx_dev, int n, cudaStream_t s) {
     phase = "enc";
     arena.reset();
+    // every kernel of the chunk is a programmatic dependent launch of its predecessor: its CTAs are scheduled and set up
+    // (barriers, TMEM, descriptors, resident weights) under the predecessor's tail and wait in griddepcontrol.wait
+    struct EncPdl {
+      explicit EncPdl(bool on) { g_pdl = on; }
+      ~EncPdl() { g_pdl = false; }
+    } enc_pdl(chain_pdl() && !profiling && std::getenv("CXRM_NO_ENC_PDL") == nullptr);
     int H = cfg.image_h, W = cfg.image_w;
     const long long tok0 = static_cast<long long>(H / 4) * (W / 4);
     const long long nt = static_cast<long long>(n) * tok0;   // largest token count (stage 1)

@@ -221,7 +221,11 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const __grid_constant
   // several CTAs share an SM and one CTA's epilogue overlaps another's loads and MMAs.
   using C_ = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
-  if (g.skip_flag && *g.skip_flag) return;
+  pdl_launch_dependents();   // programmatic dependent launch (encoder chain): set-up below overlaps the previous kernel's tail
+  if (g.skip_flag) {
+    pdl_wait();
+    if (*g.skip_flag) return;
+  }
 
   uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(tiles + STAGES * C_::STAGE_BYTES);
@@ -255,6 +259,7 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(kFull, *tmem_slot, 0);   // provably warp-uniform: no R2UR waterfall around each tcgen05.mma
   if (threadIdx.x == 0) TRACE(1);
+  pdl_wait();   // barriers, TMEM and descriptors are ready; operands / residual / output belong to the previous kernels
 
   if (warp == 0) {
     if (lane == 0) {
@@ -437,6 +442,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_persist_kernel(const __gr
   using C_ = PCfg<BN>;
   constexpr int STAGES = C_::stages();
   extern __shared__ uint8_t smem_raw[];
+  pdl_launch_dependents();
   uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* staging = tiles + STAGES * C_::STAGE_BYTES;
   uint64_t* full = reinterpret_cast<uint64_t*>(staging + C_::STAGING);
@@ -472,6 +478,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_persist_kernel(const __gr
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(kFull, *tmem_slot, 0);   // provably warp-uniform: no R2UR waterfall around each tcgen05.mma
+  pdl_wait();   // (encoder chain) set-up done under the previous kernel's tail; its outputs are visible from here on
 
   if (warp == 0) {
     if (lane == 0) {
@@ -636,6 +643,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) gemm_tc_wres_kernel(const __grid
 #define WTRACE(i) do { if (g.trace) g.trace[static_cast<long long>(blockIdx.x) * 16 + (i)] = gtimer(); } while (0)
 #define WTRACE_ADD(i, v) do { if (g.trace) g.trace[static_cast<long long>(blockIdx.x) * 16 + (i)] += (v); } while (0)
   const int num_kb = (g.K + BK - 1) / BK;
+  pdl_launch_dependents();   // (encoder chain) the next kernel may start its set-up
   if (threadIdx.x == 0) WTRACE(0);
   uint8_t* wres = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* ring = wres + num_kb * (BN * 128);
@@ -689,6 +697,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) gemm_tc_wres_kernel(const __grid
       for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(wres + kb * (BN * 128), &tmB, kb * BK, n0, wfull);
     }
     __syncwarp();
+    pdl_wait();   // the weights above are constants; the activations belong to the previous kernel
     int it = 0;
 #pragma unroll 1
     for (int mt = mt0; mt < tiles_m; mt += mstride) {
@@ -706,6 +715,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) gemm_tc_wres_kernel(const __grid
   } else if (warp == 1) {
     // MMA issuer: uniform loops, one elected lane issues the MMAs and their commits
     constexpr uint32_t idesc = make_idesc(BN);
+    pdl_wait();
     mbar_wait(wfull, 0);
     tc_fence_after();
     if (lane == 0) WTRACE(2);
@@ -775,6 +785,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) gemm_tc_wres_kernel(const __grid
     constexpr int NCH = BN / 32;
     int t = 0, pi = 0;
     unsigned long long wait_epi = 0;
+    pdl_wait();   // residual rows and the output buffer belong to the previous kernels
 #pragma unroll 1
     for (int mt = mt0; mt < tiles_m; mt += mstride, ++t) {
       const int buf = t & 1;
@@ -1716,19 +1727,19 @@ void launch(const GemmArgs& g, int stages, cudaStream_t stream) {
     }
     const int ctas = std::min(n_tiles, persist_sms());
     if (g.act == ACT_GELU)
-      gemm_tc_persist_kernel<BN, 2><<<ctas, NTHREADS, PCfg<BN>::smem(), stream>>>(ta, tb, tc, g, vec_ok, static_cast<int>(grid.x), n_tiles);
+      launch_chain(gemm_tc_persist_kernel<BN, 2>, dim3(ctas), dim3(NTHREADS), PCfg<BN>::smem(), stream, ta, tb, tc, g, vec_ok, static_cast<int>(grid.x), n_tiles);
     else
-      gemm_tc_persist_kernel<BN, 1><<<ctas, NTHREADS, PCfg<BN>::smem(), stream>>>(ta, tb, tc, g, vec_ok, static_cast<int>(grid.x), n_tiles);
+      launch_chain(gemm_tc_persist_kernel<BN, 1>, dim3(ctas), dim3(NTHREADS), PCfg<BN>::smem(), stream, ta, tb, tc, g, vec_ok, static_cast<int>(grid.x), n_tiles);
     check_launch("gemm_tcgen05_persist");
     return;
   }
   const size_t smem = Cfg<BN>::smem(stages);
   if (tma_store && g.act == ACT_GELU)
-    gemm_tc_kernel<BN, 2><<<grid, NTHREADS, smem, stream>>>(ta, tb, tc, g, vec_ok, stages, tma_store);
+    launch_chain(gemm_tc_kernel<BN, 2>, grid, dim3(NTHREADS), smem, stream, ta, tb, tc, g, vec_ok, stages, tma_store);
   else if (tma_store)
-    gemm_tc_kernel<BN, 1><<<grid, NTHREADS, smem, stream>>>(ta, tb, tc, g, vec_ok, stages, tma_store);
+    launch_chain(gemm_tc_kernel<BN, 1>, grid, dim3(NTHREADS), smem, stream, ta, tb, tc, g, vec_ok, stages, tma_store);
   else
-    gemm_tc_kernel<BN, 0><<<grid, NTHREADS, smem, stream>>>(ta, tb, tc, g, vec_ok, stages, tma_store);
+    launch_chain(gemm_tc_kernel<BN, 0>, grid, dim3(NTHREADS), smem, stream, ta, tb, tc, g, vec_ok, stages, tma_store);
   check_launch("gemm_tcgen05");
 }
 
@@ -1774,9 +1785,9 @@ void launch_wres(const GemmArgs& g, int stages, int n_slices, int grid, cudaStre
   const CUtensorMap tc = make_map_out(g.C, g.M, g.N, g.ldc);
   const int tiles_m = ceil_div(g.M, BM);
   if (g.act == ACT_GELU)
-    gemm_tc_wres_kernel<BN, 2><<<grid, W_THREADS, smem, stream>>>(ta, tb, tc, g, tiles_m, n_slices, stages);
+    launch_chain(gemm_tc_wres_kernel<BN, 2>, dim3(grid), dim3(W_THREADS), smem, stream, ta, tb, tc, g, tiles_m, n_slices, stages);
   else
-    gemm_tc_wres_kernel<BN, 1><<<grid, W_THREADS, smem, stream>>>(ta, tb, tc, g, tiles_m, n_slices, stages);
+    launch_chain(gemm_tc_wres_kernel<BN, 1>, dim3(grid), dim3(W_THREADS), smem, stream, ta, tb, tc, g, tiles_m, n_slices, stages);
   check_launch("gemm_tcgen05_wres");
 }
 
@@ -1923,6 +1934,9 @@ void gemm_tcgen05_skinny(const GemmArgs& g, float* partial, int* nsplit_out, cud
   // split-K: every tcgen05.mma of this kernel costs ~93 clocks whatever its width (the 128 x 16 A slice is read from shared
   // memory per instruction: tools/mb_mma.cu), so a CTA's floor is 4 * k-blocks * 93 clocks - 2.3 us for K = 768 unsplit.
   // The GEMMs that feed the reduce + LayerNorm kernel split as far as kSkMaxSplit partials of >= kb_min k-blocks.
+  // (The direct-epilogue GEMMs - QKV, cross-Q, FFN-up - were tried with split-K across a 2- / 4-CTA cluster reduced
+  // through distributed shared memory: correct, but 152.3 / 159.6 ms of rollout against 146.7 without - the cluster
+  // launch and its barrier cost more than the 24-36 MMAs they save; removed)
   static const int max_split = std::getenv("CXRM_SK_MAXSPLIT") ? std::max(1, std::min(kSkMaxSplit, std::atoi(std::getenv("CXRM_SK_MAXSPLIT")))) : kSkMaxSplit;
   static const int kb_min = std::getenv("CXRM_SK_KBMIN") ? std::max(1, std::atoi(std::getenv("CXRM_SK_KBMIN"))) : 3;   // measured: 8 x >= 3 k-blocks, -3.2 ms per SCST step vs 4 x >= 6
   int nsplit = 1;
