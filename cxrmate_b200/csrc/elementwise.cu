@@ -395,6 +395,134 @@ __global__ void __launch_bounds__(256, 3) ln_dwconv_qkv_kernel(const T* __restri
   }
 }
 
+// ---- the same front end, tiled through shared memory (round 2; C % 64 == 0) ---------------------------------------
+// ncu of the register-window kernel above (stage 3, 18432 x 384): 41 us, ~100 executed instructions per output element
+// (27 weight vectors re-read through L1 per output row, 64-bit address arithmetic per tap), issue slots 48 % busy, 61 %
+// of the stalls on L1TEX scoreboards - instruction-bound at 5x the time its 35 MB of traffic needs.  Here a block owns
+// a TH x 8 spatial tile and 64 channels: the NORMALISED tile + halo goes to shared memory once (one 128-byte row per
+// token and warp), a warp is one output column x 32 channel pairs, its 27 x 2 weights and the folded BatchNorm constants
+// live in registers for the whole tile, and each output row costs 3 conflict-free shared loads for the rolling window.
+template <typename T>
+__device__ __forceinline__ float2 load_pair(const T* p);
+template <>
+__device__ __forceinline__ float2 load_pair<float>(const float* p) { return *reinterpret_cast<const float2*>(p); }
+template <>
+__device__ __forceinline__ float2 load_pair<bf16>(const bf16* p) {
+  const uint32_t r = *reinterpret_cast<const uint32_t*>(p);
+  return make_float2(__uint_as_float(r << 16), __uint_as_float(r & 0xffff0000u));
+}
+__device__ __forceinline__ void store_pair(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+__device__ __forceinline__ void store_pair(bf16* p, float a, float b) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  *reinterpret_cast<uint32_t*>(p) = *reinterpret_cast<const uint32_t*>(&v);
+}
+
+template <typename T, int TH>
+__global__ void __launch_bounds__(256, 2) ln_dwconv_tile_kernel(const T* __restrict__ x, T* __restrict__ q, T* __restrict__ k,
+                                                              T* __restrict__ v, const float2* __restrict__ stats,
+                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                              const float* __restrict__ w, const float* __restrict__ scale,
+                                                              const float* __restrict__ shift, int H, int W, int C, int cls,
+                                                              int Hk, int Wk, int tiles_x) {
+  constexpr int TW = 8, PW = TW + 2, PH = TH + 2;
+  __shared__ float2 tile[PH * PW][32];
+  pdl_launch_dependents();
+  const int cp = threadIdx.x % 32, col = threadIdx.x / 32;      // a warp = one tile column x 32 channel pairs
+  const int c = blockIdx.y * 64 + 2 * cp;
+  const int ty0 = (blockIdx.x / tiles_x) * TH, tx0 = (blockIdx.x % tiles_x) * TW, n = blockIdx.z;
+  const long long tok0 = static_cast<long long>(n) * (cls + H * W) + cls;
+  // constants of the layer (weights): ahead of the dependency wait
+  const float2 g = *reinterpret_cast<const float2*>(gamma + c), b = *reinterpret_cast<const float2*>(beta + c);
+  float2 wq[9], wk[9], wv[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    wq[t] = *reinterpret_cast<const float2*>(w + static_cast<long long>(t) * C + c);
+    wk[t] = *reinterpret_cast<const float2*>(w + static_cast<long long>(9 + t) * C + c);
+    wv[t] = *reinterpret_cast<const float2*>(w + static_cast<long long>(18 + t) * C + c);
+  }
+  float2 sc[3], sh[3];
+#pragma unroll
+  for (int o = 0; o < 3; ++o) {
+    sc[o] = *reinterpret_cast<const float2*>(scale + o * C + c);
+    sh[o] = *reinterpret_cast<const float2*>(shift + o * C + c);
+  }
+  pdl_wait();
+  // ---- normalised tile + halo -> shared memory (zero outside the image: the convolution pads the NORMALISED map) ----
+  // (batches of LB positions: all their loads are issued before the first use - one L2 round trip per batch)
+  constexpr int NP = PH * PW, LB = 5;
+#pragma unroll 1
+  for (int p0 = col; p0 < NP; p0 += 8 * LB) {
+    float2 xv[LB], st[LB];
+    bool in[LB];
+#pragma unroll
+    for (int i = 0; i < LB; ++i) {
+      const int p = p0 + 8 * i;
+      const int iy = ty0 - 1 + p / PW, ix = tx0 - 1 + p % PW;
+      in[i] = p < NP && iy >= 0 && iy < H && ix >= 0 && ix < W;
+      xv[i] = st[i] = make_float2(0.f, 0.f);
+      if (in[i]) {
+        const long long tok = tok0 + static_cast<long long>(iy) * W + ix;
+        xv[i] = load_pair<T>(x + tok * C + c);
+        st[i] = stats[tok];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < LB; ++i) {
+      const int p = p0 + 8 * i;
+      if (p < NP)
+        tile[p][cp] = in[i] ? make_float2((xv[i].x - st[i].x) * st[i].y * g.x + b.x, (xv[i].y - st[i].x) * st[i].y * g.y + b.y)
+                            : make_float2(0.f, 0.f);
+    }
+  }
+  __syncthreads();
+  const int ox = tx0 + col;
+  if (ox >= W) return;
+  // ---- rolling 3 x 3 window down the column ----
+  float2 win[3][3];
+#pragma unroll
+  for (int dx = 0; dx < 3; ++dx) {
+    win[0][dx] = tile[0 * PW + col + dx][cp];
+    win[1][dx] = tile[1 * PW + col + dx][cp];
+  }
+  const bool col_even = (ox & 1) == 0;
+#pragma unroll 1
+  for (int t = 0; t < TH; ++t) {
+    const int oy = ty0 + t;
+    if (oy >= H) break;
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) win[2][dx] = tile[(t + 2) * PW + col + dx][cp];
+    float2 a = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        a.x = fmaf(win[ky][kx].x, wq[ky * 3 + kx].x, a.x);
+        a.y = fmaf(win[ky][kx].y, wq[ky * 3 + kx].y, a.y);
+      }
+    store_pair(q + (tok0 + static_cast<long long>(oy) * W + ox) * C + c, fmaf(a.x, sc[0].x, sh[0].x), fmaf(a.y, sc[0].y, sh[0].y));
+    if (col_even && (oy & 1) == 0) {   // warp-uniform: stride-2 window centres are the even coordinates
+      float2 ak = make_float2(0.f, 0.f), av = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          ak.x = fmaf(win[ky][kx].x, wk[ky * 3 + kx].x, ak.x);
+          ak.y = fmaf(win[ky][kx].y, wk[ky * 3 + kx].y, ak.y);
+          av.x = fmaf(win[ky][kx].x, wv[ky * 3 + kx].x, av.x);
+          av.y = fmaf(win[ky][kx].y, wv[ky * 3 + kx].y, av.y);
+        }
+      const long long orow = static_cast<long long>(n) * (cls + Hk * Wk) + cls + static_cast<long long>(oy >> 1) * Wk + (ox >> 1);
+      store_pair(k + orow * C + c, fmaf(ak.x, sc[1].x, sh[1].x), fmaf(ak.y, sc[1].y, sh[1].y));
+      store_pair(v + orow * C + c, fmaf(av.x, sc[2].x, sh[2].x), fmaf(av.y, sc[2].y, sh[2].y));
+    }
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) {
+      win[0][dx] = win[1][dx];
+      win[1][dx] = win[2][dx];
+    }
+  }
+}
+
 // cls rows bypass the convolution: q = k = v = LayerNorm(x[cls]) (modeling_cvt.py:215-228)
 template <typename T>
 __global__ void ln_cls_kernel(const T* __restrict__ x, const float2* __restrict__ stats, const float* __restrict__ gamma,
@@ -631,12 +759,29 @@ void ln_dwconv_qkv(const T* x, T* q, T* k, T* v, float* stats, const float* gamm
   const long long rows = static_cast<long long>(n_img) * (cls + H * W);
   const bool ok = ln_rows_launch<T, true>(x, C, nullptr, 0, st, nullptr, nullptr, rows, C, eps, stream);
   CXRM_CHECK(ok, "ln_dwconv_qkv: row statistics need 16-byte aligned rows");
-  const int cols = std::min(W, 256 / cv);
-  dim3 grid(ceil_div(W, cols), ceil_div(H, TY), n_img);
-  CXRM_CHECK(grid.z <= 65535, "ln_dwconv_qkv: too many images per chunk");
-  launch_chain(ln_dwconv_qkv_kernel<T, TY, V>, grid, dim3(cols * cv), 0, stream, x, q, k, v, st, gamma, beta, w, scale, shift, H, W, C, cls,
-               Hk, Wk, cols);
-  check_launch("ln_dwconv_qkv");
+  static const bool tiled = std::getenv("CXRM_NO_DWCONV_TILE") == nullptr;
+  if (tiled && C % 64 == 0 && n_img <= 65535) {
+    // tile height: the tallest of 16 / 8 that still gives every SM a few blocks
+    const int tiles_x = ceil_div(W, 8);
+    const long long blocks16 = static_cast<long long>(tiles_x) * ceil_div(H, 16) * (C / 64) * n_img;
+    if (blocks16 >= 148 * 8) {
+      dim3 grid(tiles_x * ceil_div(H, 16), C / 64, n_img);
+      launch_chain(ln_dwconv_tile_kernel<T, 16>, grid, dim3(256), 0, stream, x, q, k, v, st, gamma, beta, w, scale, shift, H, W, C, cls,
+                   Hk, Wk, tiles_x);
+    } else {
+      dim3 grid(tiles_x * ceil_div(H, 8), C / 64, n_img);
+      launch_chain(ln_dwconv_tile_kernel<T, 8>, grid, dim3(256), 0, stream, x, q, k, v, st, gamma, beta, w, scale, shift, H, W, C, cls,
+                   Hk, Wk, tiles_x);
+    }
+    check_launch("ln_dwconv_tile");
+  } else {
+    const int cols = std::min(W, 256 / cv);
+    dim3 grid(ceil_div(W, cols), ceil_div(H, TY), n_img);
+    CXRM_CHECK(grid.z <= 65535, "ln_dwconv_qkv: too many images per chunk");
+    launch_chain(ln_dwconv_qkv_kernel<T, TY, V>, grid, dim3(cols * cv), 0, stream, x, q, k, v, st, gamma, beta, w, scale, shift, H, W, C, cls,
+                 Hk, Wk, cols);
+    check_launch("ln_dwconv_qkv");
+  }
   if (cls) {
     launch_chain(ln_cls_kernel<T>, dim3(ceil_div(n_img * C, 256)), dim3(256), 0, stream, x, st, gamma, beta, q, k, v, n_img, H * W, Hk * Wk, C);
     check_launch("ln_cls");
