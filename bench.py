@@ -298,7 +298,7 @@ def run_b200(a):
     B, N, T = a.studies, a.images, a.tokens
 
     eng = Engine(dtype=a.dtype, device=local, max_studies=B, max_images=N, max_prompt=a.prompt, max_new_tokens=T,
-                 rwd_max_seqs=3 * B, enc_chunk=32, use_cuda_graph=not a.no_graph)
+                 rwd_max_seqs=3 * B, enc_chunk=64, use_cuda_graph=not a.no_graph)
     eng.load_state_dict(W.make_cxrmate_weights(seed=0))
     eng.load_state_dict(W.make_cxrbert_weights(seed=1), prefix="reward.")
     eng.finalize()
@@ -560,7 +560,7 @@ def run_generation(a):
         eng = None
         try:
             eng = Engine(dtype=a.dtype, max_studies=B, max_images=N, max_prompt=8, max_new_tokens=T, rwd_layers=0,
-                         enc_chunk=32, use_cuda_graph=not a.no_graph)
+                         enc_chunk=64, use_cuda_graph=not a.no_graph)
             eng.load_state_dict(sd)
             eng.finalize()
             counts = [1] * B if a.config == 1 else global_image_counts(B, N)

@@ -49,7 +49,7 @@ void cxrm_default_config(cxrm_config* c) {
   c->rwd_vocab = 30522;
   c->rwd_max_len = 512;
   c->rwd_max_seqs = 96;
-  c->enc_chunk = 32;
+  c->enc_chunk = 64;
   c->use_tensor_cores = 1;
   c->use_cuda_graph = 1;
   c->max_train_tokens = 0;

@@ -450,7 +450,7 @@ class Engine : public EngineBase {
     CXRM_CHECK(cfg.image_h % 16 == 0 && cfg.image_w % 16 == 0, "image size must be a multiple of 16");
     CXRM_CHECK(cfg.max_prompt + cfg.max_new_tokens <= 512, "prompt + new tokens must fit 512 positions");
     CXRM_CHECK(cfg.rwd_layers == 0 || (cfg.rwd_max_len >= 1 && cfg.rwd_max_len <= 512), "rwd_max_len must fit the 512 learned positions");
-    if (cfg.enc_chunk <= 0) cfg.enc_chunk = 32;
+    if (cfg.enc_chunk <= 0) cfg.enc_chunk = 64;
     T2 = (cfg.image_h / 16) * (cfg.image_w / 16);
     Smax = cfg.max_images * T2;
     Rmax = 2 * cfg.max_studies;
@@ -826,6 +826,13 @@ class Engine : public EngineBase {
       CXRM_CUDA_CHECK(cudaMemcpyAsync(mask_out, mem_mask, static_cast<size_t>(B) * enc_S, cudaMemcpyDeviceToDevice, s));
   }
 
+  // images per encoder pass: the valid images split into equal passes of at most enc_chunk (a 4-image tail pass costs
+  // the same ~240 launches as a full one)
+  size_t balanced_chunk(size_t n_valid) const {
+    if (n_valid == 0) return static_cast<size_t>(cfg.enc_chunk);
+    const size_t passes = (n_valid + cfg.enc_chunk - 1) / cfg.enc_chunk;
+    return (n_valid + passes - 1) / passes;
+  }
   // Encode the valid images: the k-th one is image src[k] of `pixels` and lands in slot dst[k] (= b*N + n) of the
   // encoder memory [B, N*T2, 768]; valid_img (device flags per slot) must be set.  chunk_ready (nullable): event c
   // is awaited before chunk c is touched (host-buffer path: the chunk's pixels arrive on the copy stream meanwhile).
@@ -840,8 +847,9 @@ class Engine : public EngineBase {
     check_launch("expand_mask");
     if (dst.empty()) return;
     CXRM_CUDA_CHECK(cudaMemcpyAsync(img_idx, src.data(), src.size() * sizeof(int), cudaMemcpyHostToDevice, s));
-    for (size_t c0 = 0, c = 0; c0 < dst.size(); c0 += cfg.enc_chunk, ++c) {
-      const int n = static_cast<int>(std::min<size_t>(cfg.enc_chunk, dst.size() - c0));
+    const size_t per = balanced_chunk(dst.size());
+    for (size_t c0 = 0, c = 0; c0 < dst.size(); c0 += per, ++c) {
+      const int n = static_cast<int>(std::min<size_t>(per, dst.size() - c0));
       if (chunk_ready) CXRM_CUDA_CHECK(cudaStreamWaitEvent(s, chunk_ready[c], 0));
       T* proj = encode_chunk(pixels, img_idx + c0, n, s);
       for (int i = 0; i < n;) {   // consecutive slots leave as one copy
@@ -2013,7 +2021,8 @@ class Engine : public EngineBase {
         }
       }
       CXRM_CUDA_CHECK(cudaMemcpyAsync(valid_img, valid.data(), n_all, cudaMemcpyHostToDevice, s));
-      const size_t n_chunks = (dst.size() + cfg.enc_chunk - 1) / cfg.enc_chunk;
+      const size_t per = balanced_chunk(dst.size());
+      const size_t n_chunks = dst.empty() ? 0 : (dst.size() + per - 1) / per;
       while (ev_chunk.size() < n_chunks + 1) {
         cudaEvent_t e;
         CXRM_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -2024,7 +2033,7 @@ class Engine : public EngineBase {
       CXRM_CUDA_CHECK(cudaStreamWaitEvent(pf_stream, ev_chunk[n_chunks], 0));
       h2d_pixel_bytes = 0;
       for (size_t c = 0; c < n_chunks; ++c) {
-        const size_t k0 = c * cfg.enc_chunk, k1 = std::min(dst.size(), k0 + cfg.enc_chunk);
+        const size_t k0 = c * per, k1 = std::min(dst.size(), k0 + per);
         for (size_t k = k0; k < k1;) {   // consecutive source slots travel as one copy
           size_t j = k + 1;
           while (j < k1 && dst[j] == dst[j - 1] + 1) ++j;

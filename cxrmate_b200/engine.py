@@ -57,7 +57,7 @@ class Engine:
                  max_images: int = 5, max_prompt: int = 256, max_new_tokens: int = 255, vocab: int = 30000,
                  cvt_depth: Sequence[int] = (1, 4, 16), dec_layers: int = 6, rwd_layers: int = 12,
                  rwd_vocab: int = 30522, rwd_max_len: int = 512, rwd_max_seqs: Optional[int] = None,
-                 enc_chunk: int = 32, use_tensor_cores: bool = True, use_cuda_graph: bool = True,
+                 enc_chunk: int = 64, use_tensor_cores: bool = True, use_cuda_graph: bool = True,
                  max_train_tokens: int = 0):
         if not torch.cuda.is_available():
             raise RuntimeError("cxrmate_b200.Engine needs a CUDA device (B200, sm_100a); there is no CPU fallback")

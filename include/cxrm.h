@@ -72,7 +72,7 @@ typedef struct cxrm_config {
   int rwd_vocab;           /* 30522 */
   int rwd_max_len;         /* 512 */
   int rwd_max_seqs;        /* sequences per cxrm_reward_embed call (>= 3 * B to batch sample+greedy+labels) */
-  int enc_chunk;           /* images encoded per pass (0 = default 32) */
+  int enc_chunk;           /* most images encoded per pass (0 = default 64); the valid images split into equal passes */
   int use_tensor_cores;    /* bf16 only: 1 = tcgen05 GEMMs (default), 0 = SIMT debug path */
   int use_cuda_graph;      /* 1 = replay the decode step as a CUDA graph */
   int max_train_tokens;    /* rows x tokens of the largest cxrm_train_step batch; 0 = no training workspace (default) */
