@@ -49,7 +49,10 @@ __global__ void __launch_bounds__(NT) attention_simt_kernel(AttnArgs a) {
   const int kvb = a.kv_batch_mod > 0 ? b % a.kv_batch_mod : b;
   const int Lk = a.Lk_per_batch ? a.Lk_per_batch[kvb] : a.Lk;
   const long long koff = a.kv_offset ? a.kv_offset[kvb] : 0;
-  const T* __restrict__ Q = static_cast<const T*>(a.q) + b * a.q_bs + h * a.q_hs;
+  const int Lq = a.Lq_per_batch ? a.Lq_per_batch[b] : a.Lq;
+  if (q0 >= Lq) return;   // packed queries: the grid is sized for the longest row
+  const long long qtok0 = a.q_offset ? a.q_offset[b] : 0;
+  const T* __restrict__ Q = static_cast<const T*>(a.q) + (a.q_offset ? qtok0 * a.q_ts : b * a.q_bs) + h * a.q_hs;
   const T* __restrict__ K = static_cast<const T*>(a.k) + kvb * a.k_bs + h * a.k_hs + koff * a.k_ts;
   const T* __restrict__ V = static_cast<const T*>(a.v) + kvb * a.v_bs + h * a.v_hs + koff * a.v_ts;
   const uint8_t* __restrict__ km =
@@ -59,7 +62,7 @@ __global__ void __launch_bounds__(NT) attention_simt_kernel(AttnArgs a) {
   const int lrow = tid >> 2, ld0 = (tid & 3) * 16;
   {
     float f[16];
-    if (q0 + lrow < a.Lq) {
+    if (q0 + lrow < Lq) {
       load16<T>(Q + static_cast<long long>(q0 + lrow) * a.q_ts + ld0, f);
     } else {
 #pragma unroll
@@ -81,7 +84,7 @@ __global__ void __launch_bounds__(NT) attention_simt_kernel(AttnArgs a) {
   // causal: keys beyond the last query of this tile are never visible
   int k_end = Lk;
   if (a.causal) {
-    const int last_q = min(q0 + BQ, a.Lq) - 1 + a.q_pos_offset;
+    const int last_q = min(q0 + BQ, Lq) - 1 + a.q_pos_offset;
     k_end = min(k_end, last_q + 1);
   }
 
@@ -176,11 +179,11 @@ __global__ void __launch_bounds__(NT) attention_simt_kernel(AttnArgs a) {
     }
   }
 
-  T* __restrict__ O = static_cast<T*>(a.o) + b * a.o_bs + h * a.o_hs;
+  T* __restrict__ O = static_cast<T*>(a.o) + (a.q_offset ? qtok0 * a.o_ts : b * a.o_bs) + h * a.o_hs;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int qi = q0 + ty * 4 + i;
-    if (qi >= a.Lq) continue;
+    if (qi >= Lq) continue;
     const float inv = l[i] > 0.f ? 1.f / l[i] : 0.f;
     T* dst = O + static_cast<long long>(qi) * a.o_ts + tx * 4;
 #pragma unroll
@@ -262,17 +265,20 @@ __global__ void __launch_bounds__(TNT) attention_mma_kernel(AttnArgs a) {
   const int kvb = a.kv_batch_mod > 0 ? b % a.kv_batch_mod : b;
   const int Lk = a.Lk_per_batch ? a.Lk_per_batch[kvb] : a.Lk;
   const long long koff = a.kv_offset ? a.kv_offset[kvb] : 0;
-  const bf16* __restrict__ Q = static_cast<const bf16*>(a.q) + b * a.q_bs + h * a.q_hs;
+  const int Lq = a.Lq_per_batch ? a.Lq_per_batch[b] : a.Lq;
+  if (q0 >= Lq) return;   // packed queries: the grid is sized for the longest row (whole CTA leaves, after the PDL wait)
+  const long long qtok0 = a.q_offset ? a.q_offset[b] : 0;
+  const bf16* __restrict__ Q = static_cast<const bf16*>(a.q) + (a.q_offset ? qtok0 * a.q_ts : b * a.q_bs) + h * a.q_hs;
   const bf16* __restrict__ K = static_cast<const bf16*>(a.k) + kvb * a.k_bs + h * a.k_hs + koff * a.k_ts;
   const bf16* __restrict__ V = static_cast<const bf16*>(a.v) + kvb * a.v_bs + h * a.v_hs + koff * a.v_ts;
   const uint8_t* __restrict__ km =
       a.key_mask ? a.key_mask + static_cast<long long>(a.key_mask_per_q_batch ? b : kvb) * a.key_mask_ld : nullptr;
 
   int k_end = Lk;
-  if (a.causal) k_end = min(k_end, min(q0 + TBQ, a.Lq) + a.q_pos_offset);   // keys beyond the tile's last query
+  if (a.causal) k_end = min(k_end, min(q0 + TBQ, Lq) + a.q_pos_offset);   // keys beyond the tile's last query
   const int n_tiles = (k_end + TBK - 1) / TBK;
 
-  load_tile(sQ, Q + static_cast<long long>(q0) * a.q_ts, a.q_ts, a.Lq - q0);
+  load_tile(sQ, Q + static_cast<long long>(q0) * a.q_ts, a.q_ts, Lq - q0);
   if (n_tiles > 0) {
     load_tile(sK, K, a.k_ts, Lk);
     load_tile(sV, V, a.v_ts, Lk);
@@ -391,11 +397,11 @@ __global__ void __launch_bounds__(TNT) attention_mma_kernel(AttnArgs a) {
   }
   if (n_tiles == 0) cp_wait<0>();
 
-  bf16* __restrict__ O = static_cast<bf16*>(a.o) + b * a.o_bs + h * a.o_hs;
+  bf16* __restrict__ O = static_cast<bf16*>(a.o) + (a.q_offset ? qtok0 * a.o_ts : b * a.o_bs) + h * a.o_hs;
 #pragma unroll
   for (int rr = 0; rr < 2; ++rr) {
     const int qi = qi0 + rr * 8;
-    if (qi >= a.Lq) continue;
+    if (qi >= Lq) continue;
     const float inv = l_[rr] > 0.f ? 1.f / l_[rr] : 0.f;
     bf16* dst = O + static_cast<long long>(qi) * a.o_ts + 2 * t;
 #pragma unroll

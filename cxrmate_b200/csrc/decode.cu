@@ -84,6 +84,64 @@ __global__ void rollout_init_kernel(RolloutState st, RolloutParams p, const int*
 }
 
 // =============================================================================
+// packed prompt pass (kernels.h PromptPack)
+// =============================================================================
+__global__ void pack_prompt_count_kernel(PromptPack pk, const uint8_t* __restrict__ pre_valid, int R, int P) {
+  __shared__ int s_lq[1024];
+  const int r = threadIdx.x;
+  int nv = 0, extra = 0;
+  if (r < R) {
+    const uint8_t* v = pre_valid + static_cast<long long>(r) * P;
+    for (int c = 0; c < P; ++c) nv += v[c] ? 1 : 0;
+    extra = v[P - 1] ? 0 : 1;          // the last column is masked: it still is the query of the first new token
+    pk.row_lk[r] = nv;
+    pk.row_lq[r] = nv + extra;
+    s_lq[r] = nv + extra;
+  }
+  __syncthreads();
+  if (r == 0) {
+    int off = 0;
+    for (int i = 0; i < R; ++i) {
+      pk.row_off[i] = off;
+      off += s_lq[i];
+      pk.last_idx[i] = off - 1;
+    }
+    *pk.total = off;
+  }
+}
+// one warp per row: ballot compaction of the visible columns, 32 columns per round
+__global__ void __launch_bounds__(32) pack_prompt_fill_kernel(PromptPack pk, const int* __restrict__ pre_ids,
+                                                              const int* __restrict__ pre_types, const int* __restrict__ pre_pos,
+                                                              const uint8_t* __restrict__ pre_valid, int P) {
+  const int r = blockIdx.x, lane = threadIdx.x;
+  const long long base = static_cast<long long>(r) * P;
+  int out = pk.row_off[r];
+  for (int c0 = 0; c0 < P; c0 += 32) {
+    const int c = c0 + lane;
+    const bool vis = c < P && pre_valid[base + c] != 0;
+    const unsigned m = __ballot_sync(kFull, vis);
+    if (vis) {
+      const int i = out + __popc(m & ((1u << lane) - 1u));
+      pk.ids[i] = pre_ids[base + c];
+      pk.types[i] = pre_types[base + c];
+      pk.pos[i] = pre_pos[base + c];
+      pk.tok_row[i] = r;
+      pk.tok_slot[i] = pre_pos[base + c];      // compact cache: a visible token sits at slot cumsum(mask) - 1 = its position
+      pk.tok_cache[i] = 1;
+    }
+    out += __popc(m);
+  }
+  if (lane == 0 && pre_valid[base + P - 1] == 0) {
+    pk.ids[out] = pre_ids[base + P - 1];
+    pk.types[out] = pre_types[base + P - 1];
+    pk.pos[out] = pre_pos[base + P - 1];
+    pk.tok_row[out] = r;
+    pk.tok_slot[out] = 0;
+    pk.tok_cache[out] = 0;
+  }
+}
+
+// =============================================================================
 // sampling head
 // =============================================================================
 constexpr int SNT = 512;
@@ -477,6 +535,15 @@ void rollout_init(const RolloutState& st, const RolloutParams& p, const int* pro
                   int* pre_pos, uint8_t* pre_valid, cudaStream_t stream) {
   rollout_init_kernel<<<ceil_div(p.R, 64), 64, 0, stream>>>(st, p, prompt_ids, pre_ids, pre_types, pre_pos, pre_valid);
   check_launch("rollout_init");
+}
+
+void pack_prompt(const PromptPack& pk, const int* pre_ids, const int* pre_types, const int* pre_pos, const uint8_t* pre_valid,
+                 int R, int P, cudaStream_t stream) {
+  CXRM_CHECK(R >= 1 && R <= 1024 && P >= 1, "pack_prompt shape");
+  pack_prompt_count_kernel<<<1, 1024, 0, stream>>>(pk, pre_valid, R, P);
+  check_launch("pack_prompt_count");
+  pack_prompt_fill_kernel<<<R, 32, 0, stream>>>(pk, pre_ids, pre_types, pre_pos, pre_valid, P);
+  check_launch("pack_prompt_fill");
 }
 
 void sample_step(const RolloutState& st, const RolloutParams& p, const float* logits, int ldl, const float* exp_noise,

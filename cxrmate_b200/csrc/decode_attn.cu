@@ -970,7 +970,7 @@ __global__ void __launch_bounds__(PNT, 2) decode_self_persist_kernel(const __gri
 template <typename T>
 __global__ void prefill_store_kv_kernel(const T* __restrict__ qkv, T* __restrict__ kcache, T* __restrict__ vcache,
                                         const int* __restrict__ slot, const uint8_t* __restrict__ valid, int R, int P,
-                                        int Lmax) {
+                                        int Lmax, const int* __restrict__ row_of) {
   constexpr int VN = Vec16<T>::N;
   const int cv = H / VN;
   const long long total = static_cast<long long>(R) * P * cv * 2;
@@ -980,13 +980,12 @@ __global__ void prefill_store_kv_kernel(const T* __restrict__ qkv, T* __restrict
     long long t = i / cv;
     const int which = static_cast<int>(t % 2);
     t /= 2;
-    const int pcol = static_cast<int>(t % P);
-    const long long r = t / P;
-    if (!valid[r * P + pcol]) continue;
+    if (!valid[t]) continue;
+    const long long r = row_of ? row_of[t] : t / P;       // (token index t = r * P + column in the padded layout)
     Vec16<T> v;
-    v.load(qkv + (r * P + pcol) * 3 * H + (1 + which) * H + c);
+    v.load(qkv + t * 3 * H + (1 + which) * H + c);
     const int h = c / HD, d = c % HD;
-    v.store((which ? vcache : kcache) + ((r * NH + h) * Lmax + slot[r * P + pcol]) * HD + d);
+    v.store((which ? vcache : kcache) + ((r * NH + h) * Lmax + slot[t]) * HD + d);
   }
 }
 
@@ -1102,12 +1101,12 @@ void decode_cross_attention(const T* q, int ldq, const T* kc, const T* vc, long 
 
 template <typename T>
 void prefill_store_kv(const T* qkv, T* kcache, T* vcache, const int* slot, const uint8_t* valid, int R, int P, int Lmax,
-                      cudaStream_t stream) {
+                      cudaStream_t stream, const int* row_of) {
   const long long total = static_cast<long long>(R) * P * (H / Vec16<T>::N) * 2;
   if (total <= 0) return;
   long long grid = ceil_div_ll(total, 256);
   if (grid > 148 * 32) grid = 148 * 32;
-  prefill_store_kv_kernel<T><<<static_cast<unsigned>(grid), 256, 0, stream>>>(qkv, kcache, vcache, slot, valid, R, P, Lmax);
+  prefill_store_kv_kernel<T><<<static_cast<unsigned>(grid), 256, 0, stream>>>(qkv, kcache, vcache, slot, valid, R, P, Lmax, row_of);
   check_launch("prefill_store_kv");
 }
 
@@ -1117,7 +1116,7 @@ void prefill_store_kv(const T* qkv, T* kcache, T* vcache, const int* slot, const
   template void decode_cross_attention<T>(const T*, int, const T*, const T*, long long, T*, const CrossUnits&,        \
                                           const RolloutState&, int, int, float*, unsigned*, const AttnMaps*, int,     \
                                           cudaStream_t);                                                              \
-  template void prefill_store_kv<T>(const T*, T*, T*, const int*, const uint8_t*, int, int, int, cudaStream_t);
+  template void prefill_store_kv<T>(const T*, T*, T*, const int*, const uint8_t*, int, int, int, cudaStream_t, const int*);
 INST(float)
 INST(bf16)
 #undef INST

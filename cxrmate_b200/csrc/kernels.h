@@ -175,6 +175,10 @@ struct AttnArgs {
   int kv_batch_mod;              // > 0: kv batch = q batch % kv_batch_mod
   const int* kv_offset;          // nullable: per kv-batch token offset added to the key index (ragged caches)
   float scale;
+  // packed (ragged) queries, nullable: batch b's queries are tokens q_offset[b] .. + Lq_per_batch[b] of q / o (q_bs / o_bs
+  // unused); Lq is then only the upper bound that sizes the grid
+  const int* q_offset;
+  const int* Lq_per_batch;
 };
 template <typename T> void attention_simt(const AttnArgs& a, cudaStream_t stream);
 // bf16 tensor-core (mma.sync m16n8k16) flash attention with the same contract; returns 0 from _supported when usable
@@ -318,9 +322,25 @@ void decode_cross_attention(const T* q, int ldq, const T* kc, const T* vc, long 
 
 // qkv [R*P, 3*768] -> head-major kcache/vcache [R][12][Lmax][64]: token (r, c) goes to slot[r*P + c] when valid[r*P + c]
 // (masked prompt tokens are not cached)
+// row_of (nullable): token t belongs to row row_of[t] instead of t / P (packed prompts: R = 1, P = tokens)
 template <typename T>
 void prefill_store_kv(const T* qkv, T* kcache, T* vcache, const int* slot, const uint8_t* valid, int R, int P, int Lmax,
-                      cudaStream_t stream);
+                      cudaStream_t stream, const int* row_of = nullptr);
+
+// Packed prompt pass: the visible tokens of every row, in order, plus - where the last prompt column is masked - that
+// column as a query-only token (the reference takes the first new token's logits from the LAST column of the padded
+// prompt, modelling_longitudinal.py:251-295: a PAD-token query at the position of the last visible token that attends
+// the visible keys only).  pack_prompt_count: per-row counts, offsets and the total (one block); pack_prompt_fill: the
+// packed ids / types / positions and, per packed token, its row, cache slot and whether it is cached.
+struct PromptPack {
+  int* ids; int* types; int* pos;      // [<= R * P] packed decoder inputs
+  int* tok_row; int* tok_slot;         // [<= R * P] row and self-attention cache slot of each packed token
+  uint8_t* tok_cache;                  // [<= R * P] 1: a visible token (cached), 0: the query-only last column
+  int* row_off; int* row_lq; int* row_lk; int* last_idx;   // [R] offset, queries, keys, packed index of the row's last query
+  int* total;                          // scalar: packed tokens
+};
+void pack_prompt(const PromptPack& pk, const int* pre_ids, const int* pre_types, const int* pre_pos, const uint8_t* pre_valid,
+                 int R, int P, cudaStream_t stream);
 
 // issue the prefetch described by p (plain launch: belongs on a side stream / parallel graph branch)
 void l2_prefetch(const L2Prefetch& p, cudaStream_t stream);
