@@ -77,9 +77,27 @@ __global__ void compact_rows_kernel(const uint8_t* mask, const int* off, int* id
   for (int j = 0; j < S; ++j)
     if (!mask || mask[static_cast<long long>(b) * S + j]) idx[k++] = b * S + j;
 }
-__global__ void iota_pos_kernel(int* pos, int n, int L) {
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < static_cast<long long>(n) * L) pos[i] = static_cast<int>(i % L);
+// Packed (variable-length) reward batch: offsets of the sequences and the packed token count (one block) ...
+__global__ void seq_offsets_kernel(const int* __restrict__ lens, int n, int L, int* __restrict__ off, int* __restrict__ total) {
+  if (threadIdx.x == 0) {
+    int o = 0;
+    for (int i = 0; i < n; ++i) {
+      off[i] = o;
+      o += max(0, min(lens[i], L));
+    }
+    *total = o;
+  }
+}
+// ... and the packed ids / positions (one warp per sequence)
+__global__ void __launch_bounds__(32) seq_pack_kernel(const int* __restrict__ ids, const int* __restrict__ lens,
+                                                      const int* __restrict__ off, int L, int* __restrict__ pk_ids,
+                                                      int* __restrict__ pk_pos, int* __restrict__ len_clamped) {
+  const int i = blockIdx.x, len = max(0, min(lens[i], L));
+  for (int j = threadIdx.x; j < len; j += 32) {
+    pk_ids[off[i] + j] = ids[static_cast<long long>(i) * L + j];
+    pk_pos[off[i] + j] = j;
+  }
+  if (threadIdx.x == 0) len_clamped[i] = len;
 }
 
 // Device-side id bridge standing in for split_and_decode_sections + re-tokenisation
@@ -1951,23 +1969,39 @@ class Engine : public EngineBase {
                    static_cast<long long>(std::max(cfg.rwd_max_seqs, 1)) * cfg.rwd_max_len, "reward batch too large");
     phase = "rwd";
     arena.reset();
-    const long long M = static_cast<long long>(n) * L;
+    // Variable-length batch: the sequences are PACKED (tokens beyond a sequence's length are never computed: labels
+    // are 32..256 tokens against 257-token generated reports, real reports are shorter still); attention runs per
+    // sequence over its own tokens through the packed-query / ragged-key arguments, so no padding mask is needed.
+    // One small device -> host read (the packed token count) sizes the launches.
+    const long long Mmax = static_cast<long long>(n) * L;
+    int* off = arena.get<int>(n);
+    int* lenc = arena.get<int>(n);
+    int* total_d = arena.get<int>(1);
+    int* pk_ids = arena.get<int>(Mmax);
+    int* pos = arena.get<int>(Mmax);
+    seq_offsets_kernel<<<1, 32, 0, s>>>(lens, n, L, off, total_d);
+    check_launch("seq_offsets");
+    seq_pack_kernel<<<n, 32, 0, s>>>(ids, lens, off, L, pk_ids, pos, lenc);
+    check_launch("seq_pack");
+    int total = 0;
+    CXRM_CUDA_CHECK(cudaMemcpyAsync(&total, total_d, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CXRM_CUDA_CHECK(cudaStreamSynchronize(s));
+    CXRM_CHECK(total >= 1 && total <= Mmax, "reward batch: every sequence is empty");
+    const long long M = total;
     DecBufs b = dec_bufs(M);
-    int* pos = arena.get<int>(M);
-    iota_pos_kernel<<<static_cast<unsigned>(ceil_div_ll(M, 256)), 256, 0, s>>>(pos, n, L);
-    check_launch("iota_pos");
-    PF("embed_ln", s, [&] { embed_ln<T>(ids, nullptr, pos, rwd.word, rwd.type, rwd.pos, rwd.emb_ln.g, rwd.emb_ln.b, b.x, M, DH, LN_EPS_BERT, s); });
+    PF("embed_ln", s, [&] { embed_ln<T>(pk_ids, nullptr, pos, rwd.word, rwd.type, rwd.pos, rwd.emb_ln.g, rwd.emb_ln.b, b.x, M, DH, LN_EPS_BERT, s); });
     for (int l = 0; l < cfg.rwd_layers; ++l) {
       const BertLayerW& w = rwd.layers[l];
       gemm(b.x, DH, w.qkv, b.qkv, 3 * DH, M, ACT_NONE, nullptr, 0, false, nullptr, s);
       AttnArgs a{};
       a.q = b.qkv; a.k = b.qkv + DH; a.v = b.qkv + 2 * DH; a.o = b.ctx;
-      a.q_bs = static_cast<long long>(L) * 3 * DH; a.q_hs = 64; a.q_ts = 3 * DH;
-      a.k_bs = a.q_bs; a.k_hs = 64; a.k_ts = 3 * DH;
-      a.v_bs = a.q_bs; a.v_hs = 64; a.v_ts = 3 * DH;
-      a.o_bs = static_cast<long long>(L) * DH; a.o_hs = 64; a.o_ts = DH;
+      a.q_bs = 0; a.q_hs = 64; a.q_ts = 3 * DH;
+      a.k_bs = 0; a.k_hs = 64; a.k_ts = 3 * DH;
+      a.v_bs = 0; a.v_hs = 64; a.v_ts = 3 * DH;
+      a.o_bs = 0; a.o_hs = 64; a.o_ts = DH;
       a.batch = n; a.heads = NHEAD; a.Lq = L; a.Lk = L;
-      a.Lk_per_batch = lens;      // attention_mask from padding='longest' == (j < len)
+      a.q_offset = off; a.Lq_per_batch = lenc;      // attention_mask from padding='longest' == (j < len)
+      a.kv_offset = off; a.Lk_per_batch = lenc;
       a.scale = 0.125f;
       PF("attn", s, [&] { attention(a, s); });
       gemm(b.ctx, DH, w.o, b.x1, DH, M, ACT_NONE, b.x, DH, false, nullptr, s);
@@ -1976,13 +2010,13 @@ class Engine : public EngineBase {
       gemm(b.hid, DFF, w.fc2, b.x, DH, M, ACT_NONE, b.x1, DH, false, nullptr, s);
       PF("layernorm", s, [&] { layernorm<T>(b.x, DH, b.x, DH, w.ln3.g, w.ln3.b, M, DH, LN_EPS_BERT, s); });
     }
-    // [CLS] rows (token 0 of every sequence: row stride L*768) -> 768 -> 128 GELU -> LN -> 128
+    // [CLS] rows (the first packed token of every sequence) -> 768 -> 128 GELU -> LN -> 128
+    T* cls = b.qkv;
+    PF("gather", s, [&] { gather_rows<T>(b.x, off, cls, n, DH, s); });
     T* h1 = b.ctx;
-    T* h2 = b.x1;
-    gemm(b.x, L * DH, rp1, h1, 128, n, ACT_GELU, nullptr, 0, false, nullptr, s);
+    gemm(cls, DH, rp1, h1, 128, n, ACT_GELU, nullptr, 0, false, nullptr, s);
     PF("layernorm", s, [&] { layernorm<T>(h1, 128, h1, 128, rp_ln.g, rp_ln.b, n, 128, LN_EPS_BERT, s); });
     gemm(h1, 128, rp2, emb_out, 128, n, ACT_NONE, nullptr, 0, true, nullptr, s);
-    (void)h2;
   }
 
   // =========================================================================== host-buffer SCST step
