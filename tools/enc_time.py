@@ -21,7 +21,7 @@ def main():
     counts = bench.global_image_counts(a.studies, a.images)
     px = torch.stack([bench.make_study(a, g, counts[g])[0] for g in range(a.studies)]).cuda()
     e = Engine(dtype="bf16", max_studies=a.studies, max_images=a.images, max_prompt=a.prompt, max_new_tokens=a.tokens, rwd_layers=0,
-               enc_chunk=int(os.environ.get("ENC_CHUNK", "32")))
+               enc_chunk=int(os.environ.get("ENC_CHUNK", "64")))
     e.load_state_dict(W.make_cxrmate_weights(seed=0))
     e.finalize()
     for _ in range(3):
