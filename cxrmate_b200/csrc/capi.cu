@@ -281,12 +281,7 @@ int cxrm_test_gemm_ln(const void* A, const void* W, void* out, int M, int N, int
     g.bias = nullptr; g.act = 0; g.residual = nullptr; g.ldr = 0; g.out_f32 = 0; g.skip_flag = nullptr; g.c_head_stride = 0; g.trace = nullptr;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (gemm_skinny_supported(g) != 0 || N > 1024 || N % 4 != 0) return CXRM_ERR_INVALID;
-    if (partial_ws == nullptr) {   // cluster kernel: GEMM + LayerNorm fused
-      g.C = out; g.ldc = N; g.bias = bias; g.act = act; g.residual = residual; g.ldr = N;
-      if (gemm_ln_cluster_supported(g) != 0) return CXRM_ERR_INVALID;
-      gemm_ln_cluster(g, gamma, beta, eps, s);
-      return CXRM_OK;
-    }
+    if (partial_ws == nullptr) return CXRM_ERR_INVALID;
     int nsplit = 0;
     gemm_tcgen05_skinny(g, partial_ws, &nsplit, s);
     splitk_ln(partial_ws, nsplit, M, N, bias, act, residual, N, gamma, beta, eps, out, N, nullptr, s);

@@ -604,53 +604,6 @@ void sample_rows_test(const float* logits, int R, int V, int top_k, float temper
   CXRM_CUDA_CHECK(cudaFreeAsync(base, stream));
 }
 
-// Pull the described segments into L2 without keeping anything in the SM.  MODE 0: one prefetch.global.L2 hint per
-// 128-byte line; MODE 1: cp.async.bulk.prefetch.L2 (TMA prefetch engine), one 4 KiB request per thread-iteration;
-// MODE 2: real 16-byte loads (L1 no-allocate) whose results are discarded.  Runs on a parallel branch of the
-// decode-step graph (engine.cu fork_prefetch), so its duration is off the critical path.
-template <int MODE>
-static __global__ void __launch_bounds__(256) l2_prefetch_kernel(L2Prefetch p) {
-  const int nb = p.base[1] ? 2 : 1;
-  long long bytes = p.dyn ? static_cast<long long>(*p.dyn + p.dyn_add) * p.dyn_unit : p.seg_bytes;
-  bytes = bytes < p.seg_stride ? bytes : p.seg_stride;
-  constexpr int UNIT = MODE == 0 ? 128 : MODE == 1 ? 4096 : 16;
-  const int units = static_cast<int>((bytes + UNIT - 1) / UNIT);
-  if (units <= 0) return;
-  const long long total = static_cast<long long>(units) * p.n_seg * nb;
-  unsigned sink = 0;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int seg = static_cast<int>(i / units), u = static_cast<int>(i - static_cast<long long>(seg) * units);
-    const char* a = p.base[seg / p.n_seg] + (seg % p.n_seg) * p.seg_stride + static_cast<long long>(u) * UNIT;
-    if (MODE == 0) {
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
-    } else if (MODE == 1) {
-      const unsigned sz = static_cast<unsigned>(min(static_cast<long long>(UNIT), ((bytes - static_cast<long long>(u) * UNIT) + 15) & ~15LL));
-      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(sz) : "memory");
-    } else {
-      unsigned x, y, z, w;
-      asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x), "=r"(y), "=r"(z), "=r"(w) : "l"(a));
-      sink ^= x ^ y ^ z ^ w;
-    }
-  }
-  if (MODE == 2 && sink == 0x9e3779b9u && p.n_seg < 0) *const_cast<char*>(p.base[0]) = 0;   // keeps the loads alive
-}
-
-void l2_prefetch(const L2Prefetch& p, cudaStream_t stream) {
-  if (p.n_seg <= 0) return;
-  static int ctas = 0, mode = 0;
-  if (ctas == 0) {
-    const char* e = std::getenv("CXRM_PF_CTAS");
-    ctas = e ? std::max(1, std::atoi(e)) : 148;
-    const char* m = std::getenv("CXRM_PF_MODE");
-    mode = m ? std::atoi(m) : 1;
-  }
-  if (mode == 0) l2_prefetch_kernel<0><<<ctas, 256, 0, stream>>>(p);
-  else if (mode == 1) l2_prefetch_kernel<1><<<ctas, 256, 0, stream>>>(p);
-  else l2_prefetch_kernel<2><<<ctas, 256, 0, stream>>>(p);
-  check_launch("l2_prefetch");
-}
-
 template <typename T>
 void take_last_token(const T* x, T* out, int R, int P, int C, cudaStream_t stream) {
   const long long total = static_cast<long long>(R) * C;

@@ -157,9 +157,6 @@ class Engine : public EngineBase {
     if (graph_exec) cudaGraphExecDestroy(graph_exec);
     if (side_stream) cudaStreamDestroy(side_stream);
     if (pf_stream) cudaStreamDestroy(pf_stream);
-    for (cudaEvent_t e : ev_pf)
-      if (e) cudaEventDestroy(e);
-    if (ev_pf_join) cudaEventDestroy(ev_pf_join);
     for (cudaEvent_t e : ev_chunk) cudaEventDestroy(e);
     for (cudaEvent_t e : phase_ev)
       if (e) cudaEventDestroy(e);
@@ -224,7 +221,7 @@ class Engine : public EngineBase {
     CXRM_CUDA_CHECK(cudaMemcpyAsync(d, t.data, n * sizeof(float), cudaMemcpyDeviceToDevice, 0));
     return d;
   }
-  struct Lin { T* w = nullptr; float* b = nullptr; int n_out = 0, n_in = 0; float* s = nullptr; /* LN-folded: column sums; b = c */ };
+  struct Lin { T* w = nullptr; float* b = nullptr; int n_out = 0, n_in = 0; };
   struct LNp { float* g = nullptr; float* b = nullptr; };
   LNp lnp(const std::string& prefix, int n) { return LNp{vecf(prefix + ".weight", n), vecf(prefix + ".bias", n)}; }
   Lin lin(const std::string& prefix, int n_out, int n_in, bool bias = true) {
@@ -260,40 +257,9 @@ class Engine : public EngineBase {
     return L;
   }
 
-  // ---- LN-folded weights of the decode step (bf16 tensor-core mode only; kernels.h LnFold) ----
-  // W' = W.diag(gamma) in bf16, s = row sums of W', c = bias + W.beta; `parts` stacks several [n_each, n_in]
-  // matrices (q|k|v), each with its optional LoRA update merged first.
-  Lin lin_fold(const std::vector<std::string>& parts, int n_each, int n_in, const std::string& ln_prefix) {
-    Lin L;
-    if constexpr (std::is_same<T, bf16>::value) {
-      const float* gamma = need(ln_prefix + ".weight", {n_in}).data;
-      const float* beta = need(ln_prefix + ".bias", {n_in}).data;
-      L.n_out = n_each * static_cast<int>(parts.size());
-      L.n_in = n_in;
-      L.w = dalloc<T>(static_cast<long long>(L.n_out) * n_in);
-      L.b = dalloc<float>(L.n_out);
-      L.s = dalloc<float>(L.n_out);
-      float* tmp = nullptr;
-      CXRM_CUDA_CHECK(cudaMalloc(&tmp, static_cast<size_t>(n_each) * n_in * sizeof(float)));
-      for (size_t i = 0; i < parts.size(); ++i) {
-        const std::string& p = parts[i];
-        const RawTensor& w = need(p + ".weight", {n_each, n_in});
-        const float* bias = has(p + ".bias") ? need(p + ".bias", {n_each}).data : nullptr;
-        CXRM_CUDA_CHECK(cudaMemcpyAsync(tmp, w.data, static_cast<size_t>(n_each) * n_in * sizeof(float), cudaMemcpyDeviceToDevice, 0));
-        merge_lora(p, tmp, n_each, n_in);
-        fold_ln_weights(tmp, n_each, n_in, gamma, beta, bias, L.w + static_cast<long long>(i) * n_each * n_in,
-                        L.s + i * n_each, L.b + i * n_each, 0);
-      }
-      CXRM_CUDA_CHECK(cudaStreamSynchronize(0));
-      cudaFree(tmp);
-    }
-    return L;
-  }
-
   struct CvtLayerW { LNp ln1, ln2; float* dw; float* bn_scale; float* bn_shift; Lin q, k, v, o, fc1, fc2; };
   struct CvtStageW { Lin emb; LNp emb_ln; std::vector<CvtLayerW> layers; };
-  struct BertLayerW { Lin qkv, o; LNp ln1; Lin cq, ckv, co; LNp ln2; Lin fc1, fc2; LNp ln3;
-                      Lin cq_f, fc1_f; /* decode step, bf16: consumers of a folded LayerNorm (kernels.h LnFold) */ };
+  struct BertLayerW { Lin qkv, o; LNp ln1; Lin cq, ckv, co; LNp ln2; Lin fc1, fc2; LNp ln3; };
   struct BertW { T* word = nullptr; T* pos = nullptr; T* type = nullptr; LNp emb_ln; std::vector<BertLayerW> layers; int vocab = 0; };
 
   T* table(const std::string& name, int rows, int cols) {
@@ -391,16 +357,6 @@ class Engine : public EngineBase {
     dec_lm.b = dec_vocab_bias;
     dec_lm.n_out = cfg.vocab;
     dec_lm.n_in = DH;
-    if (std::is_same<T, bf16>::value && cfg.use_tensor_cores) {
-      for (int l = 0; l < cfg.dec_layers; ++l) {
-        const std::string p = "decoder.bert.encoder.layer." + std::to_string(l) + ".";
-        BertLayerW& w = dec.layers[l];
-        w.cq_f = lin_fold({p + "crossattention.self.query"}, DH, DH, p + "attention.output.LayerNorm");
-        w.fc1_f = lin_fold({p + "intermediate.dense"}, DFF, DH, p + "crossattention.output.LayerNorm");
-      }
-      dec_stats = dalloc<float2>(2LL * kStatTiles * 64);
-      CXRM_CUDA_CHECK(cudaMemset(dec_stats, 0, sizeof(float2) * 2 * kStatTiles * 64));
-    }
     // ---- training: the LoRA factors themselves (the merged weights above serve the forward pass) ----
     lora_r.assign(cfg.dec_layers, 0);
     lora_A.assign(cfg.dec_layers, {nullptr, nullptr});
@@ -561,8 +517,6 @@ class Engine : public EngineBase {
     CXRM_CUDA_CHECK(cudaEventCreateWithFlags(&ev_a, cudaEventDisableTiming));
     CXRM_CUDA_CHECK(cudaEventCreateWithFlags(&ev_b, cudaEventDisableTiming));
     CXRM_CUDA_CHECK(cudaStreamCreateWithFlags(&pf_stream, cudaStreamNonBlocking));
-    for (int i = 0; i < kMaxForks; ++i) CXRM_CUDA_CHECK(cudaEventCreateWithFlags(&ev_pf[i], cudaEventDisableTiming));
-    CXRM_CUDA_CHECK(cudaEventCreateWithFlags(&ev_pf_join, cudaEventDisableTiming));
     std::memset(&graph_key, 0, sizeof(graph_key));
   }
   void setup_attn_maps();
@@ -643,11 +597,6 @@ class Engine : public EngineBase {
   void gemm_ln(const T* A, int lda, const Lin& L, int act, const T* residual, int ldr, const LNp& ln, T* out, int ldo,
                long long M, const int* skip, cudaStream_t s) {
     if (use_skinny(M, L)) {
-      GemmArgs gc = make_args(A, lda, L, out, ldo, M, act, residual, ldr, false, skip);
-      if (!no_cluster_ln() && gemm_ln_cluster_supported(gc) == 0) {
-        PF("gemm_ln", s, [&] { gemm_ln_cluster(gc, ln.g, ln.b, LN_EPS_BERT, s); });
-        return;
-      }
       GemmArgs g = make_args(A, lda, L, nullptr, 0, M, ACT_NONE, nullptr, 0, false, skip);
       int nsplit = 0;
       PF("gemm", s, [&] { gemm_tcgen05_skinny(g, skinny_ws, &nsplit, s); });
@@ -659,67 +608,8 @@ class Engine : public EngineBase {
     gemm(A, lda, L, tmp, ldo, M, act, residual, ldr, false, skip, s);
     PF("layernorm", s, [&] { layernorm<T>(tmp, ldo, out, ldo, ln.g, ln.b, M, L.n_out, LN_EPS_BERT, s); });
   }
-  // ---- software L2 prefetch of the decode step: EXPERIMENT, off by default (fractions via CXRM_PF_CROSS /
-  // CXRM_PF_SELF).  Measured on B200 (profiles/l2_prefetch_r01.md): the attention kernels run no faster from an
-  // L2-resident cache - L2 delivers ~6.2 TB/s (the LTS cap), the same as streaming HBM - and the extra branch costs
-  // 2-8 % of the step, so the idle HBM time of the GEMM/LayerNorm chain cannot be bought back this way.
-  static float env_frac(const char* name, float dflt) {
-    const char* e = std::getenv(name);
-    return e ? std::min(1.0f, std::max(0.0f, static_cast<float>(std::atof(e)))) : dflt;
-  }
-  L2Prefetch pf_cross(int l) {
-    static const float frac = env_frac("CXRM_PF_CROSS", 0.0f);
-    if (sizeof(T) != 2 || frac <= 0.f) return L2Prefetch{};
-    const T* kvl = cross_kv + static_cast<long long>(l) * cross_layer_stride();
-    L2Prefetch p;
-    p.base[0] = reinterpret_cast<const char*>(kvl);
-    p.base[1] = reinterpret_cast<const char*>(kvl + NHEAD * cross_head_stride());
-    p.seg_stride = cross_head_stride() * static_cast<long long>(sizeof(T));
-    p.n_seg = NHEAD;
-    p.seg_bytes = static_cast<int>(static_cast<long long>(frac * kv_total) * 64 * sizeof(T));
-    return p;
-  }
-  L2Prefetch pf_self(int l, int R, int P, int extra) {
-    static const float frac = env_frac("CXRM_PF_SELF", 0.0f);
-    if (sizeof(T) != 2 || frac <= 0.f) return L2Prefetch{};
-    L2Prefetch p;
-    p.base[0] = reinterpret_cast<const char*>(self_k + l * self_layer_stride());
-    p.base[1] = reinterpret_cast<const char*>(self_v + l * self_layer_stride());
-    p.seg_stride = static_cast<long long>(Lmax) * 64 * sizeof(T);
-    p.n_seg = static_cast<int>(R * NHEAD * frac);
-    p.dyn = st.step;
-    p.dyn_add = P + extra;
-    p.dyn_unit = 64 * sizeof(T);
-    return p;
-  }
-  // Fork: the prefetch kernel depends on everything launched on `s` so far and runs on pf_stream beside the chain
-  // (a parallel branch of the captured step graph); decode_step joins the branch at the end of the step.
-  void fork_prefetch(const L2Prefetch& p, cudaStream_t s) {
-    if (p.n_seg <= 0) return;
-    if (profiling) {   // serialised on the main stream so that the event profiler sees its duration and its effect
-      PF("prefetch", s, [&] { l2_prefetch(p, s); });
-      return;
-    }
-    CXRM_CHECK(pf_forks < kMaxForks, "too many prefetch forks in one decode step");
-    cudaEvent_t ev = ev_pf[pf_forks++];
-    CXRM_CUDA_CHECK(cudaEventRecord(ev, s));
-    CXRM_CUDA_CHECK(cudaStreamWaitEvent(pf_stream, ev, 0));
-    l2_prefetch(p, pf_stream);
-  }
-  void join_prefetch(cudaStream_t s) {
-    if (pf_forks == 0) return;
-    CXRM_CUDA_CHECK(cudaEventRecord(ev_pf_join, pf_stream));
-    CXRM_CUDA_CHECK(cudaStreamWaitEvent(s, ev_pf_join, 0));
-    pf_forks = 0;
-  }
-  // The single-kernel cluster GEMM+LayerNorm (gemm_ln_cluster) is correct but MEASURED SLOWER than the split-K pair
-  // (17 us vs 8 us per call in tools/microbench_decode.py: the three cluster barriers dominate, ncu UCGABAR_WAIT), so
-  // it is opt-in for experiments only: CXRM_CLUSTER_LN=1.
-  static bool no_cluster_ln() {
-    static int v = -1;
-    if (v < 0) v = std::getenv("CXRM_CLUSTER_LN") ? 0 : 1;
-    return v != 0;
-  }
+  // (A single-kernel version of the pair - 8-CTA cluster, LayerNorm statistics through distributed shared memory - was
+  // built in round 1 and measured 17 us against 8 us per call: three cluster barriers; removed in round 2.)
   bool use_skinny(long long M, const Lin& L) const;
   bool chain_pdl() const;
   GemmArgs make_args(const T* A, int lda, const Lin& L, void* C, int ldc, long long M, int act, const T* residual,
@@ -1066,75 +956,6 @@ class Engine : public EngineBase {
     return static_cast<unsigned>(m);
   }
 
-  // ---- decode step with the attention-output and cross-attention-output LayerNorms folded into their neighbours
-  // (bf16 tensor-core mode; kernels.h LnFold): per layer QKV, self, O, cross-Q, cross, cross-O, FFN1, FFN2, LN = 9
-  // launches instead of 11.  The O / cross-O projections lose their split-K (the pre-LN sum must leave the GEMM
-  // complete), which K = 768 affords; FFN2 (K = 3072) keeps split-K + the fused reduce/LayerNorm kernel, whose
-  // residual LN2(x2_pre) is recomputed inside it.
-  // EXPERIMENT, off by default (CXRM_LNFOLD=1): parity-green but MEASURED 3.5 % SLOWER than the unfused chain on B200
-  // (213.6 vs 206.2 ms per step): the un-split O projections and the heavier epilogue code cost more than the 12
-  // LayerNorm launches they remove (profiles/decode_chain_r01.md).
-  bool use_lnfold() const {
-    static int v = -1;
-    if (v < 0) v = std::getenv("CXRM_LNFOLD") ? 1 : 0;
-    return v != 0 && std::is_same<T, bf16>::value && cfg.use_tensor_cores && dec_stats != nullptr && ablate_mask() == 0;
-  }
-  void decode_step_folded(DecBufs& b, T* head_tmp, const RolloutParams& rp, const float* noise, cudaStream_t s) {
-    phase = "decode";
-    const int R = rp.R, B = rp.B;
-    const int* skip = st.done;
-    PF("embed_ln", s, [&] { embed_ln<T>(st.cur_token, st.cur_type, st.cur_pos, dec.word, dec.type, dec.pos, dec.emb_ln.g, dec.emb_ln.b, b.x, R,
-                DH, LN_EPS_BERT, s); });
-    struct PdlScope {
-      explicit PdlScope(bool on) { g_pdl = on; }
-      ~PdlScope() { g_pdl = false; }
-    } pdl_scope(chain_pdl() && !profiling);
-    float2* st1 = dec_stats, *st2 = dec_stats + kStatTiles * 64;
-    T* xp1 = fold_buf[0]; T* xp2 = fold_buf[1];
-    constexpr int kCols = DH / kStatTiles;
-    // consumer: C = act(LN(A_pre).W^T + b) with the LayerNorm folded into L (L.s set)
-    auto consume = [&](const T* A, const Lin& L, const float2* stats, void* C, int ldc, int act) {
-      GemmArgs g = make_args(A, DH, L, C, ldc, R, act, nullptr, 0, false, skip);
-      FoldArgs f;
-      f.ln_in.stats = stats; f.ln_in.tiles = kStatTiles; f.ln_in.cols = kCols; f.ln_in.s = L.s; f.ln_in.eps = LN_EPS_BERT;
-      PF("gemm", s, [&] { gemm_tcgen05_skinny(g, nullptr, nullptr, s, &f); });
-    };
-    // producer: out_pre = A.W^T + b + residual (LayerNorm of res_pre recomputed when res_stats), + tile statistics
-    auto produce = [&](const T* A, const Lin& L, const T* res, const float2* res_stats, const LNp* res_ln, T* out,
-                       float2* stats_out) {
-      GemmArgs g = make_args(A, DH, L, out, DH, R, ACT_NONE, res, DH, false, skip);
-      FoldArgs f;
-      if (res_stats) {
-        f.ln_res.stats = res_stats; f.ln_res.tiles = kStatTiles; f.ln_res.cols = kCols;
-        f.ln_res.gamma = res_ln->g; f.ln_res.beta = res_ln->b; f.ln_res.eps = LN_EPS_BERT;
-      }
-      f.stats_out = stats_out;
-      CXRM_CHECK(gemm_skinny_tile_n(g, false) == kCols, "producer tile width != statistics tile width");
-      PF("gemm", s, [&] { gemm_tcgen05_skinny(g, nullptr, nullptr, s, &f); });
-    };
-    for (int l = 0; l < cfg.dec_layers; ++l) {
-      const BertLayerW& w = dec.layers[l];
-      gemm(b.x, DH, w.qkv, b.qkv, 3 * DH, R, ACT_NONE, nullptr, 0, false, skip, s);
-      PF("self_attn", s, [&] { decode_self_attention<T>(b.qkv, self_k + l * self_layer_stride(), self_v + l * self_layer_stride(), b.ctx, st, R,
-                               rp.P, Lmax, self_ws, self_tickets, attn_maps_ptr, l, s); });
-      produce(b.ctx, w.o, b.x, nullptr, nullptr, xp1, st1);                 // x1_pre = ctx.Wo + b + x
-      consume(xp1, w.cq_f, st1, b.qkv, DH, ACT_NONE);                       // q = LN1(x1_pre).Wq + b
-      const T* kvl = cross_kv + static_cast<long long>(l) * cross_layer_stride();
-      PF("cross_attn", s, [&] { decode_cross_attention<T>(b.qkv, DH, kvl, kvl + NHEAD * cross_head_stride(), cross_head_stride(), b.ctx,
-                                cross_units(), st, R, B, cross_ws, cross_tickets, attn_maps_ptr, l, s); });
-      produce(b.ctx, w.co, xp1, st1, &w.ln1, xp2, st2);                     // x2_pre = ctx.Wco + b + LN1(x1_pre)
-      consume(xp2, w.fc1_f, st2, b.hid, DFF, ACT_GELU);                     // hid = GELU(LN2(x2_pre).W1 + b)
-      // x = LN3(hid.W2 + b + LN2(x2_pre)): split-K partials + one reduce / residual-LayerNorm / LayerNorm kernel
-      GemmArgs g = make_args(b.hid, DFF, w.fc2, nullptr, 0, R, ACT_NONE, nullptr, 0, false, skip);
-      int nsplit = 0;
-      PF("gemm", s, [&] { gemm_tcgen05_skinny(g, skinny_ws, &nsplit, s); });
-      PF("layernorm", s, [&] { splitk_ln(skinny_ws, nsplit, R, DH, w.fc2.b, ACT_NONE, xp2, DH, w.ln3.g, w.ln3.b, LN_EPS_BERT, b.x, DH, skip, s,
-                                         w.ln2.g, w.ln2.b); });
-    }
-    lm_head(b.x, R, head_tmp, logits, cfg.vocab, skip, s);
-    PF("sample", s, [&] { sample_step(st, rp, logits, cfg.vocab, noise, s); });
-  }
-
   // ---- decode step with every (split-K GEMM, reduce + LayerNorm) pair as ONE persistent two-phase launch
   // (decode_chain.cu): the GEMM phase leaves fp32 partials, a grid barrier replaces the kernel boundary, the second
   // phase reduces + normalises one row per CTA.  The projections that feed an attention kernel (QKV, cross-Q) and FFN-up
@@ -1142,7 +963,7 @@ class Engine : public EngineBase {
   // A version that ran ALL GEMM / LayerNorm work between two attention kernels as one launch measured slower than the
   // PDL chain.  Per step 58 launches instead of 71.
   bool use_chain(int R) const {
-    return std::is_same<T, bf16>::value && cfg.use_tensor_cores && R <= 64 && ablate_mask() == 0 && !use_lnfold() &&
+    return std::is_same<T, bf16>::value && cfg.use_tensor_cores && R <= 64 && ablate_mask() == 0 &&
            decode_chain_available();
   }
   void ensure_chain(const DecBufs& b, T* head_tmp, int R) {
@@ -1238,10 +1059,6 @@ class Engine : public EngineBase {
       decode_step_chain(b, head_tmp, rp, noise, s);
       return;
     }
-    if (rp.beams == 0 && use_lnfold()) {
-      decode_step_folded(b, head_tmp, rp, noise, s);
-      return;
-    }
     phase = "decode";
     // beam search: every running beam is a virtual study (B == R) whose units point at its real study's encoder K/V
     const int R = rp.R, B = rp.B;
@@ -1275,7 +1092,6 @@ class Engine : public EngineBase {
       if (!no_self)
         PF("self_attn", s, [&] { decode_self_attention<T>(b.qkv, self_k + l * self_layer_stride(), self_v + l * self_layer_stride(), b.ctx, st, R,
                                  rp.P, Lmax, self_ws, self_tickets, attn_maps_ptr, l, s); });
-      fork_prefetch(pf_cross(l), s);   // this layer's encoder K/V stream into L2 beside O-proj / LN / cross-Q
       GL(b.ctx, DH, w.o, ACT_NONE, b.x, w.ln1, b.x1);
       G(b.x1, DH, w.cq, b.qkv, DH, ACT_NONE);
       const T* kvl = cross_kv + static_cast<long long>(l) * cross_layer_stride();
@@ -1283,8 +1099,6 @@ class Engine : public EngineBase {
       if (!no_cross)
         PF("cross_attn", s, [&] { decode_cross_attention<T>(b.qkv, DH, kvl, kvl + NHEAD * cross_head_stride(), cross_head_stride(), b.ctx,
                                   cunits, st, R, B, cross_ws, cross_tickets, attn_maps_ptr, l, s); });
-      // ... and the next self-attention's K/V (layer 0 of the NEXT step after the last layer) beside cross-out / FFN
-      fork_prefetch(l + 1 < cfg.dec_layers ? pf_self(l + 1, R, rp.P, 0) : pf_self(0, R, rp.P, 1), s);
       GL(b.ctx, DH, w.co, ACT_NONE, b.x1, w.ln2, b.x);
       G(b.x, DH, w.fc1, b.hid, DFF, ACT_GELU);
       GL(b.hid, DFF, w.fc2, ACT_NONE, b.x, w.ln3, b.x);
@@ -1307,7 +1121,6 @@ class Engine : public EngineBase {
     } else if (!no_sample) {
       PF("sample", s, [&] { sample_step(st, rp, logits, cfg.vocab, noise, s); });
     }
-    join_prefetch(s);
   }
 
   void rollout(const cxrm_rollout_args& a, cudaStream_t s_user) override {
@@ -1358,7 +1171,6 @@ class Engine : public EngineBase {
     DecBufs db = dec_bufs(R);     // first: keeps the decode-step pointers (and the captured graph) independent of P
     T* last = arena.get<T>(static_cast<long long>(R) * DH);
     T* head_tmp = arena.get<T>(static_cast<long long>(R) * DH);
-    for (T*& fb : fold_buf) fb = arena.get<T>(static_cast<long long>(R) * DH);
     // Prompt pass over the PACKED prompts: right-padded (masked) columns cost nothing - the benchmark's prompts fill 40 %
     // of their 64 x 247 grid - except each padded row's last column, which the reference still uses as the query of the
     // first new token (kernels.h PromptPack).  One small device -> host read (the packed token count) sizes the launches.
@@ -1564,7 +1376,6 @@ class Engine : public EngineBase {
     DecBufs db = dec_bufs(R);
     T* last = arena.get<T>(static_cast<long long>(R) * DH);
     T* head_tmp = arena.get<T>(static_cast<long long>(R) * DH);
-    for (T*& fb : fold_buf) fb = arena.get<T>(static_cast<long long>(R) * DH);
     DecBufs pb = dec_bufs(M);
     phase = "prefill";
     PF("embed_ln", s, [&] { embed_ln<T>(pre_ids, pre_types, pre_pos, dec.word, dec.type, dec.pos, dec.emb_ln.g, dec.emb_ln.b, pb.x, M, DH,
@@ -2189,9 +2000,6 @@ class Engine : public EngineBase {
   Lin head_proj;
   BertW dec, rwd;
   Lin dec_head_t, dec_lm, rp1, rp2;
-  static constexpr int kStatTiles = 48;           // 768 columns / 16-column producer tiles
-  float2* dec_stats = nullptr;                    // [2][64][kStatTiles]: tile statistics of x1_pre, x2_pre
-  T* fold_buf[2] = {nullptr, nullptr};            // pre-LN tensors x1, x2 (arena, set by rollout)
   LNp dec_head_ln, rp_ln;
   float* dec_vocab_bias = nullptr;
   // geometry
@@ -2214,11 +2022,7 @@ class Engine : public EngineBase {
   AttnMaps attn_maps{};
   const AttnMaps* attn_maps_ptr = nullptr;
   float* skinny_ws = nullptr;
-  static constexpr int kMaxForks = 16;
-  cudaStream_t pf_stream = nullptr;
-  cudaEvent_t ev_pf[kMaxForks] = {};
-  cudaEvent_t ev_pf_join = nullptr;
-  int pf_forks = 0;
+  cudaStream_t pf_stream = nullptr;       // copy stream of the host-buffer step (pixel chunks travel under the encoding)
   cudaEvent_t phase_ev[5] = {};           // scst step: start, encoded, cross K/V, rollout, reward
   cudaEvent_t prefill_done_ev = nullptr;
   bool prefill_recorded = false;

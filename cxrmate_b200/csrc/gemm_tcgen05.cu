@@ -895,19 +895,17 @@ __global__ void __launch_bounds__(W_THREADS, 1) gemm_tc_wres_kernel(const __grid
 constexpr int kSkMaxSplit = 8;   // split-K partials of the skinny GEMM (workspace: gemm_skinny_partial_floats)
 constexpr int SK_ROWS = 64, SK_A_BYTES = SK_ROWS * BK * 2, SK_MAX_STAGES = 16, SK_SLACK = A_BYTES - SK_A_BYTES;
 
-struct NoFold {};
 // EPI selects a LEAN epilogue.  The decode-step kernels are latency-bound launches whose code is fetched cold on
 // every launch (~330 KB of distinct kernels per step against a 128 KB instruction cache; ncu: `no_instruction` is the
 // third-largest stall of the skinny GEMM), so the chain runs specialisations that carry only the path they execute:
 //   0 general (every flag of GemmArgs; test hooks and odd shapes)   1 split-K fp32 partial tile
 //   2 bias -> bf16, 16-byte stores   3 bias -> GELU -> bf16   4 bias -> fp32 (LM head; last tile may be partial)
 // 1-3 need whole tiles (N % BN == 0) and 16-byte aligned rows, no residual, no head-major store.
-template <int BN, bool FOLD, int EPI = 0>
+template <int BN, int EPI = 0>
 __global__ void __launch_bounds__(NTHREADS) gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                   const __grid_constant__ CUtensorMap tmB, GemmArgs g,
                                                                   int stages, int kb_per_split,
-                                                                  float* __restrict__ partial, int vec_ok,
-                                                                  std::conditional_t<FOLD, FoldArgs, NoFold> fa) {
+                                                                  float* __restrict__ partial, int vec_ok) {
   constexpr int B_BYTES = BN * BK * 2;
   constexpr int STAGE_BYTES = SK_A_BYTES + B_BYTES;
   constexpr int TMEM_COLS = BN <= 32 ? 32 : 64;
@@ -1008,143 +1006,6 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_skinny_kernel(const __grid_c
       }
       __syncwarp();
     }
-  } else if (FOLD && warp % 4 < 2) {
-   if constexpr (FOLD) {
-    // ---- epilogue with folded LayerNorms (kernels.h LnFold): thread <-> output row ----------------
-    const int quarter = warp % 4;
-    constexpr int W = BN >= 32 ? 32 : BN;          // columns per TMEM load
-    float* cst = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full) + 512);   // [4][BN]: bias|c, s, gamma, beta
-    const int et = threadIdx.x - 128;              // 0..63
-    for (int j = et; j < BN; j += 64) {            // constants of the chain: staged before the dependency wait
-      const int n = n0 + j;
-      const bool ok = n < g.N;
-      cst[j] = (ok && g.bias) ? g.bias[n] : 0.f;
-      cst[BN + j] = (ok && fa.ln_in.stats) ? fa.ln_in.s[n] : 0.f;
-      cst[2 * BN + j] = (ok && fa.ln_res.stats) ? fa.ln_res.gamma[n] : 0.f;
-      cst[3 * BN + j] = (ok && fa.ln_res.stats) ? fa.ln_res.beta[n] : 0.f;
-    }
-    asm volatile("bar.sync 2, 64;" ::: "memory");
-    pdl_wait();
-    const bool skip = g.skip_flag && *g.skip_flag;
-    const int m = quarter * 32 + lane;
-    const bool row_ok = m < g.M && !skip;
-    // per-row (mean, rstd) from the producers' column-tile statistics: shifted sums, equal tile sizes
-    auto row_stats = [&](const float2* st, int tiles, int cols, float eps, float& mu, float& rstd) {
-      // the row's tile statistics are contiguous ([64][tiles]): every 16-byte load is issued before the first use
-      constexpr int MAXT = 48;
-      float4 pp[MAXT / 2];
-      const float4* src = reinterpret_cast<const float4*>(st + static_cast<long long>(m) * tiles);
-#pragma unroll
-      for (int t = 0; t < MAXT / 2; ++t)
-        if (2 * t < tiles) pp[t] = __ldcg(src + t);
-      const float2 p0 = make_float2(pp[0].x, pp[0].y);
-      float sd = 0.f, sd2 = 0.f, sm2 = 0.f;
-#pragma unroll
-      for (int t = 0; t < MAXT / 2; ++t)
-        if (2 * t < tiles) {
-          const float d0 = pp[t].x - p0.x, d1 = pp[t].z - p0.x;
-          sd += d0 + d1;
-          sd2 += d0 * d0 + d1 * d1;
-          sm2 += pp[t].y + pp[t].w;
-        }
-      const float md = sd / tiles;
-      mu = p0.x + md;
-      const float m2 = sm2 + cols * fmaxf(sd2 - tiles * md * md, 0.f);
-      rstd = rsqrtf(m2 / (tiles * cols) + eps);
-    };
-    float mu_in = 0.f, r_in = 1.f, mu_rs = 0.f, r_rs = 1.f;
-    if (fa.ln_in.stats) row_stats(fa.ln_in.stats, fa.ln_in.tiles, fa.ln_in.cols, fa.ln_in.eps, mu_in, r_in);
-    if (fa.ln_res.stats) row_stats(fa.ln_res.stats, fa.ln_res.tiles, fa.ln_res.cols, fa.ln_res.eps, mu_rs, r_rs);
-    const bf16* __restrict__ R = static_cast<const bf16*>(g.residual);
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
-    float ssum = 0.f, vals[BN >= 32 ? 32 : W];     // stats_out needs BN <= 32 (one chunk): checked by the launcher
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      if (n0 + c0 >= g.N || skip) break;
-      uint32_t r[32];
-      if (BN >= 32) {
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(c0), r);
-      } else {
-        tmem_ld16(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(c0), r);
-      }
-      if (!row_ok) continue;
-      const int nb = n0 + c0;
-      float v[W];
-#pragma unroll
-      for (int j = 0; j < W; ++j) {
-        float a = __uint_as_float(r[j]);
-        a = fa.ln_in.stats ? fmaf(r_in, a - mu_in * cst[BN + c0 + j], cst[c0 + j]) : a + cst[c0 + j];
-        v[j] = a;
-      }
-      if (g.act == ACT_GELU) {
-#pragma unroll
-        for (int j = 0; j < W; ++j) v[j] = gelu_fast(v[j]);
-      }
-      const bool full_w = nb + W <= g.N;
-      if (R) {
-        const bf16* rp = R + static_cast<long long>(m) * g.ldr + nb;
-#pragma unroll
-        for (int q = 0; q < W / 8; ++q) {
-          float rf[8];
-          if (full_w && vec_ok) {
-            Vec16<bf16> rv;
-            rv.load(rp + 8 * q);
-            rv.unpack(rf);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) rf[j] = (nb + 8 * q + j < g.N) ? to_f(rp[8 * q + j]) : 0.f;
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float x = rf[j];
-            if (fa.ln_res.stats)
-              x = to_f(from_f<bf16>((x - mu_rs) * r_rs * cst[2 * BN + c0 + 8 * q + j] + cst[3 * BN + c0 + 8 * q + j]));
-            v[8 * q + j] += x;
-          }
-        }
-      }
-      if (g.out_f32) {
-        float* cp = static_cast<float*>(g.C) + static_cast<long long>(m) * g.ldc + nb;
-        if (full_w && vec_ok) {
-#pragma unroll
-          for (int q = 0; q < W / 4; ++q)
-            *reinterpret_cast<float4*>(cp + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < W; ++j)
-            if (nb + j < g.N) cp[j] = v[j];
-        }
-      } else {
-        bf16* cp = static_cast<bf16*>(g.C) + static_cast<long long>(m) * g.ldc + nb;
-        if (full_w && vec_ok) {
-#pragma unroll
-          for (int q = 0; q < W / 8; ++q) {
-            Vec16<bf16> ov;
-            ov.pack(v + 8 * q);
-            ov.store(cp + 8 * q);
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < W; ++j)
-            if (nb + j < g.N) cp[j] = from_f<bf16>(v[j]);
-        }
-        if (fa.stats_out) {      // statistics of the values as stored (bf16-rounded), like a LayerNorm over the stored tensor
-#pragma unroll
-          for (int j = 0; j < W; ++j) {
-            vals[j] = to_f(from_f<bf16>(v[j]));
-            ssum += vals[j];
-          }
-        }
-      }
-    }
-    if (fa.stats_out && row_ok) {
-      const float mean = ssum / W;
-      float m2 = 0.f;
-#pragma unroll
-      for (int j = 0; j < W; ++j) m2 += (vals[j] - mean) * (vals[j] - mean);
-      fa.stats_out[static_cast<long long>(m) * gridDim.x + blockIdx.x] = make_float2(mean, m2);
-    }
-   }
   } else if (EPI != 0 && warp % 4 < 2) {
    if constexpr (EPI != 0) {
     // ---- lean epilogues (see the template comment) ------------------------------------------------
@@ -1274,216 +1135,6 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_skinny_kernel(const __grid_c
 }
 
 
-// =====================================================================================================
-// Decoder GEMM + LayerNorm in ONE kernel: out = LN(act(A.W^T + bias) + residual) for the 768-wide
-// projections that are followed by a post-LN (attention output, cross-attention output, FFN output, LM-head
-// transform).  A thread-block CLUSTER of 8 CTAs covers the 768 output columns (96 each, UMMA 128 x 96 x 16);
-// the row statistics LayerNorm needs are reduced across the cluster through distributed shared memory
-// (two rounds: mean, then variance about the mean - the same two-pass arithmetic as the reference), so the
-// pre-LN activations never leave registers.  Replaces the split-K GEMM + splitk_ln pair: one dependent launch
-// (~5 us in the step chain) less per LayerNorm, 19 per decode step.
-// =====================================================================================================
-constexpr int CL_SIZE = 8, CL_BN = 96, CL_N = CL_SIZE * CL_BN;
-constexpr int CL_B_BYTES = CL_BN * BK * 2;                 // 12 KiB
-constexpr int CL_STAGE = SK_A_BYTES + CL_B_BYTES;          // 20 KiB
-constexpr int CL_MAX_STAGES = 8;
-
-__device__ __forceinline__ void cluster_sync_all() {
-  __syncwarp();   // the single-lane producer / MMA roles reconverge before the warp-aligned barrier
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t cluster_rank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void st_cluster_f32(uint32_t local_addr, uint32_t peer, float v) {
-  uint32_t remote;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(peer));
-  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(v) : "memory");
-}
-
-__global__ void __cluster_dims__(CL_SIZE, 1, 1) __launch_bounds__(NTHREADS)
-    gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmArgs g,
-                           const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int stages) {
-  constexpr int TMEM_COLS = 128;
-  extern __shared__ uint8_t smem_raw[];
-  pdl_launch_dependents();
-
-  uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(tiles + stages * CL_STAGE + SK_SLACK);
-  uint64_t* empty = full + CL_MAX_STAGES;
-  uint64_t* tmem_full = empty + CL_MAX_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
-  float* xch = reinterpret_cast<float*>(tmem_slot + 2);          // [2 rounds][CL_SIZE][64 rows]
-
-  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const uint32_t rank = cluster_rank();
-  const int n0 = static_cast<int>(rank) * CL_BN;
-  const int nkb = (g.K + BK - 1) / BK;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < stages; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
-    }
-    mbar_init(tmem_full, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "n"(TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = __shfl_sync(kFull, *tmem_slot, 0);   // provably warp-uniform: no R2UR waterfall around each tcgen05.mma
-  const int npre = min(nkb, stages);
-  cluster_sync_all();   // every CTA of the cluster is running before anyone writes into a peer's shared memory
-
-  float v[CL_BN];       // this thread's row slice (epilogue warps only)
-  const int quarter = warp % 4;
-  const int m = quarter * 32 + lane;
-  const bool epi = warp >= 2 && quarter < 2;
-  const bool row_ok = epi && m < g.M;
-  bool skip = false;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      for (int i = 0; i < npre; ++i) {   // weights first: they do not depend on the previous kernel
-        mbar_expect_tx(&full[i], CL_STAGE);
-        tma_load_2d(tiles + i * CL_STAGE + SK_A_BYTES, &tmB, i * BK, n0, &full[i]);
-      }
-      pdl_wait();
-      skip = g.skip_flag && *g.skip_flag;
-      for (int i = 0; i < npre; ++i) tma_load_2d(tiles + i * CL_STAGE, &tmA, i * BK, 0, &full[i]);
-      if (!skip) {
-        for (int i = npre; i < nkb; ++i) {
-          const int s = i % stages;
-          mbar_wait(&empty[s], ((i / stages) & 1) ^ 1);
-          mbar_expect_tx(&full[s], CL_STAGE);
-          tma_load_2d(tiles + s * CL_STAGE, &tmA, i * BK, 0, &full[s]);
-          tma_load_2d(tiles + s * CL_STAGE + SK_A_BYTES, &tmB, i * BK, n0, &full[s]);
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      pdl_wait();
-      skip = g.skip_flag && *g.skip_flag;
-      const int n_do = skip ? npre : nkb;
-      constexpr uint32_t idesc = make_idesc(CL_BN);
-      for (int i = 0; i < n_do; ++i) {
-        const int s = i % stages;
-        mbar_wait(&full[s], (i / stages) & 1);
-        tc_fence_after();
-        if (!skip) {
-          const uint32_t a_addr = smem_u32(tiles + s * CL_STAGE);
-          const uint64_t da = make_desc(a_addr), db = make_desc(a_addr + SK_A_BYTES);
-#pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            umma(tmem_base, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
-                 (i | k) != 0 ? 1u : 0u);
-        }
-        umma_commit(&empty[s]);
-      }
-      umma_commit(tmem_full);
-    }
-  } else {
-    pdl_wait();
-    skip = g.skip_flag && *g.skip_flag;
-    if (epi) {
-      mbar_wait(tmem_full, 0);
-      tc_fence_after();
-      if (!skip) {
-#pragma unroll
-        for (int c0 = 0; c0 < CL_BN; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(c0), r);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[c0 + j] = __uint_as_float(r[j]);
-        }
-      }
-    }
-  }
-  // ---- LayerNorm across the cluster: every thread of every CTA passes the two cluster barriers ----
-  float psum = 0.f;
-  if (row_ok && !skip) {
-    const bf16* __restrict__ R = static_cast<const bf16*>(g.residual);
-#pragma unroll
-    for (int c = 0; c < CL_BN; ++c) {
-      float x = v[c] + (g.bias ? g.bias[n0 + c] : 0.f);
-      if (g.act == ACT_GELU) x = gelu_fast(x);
-      v[c] = x;
-    }
-    if (R) {
-      const bf16* rp = R + static_cast<long long>(m) * g.ldr + n0;
-#pragma unroll
-      for (int q = 0; q < CL_BN / 8; ++q) {
-        Vec16<bf16> rv;
-        rv.load(rp + 8 * q);
-        float rf[8];
-        rv.unpack(rf);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[8 * q + j] += rf[j];
-      }
-    }
-#pragma unroll
-    for (int c = 0; c < CL_BN; ++c) {
-      v[c] = __bfloat162float(__float2bfloat16_rn(v[c]));   // the reference stores the pre-LN sum in bf16
-      psum += v[c];
-    }
-  }
-  if (epi) {
-    const uint32_t slot = smem_u32(&xch[(0 * CL_SIZE + rank) * SK_ROWS + m]);
-#pragma unroll
-    for (uint32_t peer = 0; peer < CL_SIZE; ++peer) st_cluster_f32(slot, peer, psum);
-  }
-  cluster_sync_all();
-  float mean = 0.f, pvar = 0.f;
-  if (epi) {
-#pragma unroll
-    for (int r2 = 0; r2 < CL_SIZE; ++r2) mean += xch[(0 * CL_SIZE + r2) * SK_ROWS + m];
-    mean *= (1.0f / CL_N);
-    if (row_ok && !skip) {
-#pragma unroll
-      for (int c = 0; c < CL_BN; ++c) pvar += (v[c] - mean) * (v[c] - mean);
-    }
-    const uint32_t slot = smem_u32(&xch[(1 * CL_SIZE + rank) * SK_ROWS + m]);
-#pragma unroll
-    for (uint32_t peer = 0; peer < CL_SIZE; ++peer) st_cluster_f32(slot, peer, pvar);
-  }
-  cluster_sync_all();
-  if (row_ok && !skip) {
-    float var = 0.f;
-#pragma unroll
-    for (int r2 = 0; r2 < CL_SIZE; ++r2) var += xch[(1 * CL_SIZE + r2) * SK_ROWS + m];
-    const float rstd = rsqrtf(var * (1.0f / CL_N) + eps);
-    bf16* dst = static_cast<bf16*>(g.C) + static_cast<long long>(m) * g.ldc + n0;
-#pragma unroll
-    for (int q = 0; q < CL_BN / 8; ++q) {
-      float o[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int c = 8 * q + j;
-        o[j] = (v[c] - mean) * rstd * gamma[n0 + c] + beta[n0 + c];
-      }
-      Vec16<bf16> ov;
-      ov.pack(o);
-      ov.store(dst + 8 * q);
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
-  }
-}
 
 // out[m, :] = LayerNorm( act( sum_s partial[s][m][:] + bias ) + residual[m, :] ) for m < M; one CTA per row.
 __global__ void __launch_bounds__(256) splitk_ln_kernel(const float* __restrict__ partial, int nsplit, int N,
@@ -1591,28 +1242,6 @@ __global__ void __launch_bounds__(256) splitk_ln_kernel(const float* __restrict_
   }
 }
 
-
-// ---- weight preparation for the LN-folded decode GEMMs: one warp per output row ----
-__global__ void fold_ln_weights_kernel(const float* __restrict__ W, int n_out, int n_in, const float* __restrict__ gamma,
-                                       const float* __restrict__ beta, const float* __restrict__ bias,
-                                       bf16* __restrict__ Wf, float* __restrict__ s, float* __restrict__ c) {
-  const int n = (blockIdx.x * blockDim.x + threadIdx.x) / kWarp, lane = threadIdx.x % kWarp;
-  if (n >= n_out) return;
-  float ss = 0.f, cc = 0.f;
-  for (int k = lane; k < n_in; k += kWarp) {
-    const float w = W[static_cast<long long>(n) * n_in + k];
-    const bf16 wf = __float2bfloat16_rn(w * gamma[k]);
-    Wf[static_cast<long long>(n) * n_in + k] = wf;
-    ss += __bfloat162float(wf);
-    cc += beta[k] * w;
-  }
-  ss = warp_sum(ss);
-  cc = warp_sum(cc);
-  if (lane == 0) {
-    s[n] = ss;
-    c[n] = cc + (bias ? bias[n] : 0.f);
-  }
-}
 
 // ---- host side -------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -1797,52 +1426,39 @@ void launch_wres(const GemmArgs& g, int stages, int n_slices, int grid, cudaStre
 
 // ---- skinny path (M <= 64) -------------------------------------------------------------------------
 template <int BN>
-void launch_skinny(const GemmArgs& g, int stages, int nsplit, int kb_per_split, float* partial, cudaStream_t stream,
-                   const FoldArgs* fold) {
-  // tiles | slack | barriers (512 B) | per-CTA column constants of the LN-folded epilogue (4 x BN floats) | alignment
-  const size_t smem = static_cast<size_t>(stages) * (SK_A_BYTES + BN * BK * 2) + SK_SLACK + 1024 + 512 +
-                      (fold ? 4 * BN * sizeof(float) : 0);
+void launch_skinny(const GemmArgs& g, int stages, int nsplit, int kb_per_split, float* partial, cudaStream_t stream) {
+  // tiles | slack | barriers (512 B) | alignment
+  const size_t smem = static_cast<size_t>(stages) * (SK_A_BYTES + BN * BK * 2) + SK_SLACK + 1024 + 512;
   const CUtensorMap ta = make_map(g.A, g.M, g.K, g.lda, SK_ROWS);
   const CUtensorMap tb = make_map(g.W, g.N, g.K, g.ldw, BN);
   const int esz = g.out_f32 ? 4 : 2;
   int vec_ok = (reinterpret_cast<uintptr_t>(g.C) % 16 == 0) && ((static_cast<long long>(g.ldc) * esz) % 16 == 0);
   if (g.residual) vec_ok = vec_ok && (reinterpret_cast<uintptr_t>(g.residual) % 16 == 0) && (g.ldr % 8 == 0);
   dim3 grid(ceil_div(g.N, BN), nsplit);
-  if (fold) {
-    static size_t configured = 0;
-    if (smem > configured) {
-      CXRM_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_skinny_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           static_cast<int>(smem)));
-      configured = smem;
+  // lean epilogue when the call fits one (always the case for the decode step), else the general kernel
+  int epi = 0;
+  static const bool lean = std::getenv("CXRM_NO_LEAN_EPILOGUE") == nullptr;
+  if (lean && g.c_head_stride == 0 && !g.residual && vec_ok) {
+    if (partial && g.N % BN == 0) epi = 1;
+    else if (!partial && !g.out_f32 && g.N % BN == 0 && g.M <= SK_ROWS) epi = g.act == ACT_GELU ? 3 : 2;
+    else if (!partial && g.out_f32 && g.act == ACT_NONE && BN == 64) epi = 4;
+  }
+  auto go = [&](auto kern) {
+    // keyed by the function: the instantiations share one function-pointer type, so a static in this lambda would too
+    static std::unordered_map<const void*, size_t> configured;
+    size_t& have = configured[reinterpret_cast<const void*>(kern)];
+    if (smem > have) {
+      CXRM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+      have = smem;
     }
-    launch_chain(gemm_tc_skinny_kernel<BN, true>, grid, dim3(NTHREADS), smem, stream, ta, tb, g, stages, kb_per_split, partial,
-                 vec_ok, *fold);
-  } else {
-    // lean epilogue when the call fits one (always the case for the decode step), else the general kernel
-    int epi = 0;
-    static const bool lean = std::getenv("CXRM_NO_LEAN_EPILOGUE") == nullptr;
-    if (lean && g.c_head_stride == 0 && !g.residual && vec_ok) {
-      if (partial && g.N % BN == 0) epi = 1;
-      else if (!partial && !g.out_f32 && g.N % BN == 0 && g.M <= SK_ROWS) epi = g.act == ACT_GELU ? 3 : 2;
-      else if (!partial && g.out_f32 && g.act == ACT_NONE && BN == 64) epi = 4;
-    }
-    auto go = [&](auto kern) {
-      // keyed by the function: the instantiations share one function-pointer type, so a static in this lambda would too
-      static std::unordered_map<const void*, size_t> configured;
-      size_t& have = configured[reinterpret_cast<const void*>(kern)];
-      if (smem > have) {
-        CXRM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        have = smem;
-      }
-      launch_chain(kern, grid, dim3(NTHREADS), smem, stream, ta, tb, g, stages, kb_per_split, partial, vec_ok, NoFold{});
-    };
-    switch (epi) {
-      case 1: go(gemm_tc_skinny_kernel<BN, false, 1>); break;
-      case 2: go(gemm_tc_skinny_kernel<BN, false, 2>); break;
-      case 3: go(gemm_tc_skinny_kernel<BN, false, 3>); break;
-      case 4: go(gemm_tc_skinny_kernel<BN, false, 4>); break;
-      default: go(gemm_tc_skinny_kernel<BN, false, 0>); break;
-    }
+    launch_chain(kern, grid, dim3(NTHREADS), smem, stream, ta, tb, g, stages, kb_per_split, partial, vec_ok);
+  };
+  switch (epi) {
+    case 1: go(gemm_tc_skinny_kernel<BN, 1>); break;
+    case 2: go(gemm_tc_skinny_kernel<BN, 2>); break;
+    case 3: go(gemm_tc_skinny_kernel<BN, 3>); break;
+    case 4: go(gemm_tc_skinny_kernel<BN, 4>); break;
+    default: go(gemm_tc_skinny_kernel<BN, 0>); break;
   }
   check_launch("gemm_tcgen05_skinny");
 }
@@ -1883,32 +1499,6 @@ CUtensorMap make_tensor_map_bf16_kblocks(const void* ptr, long long rows, long l
   return m;
 }
 
-int gemm_ln_cluster_supported(const GemmArgs& g) {
-  if (gemm_tcgen05_supported(g) != 0) return 1;
-  if (g.M > SK_ROWS || g.N != CL_N) return 2;
-  if (g.ldc % 8 != 0 || reinterpret_cast<uintptr_t>(g.C) % 16 != 0) return 3;
-  if (g.residual && (g.ldr % 8 != 0 || reinterpret_cast<uintptr_t>(g.residual) % 16 != 0)) return 4;
-  return 0;
-}
-
-// C (bf16) = LayerNorm(act(A.W^T + bias) + residual) with gamma/beta/eps; M <= 64, N == 768
-void gemm_ln_cluster(const GemmArgs& g, const float* gamma, const float* beta, float eps, cudaStream_t stream) {
-  CXRM_CHECK(gemm_ln_cluster_supported(g) == 0, "shape not supported by the cluster GEMM+LayerNorm");
-  const int nkb = ceil_div(g.K, BK);
-  const int stages = std::min(CL_MAX_STAGES, nkb);
-  const size_t smem = static_cast<size_t>(stages) * CL_STAGE + SK_SLACK + 1024 + 512 + 2 * CL_SIZE * SK_ROWS * sizeof(float);
-  static size_t configured = 0;
-  if (smem > configured) {
-    CXRM_CUDA_CHECK(cudaFuncSetAttribute(gemm_ln_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(smem)));
-    configured = smem;
-  }
-  const CUtensorMap ta = make_map(g.A, g.M, g.K, g.lda, SK_ROWS);
-  const CUtensorMap tb = make_map(g.W, g.N, g.K, g.ldw, CL_BN);
-  launch_chain(gemm_ln_cluster_kernel, dim3(CL_SIZE), dim3(NTHREADS), smem, stream, ta, tb, g, gamma, beta, eps, stages);
-  check_launch("gemm_ln_cluster");
-}
-
 int gemm_skinny_supported(const GemmArgs& g) {
   if (gemm_tcgen05_supported(g) != 0) return 1;
   if (g.M > SK_ROWS) return 2;
@@ -1922,19 +1512,11 @@ int gemm_skinny_tile_n(const GemmArgs& g, bool split_allowed) {
   return 32;
 }
 
-void gemm_tcgen05_skinny(const GemmArgs& g, float* partial, int* nsplit_out, cudaStream_t stream, const FoldArgs* fold) {
+void gemm_tcgen05_skinny(const GemmArgs& g, float* partial, int* nsplit_out, cudaStream_t stream) {
   CXRM_CHECK(gemm_skinny_supported(g) == 0, "shape not supported by the skinny tcgen05 GEMM");
   const int num_kb = ceil_div(g.K, BK);
   const int bn = gemm_skinny_tile_n(g, partial != nullptr);
   int stages = bn == 64 ? 6 : SK_MAX_STAGES;
-  if (fold && !fold->any()) fold = nullptr;
-  if (fold) {
-    CXRM_CHECK(!partial && g.c_head_stride == 0, "LN-folded epilogue: direct bf16/fp32 stores only");
-    CXRM_CHECK(!fold->stats_out || (bn <= 32 && g.N % bn == 0 && !g.out_f32), "stats_out needs whole tiles of <= 32 bf16 columns");
-    CXRM_CHECK(!fold->ln_res.stats || g.residual, "ln_res without a residual tensor");
-    CXRM_CHECK(fold->ln_in.tiles <= 48 && fold->ln_res.tiles <= 48 && fold->ln_in.tiles % 2 == 0 && fold->ln_res.tiles % 2 == 0,
-               "LN-folded epilogue: at most 48 (even) statistics tiles per row");
-  }
   // split-K: every tcgen05.mma of this kernel costs ~93 clocks whatever its width (the 128 x 16 A slice is read from shared
   // memory per instruction: tools/mb_mma.cu), so a CTA's floor is 4 * k-blocks * 93 clocks - 2.3 us for K = 768 unsplit.
   // The GEMMs that feed the reduce + LayerNorm kernel split as far as kSkMaxSplit partials of >= kb_min k-blocks.
@@ -1954,9 +1536,9 @@ void gemm_tcgen05_skinny(const GemmArgs& g, float* partial, int* nsplit_out, cud
   }
   if (nsplit_out) *nsplit_out = partial ? nsplit : 0;
   switch (bn) {
-    case 16: launch_skinny<16>(g, stages, nsplit, kb_per_split, partial, stream, fold); break;
-    case 64: launch_skinny<64>(g, stages, nsplit, kb_per_split, partial, stream, fold); break;
-    default: launch_skinny<32>(g, stages, nsplit, kb_per_split, partial, stream, fold); break;
+    case 16: launch_skinny<16>(g, stages, nsplit, kb_per_split, partial, stream); break;
+    case 64: launch_skinny<64>(g, stages, nsplit, kb_per_split, partial, stream); break;
+    default: launch_skinny<32>(g, stages, nsplit, kb_per_split, partial, stream); break;
   }
 }
 
@@ -1971,13 +1553,6 @@ void splitk_ln(const float* partial, int nsplit, int M, int N, const float* bias
                static_cast<const bf16*>(residual), ldr, gamma, beta, eps, static_cast<bf16*>(out), ldo, skip_flag, res_gamma,
                res_beta);
   check_launch("splitk_ln");
-}
-
-void fold_ln_weights(const float* W, int n_out, int n_in, const float* gamma, const float* beta, const float* bias,
-                     void* Wf_bf16, float* s, float* c, cudaStream_t stream) {
-  fold_ln_weights_kernel<<<ceil_div(n_out * kWarp, 256), 256, 0, stream>>>(W, n_out, n_in, gamma, beta, bias,
-                                                                          static_cast<bf16*>(Wf_bf16), s, c);
-  check_launch("fold_ln_weights");
 }
 
 size_t gemm_skinny_partial_floats(int N) { return static_cast<size_t>(kSkMaxSplit) * SK_ROWS * N; }

@@ -12,44 +12,6 @@ namespace cxrm {
 
 enum Act : int { ACT_NONE = 0, ACT_GELU = 1 };
 
-// Software L2 prefetch of the decode step (l2_prefetch_kernel, decode.cu): the GEMM/LayerNorm chain between two
-// attention kernels is latency-bound and leaves HBM idle, so a kernel on a PARALLEL graph branch pulls the next
-// attention kernel's K/V (rollout constants / already-written cache rows) into the 126 MB L2 while the chain runs.
-//   n_seg segments per base pointer at base[i] + s * seg_stride, the first `seg_bytes` of each
-//   (or (*dyn + dyn_add) * dyn_unit bytes when dyn != nullptr, clamped to seg_stride).  n_seg == 0: nothing.
-struct L2Prefetch {
-  const char* base[2] = {nullptr, nullptr};
-  long long seg_stride = 0;
-  int n_seg = 0;
-  int seg_bytes = 0;
-  const int* dyn = nullptr;
-  int dyn_add = 0, dyn_unit = 0;
-};
-
-// ---- LayerNorm folded into the decode-step GEMMs (gemm_tc_skinny_kernel) ---------------------
-// The decoder is post-LN: every 768-wide projection is followed by LayerNorm(x + residual), whose output feeds the
-// next GEMM and the next residual add.  In the decode step (M <= 64 rows, a chain of latency-bound launches) the 19
-// stand-alone LayerNorm launches are removed algebraically:
-//   producer  GEMM epilogue stores the PRE-LayerNorm sum (bf16) and, per row, the (mean, M2) of its own column tile
-//             -> stats_out[tile][64];
-//   consumer  GEMM runs on the pre-LN tensor with weights W' = W.diag(gamma):  LN(x).W^T + b = r.(x.W'^T - mu.s) + c,
-//             s[n] = sum_k W'[n,k], c[n] = b[n] + sum_k beta[k].W[n,k]; mu, r per row from the tile statistics
-//             (Chan's combination, in the epilogue thread that owns the row);
-//   residual  adds of a LayerNorm output are recomputed from the pre-LN tensor + statistics + gamma/beta.
-struct LnFold {               // A is a pre-LayerNorm tensor (consumer side); GemmArgs::bias carries c[n]
-  const float2* stats = nullptr;   // [64][tiles] (mean, M2) of each producer column tile; nullptr = off
-  int tiles = 0, cols = 0;         // producer tiles, columns per tile
-  const float* s = nullptr;        // [N]
-  float eps = 0.f;
-};
-struct LnResidual {           // residual = LayerNorm(residual_pre) * gamma + beta, rounded to bf16 like a stored LN output
-  const float2* stats = nullptr;
-  int tiles = 0, cols = 0;
-  const float* gamma = nullptr;
-  const float* beta = nullptr;
-  float eps = 0.f;
-};
-
 // C[M,N] = epi(A[M,K] . W[N,K]^T): + bias[N] (fp32, nullable) -> act -> + residual[M,N] (T, nullable);
 // stored as T, or as fp32 when out_f32.  K % 8 == 0, lda/ldw % 8 == 0.
 struct GemmArgs {
@@ -66,19 +28,8 @@ struct GemmArgs {
   long long c_head_stride;
   unsigned long long* trace;   // nullable debug buffer: 8 globaltimer stamps per CTA (gemm_tc_kernel only)
 };
-// optional LayerNorm folding of a skinny (decode-step) GEMM; passed beside GemmArgs so that the plain kernel's
-// parameter block and code stay as they were
-struct FoldArgs {
-  LnFold ln_in;
-  LnResidual ln_res;
-  float2* stats_out = nullptr;   // [64][N / BN] (mean, M2) of this GEMM's bf16 output rows per column tile
-  bool any() const { return ln_in.stats || ln_res.stats || stats_out; }
-};
-// column tile width the skinny kernel will use for g (what stats_out / LnFold::cols must be sized with)
+// column tile width the skinny kernel will use for g
 int gemm_skinny_tile_n(const GemmArgs& g, bool split_allowed);
-// W [n_out, n_in] fp32 -> Wf = bf16(W . diag(gamma)), s[n] = sum_k Wf[n,k], c[n] = bias[n] + sum_k beta[k] . W[n,k]
-void fold_ln_weights(const float* W, int n_out, int n_in, const float* gamma, const float* beta, const float* bias,
-                     void* Wf_bf16, float* s, float* c, cudaStream_t stream);
 
 // strict-fp32 FMA path (validation mode; also the bf16-storage SIMT debug path)
 template <typename T> void gemm_simt(const GemmArgs& g, cudaStream_t stream);
@@ -89,13 +40,8 @@ int gemm_tcgen05_supported(const GemmArgs& g);
 // decode-step GEMMs (M <= 64): deep TMA ring, optional split-K into fp32 partials [nsplit][64][N]
 // (partial == nullptr: direct fused epilogue).  *nsplit_out = splits written (0 = direct).
 int gemm_skinny_supported(const GemmArgs& g);
-void gemm_tcgen05_skinny(const GemmArgs& g, float* partial, int* nsplit_out, cudaStream_t stream,
-                         const FoldArgs* fold = nullptr);
+void gemm_tcgen05_skinny(const GemmArgs& g, float* partial, int* nsplit_out, cudaStream_t stream);
 size_t gemm_skinny_partial_floats(int N);
-// one kernel: C (bf16) = LayerNorm(act(A.W^T + bias) + residual); 8-CTA cluster, row statistics through DSMEM.
-// M <= 64, N == 768 (the decoder's hidden width).
-int gemm_ln_cluster_supported(const GemmArgs& g);
-void gemm_ln_cluster(const GemmArgs& g, const float* gamma, const float* beta, float eps, cudaStream_t stream);
 // out[M, N] (bf16) = LayerNorm(act(sum_s partial[s] + bias) + residual): consumer of the split-K partials
 // res_gamma/res_beta (nullable): the residual is itself a LayerNorm output that was never stored: `residual` then holds
 // the PRE-LayerNorm rows and LN(residual) * res_gamma + res_beta (same eps, rounded to bf16) is added instead.
@@ -342,8 +288,6 @@ struct PromptPack {
 void pack_prompt(const PromptPack& pk, const int* pre_ids, const int* pre_types, const int* pre_pos, const uint8_t* pre_valid,
                  int R, int P, cudaStream_t stream);
 
-// issue the prefetch described by p (plain launch: belongs on a side stream / parallel graph branch)
-void l2_prefetch(const L2Prefetch& p, cudaStream_t stream);
 
 // ---- persistent GEMM / LayerNorm chain of the decode step (decode_chain.cu) ---------------------------------------
 enum ChainPhaseType : int { CH_GEMM = 0, CH_LN = 1, CH_EMBED = 2 };

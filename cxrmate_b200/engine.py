@@ -440,14 +440,13 @@ def sample_hook(logits: torch.Tensor, top_k: int, temperature: float, seed: int,
     return tok, lp
 
 
-def gemm_ln_hook(A, W, bias, act, residual, gamma, beta, eps=1e-12, cluster=False):
-    """bf16 decode-step GEMM + LayerNorm.  cluster=False: skinny split-K GEMM + fused reduce/bias/act/residual/LN pair;
-    cluster=True: the single 8-CTA cluster kernel (N == 768).  A [M<=64,K], W [N,K]."""
+def gemm_ln_hook(A, W, bias, act, residual, gamma, beta, eps=1e-12):
+    """bf16 decode-step GEMM + LayerNorm: skinny split-K GEMM + fused reduce/bias/act/residual/LN pair.  A [M<=64,K], W [N,K]."""
     lib = _lib.load()
     M, K = A.shape
     N = W.shape[0]
     out = torch.empty(M, N, dtype=torch.bfloat16, device=A.device)
-    ws = None if cluster else torch.empty(4 * 64 * N, dtype=torch.float32, device=A.device)
+    ws = torch.empty(8 * 64 * N, dtype=torch.float32, device=A.device)      # up to 8 K-splits of [64, N] fp32
     rc = lib.cxrm_test_gemm_ln(_ptr(A), _ptr(W), _ptr(out), M, N, K, _ptr(bias), act, _ptr(residual), _ptr(gamma),
                                _ptr(beta), float(eps), _ptr(ws), _stream())
     if rc != 0:

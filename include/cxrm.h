@@ -343,8 +343,7 @@ CXRM_API int cxrm_profile_report(cxrm_engine* e, char* buf, size_t len);
 CXRM_API int cxrm_test_gemm(int impl, int dtype, const void* A, const void* W, void* C, int M, int N, int K,
                    const float* bias, int act, const void* residual, int out_f32, void* stream);
 /* Decode-step pair used by the kernel tests: skinny split-K tcgen05 GEMM (M <= 64, bf16) into fp32 partials, then the
- * fused reduce + bias + act + residual + LayerNorm kernel.  partial_ws: dev fp32 [4 * 64 * N]; NULL selects the single
- * cluster kernel (8 CTAs, LayerNorm statistics through distributed shared memory; N == 768 only). */
+ * fused reduce + bias + act + residual + LayerNorm kernel.  partial_ws: dev fp32 [8 * 64 * N] (up to 8 K-splits). */
 CXRM_API int cxrm_test_gemm_ln(const void* A, const void* W, void* out, int M, int N, int K, const float* bias, int act,
                       const void* residual, const float* gamma, const float* beta, float eps, float* partial_ws,
                       void* stream);

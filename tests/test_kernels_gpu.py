@@ -102,27 +102,6 @@ def test_gemm_splitk_layernorm(M, N, K, act, use_res):
     assert err < 4e-2, f"gemm_ln {M}x{N}x{K} act={act} res={use_res}: max err {err}"   # one bf16 ulp at |y| ~ 4
 
 
-@pytest.mark.parametrize("M,K", [(64, 768), (64, 3072), (5, 768), (33, 512), (64, 64)])
-@pytest.mark.parametrize("act,use_res", [(0, True), (1, False)])
-def test_gemm_layernorm_cluster(M, K, act, use_res):
-    """one kernel: tcgen05 GEMM (8-CTA cluster over the 768 columns) + LayerNorm through distributed shared memory"""
-    from cxrmate_b200.engine import gemm_ln_hook
-    N = 768
-    g = torch.Generator(device="cuda").manual_seed(M + K + act)
-    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
-    W = (torch.randn(N, K, device="cuda", generator=g) * K ** -0.5).bfloat16()
-    bias = torch.randn(N, device="cuda", generator=g)
-    res = torch.randn(M, N, device="cuda", generator=g).bfloat16() if use_res else None
-    gamma = 1 + 0.1 * torch.randn(N, device="cuda", generator=g)
-    beta = 0.1 * torch.randn(N, device="cuda", generator=g)
-    out = gemm_ln_hook(A, W, bias, act, res, gamma, beta, cluster=True)
-    torch.cuda.synchronize()
-    pre = _ref_gemm(A, W, bias, act, res).bfloat16().float()
-    ref = torch.nn.functional.layer_norm(pre, (N,), gamma, beta, 1e-12)
-    err = (out.float() - ref).abs().max().item()
-    assert err < 4e-2, f"cluster gemm_ln {M}x{N}x{K} act={act} res={use_res}: max err {err}"
-
-
 def _ref_attn(q, k, v, heads, key_mask, causal, scale):
     b, Lq, C = q.shape
     Lk = k.shape[1]

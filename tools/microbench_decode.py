@@ -52,8 +52,6 @@ for pdl in (0, 1):
         if N <= 1024:
             gm, bt = torch.ones(N, device=dev), torch.zeros(N, device=dev)
             bench(f"skinny split-K + LN {M}x{N}x{K}", lambda: gemm_ln_hook(A, W, bias, 0, res, gm, bt), n=30)
-            if N == 768:
-                bench(f"cluster GEMM+LN {M}x{N}x{K}", lambda: gemm_ln_hook(A, W, bias, 0, res, gm, bt, cluster=True), n=30)
         bench(f"generic tcgen05 {M}x{N}x{K}", lambda: gemm_hook("tcgen05", A, W, bias, 0, None, N > 8192))
 lib.cxrm_test_set_pdl(0)
 x = torch.zeros(64, 768, device=dev)
