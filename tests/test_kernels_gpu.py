@@ -124,6 +124,9 @@ def _ref_attn(q, k, v, heads, key_mask, causal, scale):
 @pytest.mark.parametrize("b,h,Lq,Lk,masked,causal", [
     (2, 1, 256, 64, False, False), (3, 6, 577, 145, False, False), (2, 12, 37, 37, True, True),
     (2, 12, 200, 200, True, False), (1, 3, 130, 70, False, False), (4, 12, 5, 5, True, True),
+    # dense multi-tile cases of the tcgen05 kernel: CvT stage 1 / stage 2 shapes, ragged key and query tails
+    (1, 1, 2304, 576, False, False), (2, 3, 576, 144, False, False), (2, 2, 300, 401, False, False),
+    (1, 1, 64, 16, False, False), (3, 6, 129, 257, False, False),
 ])
 def test_attention(dtype, b, h, Lq, Lk, masked, causal):
     from cxrmate_b200.engine import attention_hook
