@@ -185,38 +185,55 @@ __global__ void im2col_pixels_kernel(const float* __restrict__ pixels, const int
 // memory with coalesced loads (the element-per-thread kernel above gathers 4-byte pixels with a div / mod chain per
 // element: 350 us for a 32-image chunk whose 57 MB in + 90 MB out need ~25 us), then the row's Wo patches leave as
 // consecutive 2-element stores.  Needs an even Kpad.
+// (First version: one flat index per element, decomposed with runtime divisions by ksz / W / Kpad in both phases: ncu
+// 400 us per 50-image pass for 88 MB in + 140 MB out, integer-division bound.  Now a warp owns whole rows: input rows as
+// float4 per lane, output patches with the (channel, ky, kx) decomposition of a lane's <= 3 element pairs hoisted out
+// of the loop over the row's patches.)
 template <typename T>
 __global__ void __launch_bounds__(256) im2col_pixels_rows_kernel(const float* __restrict__ pixels, const int* __restrict__ img_idx,
                                                                  T* __restrict__ out, int H, int W, int Ho, int Wo, int ksz,
                                                                  int stride, int pad, int Kpad) {
-  extern __shared__ float rows_sm[];   // [3][ksz][W]
+  extern __shared__ __align__(16) float rows_sm[];   // [3 * ksz][W + 8]: the row pad spreads a patch's ksz rows over the banks
   pdl_launch_dependents();
   pdl_wait();
   const int oy = blockIdx.x % Ho, n = blockIdx.x / Ho;
+  const int lane = threadIdx.x % 32, wrp = threadIdx.x / 32;
   const long long src = img_idx ? img_idx[n] : n;
-  const int K = 3 * ksz * ksz;
-  for (int i = threadIdx.x; i < 3 * ksz * W; i += blockDim.x) {
-    const int ix = i % W, ky = (i / W) % ksz, c = i / (W * ksz);
+  const int K = 3 * ksz * ksz, W4 = W / 4, RS = W + 8;
+  for (int r = wrp; r < 3 * ksz; r += 8) {            // r = c * ksz + ky
+    const int c = r / ksz, ky = r - c * ksz;
     const int iy = oy * stride - pad + ky;
-    rows_sm[i] = (iy >= 0 && iy < H) ? pixels[((src * 3 + c) * H + iy) * static_cast<long long>(W) + ix] : 0.f;
+    const bool in = iy >= 0 && iy < H;
+    const float4* g = reinterpret_cast<const float4*>(pixels + ((src * 3 + c) * H + (in ? iy : 0)) * static_cast<long long>(W));
+    float4* d = reinterpret_cast<float4*>(rows_sm + r * RS);
+    for (int i = lane; i < W4; i += 32) d[i] = in ? __ldg(g + i) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   __syncthreads();
-  T* orow = out + (static_cast<long long>(n) * Ho + oy) * Wo * Kpad;
+  // this lane's element pairs kk0 = 2 * (lane + 32 j) of a patch: source offsets relative to the patch's first column
   const int half = Kpad / 2;
-  for (int i = threadIdx.x; i < Wo * half; i += blockDim.x) {
-    const int ox = i / half, kk0 = (i % half) * 2;
-    float v[2];
+  int off[3][2], dx[3][2];
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const int kk = kk0 + j;
-      v[j] = 0.f;
-      if (kk < K) {
-        const int kx = kk % ksz, ky = (kk / ksz) % ksz, c = kk / (ksz * ksz);
-        const int ix = ox * stride - pad + kx;
-        if (ix >= 0 && ix < W) v[j] = rows_sm[(c * ksz + ky) * W + ix];
+  for (int j = 0; j < 3; ++j)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int kk = 2 * (lane + 32 * j) + e;
+      const int c = kk / (ksz * ksz), rem = kk - c * ksz * ksz, ky = rem / ksz, kx = rem - ky * ksz;
+      dx[j][e] = kk < K ? kx - pad : -(1 << 20);       // padding columns of the patch: always out of range
+      off[j][e] = (c * ksz + ky) * RS;
+    }
+  T* orow = out + (static_cast<long long>(n) * Ho + oy) * Wo * Kpad;
+  for (int ox = wrp; ox < Wo; ox += 8) {
+    const int x0 = ox * stride;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int pr = lane + 32 * j;
+      if (pr < half) {
+        const int ix0 = x0 + dx[j][0], ix1 = x0 + dx[j][1];
+        const float v0 = (ix0 >= 0 && ix0 < W) ? rows_sm[off[j][0] + ix0] : 0.f;
+        const float v1 = (ix1 >= 0 && ix1 < W) ? rows_sm[off[j][1] + ix1] : 0.f;
+        store_pair2(orow + static_cast<long long>(ox) * Kpad + 2 * pr, v0, v1);
       }
     }
-    store_pair2(orow + static_cast<long long>(ox) * Kpad + kk0, v[0], v[1]);
   }
 }
 
@@ -443,9 +460,9 @@ __global__ void __launch_bounds__(256, 3) ln_dwconv_qkv_kernel(const T* __restri
 // ncu of the register-window kernel above (stage 3, 18432 x 384): 41 us, ~100 executed instructions per output element
 // (27 weight vectors re-read through L1 per output row, 64-bit address arithmetic per tap), issue slots 48 % busy, 61 %
 // of the stalls on L1TEX scoreboards - instruction-bound at 5x the time its 35 MB of traffic needs.  Here a block owns
-// a TH x 8 spatial tile and 64 channels: the NORMALISED tile + halo goes to shared memory once (one 128-byte row per
-// token and warp), a warp is one output column x 32 channel pairs, its 27 x 2 weights and the folded BatchNorm constants
-// live in registers for the whole tile, and each output row costs 3 conflict-free shared loads for the rolling window.
+// a TH x 8 spatial tile and 64 channels: the NORMALISED tile + halo goes to shared memory once, a warp is one output
+// column x 32 channel pairs with its weights and the folded BatchNorm constants in registers, and each output row costs
+// 3 conflict-free shared loads for the rolling window.  (First version: register-staged loads, 27 x 2 weights live.)
 template <typename T>
 __device__ __forceinline__ float2 load_pair(const T* p);
 template <>
@@ -461,108 +478,158 @@ __device__ __forceinline__ void store_pair(bf16* p, float a, float b) {
   *reinterpret_cast<uint32_t*>(p) = *reinterpret_cast<const uint32_t*>(&v);
 }
 
+// Second version: the tile arrives RAW through cp.async, the three convolutions run as two passes.
+// ncu of the first version over an encoder pass: 100 us per launch at 330 GB/s of DRAM traffic, neither issue- nor
+// bandwidth-bound: ~120 registers (27 x 2 weights) held it to 2 blocks per SM, and a block alternated between five
+// serial batches of register-staged loads and its compute phase.  Here every 16-byte chunk of the tile + halo is
+// requested at once with cp.async (no registers, zero-filled outside the image), tokens are
+// normalised once in a sweep through registers, and q / (k | v) are separate passes with 9 weights live each (the k and v
+// pass maps the 8 warps to the 4 even columns x {k, v}): 64 registers, 47 KB of shared memory, 4 blocks per SM.
+__device__ __forceinline__ void cp_async16_zfill(void* dst, const void* src, bool valid) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(dst));
+  const int n = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
+}
+
 template <typename T, int TH>
-__global__ void __launch_bounds__(256, 2) ln_dwconv_tile_kernel(const T* __restrict__ x, T* __restrict__ q, T* __restrict__ k,
-                                                              T* __restrict__ v, const float2* __restrict__ stats,
-                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                              const float* __restrict__ w, const float* __restrict__ scale,
-                                                              const float* __restrict__ shift, int H, int W, int C, int cls,
-                                                              int Hk, int Wk, int tiles_x) {
-  constexpr int TW = 8, PW = TW + 2, PH = TH + 2;
-  __shared__ float2 tile[PH * PW][32];
+__global__ void __launch_bounds__(256, 4) ln_dwconv_async_kernel(const T* __restrict__ x, T* __restrict__ q, T* __restrict__ k,
+                                                               T* __restrict__ v, const float2* __restrict__ stats,
+                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                               const float* __restrict__ w, const float* __restrict__ scale,
+                                                               const float* __restrict__ shift, int H, int W, int C, int cls,
+                                                               int Hk, int Wk, int tiles_x) {
+  constexpr int TW = 8, PW = TW + 2, PH = TH + 2, NP = PH * PW;
+  constexpr int ROWB = 64 * static_cast<int>(sizeof(T));   // bytes of one position's 64 raw channels
+  constexpr int CPR = ROWB / 16;                           // 16-byte chunks per position
+  constexpr int PPW = (NP + 7) / 8;                        // positions per warp in the normalisation sweep
+  // the raw tile lands at the START of the buffer the normalised fp32 tile will occupy
+  __shared__ __align__(16) float2 tile[NP][32];
+  __shared__ float2 sst[NP];                               // (mean, rstd); rstd = 0 marks a position outside the image
+  unsigned char* raw = reinterpret_cast<unsigned char*>(&tile[0][0]);
   pdl_launch_dependents();
-  const int cp = threadIdx.x % 32, col = threadIdx.x / 32;      // a warp = one tile column x 32 channel pairs
-  const int c = blockIdx.y * 64 + 2 * cp;
+  const int cp = threadIdx.x % 32, wrp = threadIdx.x / 32;
+  const int c0 = blockIdx.y * 64, c = c0 + 2 * cp;
   const int ty0 = (blockIdx.x / tiles_x) * TH, tx0 = (blockIdx.x % tiles_x) * TW, n = blockIdx.z;
   const long long tok0 = static_cast<long long>(n) * (cls + H * W) + cls;
-  // constants of the layer (weights): ahead of the dependency wait
+  // constants of the layer: ahead of the dependency wait
   const float2 g = *reinterpret_cast<const float2*>(gamma + c), b = *reinterpret_cast<const float2*>(beta + c);
-  float2 wq[9], wk[9], wv[9];
+  float2 wt[9];
 #pragma unroll
-  for (int t = 0; t < 9; ++t) {
-    wq[t] = *reinterpret_cast<const float2*>(w + static_cast<long long>(t) * C + c);
-    wk[t] = *reinterpret_cast<const float2*>(w + static_cast<long long>(9 + t) * C + c);
-    wv[t] = *reinterpret_cast<const float2*>(w + static_cast<long long>(18 + t) * C + c);
-  }
-  float2 sc[3], sh[3];
-#pragma unroll
-  for (int o = 0; o < 3; ++o) {
-    sc[o] = *reinterpret_cast<const float2*>(scale + o * C + c);
-    sh[o] = *reinterpret_cast<const float2*>(shift + o * C + c);
-  }
+  for (int t = 0; t < 9; ++t) wt[t] = *reinterpret_cast<const float2*>(w + static_cast<long long>(t) * C + c);
+  float2 sc = *reinterpret_cast<const float2*>(scale + c), sh = *reinterpret_cast<const float2*>(shift + c);
   pdl_wait();
-  // ---- normalised tile + halo -> shared memory (zero outside the image: the convolution pads the NORMALISED map) ----
-  // (batches of LB positions: all their loads are issued before the first use - one L2 round trip per batch)
-  constexpr int NP = PH * PW, LB = 5;
-#pragma unroll 1
-  for (int p0 = col; p0 < NP; p0 += 8 * LB) {
-    float2 xv[LB], st[LB];
-    bool in[LB];
+  for (int i = threadIdx.x; i < NP * CPR; i += 256) {
+    const int p = i / CPR, ch = i % CPR;
+    const int iy = ty0 - 1 + p / PW, ix = tx0 - 1 + p % PW;
+    const bool in = iy >= 0 && iy < H && ix >= 0 && ix < W;
+    const T* src = in ? x + (tok0 + static_cast<long long>(iy) * W + ix) * C + c0 + ch * (16 / static_cast<int>(sizeof(T))) : x;
+    cp_async16_zfill(raw + p * ROWB + ch * 16, src, in);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  for (int p = threadIdx.x; p < NP; p += 256) {
+    const int iy = ty0 - 1 + p / PW, ix = tx0 - 1 + p % PW;
+    const bool in = iy >= 0 && iy < H && ix >= 0 && ix < W;
+    sst[p] = in ? stats[tok0 + static_cast<long long>(iy) * W + ix] : make_float2(0.f, 0.f);
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  // ---- normalise ONCE per position (zero outside the image: the convolution pads the NORMALISED map); the raw values
+  // pass through registers because the fp32 tile overlays them ----
+  {
+    float2 xr[PPW];
 #pragma unroll
-    for (int i = 0; i < LB; ++i) {
-      const int p = p0 + 8 * i;
-      const int iy = ty0 - 1 + p / PW, ix = tx0 - 1 + p % PW;
-      in[i] = p < NP && iy >= 0 && iy < H && ix >= 0 && ix < W;
-      xv[i] = st[i] = make_float2(0.f, 0.f);
-      if (in[i]) {
-        const long long tok = tok0 + static_cast<long long>(iy) * W + ix;
-        xv[i] = load_pair<T>(x + tok * C + c);
-        st[i] = stats[tok];
+    for (int i = 0; i < PPW; ++i) {
+      const int p = wrp + 8 * i;
+      xr[i] = p < NP ? load_pair<T>(reinterpret_cast<const T*>(raw + p * ROWB) + 2 * cp) : make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < PPW; ++i) {
+      const int p = wrp + 8 * i;
+      if (p < NP) {
+        const float2 st = sst[p];
+        const bool in = st.y != 0.f;
+        tile[p][cp] = make_float2(in ? (xr[i].x - st.x) * st.y * g.x + b.x : 0.f, in ? (xr[i].y - st.x) * st.y * g.y + b.y : 0.f);
       }
     }
+    __syncthreads();
+  }
+  auto ld = [&](int p) -> float2 { return tile[p][cp]; };
+  // ---- q: stride 1, a warp = one tile column, rolling window down the column ----
+  {
+    const int col = wrp, ox = tx0 + col;
+    if (ox < W) {
+      float2 win[3][3];
 #pragma unroll
-    for (int i = 0; i < LB; ++i) {
-      const int p = p0 + 8 * i;
-      if (p < NP)
-        tile[p][cp] = in[i] ? make_float2((xv[i].x - st[i].x) * st[i].y * g.x + b.x, (xv[i].y - st[i].x) * st[i].y * g.y + b.y)
-                            : make_float2(0.f, 0.f);
+      for (int dx = 0; dx < 3; ++dx) {
+        win[0][dx] = ld(0 * PW + col + dx);
+        win[1][dx] = ld(1 * PW + col + dx);
+      }
+#pragma unroll
+      for (int t = 0; t < TH; ++t) {
+        const int oy = ty0 + t;
+        if (oy >= H) break;
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) win[2][dx] = ld((t + 2) * PW + col + dx);
+        float2 a = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            a.x = fmaf(win[ky][kx].x, wt[ky * 3 + kx].x, a.x);
+            a.y = fmaf(win[ky][kx].y, wt[ky * 3 + kx].y, a.y);
+          }
+        store_pair(q + (tok0 + static_cast<long long>(oy) * W + ox) * C + c, fmaf(a.x, sc.x, sh.x), fmaf(a.y, sc.y, sh.y));
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          win[0][dx] = win[1][dx];
+          win[1][dx] = win[2][dx];
+        }
+      }
     }
   }
-  __syncthreads();
-  const int ox = tx0 + col;
-  if (ox >= W) return;
-  // ---- rolling 3 x 3 window down the column ----
-  float2 win[3][3];
+  // ---- k | v: stride 2 (window centres at the even coordinates; the tile origin is even), warp = (even column, k or v) ----
+  {
+    const int col = 2 * (wrp % 4), o = 1 + wrp / 4, ox = tx0 + col;
+    if (ox >= W) return;
 #pragma unroll
-  for (int dx = 0; dx < 3; ++dx) {
-    win[0][dx] = tile[0 * PW + col + dx][cp];
-    win[1][dx] = tile[1 * PW + col + dx][cp];
-  }
-  const bool col_even = (ox & 1) == 0;
-#pragma unroll 1
-  for (int t = 0; t < TH; ++t) {
-    const int oy = ty0 + t;
-    if (oy >= H) break;
+    for (int t = 0; t < 9; ++t) wt[t] = *reinterpret_cast<const float2*>(w + static_cast<long long>(o * 9 + t) * C + c);
+    sc = *reinterpret_cast<const float2*>(scale + o * C + c);
+    sh = *reinterpret_cast<const float2*>(shift + o * C + c);
+    T* out = o == 1 ? k : v;
+    float2 top[3];
 #pragma unroll
-    for (int dx = 0; dx < 3; ++dx) win[2][dx] = tile[(t + 2) * PW + col + dx][cp];
-    float2 a = make_float2(0.f, 0.f);
+    for (int dx = 0; dx < 3; ++dx) top[dx] = ld(col + dx);
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky)
+    for (int t = 0; t < TH; t += 2) {
+      const int oy = ty0 + t;
+      if (oy >= H) break;
+      float2 mid[3], bot[3];
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        mid[dx] = ld((t + 1) * PW + col + dx);
+        bot[dx] = ld((t + 2) * PW + col + dx);
+      }
+      float2 a = make_float2(0.f, 0.f);
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
-        a.x = fmaf(win[ky][kx].x, wq[ky * 3 + kx].x, a.x);
-        a.y = fmaf(win[ky][kx].y, wq[ky * 3 + kx].y, a.y);
+        a.x = fmaf(top[kx].x, wt[kx].x, a.x);
+        a.y = fmaf(top[kx].y, wt[kx].y, a.y);
       }
-    store_pair(q + (tok0 + static_cast<long long>(oy) * W + ox) * C + c, fmaf(a.x, sc[0].x, sh[0].x), fmaf(a.y, sc[0].y, sh[0].y));
-    if (col_even && (oy & 1) == 0) {   // warp-uniform: stride-2 window centres are the even coordinates
-      float2 ak = make_float2(0.f, 0.f), av = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int ky = 0; ky < 3; ++ky)
+      for (int kx = 0; kx < 3; ++kx) {
+        a.x = fmaf(mid[kx].x, wt[3 + kx].x, a.x);
+        a.y = fmaf(mid[kx].y, wt[3 + kx].y, a.y);
+      }
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-          ak.x = fmaf(win[ky][kx].x, wk[ky * 3 + kx].x, ak.x);
-          ak.y = fmaf(win[ky][kx].y, wk[ky * 3 + kx].y, ak.y);
-          av.x = fmaf(win[ky][kx].x, wv[ky * 3 + kx].x, av.x);
-          av.y = fmaf(win[ky][kx].y, wv[ky * 3 + kx].y, av.y);
-        }
+      for (int kx = 0; kx < 3; ++kx) {
+        a.x = fmaf(bot[kx].x, wt[6 + kx].x, a.x);
+        a.y = fmaf(bot[kx].y, wt[6 + kx].y, a.y);
+      }
       const long long orow = static_cast<long long>(n) * (cls + Hk * Wk) + cls + static_cast<long long>(oy >> 1) * Wk + (ox >> 1);
-      store_pair(k + orow * C + c, fmaf(ak.x, sc[1].x, sh[1].x), fmaf(ak.y, sc[1].y, sh[1].y));
-      store_pair(v + orow * C + c, fmaf(av.x, sc[2].x, sh[2].x), fmaf(av.y, sc[2].y, sh[2].y));
-    }
+      store_pair(out + orow * C + c, fmaf(a.x, sc.x, sh.x), fmaf(a.y, sc.y, sh.y));
 #pragma unroll
-    for (int dx = 0; dx < 3; ++dx) {
-      win[0][dx] = win[1][dx];
-      win[1][dx] = win[2][dx];
+      for (int dx = 0; dx < 3; ++dx) top[dx] = bot[dx];
     }
   }
 }
@@ -774,8 +841,9 @@ void im2col_pixels(const float* pixels, const int* img_idx, T* out, int n_img, i
   const int Ho = (H + 2 * pad - ksz) / stride + 1, Wo = (W + 2 * pad - ksz) / stride + 1;
   const long long total = static_cast<long long>(n_img) * Ho * Wo * Kpad;
   if (total <= 0) return;
-  const size_t smem = static_cast<size_t>(3) * ksz * W * sizeof(float);
-  if (Kpad % 2 == 0 && smem <= 48 * 1024 && reinterpret_cast<uintptr_t>(out) % 8 == 0) {
+  const size_t smem = static_cast<size_t>(3) * ksz * (W + 8) * sizeof(float);
+  if (Kpad % 2 == 0 && Kpad <= 192 && W % 4 == 0 && reinterpret_cast<uintptr_t>(pixels) % 16 == 0 && smem <= 48 * 1024 &&
+      reinterpret_cast<uintptr_t>(out) % 8 == 0) {
     launch_chain(im2col_pixels_rows_kernel<T>, dim3(static_cast<unsigned>(n_img * Ho)), dim3(256), smem, stream, pixels, img_idx, out, H, W,
                  Ho, Wo, ksz, stride, pad, Kpad);
   } else {
@@ -811,19 +879,18 @@ void ln_dwconv_qkv(const T* x, T* q, T* k, T* v, float* stats, const float* gamm
   CXRM_CHECK(ok, "ln_dwconv_qkv: row statistics need 16-byte aligned rows");
   static const bool tiled = std::getenv("CXRM_NO_DWCONV_TILE") == nullptr;
   if (tiled && C % 64 == 0 && n_img <= 65535) {
-    // tile height: the tallest of 16 / 8 that still gives every SM a few blocks
     const int tiles_x = ceil_div(W, 8);
     const long long blocks16 = static_cast<long long>(tiles_x) * ceil_div(H, 16) * (C / 64) * n_img;
     if (blocks16 >= 148 * 8) {
       dim3 grid(tiles_x * ceil_div(H, 16), C / 64, n_img);
-      launch_chain(ln_dwconv_tile_kernel<T, 16>, grid, dim3(256), 0, stream, x, q, k, v, st, gamma, beta, w, scale, shift, H, W, C, cls,
+      launch_chain(ln_dwconv_async_kernel<T, 16>, grid, dim3(256), 0, stream, x, q, k, v, st, gamma, beta, w, scale, shift, H, W, C, cls,
                    Hk, Wk, tiles_x);
     } else {
       dim3 grid(tiles_x * ceil_div(H, 8), C / 64, n_img);
-      launch_chain(ln_dwconv_tile_kernel<T, 8>, grid, dim3(256), 0, stream, x, q, k, v, st, gamma, beta, w, scale, shift, H, W, C, cls,
+      launch_chain(ln_dwconv_async_kernel<T, 8>, grid, dim3(256), 0, stream, x, q, k, v, st, gamma, beta, w, scale, shift, H, W, C, cls,
                    Hk, Wk, tiles_x);
     }
-    check_launch("ln_dwconv_tile");
+    check_launch("ln_dwconv_async");
   } else {
     const int cols = std::min(W, 256 / cv);
     dim3 grid(ceil_div(W, cols), ceil_div(H, TY), n_img);

@@ -24,10 +24,11 @@ def main():
                enc_chunk=int(os.environ.get("ENC_CHUNK", "64")))
     e.load_state_dict(W.make_cxrmate_weights(seed=0))
     e.finalize()
-    for _ in range(3):
+    reps = int(os.environ.get("ENC_REPS", "3"))
+    for _ in range(reps):
         e.encode(px)
     torch.cuda.synchronize()
-    for _ in range(3):
+    for _ in range(reps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record()
