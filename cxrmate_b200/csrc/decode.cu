@@ -295,6 +295,14 @@ __global__ void __launch_bounds__(SNT) sample_step_kernel(RolloutState st, Rollo
   int next = p.pad;
   float lp = 0.f, margin = 0.f;
   int n_surv = 0;
+  // the row state thread 0 updates at the end: requested now, so the loads ride under the sampling work
+  int pre_len = 0, pre_nv = 0;
+  unsigned pre_seen = 0;
+  if (tid == 0 && !was_finished) {
+    pre_len = st.cur_len[r];
+    pre_nv = st.n_valid[r];
+    pre_seen = st.seen[r];
+  }
 
   if (!was_finished) {
     // ---- pass 1: stage the row as sortable keys; per-thread and block maximum ---------------------
@@ -469,13 +477,13 @@ __global__ void __launch_bounds__(SNT) sample_step_kernel(RolloutState st, Rollo
     st.topk_cnt[ro * p.Tmax + t] = n_surv;
     if (!was_finished) {
       const bool valid = p.mask_token_id < 0 || next != p.mask_token_id;
-      const int cslot = st.cur_len[r] + 1;     // cache slot of the emitted token (visible prompt tokens + emitted so far)
+      const int cslot = pre_len + 1;           // cache slot of the emitted token (visible prompt tokens + emitted so far)
       st.key_valid[ro * p.Lmax + cslot] = valid ? 1 : 0;
-      const int nv = st.n_valid[r] + (valid ? 1 : 0);
+      const int nv = pre_nv + (valid ? 1 : 0);
       st.n_valid[r] = nv;
       st.cur_pos[r] = max(nv - 1, 0);
       // `_past` rule: the last listed special token seen strictly before this token decides its type
-      const unsigned seen = st.seen[r];
+      const unsigned seen = pre_seen;
       int tt = p.sections[blk][0];
       for (int i = 0; i < p.n_special[blk]; ++i)
         if (seen & (1u << i)) tt = p.sections[blk][i + 1];
@@ -488,13 +496,14 @@ __global__ void __launch_bounds__(SNT) sample_step_kernel(RolloutState st, Rollo
       st.cur_len[r] = cslot;
       if (next == p.eos) st.finished[r] = 1;
     }
+    // the arrival ticket also counts the finished rows (high half): the last block knows whether every row is finished
+    // without reading the flags back (a short-circuit loop of R volatile loads was ~10 us of serial L2 round trips at
+    // the very end of every decode step)
+    const unsigned fin_now = (was_finished || next == p.eos) ? 1u : 0u;
     __threadfence();
-    const unsigned prev = atomicAdd(st.arrive, 1u);
-    if (prev == static_cast<unsigned>(p.R) - 1) {
-      // last block of this step: all rows' flags are visible
-      __threadfence();
-      bool all = true;
-      for (int i = 0; i < p.R; ++i) all = all && (reinterpret_cast<volatile uint8_t*>(st.finished)[i] != 0);
+    const unsigned prev = atomicAdd(st.arrive, 1u | (fin_now << 16));
+    if ((prev & 0xffffu) == static_cast<unsigned>(p.R) - 1) {
+      const bool all = (prev >> 16) + fin_now == static_cast<unsigned>(p.R);
       *st.step = t + 1;
       if (all || t + 1 >= p.Tmax) *st.done = 1;
       *st.arrive = 0;

@@ -1137,7 +1137,7 @@ class Engine : public EngineBase {
     CXRM_CHECK(kv_B == a.B && kv_total > 0, "cxrm_rollout needs cxrm_prefill_cross_kv for the same B");
     const int nm = a.mode == CXRM_BOTH ? 2 : 1;
     const int R = a.B * nm, P = a.P, Tn = a.max_new_tokens;
-    CXRM_CHECK(R <= Rmax && P >= 1 && P <= cfg.max_prompt && Tn >= 1 && Tn <= cfg.max_new_tokens, "rollout shape");
+    CXRM_CHECK(R <= Rmax && R < 65536 && P >= 1 && P <= cfg.max_prompt && Tn >= 1 && Tn <= cfg.max_new_tokens, "rollout shape");
     CXRM_CHECK(a.n_special_sample <= kMaxSpecial && a.n_special_greedy <= kMaxSpecial, "too many special tokens");
     RolloutParams rp{};
     rp.R = R; rp.B = a.B; rp.P = P; rp.Lmax = Lmax; rp.Tmax = Tn; rp.V = cfg.vocab;

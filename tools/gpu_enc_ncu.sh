@@ -3,7 +3,7 @@
 # Usage: bash tools/gpu_enc_ncu.sh <tag> [env assignments...]
 tag=$1; shift
 mkdir -p gpurun_out
-env "$@" ENC_REPS=1 timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
+env "$@" ENC_REPS=1 timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active --clock-control none \
   --csv --log-file gpurun_out/enclist_$tag.csv python tools/enc_time.py > gpurun_out/enclist_$tag.log 2>&1
 echo "rc $?"
 python - <<PY
@@ -26,12 +26,13 @@ def mb(k,m):
 agg=collections.OrderedDict()
 for k in ks:
     nm=re.sub(r"^void ","",k["name"]); nm=re.sub(r"\(.*","",nm); nm=nm.replace("cxrm::<unnamed>::","").replace("cxrm::","")
-    a=agg.setdefault(nm,[0,0.0,0.0,0.0]); a[0]+=1; a[1]+=us(k); a[2]+=mb(k,"dram__bytes_read.sum"); a[3]+=mb(k,"dram__bytes_write.sum")
+    a=agg.setdefault(nm,[0,0.0,0.0,0.0,0.0]); a[0]+=1; a[1]+=us(k); a[2]+=mb(k,"dram__bytes_read.sum"); a[3]+=mb(k,"dram__bytes_write.sum")
+    a[4]+=us(k)*k.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",(0,"%"))[0]
 tot=sum(a[1] for a in agg.values())
 out=["# ncu launch list of one encoder pass (100 images, cold-cache, serialised): %d launches, %.2f ms\n"%(len(ks),tot/1e3),
-     "| kernel | launches | total us | mean us | DRAM rd MB | DRAM wr MB | GB/s |","|---|---:|---:|---:|---:|---:|---:|"]
+     "| kernel | launches | total us | mean us | DRAM rd MB | DRAM wr MB | GB/s | tensor pipe % (time-weighted) |","|---|---:|---:|---:|---:|---:|---:|---:|"]
 for nm,a in sorted(agg.items(), key=lambda kv:-kv[1][1]):
-    out.append("| \`%s\` | %d | %.0f | %.1f | %.0f | %.0f | %.0f |"%(nm[:70],a[0],a[1],a[1]/a[0],a[2],a[3],(a[2]+a[3])/a[1]*1e3 if a[1] else 0))
+    out.append("| \`%s\` | %d | %.0f | %.1f | %.0f | %.0f | %.0f | %.1f |"%(nm[:70],a[0],a[1],a[1]/a[0],a[2],a[3],(a[2]+a[3])/a[1]*1e3 if a[1] else 0,a[4]/a[1] if a[1] else 0))
 open("gpurun_out/enclist_$tag.md","w").write("\n".join(out)+"\n")
 print("\n".join(out))
 PY

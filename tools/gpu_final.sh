@@ -23,3 +23,5 @@ head -45 gpurun_out/full_dec_$tag.md
 rm -f gpurun_out/*.ncu-rep
 # encoder GEMM shapes: ncu duration + tensor-pipe activity per launch (tools/bench_gemm.py, one launch per shape)
 bash tools/gpu_gemm_ncu.sh $tag > gpurun_out/gemm_tensor_$tag.txt 2>&1; tail -40 gpurun_out/gemm_tensor_$tag.txt
+# launch list of one encoder pass: per-kernel time, DRAM bytes and tensor-pipe activity
+bash tools/gpu_enc_ncu.sh $tag > gpurun_out/enclist_$tag.txt 2>&1; tail -30 gpurun_out/enclist_$tag.txt
