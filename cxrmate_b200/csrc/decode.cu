@@ -280,8 +280,9 @@ __global__ void __launch_bounds__(SNT) sample_step_kernel(RolloutState st, Rollo
   __shared__ int sh_cnt, sh_ncand;
 
   pdl_launch_dependents();
-  pdl_wait();
-  if (*st.done) return;
+  // the rollout state was written by the PREVIOUS step's sampling kernel (or the prompt pass) and a step opens with a
+  // fully serialised launch: everything but the logits is readable ahead of the dependency wait
+  const bool all_done = *st.done != 0;
   const int r = blockIdx.x, tid = threadIdx.x;
   const int t = *st.step;
   const int blk = r / p.B;
@@ -303,6 +304,8 @@ __global__ void __launch_bounds__(SNT) sample_step_kernel(RolloutState st, Rollo
     pre_nv = st.n_valid[r];
     pre_seen = st.seen[r];
   }
+  pdl_wait();
+  if (all_done) return;
 
   if (!was_finished) {
     // ---- pass 1: stage the row as sortable keys; per-thread and block maximum ---------------------

@@ -713,7 +713,8 @@ __global__ void __launch_bounds__(PNT, 2) decode_cross_persist_kernel(const __gr
       tma_load_2d(dst + TILE_BYTES, &tm_kv, 0, row_base_v + h * tok_cap + m_j0[x], &full[x]);
     }
   }
-  pdl_wait();
+  // the finished flags are written by the PREVIOUS step's last kernel and a step opens with a fully serialised launch:
+  // they are stable for the whole step and readable ahead of the dependency wait (as in the self-attention kernel)
   const bool done = *st.done != 0;
   for (int x = tid; x < hi - lo; x += PNT) {
     bool fin = true;
@@ -722,6 +723,7 @@ __global__ void __launch_bounds__(PNT, 2) decode_cross_persist_kernel(const __gr
     m_fin[x] = (fin || done) ? 1 : 0;
   }
   __syncthreads();
+  pdl_wait();
 
   if (warp == 4) {
     // ===== producer =====

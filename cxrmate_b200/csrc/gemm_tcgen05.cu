@@ -958,8 +958,8 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_skinny_kernel(const __grid_c
       }
     }
     __syncwarp();
+    const bool skip = g.skip_flag && *g.skip_flag;   // stable for the whole step (see splitk_ln_kernel): read ahead of the wait
     pdl_wait();
-    const bool skip = g.skip_flag && *g.skip_flag;
     if (elect_one()) {
 #pragma unroll 1
       for (int i = 0; i < npre; ++i) tma_load_2d(tiles + i * STAGE_BYTES, &tmA, (kb0 + i) * BK, 0, &full[i]);
@@ -981,8 +981,8 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_skinny_kernel(const __grid_c
       }
     }
   } else if (warp == 1) {
+    const bool skip = g.skip_flag && *g.skip_flag;   // stable for the whole step (see splitk_ln_kernel): read ahead of the wait
     pdl_wait();
-    const bool skip = g.skip_flag && *g.skip_flag;
     const int n_do = skip ? npre : nkb;
     constexpr uint32_t idesc = make_idesc(BN);
     const uint32_t tiles_addr = smem_u32(tiles);
@@ -1016,8 +1016,8 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_skinny_kernel(const __grid_c
 #pragma unroll
       for (int j = 0; j < BN; ++j) bpre[j] = (g.bias && (EPI != 4 || n0 + j < g.N)) ? g.bias[n0 + j] : 0.f;
     }
+    const bool skip = g.skip_flag && *g.skip_flag;   // stable for the whole step (see splitk_ln_kernel): read ahead of the wait
     pdl_wait();
-    const bool skip = g.skip_flag && *g.skip_flag;
     mbar_wait(tmem_full, 0);
     tc_fence_after();
     const long long m = quarter * 32 + lane;
@@ -1078,8 +1078,8 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_skinny_kernel(const __grid_c
 #pragma unroll
       for (int j = 0; j < BW; ++j) bpre[j] = (j < BN && n0 + j < g.N) ? g.bias[n0 + j] : 0.f;
     }
+    const bool skip = g.skip_flag && *g.skip_flag;   // stable for the whole step (see splitk_ln_kernel): read ahead of the wait
     pdl_wait();
-    const bool skip = g.skip_flag && *g.skip_flag;
     mbar_wait(tmem_full, 0);
     tc_fence_after();
     const long long m = quarter * 32 + lane;
@@ -1162,8 +1162,11 @@ __global__ void __launch_bounds__(256) splitk_ln_kernel(const float* __restrict_
       rb = *reinterpret_cast<const float4*>(res_beta + c);
     }
   }
+  // the flag is written by the PREVIOUS step's last kernel and a step opens with a fully serialised launch: it is
+  // stable for the whole step, so its load rides ahead of the dependency wait instead of gating the partial loads
+  const bool skip = skip_flag && *skip_flag;
   pdl_wait();
-  if (skip_flag && *skip_flag) return;
+  if (skip) return;
   auto block_sum = [&](float x) {
     x = warp_sum(x);
     __syncthreads();
