@@ -151,7 +151,9 @@ class Engine:
     def rollout(self, prompt_ids: torch.Tensor, *, mode: str, max_new_tokens: int, eos_token_id: int,
                 pad_token_id: int, mask_token_id: Optional[int], special_sample=(), sections_sample=(0,),
                 special_greedy=(), sections_greedy=(0,), top_k: int = 50, temperature: float = 1.0,
-                exp_noise: Optional[torch.Tensor] = None, seed: int = 0) -> RolloutOutput:
+                exp_noise: Optional[torch.Tensor] = None, seed: int = 0, want_margins: bool = True) -> RolloutOutput:
+        """want_margins=False skips the decision-margin diagnosis (a second scan of every row per step; the SCST step
+        never asks for it) and leaves `margins` unwritten."""
         dev = prompt_ids.device
         B, P = prompt_ids.shape
         p32 = prompt_ids.to(torch.int32).contiguous()
@@ -189,7 +191,7 @@ class Engine:
             a.exp_noise = exp_noise.data_ptr()
         a.sequences = out.sequences.data_ptr()
         a.logprobs = out.logprobs.data_ptr()
-        a.margins = out.margins.data_ptr()
+        a.margins = out.margins.data_ptr() if want_margins else None
         a.topk_idx = out.topk_idx.data_ptr()
         a.topk_val = out.topk_val.data_ptr()
         a.topk_cnt = out.topk_cnt.data_ptr()
