@@ -872,15 +872,15 @@ __global__ void __launch_bounds__(PNT, 2) decode_self_persist_kernel(const __gri
       }
       bulk_g2s(dst + ST_MASK, st.key_valid + static_cast<long long>(r) * Lmax + c * CHB, mbytes, &full[s]);
     };
-    // ahead of the dependency wait: the leading live items that do not end with the token being fed stream in while
-    // the QKV projection is still running
+    // ahead of the dependency wait: the K/V + mask tiles of the leading live items stream in while the QKV projection
+    // is still running - ALL of them: the row of the token being fed is stale in the tile that holds it, and the
+    // consumer warp that owns that key overwrites it in shared memory from the projection's output (patch_new_token)
     int it0 = lo, npre = 0, pre_it[PSTAGES];
 #pragma unroll
     for (int x = 0; x < PSTAGES; ++x) pre_it[x] = 0;
     if (lane == 0) {
       for (; it0 < hi && npre < PSTAGES; ++it0) {
         if (m_n[it0 - lo] == 0) continue;
-        if (it0 % mc == m_nch[it0 - lo] - 1) break;
         request_kv(it0, npre);
 #pragma unroll
         for (int x = 0; x < PSTAGES; ++x)
@@ -900,24 +900,22 @@ __global__ void __launch_bounds__(PNT, 2) decode_self_persist_kernel(const __gri
         }
     }
     int k = npre;
-    for (int it = it0; it < hi; ++it) {
+    for (int it = lo; it < hi; ++it) {
       const int n = m_n[it - lo];
       if (n == 0) continue;
       const int c = it % mc, r = (it / mc) % R, h = it / (mc * R);
-      const long long base = (static_cast<long long>(r) * NH + h) * Lmax * HD;
       const bf16* qrow = qkv + static_cast<long long>(r) * 3 * H + h * HD;
       if (c == m_nch[it - lo] - 1) {
-        // this chunk ends with the token being fed: its K/V go from the QKV projection into the cache first, so
-        // that the TMA boxes below already contain them (generic-proxy write -> async-proxy read: proxy fence)
+        // the fed token's K/V go into the cache for the FOLLOWING steps (plain stores: this step reads them from the
+        // projection's output, the next step's kernels start after this one has completed)
+        const long long base = (static_cast<long long>(r) * NH + h) * Lmax * HD;
         const int L = m_len[it - lo];
         const uint32_t kx = *reinterpret_cast<const uint32_t*>(qrow + H + 2 * lane);
         const uint32_t vx = *reinterpret_cast<const uint32_t*>(qrow + 2 * H + 2 * lane);
         *reinterpret_cast<uint32_t*>(kcache + base + static_cast<long long>(L) * HD + 2 * lane) = kx;
         *reinterpret_cast<uint32_t*>(vcache + base + static_cast<long long>(L) * HD + 2 * lane) = vx;
-        __threadfence();
-        asm volatile("fence.proxy.async;" ::: "memory");
-        __syncwarp();
       }
+      if (it < it0) continue;   // requested ahead of the wait
       if (lane == 0) {
         const int s = k % PSTAGES;
         mbar_wait(&empty[s], ((k / PSTAGES) & 1) ^ 1);
@@ -956,8 +954,26 @@ __global__ void __launch_bounds__(PNT, 2) decode_self_persist_kernel(const __gri
       cur_nchunk = m_nch[it - lo];
     }
     const int s = k % PSTAGES;
+    // the chunk that ends with the token being fed: the warp that owns its key (the chunk's last one) takes K/V of that
+    // token straight from the QKV projection - requested before the tile wait - and overwrites the stale row of the
+    // tile (128-byte-swizzled: 16-byte chunk c of row r sits at c ^ (r & 7)).  No cache write -> fence -> TMA read-back
+    // on the critical path, and the tile itself no longer depends on the projection.
+    const bool patch = (it % mc == m_nch[it - lo] - 1) && warp == (n - 1) / WKEYS;
+    uint32_t kx = 0, vx = 0;
+    if (patch) {
+      const bf16* qrow = qkv + static_cast<long long>(r) * 3 * H + h * HD;
+      kx = *reinterpret_cast<const uint32_t*>(qrow + H + 2 * lane);
+      vx = *reinterpret_cast<const uint32_t*>(qrow + 2 * H + 2 * lane);
+    }
     mbar_wait(&full[s], (k / PSTAGES) & 1);
-    const unsigned char* stage = tiles + s * STAGE_BYTES;
+    unsigned char* stage = tiles + s * STAGE_BYTES;
+    if (patch) {
+      const int row = n - 1;
+      const int off = row * 128 + ((((lane >> 2) ^ (row & 7)) << 4) | ((lane & 3) << 2));
+      *reinterpret_cast<uint32_t*>(stage + off) = kx;
+      *reinterpret_cast<uint32_t*>(stage + TILE_BYTES + off) = vx;
+      __syncwarp();
+    }
     load_q_frags<1>(stage + ST_Q, qa0, qa2);
     const uint32_t base = smem_u32(stage);
     if (!dbg_nocompute) warp_tile_update<1>(base, base + TILE_BYTES, n, qa0, qa2, stage + ST_MASK, acc);
