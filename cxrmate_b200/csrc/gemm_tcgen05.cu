@@ -908,7 +908,7 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_skinny_kernel(const __grid_c
                                                                   float* __restrict__ partial, int vec_ok) {
   constexpr int B_BYTES = BN * BK * 2;
   constexpr int STAGE_BYTES = SK_A_BYTES + B_BYTES;
-  constexpr int TMEM_COLS = BN <= 32 ? 32 : 64;
+  constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : 128;
   extern __shared__ uint8_t smem_raw[];
   pdl_launch_dependents();   // the next kernel of the chain may start its own prologue now
 
@@ -1011,8 +1011,10 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_skinny_kernel(const __grid_c
     // ---- lean epilogues (see the template comment) ------------------------------------------------
     const int quarter = warp % 4;
     constexpr int W = BN >= 32 ? 32 : BN;
-    float bpre[EPI == 1 ? 1 : BN];
-    if (EPI != 1) {
+    // (the 128-wide LM-head tile fetches its bias per 32-column chunk: 128 prefetched values would be 128 registers)
+    constexpr bool kBiasAhead = EPI != 1 && BN <= 64;
+    float bpre[kBiasAhead ? BN : 32];
+    if (kBiasAhead) {
 #pragma unroll
       for (int j = 0; j < BN; ++j) bpre[j] = (g.bias && (EPI != 4 || n0 + j < g.N)) ? g.bias[n0 + j] : 0.f;
     }
@@ -1026,10 +1028,15 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_skinny_kernel(const __grid_c
     for (int c0 = 0; c0 < BN; c0 += 32) {
       if (skip || (EPI == 4 && n0 + c0 >= g.N)) break;
       uint32_t r[32];
+      if (EPI != 1 && !kBiasAhead) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) bpre[j] = (g.bias && n0 + c0 + j < g.N) ? g.bias[n0 + c0 + j] : 0.f;
+      }
       if (BN >= 32) tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(c0), r);
       else tmem_ld16(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(c0), r);
       if (!row_ok) continue;
       const int nb = n0 + c0;
+      const int cb = kBiasAhead ? c0 : 0;   // where this chunk's bias sits in bpre
       if (EPI == 1) {
         float4* dst = reinterpret_cast<float4*>(partial + (static_cast<long long>(split) * SK_ROWS + m) * g.N + nb);
 #pragma unroll
@@ -1043,7 +1050,7 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_skinny_kernel(const __grid_c
           float v[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            v[j] = __uint_as_float(r[8 * q + j]) + bpre[c0 + 8 * q + j];
+            v[j] = __uint_as_float(r[8 * q + j]) + bpre[cb + 8 * q + j];
             if (EPI == 3) v[j] = gelu_fast(v[j]);
           }
           Vec16<bf16> ov;
@@ -1056,12 +1063,12 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_skinny_kernel(const __grid_c
 #pragma unroll
           for (int q = 0; q < 8; ++q)
             *reinterpret_cast<float4*>(cp + 4 * q) =
-                make_float4(__uint_as_float(r[4 * q]) + bpre[c0 + 4 * q], __uint_as_float(r[4 * q + 1]) + bpre[c0 + 4 * q + 1],
-                            __uint_as_float(r[4 * q + 2]) + bpre[c0 + 4 * q + 2], __uint_as_float(r[4 * q + 3]) + bpre[c0 + 4 * q + 3]);
+                make_float4(__uint_as_float(r[4 * q]) + bpre[cb + 4 * q], __uint_as_float(r[4 * q + 1]) + bpre[cb + 4 * q + 1],
+                            __uint_as_float(r[4 * q + 2]) + bpre[cb + 4 * q + 2], __uint_as_float(r[4 * q + 3]) + bpre[cb + 4 * q + 3]);
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (nb + j < g.N) cp[j] = __uint_as_float(r[j]) + bpre[c0 + j];
+            if (nb + j < g.N) cp[j] = __uint_as_float(r[j]) + bpre[cb + j];
         }
       }
     }
@@ -1444,7 +1451,7 @@ void launch_skinny(const GemmArgs& g, int stages, int nsplit, int kb_per_split, 
   if (lean && g.c_head_stride == 0 && !g.residual && vec_ok) {
     if (partial && g.N % BN == 0) epi = 1;
     else if (!partial && !g.out_f32 && g.N % BN == 0 && g.M <= SK_ROWS) epi = g.act == ACT_GELU ? 3 : 2;
-    else if (!partial && g.out_f32 && g.act == ACT_NONE && BN == 64) epi = 4;
+    else if (!partial && g.out_f32 && g.act == ACT_NONE && BN >= 64) epi = 4;
   }
   auto go = [&](auto kern) {
     // keyed by the function: the instantiations share one function-pointer type, so a static in this lambda would too
@@ -1464,6 +1471,28 @@ void launch_skinny(const GemmArgs& g, int stages, int nsplit, int kb_per_split, 
     default: go(gemm_tc_skinny_kernel<BN, 0>); break;
   }
   check_launch("gemm_tcgen05_skinny");
+}
+
+// the 128-wide tile exists for the fp32 LM head only (EPI 4); anything else falls back to 64-wide tiles
+template <int BN>
+void launch_skinny_lm(const GemmArgs& g, int stages, int nsplit, int kb_per_split, float* partial, cudaStream_t stream) {
+  const int esz = g.out_f32 ? 4 : 2;
+  const bool vec_ok = (reinterpret_cast<uintptr_t>(g.C) % 16 == 0) && ((static_cast<long long>(g.ldc) * esz) % 16 == 0);
+  static const bool lean = std::getenv("CXRM_NO_LEAN_EPILOGUE") == nullptr;
+  if (!(lean && g.c_head_stride == 0 && !g.residual && vec_ok && !partial && g.out_f32 && g.act == ACT_NONE && nsplit == 1)) {
+    launch_skinny<64>(g, std::min(stages + 2, kb_per_split), nsplit, kb_per_split, partial, stream);
+    return;
+  }
+  const size_t smem = static_cast<size_t>(stages) * (SK_A_BYTES + BN * BK * 2) + SK_SLACK + 1024 + 512;
+  const CUtensorMap ta = make_map(g.A, g.M, g.K, g.lda, SK_ROWS);
+  const CUtensorMap tb = make_map(g.W, g.N, g.K, g.ldw, BN);
+  static size_t have = 0;
+  if (smem > have) {
+    CXRM_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_skinny_kernel<BN, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    have = smem;
+  }
+  launch_chain(gemm_tc_skinny_kernel<BN, 4>, dim3(ceil_div(g.N, BN), 1), dim3(NTHREADS), smem, stream, ta, tb, g, stages, kb_per_split, partial, 1);
+  check_launch("gemm_tcgen05_skinny_lm");
 }
 
 }  // namespace
@@ -1509,8 +1538,15 @@ int gemm_skinny_supported(const GemmArgs& g) {
 }
 
 // nsplit_out: number of K splits written to `partial` (0 when the result was stored directly through the epilogue)
+// LM head tile width: every tcgen05.mma costs >= 93 clocks whatever its width (section 4e), so 128-wide tiles halve the
+// MMA time of the 64-wide ones: 14.2 -> 11.9 us of the step's critical path (tools/trace_step.py); 235 tiles, two CTAs
+// per SM.  (208-wide tiles - 145 tiles, one CTA on each of 145 SMs - were slower, 13.8 us: nothing overlaps the epilogue.)
+static int lm_head_bn() {
+  static const int forced = std::getenv("CXRM_LM_BN") ? std::atoi(std::getenv("CXRM_LM_BN")) : 0;
+  return forced == 64 ? 64 : 128;
+}
 int gemm_skinny_tile_n(const GemmArgs& g, bool split_allowed) {
-  if (g.N >= 8192) return 64;   // LM head: many tiles, two CTAs per SM
+  if (g.N >= 8192) return lm_head_bn();   // LM head: 128-wide tiles halve the MMA instructions (each >= 93 clocks, section 4e)
   if (!split_allowed && ceil_div(g.N, 32) < 48 && g.c_head_stride == 0) return 16;   // no split possible: narrower tiles
   return 32;
 }
@@ -1519,7 +1555,7 @@ void gemm_tcgen05_skinny(const GemmArgs& g, float* partial, int* nsplit_out, cud
   CXRM_CHECK(gemm_skinny_supported(g) == 0, "shape not supported by the skinny tcgen05 GEMM");
   const int num_kb = ceil_div(g.K, BK);
   const int bn = gemm_skinny_tile_n(g, partial != nullptr);
-  int stages = bn == 64 ? 6 : SK_MAX_STAGES;
+  int stages = bn == 128 ? 4 : bn == 64 ? 6 : SK_MAX_STAGES;   // LM head: two CTAs per SM
   // split-K: every tcgen05.mma of this kernel costs ~93 clocks whatever its width (the 128 x 16 A slice is read from shared
   // memory per instruction: tools/mb_mma.cu), so a CTA's floor is 4 * k-blocks * 93 clocks - 2.3 us for K = 768 unsplit.
   // The GEMMs that feed the reduce + LayerNorm kernel split as far as kSkMaxSplit partials of >= kb_min k-blocks.
@@ -1541,6 +1577,7 @@ void gemm_tcgen05_skinny(const GemmArgs& g, float* partial, int* nsplit_out, cud
   switch (bn) {
     case 16: launch_skinny<16>(g, stages, nsplit, kb_per_split, partial, stream); break;
     case 64: launch_skinny<64>(g, stages, nsplit, kb_per_split, partial, stream); break;
+    case 128: launch_skinny_lm<128>(g, stages, nsplit, kb_per_split, partial, stream); break;
     default: launch_skinny<32>(g, stages, nsplit, kb_per_split, partial, stream); break;
   }
 }
