@@ -4,19 +4,20 @@
 //
 // One CTA = 128 queries of one (image, head); key tiles of 192 (CvT's key counts 2304 / 576 / 145 are 12 / 3 / 1 tiles).
 // Per tile:
-//   warp 0   TMA: K tile [192 keys x 64] and the matching V^T tile [64 dims x 192 keys] (one buffer each: K_(i+1) lands
-//            during softmax_i / P.V_i, V^T_(i+1) during S_(i+1) and its softmax)
+//   warp 0   TMA: K tile and V tile, both [192 keys x 64 dims] exactly as they lie in memory (one buffer each: K_(i+1)
+//            lands during softmax_i / P.V_i, V_(i+1) during S_(i+1) and its softmax)
 //   warp 1   S = Q.K^T   : 4 x tcgen05.mma 128 x 192 x 16 into TMEM columns 0..191 (N = 192 keeps the pipe 95 % busy; the
 //                          measured floor of ~93 clocks per MMA makes N <= 128 no cheaper)
-//            O_t = P.V   : 12 x tcgen05.mma 128 x 64 x 16 into TMEM columns 192..255 (P from shared memory)
+//            O_t = P.V   : 12 x tcgen05.mma 128 x 64 x 16 into TMEM columns 192..255; P from shared memory (K-major), V as
+//                          an MN-MAJOR B operand (instruction-descriptor bit 16): rows = keys = K, 128 contiguous bytes =
+//                          the 64 output dimensions, so no transposed copy of V exists (a first version transposed V per
+//                          head in a separate kernel: 42 launches, 0.6 ms per 100 images)
 //            a ragged last tile issues N (and P.V k-steps) for its own keys only, rounded up to 16
 //   warps 2-5 (one query row per thread): tcgen05.ld of S (two passes over 32-column chunks: row maximum, then
 //            p = 2^(s.scale.log2e - m) -> bf16 -> the K-major, 128-byte-swizzled P tile in shared memory), then
 //            o = o.alpha + O_t from TMEM.  The running output lives in registers, so nothing in TMEM is rescaled.
 // A CTA is serial over its tiles (S -> softmax -> P.V -> accumulate; S_(i+1) overlaps the accumulate); two CTAs per SM
 // (112 KB of shared memory, 256 TMEM columns each) overlap one's softmax with the other's MMAs.
-// V is needed K-major for the P.V product (keys contiguous per output dimension), i.e. transposed: transpose_v_heads
-// writes V^T [batch][head][64][Lk padded to 8] first (V is 1/4 of the query tokens in CvT: a small pass).
 #include <cuda.h>
 
 #include <mutex>
@@ -146,7 +147,7 @@ __device__ __forceinline__ float tile_probs(uint32_t t_s, uint8_t* sP, int row, 
 // registers are allocated per 4 warps: 2 CTAs / SM need <= 128 registers per thread, which is what a 256-thread bound asks for
 __global__ void __launch_bounds__(256, 2) attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ,
                                                                const __grid_constant__ CUtensorMap tmK,
-                                                               const __grid_constant__ CUtensorMap tmVt, bf16* __restrict__ o,
+                                                               const __grid_constant__ CUtensorMap tmV, bf16* __restrict__ o,
                                                                long long o_ts, int Lq, int Lk, int heads, float sl2) {
   extern __shared__ uint8_t smem_raw5[];   // no static shared memory in this kernel: the dynamic window starts 1 KB aligned
   pdl_launch_dependents();
@@ -154,7 +155,7 @@ __global__ void __launch_bounds__(256, 2) attention_tc5_kernel(const __grid_cons
   if ((s32(sm) & 1023u) != 0) __trap();    // the 128-byte swizzle atoms need 1 KB alignment
   uint8_t* sQ = sm;
   uint8_t* sK = sQ + Q_BYTES;              // [KT keys][128 B]
-  uint8_t* sV = sK + K_BYTES;              // [KB5 k-blocks][64 dims][64 keys]
+  uint8_t* sV = sK + K_BYTES;              // [KT keys][128 B] (MN-major B operand of P.V)
   uint8_t* sP = sV + VT_BYTES;             // [KB5 k-blocks][128 rows][64 keys]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
   uint64_t* q_full = bars;
@@ -204,13 +205,12 @@ __global__ void __launch_bounds__(256, 2) attention_tc5_kernel(const __grid_cons
       mb_wait(v_empty, (i & 1) ^ 1);
       if (elect1()) {
         mb_expect(v_full, VT_BYTES);
-#pragma unroll
-        for (int kb = 0; kb < KB5; ++kb) tma2d(sV + kb * (64 * 128), &tmVt, i * KT + kb * 64, (b * heads + h) * HD5, v_full);
+        tma2d(sV, &tmV, h * HD5, b * Lk + i * KT, v_full);
       }
       __syncwarp();
     }
   } else if (warp == 1) {
-    constexpr uint32_t id_o = idesc5(HD5);
+    constexpr uint32_t id_o = idesc5(HD5) | (1u << 16);   // B (= V) is MN-major
     const uint64_t dq = desc5(s32(sQ)), dk = desc5(s32(sK));
     const uint32_t aP = s32(sP), aV = s32(sV);
     mb_wait(q_full, 0);
@@ -232,8 +232,8 @@ __global__ void __launch_bounds__(256, 2) attention_tc5_kernel(const __grid_cons
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (elect1()) {
         for (int ks = 0; ks < n16 / 16; ++ks) {
-          const int kb = ks >> 2, k = ks & 3;
-          mma5(tmem + S_COLS, desc5(aP + kb * (QT * 128)) + 2 * k, desc5(aV + kb * (64 * 128)) + 2 * k, id_o, ks != 0);
+          const int kb = ks >> 2, k = ks & 3;   // P: 64-key k-blocks of [128 rows x 128 B]; V: 16 keys = 16 rows of 128 B per step
+          mma5(tmem + S_COLS, desc5(aP + kb * (QT * 128)) + 2 * k, desc5(aV + ks * (16 * 128)), id_o, ks != 0);
         }
         commit5(o_full);
         commit5(v_empty);
@@ -294,25 +294,6 @@ __global__ void __launch_bounds__(256, 2) attention_tc5_kernel(const __grid_cons
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TM_COLS) : "memory");
 }
 
-// v [batch * Lk, heads * 64] (token stride v_ts) -> vt [batch][heads][64][Lkp], zero in the padding columns
-__global__ void __launch_bounds__(256) transpose_v_heads_kernel(const bf16* __restrict__ v, long long v_ts, bf16* __restrict__ vt,
-                                                                int Lk, int Lkp, int heads) {
-  __shared__ bf16 tile[64][66];
-  pdl_launch_dependents();
-  pdl_wait();
-  const int k0 = blockIdx.x * 64, h = blockIdx.y, b = blockIdx.z;
-  for (int i = threadIdx.x; i < 64 * 64; i += 256) {
-    const int key = i / 64, d = i % 64;
-    tile[key][d] = (k0 + key < Lk) ? v[(static_cast<long long>(b) * Lk + k0 + key) * v_ts + h * 64 + d] : __float2bfloat16(0.f);
-  }
-  __syncthreads();
-  bf16* dst = vt + (static_cast<long long>(b) * heads + h) * 64 * Lkp;
-  for (int i = threadIdx.x; i < 64 * 64; i += 256) {
-    const int d = i / 64, key = i % 64;
-    if (k0 + key < Lkp) dst[static_cast<long long>(d) * Lkp + k0 + key] = tile[key][d];
-  }
-}
-
 typedef CUresult (*EncodeFn5)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -343,11 +324,6 @@ CUtensorMap map5(const void* ptr, long long rows, long long cols, long long ld, 
 
 }  // namespace
 
-size_t attention_tc5_scratch_elems(const AttnArgs& a) {
-  const long long Lkp = (a.Lk + 7) & ~7;
-  return static_cast<size_t>(a.batch) * a.heads * 64 * Lkp;
-}
-
 int attention_tc5_supported(const AttnArgs& a) {
   static const bool off = std::getenv("CXRM_NO_TC5_ATTN") != nullptr;
   if (off) return 9;
@@ -356,7 +332,7 @@ int attention_tc5_supported(const AttnArgs& a) {
   if (a.q_hs != 64 || a.k_hs != 64 || a.v_hs != 64 || a.o_hs != 64) return 2;
   if (a.q_ts < C || a.k_ts < C || a.v_ts < C || a.o_ts < C) return 3;
   if (a.q_bs != a.Lq * a.q_ts || a.k_bs != a.Lk * a.k_ts || a.v_bs != a.Lk * a.v_ts || a.o_bs != a.Lq * a.o_ts) return 4;   // batches contiguous
-  if (a.q_ts % 8 || a.k_ts % 8 || a.o_ts % 8) return 5;
+  if (a.q_ts % 8 || a.k_ts % 8 || a.v_ts % 8 || a.o_ts % 8) return 5;
   auto al16 = [](const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
   if (!al16(a.q) || !al16(a.k) || !al16(a.v) || !al16(a.o)) return 6;
   if (a.Lq < 64 || a.Lk < 16) return 7;              // tiny problems stay on the mma.sync kernel
@@ -364,14 +340,9 @@ int attention_tc5_supported(const AttnArgs& a) {
   return 0;
 }
 
-void attention_tc5(const AttnArgs& a, void* vt_scratch, cudaStream_t stream) {
-  CXRM_CHECK(attention_tc5_supported(a) == 0 && vt_scratch != nullptr, "attention_tc5: unsupported arguments");
+void attention_tc5(const AttnArgs& a, cudaStream_t stream) {
+  CXRM_CHECK(attention_tc5_supported(a) == 0, "attention_tc5: unsupported arguments");
   if (a.batch <= 0 || a.Lq <= 0) return;
-  const int Lkp = (a.Lk + 7) & ~7;
-  bf16* vt = static_cast<bf16*>(vt_scratch);
-  launch_chain(transpose_v_heads_kernel, dim3(ceil_div(Lkp, 64), a.heads, a.batch), dim3(256), 0, stream,
-               static_cast<const bf16*>(a.v), a.v_ts, vt, a.Lk, Lkp, a.heads);
-  check_launch("transpose_v_heads");
   static bool configured = false;
   if (!configured) {
     CXRM_CUDA_CHECK(cudaFuncSetAttribute(attention_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM5));
@@ -382,7 +353,7 @@ void attention_tc5(const AttnArgs& a, void* vt_scratch, cudaStream_t stream) {
   const long long C = static_cast<long long>(a.heads) * 64;
   const CUtensorMap tq = map5(a.q, static_cast<long long>(a.batch) * a.Lq, C, a.q_ts, QT);
   const CUtensorMap tk = map5(a.k, static_cast<long long>(a.batch) * a.Lk, C, a.k_ts, KT);
-  const CUtensorMap tv = map5(vt, static_cast<long long>(a.batch) * a.heads * 64, Lkp, Lkp, 64);
+  const CUtensorMap tv = map5(a.v, static_cast<long long>(a.batch) * a.Lk, C, a.v_ts, KT);
   launch_chain(attention_tc5_kernel, dim3(ceil_div(a.Lq, QT), a.heads, a.batch), dim3(NTH), SMEM5, stream, tq, tk, tv,
                static_cast<bf16*>(a.o), a.o_ts, a.Lq, a.Lk, a.heads, a.scale * 1.4426950408889634f);
   check_launch("attention_tc5");

@@ -308,12 +308,9 @@ int cxrm_test_attention(int dtype, const void* q, const void* k, const void* v, 
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (dtype == CXRM_F32)
       attention_simt<float>(a, s);
-    else if (attention_tc5_supported(a) == 0) {
-      void* vt = nullptr;
-      CXRM_CUDA_CHECK(cudaMallocAsync(&vt, attention_tc5_scratch_elems(a) * sizeof(bf16), s));
-      attention_tc5(a, vt, s);
-      CXRM_CUDA_CHECK(cudaFreeAsync(vt, s));
-    } else if (attention_mma_supported(a) == 0)
+    else if (attention_tc5_supported(a) == 0)
+      attention_tc5(a, s);
+    else if (attention_mma_supported(a) == 0)
       attention_mma(a, s);
     else
       attention_simt<bf16>(a, s);

@@ -690,7 +690,7 @@ class Engine : public EngineBase {
         a.o_bs = a.q_bs; a.o_hs = 64; a.o_ts = C;
         a.batch = n; a.heads = CVT_HEADS[s_]; a.Lq = Tq; a.Lk = Tk;
         a.scale = 1.0f / sqrtf(static_cast<float>(C));   // embed_dim ** -0.5 (modeling_cvt.py:183)
-        PF("attn", s, [&] { attention(a, s, hid, static_cast<size_t>(hid_elems)); });   // hid is idle: V^T scratch
+        PF("attn", s, [&] { attention(a, s); });
         gemm(q, C, L.o, x2, C, rq, ACT_NONE, x, C, false, nullptr, s);          // + residual
         PF("layernorm", s, [&] { layernorm<T>(x2, C, y, C, L.ln2.g, L.ln2.b, rq, C, LN_EPS_CVT, s); });
         gemm(y, C, L.fc1, hid, 4 * C, rq, ACT_GELU, nullptr, 0, false, nullptr, s);
@@ -855,7 +855,7 @@ class Engine : public EngineBase {
   long long cross_layer_stride() const { return cross_tok_cap() * 2 * DH; }
 
   // =========================================================================== attention dispatch
-  void attention(const AttnArgs& a, cudaStream_t s, void* scratch = nullptr, size_t scratch_elems = 0);
+  void attention(const AttnArgs& a, cudaStream_t s);
 
   // =========================================================================== decoder trunk
   // tokens M = R*qlen already embedded in x [M,768]; returns the buffer holding the output hidden states
@@ -2104,11 +2104,11 @@ class Engine : public EngineBase {
 };
 
 template <>
-void Engine<float>::attention(const AttnArgs& a, cudaStream_t s, void*, size_t) { attention_simt<float>(a, s); }
+void Engine<float>::attention(const AttnArgs& a, cudaStream_t s) { attention_simt<float>(a, s); }
 template <>
-void Engine<bf16>::attention(const AttnArgs& a, cudaStream_t s, void* scratch, size_t scratch_elems) {
-  if (cfg.use_tensor_cores && scratch && attention_tc5_supported(a) == 0 && scratch_elems >= attention_tc5_scratch_elems(a))
-    attention_tc5(a, scratch, s);
+void Engine<bf16>::attention(const AttnArgs& a, cudaStream_t s) {
+  if (cfg.use_tensor_cores && attention_tc5_supported(a) == 0)
+    attention_tc5(a, s);
   else if (cfg.use_tensor_cores && attention_mma_supported(a) == 0)
     attention_mma(a, s);
   else

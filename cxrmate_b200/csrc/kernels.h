@@ -131,10 +131,9 @@ template <typename T> void attention_simt(const AttnArgs& a, cudaStream_t stream
 int attention_mma_supported(const AttnArgs& a);
 void attention_mma(const AttnArgs& a, cudaStream_t stream);
 // bf16 tcgen05 / TMEM / TMA flash attention for dense (unmasked, non-causal, unpacked) calls with >= 64 queries
-// (attention_tc5.cu); needs attention_tc5_scratch_elems(a) bf16 of scratch for the per-head transposed V
+// (attention_tc5.cu)
 int attention_tc5_supported(const AttnArgs& a);
-size_t attention_tc5_scratch_elems(const AttnArgs& a);
-void attention_tc5(const AttnArgs& a, void* vt_scratch, cudaStream_t stream);
+void attention_tc5(const AttnArgs& a, cudaStream_t stream);
 
 }  // namespace cxrm
 
