@@ -148,7 +148,9 @@ __device__ __forceinline__ float tile_probs(uint32_t t_s, uint8_t* sP, int row, 
 __global__ void __launch_bounds__(256, 2) attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ,
                                                                const __grid_constant__ CUtensorMap tmK,
                                                                const __grid_constant__ CUtensorMap tmV, bf16* __restrict__ o,
-                                                               long long o_ts, int Lq, int Lk, int heads, float sl2) {
+                                                               long long o_ts, int Lq, int Lk, int heads, float sl2,
+                                                               const int* __restrict__ q_offset, const int* __restrict__ lq_per_batch,
+                                                               const int* __restrict__ kv_offset, const int* __restrict__ lk_per_batch) {
   extern __shared__ uint8_t smem_raw5[];   // no static shared memory in this kernel: the dynamic window starts 1 KB aligned
   pdl_launch_dependents();
   uint8_t* sm = smem_raw5;
@@ -170,7 +172,6 @@ __global__ void __launch_bounds__(256, 2) attention_tc5_kernel(const __grid_cons
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int q0 = blockIdx.x * QT, h = blockIdx.y, b = blockIdx.z;
-  const int n_tiles = (Lk + KT - 1) / KT;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 8; ++i) mb_init(&bars[i], i == 6 ? 4 : 1);   // p_full: one arrival per softmax warp
@@ -185,27 +186,33 @@ __global__ void __launch_bounds__(256, 2) attention_tc5_kernel(const __grid_cons
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = __shfl_sync(kFull, *tmem_slot, 0);
-  pdl_wait();   // q / k / v^T are the previous kernels' outputs
+  pdl_wait();   // q / k / v (and the offsets of a packed batch) are the previous kernels' outputs
+  // packed (ragged) batches: sequence b owns rows q_row0 .. + Lq of q / o and k_row0 .. + Lk of k / v
+  const int q_row0 = q_offset ? q_offset[b] : b * Lq, k_row0 = kv_offset ? kv_offset[b] : b * Lk;
+  if (lq_per_batch) Lq = lq_per_batch[b];
+  if (lk_per_batch) Lk = lk_per_batch[b];
+  const bool live = q0 < Lq && Lk > 0;            // a tile past the end of a short sequence only tears down
+  const int n_tiles = live ? (Lk + KT - 1) / KT : 0;
 
   if (warp == 0) {
     // K and V^T have one buffer each: K of tile i+1 lands while tile i is in softmax / P.V (its slot is free once S_i is
     // done), V^T of tile i+1 while S_(i+1) and its softmax run
-    if (elect1()) {
+    if (live && elect1()) {
       mb_expect(q_full, Q_BYTES);
-      tma2d(sQ, &tmQ, h * HD5, b * Lq + q0, q_full);
+      tma2d(sQ, &tmQ, h * HD5, q_row0 + q0, q_full);
     }
     __syncwarp();
     for (int i = 0; i < n_tiles; ++i) {
       mb_wait(k_empty, (i & 1) ^ 1);
       if (elect1()) {
         mb_expect(k_full, K_BYTES);
-        tma2d(sK, &tmK, h * HD5, b * Lk + i * KT, k_full);
+        tma2d(sK, &tmK, h * HD5, k_row0 + i * KT, k_full);
       }
       __syncwarp();
       mb_wait(v_empty, (i & 1) ^ 1);
       if (elect1()) {
         mb_expect(v_full, VT_BYTES);
-        tma2d(sV, &tmV, h * HD5, b * Lk + i * KT, v_full);
+        tma2d(sV, &tmV, h * HD5, k_row0 + i * KT, v_full);
       }
       __syncwarp();
     }
@@ -213,7 +220,7 @@ __global__ void __launch_bounds__(256, 2) attention_tc5_kernel(const __grid_cons
     constexpr uint32_t id_o = idesc5(HD5) | (1u << 16);   // B (= V) is MN-major
     const uint64_t dq = desc5(s32(sQ)), dk = desc5(s32(sK));
     const uint32_t aP = s32(sP), aV = s32(sV);
-    mb_wait(q_full, 0);
+    if (live) mb_wait(q_full, 0);
     for (int i = 0; i < n_tiles; ++i) {
       // a ragged last tile computes only the keys it has, rounded up to the MMA's N / K granularity of 16
       const int n16 = (min(KT, Lk - i * KT) + 15) & ~15;
@@ -278,9 +285,9 @@ __global__ void __launch_bounds__(256, 2) attention_tc5_kernel(const __grid_cons
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
-    if (q0 + row < Lq) {
+    if (live && q0 + row < Lq) {
       const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
-      bf16* dst = o + (static_cast<long long>(b) * Lq + q0 + row) * o_ts + h * HD5;
+      bf16* dst = o + (static_cast<long long>(q_row0) + q0 + row) * o_ts + h * HD5;
 #pragma unroll
       for (int d = 0; d < HD5; d += 8) {
         *reinterpret_cast<uint4*>(dst + d) =
@@ -327,11 +334,13 @@ CUtensorMap map5(const void* ptr, long long rows, long long cols, long long ld, 
 int attention_tc5_supported(const AttnArgs& a) {
   static const bool off = std::getenv("CXRM_NO_TC5_ATTN") != nullptr;
   if (off) return 9;
-  if (a.key_mask || a.causal || a.Lk_per_batch || a.kv_offset || a.kv_batch_mod || a.q_offset || a.Lq_per_batch) return 1;
+  if (a.key_mask || a.causal || a.kv_batch_mod) return 1;
+  const bool packed = a.q_offset || a.Lq_per_batch || a.kv_offset || a.Lk_per_batch;
+  if (packed && !(a.q_offset && a.Lq_per_batch && a.kv_offset && a.Lk_per_batch && a.total_q > 0 && a.total_kv > 0)) return 1;
   const long long C = static_cast<long long>(a.heads) * 64;
   if (a.q_hs != 64 || a.k_hs != 64 || a.v_hs != 64 || a.o_hs != 64) return 2;
   if (a.q_ts < C || a.k_ts < C || a.v_ts < C || a.o_ts < C) return 3;
-  if (a.q_bs != a.Lq * a.q_ts || a.k_bs != a.Lk * a.k_ts || a.v_bs != a.Lk * a.v_ts || a.o_bs != a.Lq * a.o_ts) return 4;   // batches contiguous
+  if (!packed && (a.q_bs != a.Lq * a.q_ts || a.k_bs != a.Lk * a.k_ts || a.v_bs != a.Lk * a.v_ts || a.o_bs != a.Lq * a.o_ts)) return 4;   // batches contiguous
   if (a.q_ts % 8 || a.k_ts % 8 || a.v_ts % 8 || a.o_ts % 8) return 5;
   auto al16 = [](const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
   if (!al16(a.q) || !al16(a.k) || !al16(a.v) || !al16(a.o)) return 6;
@@ -351,11 +360,15 @@ void attention_tc5(const AttnArgs& a, cudaStream_t stream) {
     configured = true;
   }
   const long long C = static_cast<long long>(a.heads) * 64;
-  const CUtensorMap tq = map5(a.q, static_cast<long long>(a.batch) * a.Lq, C, a.q_ts, QT);
-  const CUtensorMap tk = map5(a.k, static_cast<long long>(a.batch) * a.Lk, C, a.k_ts, KT);
-  const CUtensorMap tv = map5(a.v, static_cast<long long>(a.batch) * a.Lk, C, a.v_ts, KT);
+  const bool packed = a.q_offset != nullptr;
+  const long long rows_q = packed ? a.total_q : static_cast<long long>(a.batch) * a.Lq;
+  const long long rows_kv = packed ? a.total_kv : static_cast<long long>(a.batch) * a.Lk;
+  const CUtensorMap tq = map5(a.q, rows_q, C, a.q_ts, QT);
+  const CUtensorMap tk = map5(a.k, rows_kv, C, a.k_ts, KT);
+  const CUtensorMap tv = map5(a.v, rows_kv, C, a.v_ts, KT);
   launch_chain(attention_tc5_kernel, dim3(ceil_div(a.Lq, QT), a.heads, a.batch), dim3(NTH), SMEM5, stream, tq, tk, tv,
-               static_cast<bf16*>(a.o), a.o_ts, a.Lq, a.Lk, a.heads, a.scale * 1.4426950408889634f);
+               static_cast<bf16*>(a.o), a.o_ts, a.Lq, a.Lk, a.heads, a.scale * 1.4426950408889634f, a.q_offset, a.Lq_per_batch,
+               a.kv_offset, a.Lk_per_batch);
   check_launch("attention_tc5");
 }
 

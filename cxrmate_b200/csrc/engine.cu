@@ -1813,6 +1813,7 @@ class Engine : public EngineBase {
       a.batch = n; a.heads = NHEAD; a.Lq = L; a.Lk = L;
       a.q_offset = off; a.Lq_per_batch = lenc;      // attention_mask from padding='longest' == (j < len)
       a.kv_offset = off; a.Lk_per_batch = lenc;
+      a.total_q = a.total_kv = M;
       a.scale = 0.125f;
       PF("attn", s, [&] { attention(a, s); });
       gemm(b.ctx, DH, w.o, b.x1, DH, M, ACT_NONE, b.x, DH, false, nullptr, s);

@@ -125,6 +125,9 @@ struct AttnArgs {
   // unused); Lq is then only the upper bound that sizes the grid
   const int* q_offset;
   const int* Lq_per_batch;
+  // optional: rows that exist in the packed q / o and k / v buffers (lets the TMA-based kernel bound its tensor maps;
+  // 0 = unknown, that kernel then declines packed calls)
+  long long total_q, total_kv;
 };
 template <typename T> void attention_simt(const AttnArgs& a, cudaStream_t stream);
 // bf16 tensor-core (mma.sync m16n8k16) flash attention with the same contract; returns 0 from _supported when usable
