@@ -648,7 +648,7 @@ def run_teacher_forced(a):
     B = 64 if a.studies == 32 else a.studies
     N, L = a.images, 512
     eng = Engine(dtype=a.dtype, device=local, max_studies=B, max_images=N, max_prompt=8, max_new_tokens=8, rwd_layers=0,
-                 enc_chunk=32, max_train_tokens=B * L)
+                 enc_chunk=64, max_train_tokens=B * L)
     eng.load_state_dict(W.make_cxrmate_weights(seed=0))
     eng.finalize()
     counts = global_image_counts(world * B, N)
