@@ -50,15 +50,16 @@ def main():
         torch.cuda.synchronize()
     ev = [(x.name, x.time_range.start, x.time_range.end) for x in prof.events() if x.device_type == torch.autograd.DeviceType.CUDA]
     ev.sort(key=lambda t: t[1])
-    # steps open with the embedding kernel
-    starts = [i for i, x in enumerate(ev) if "embed_ln" in x[0]]
-    print(f"{len(ev)} kernel records, {len(starts)} steps")
-    if len(starts) < 4:
+    # a step ends with the sampling kernel (which also embeds the next step's input); the first one closes the prompt pass
+    ends = [i for i, x in enumerate(ev) if "sample_step" in x[0]]
+    print(f"{len(ev)} kernel records, {len(ends)} sampling kernels")
+    if len(ends) < 5:
         for x in ev[:50]:
             print(x)
         return
-    k = len(starts) - 3          # a late step (longest caches)
-    seg = ev[starts[k]: starts[k + 1]]
+    k = len(ends) - 3            # a late step (longest caches)
+    seg = ev[ends[k - 1] + 1: ends[k] + 1]
+    nxt = ev[ends[k] + 1][1] if ends[k] + 1 < len(ev) else seg[-1][2]
     t0 = seg[0][1]
     prev_end = t0
     rows = []
@@ -66,7 +67,7 @@ def main():
         short = name.replace("void ", "").replace("cxrm::", "").replace("(anonymous namespace)::", "").split("(")[0][:44]
         rows.append((short, s_ - t0, e_ - s_, e_ - prev_end))
         prev_end = max(prev_end, e_)
-    print(f"step {k}: {len(seg)} kernels, {prev_end - t0:.1f} us from the first start to the last end; next step starts {ev[starts[k + 1]][1] - t0:.1f} us after this one")
+    print(f"step {k}: {len(seg)} kernels, {prev_end - t0:.1f} us from the first start to the last end; next step starts {nxt - t0:.1f} us after this one")
     print(f"{'kernel':46s} {'start':>8s} {'dur':>7s} {'end+':>7s}")
     for r in rows:
         print(f"{r[0]:46s} {r[1]:8.1f} {r[2]:7.1f} {r[3]:7.1f}")
