@@ -321,6 +321,36 @@ int cxrm_test_attention(int dtype, const void* q, const void* k, const void* v, 
   }
 }
 
+int cxrm_test_attention_packed(int dtype, const void* qkv, void* o, int n_seq, int heads, int Lmax, const int32_t* offsets,
+                               const int32_t* lens, long long total, float scale, void* stream) {
+  try {
+    AttnArgs a{};
+    const long long C = static_cast<long long>(heads) * 64;
+    const size_t esz = dtype == CXRM_F32 ? 4 : 2;
+    const char* base = static_cast<const char*>(qkv);
+    a.q = base; a.k = base + C * esz; a.v = base + 2 * C * esz; a.o = o;
+    a.q_hs = a.k_hs = a.v_hs = a.o_hs = 64;
+    a.q_ts = a.k_ts = a.v_ts = 3 * C; a.o_ts = C;
+    a.batch = n_seq; a.heads = heads; a.Lq = Lmax; a.Lk = Lmax;
+    a.q_offset = offsets; a.Lq_per_batch = lens; a.kv_offset = offsets; a.Lk_per_batch = lens;
+    a.total_q = a.total_kv = total;
+    a.scale = scale;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dtype == CXRM_F32)
+      attention_simt<float>(a, s);
+    else if (attention_tc5_supported(a) == 0)
+      attention_tc5(a, s);
+    else if (attention_mma_supported(a) == 0)
+      attention_mma(a, s);
+    else
+      attention_simt<bf16>(a, s);
+    return CXRM_OK;
+  } catch (const std::exception& ex) {
+    g_create_error = ex.what();
+    return CXRM_ERR_CUDA;
+  }
+}
+
 int cxrm_test_layernorm(int dtype, const void* x, void* y, const float* gamma, const float* beta, long long rows, int C,
                         float eps, void* stream) {
   try {

@@ -471,6 +471,21 @@ def attention_hook(q, k, v, key_mask=None, causal: bool = False, scale: float = 
     return o
 
 
+def attention_packed_hook(qkv, offsets, lens, heads: int, scale: float = 0.125):
+    """qkv [total, 3 * heads*64] (q | k | v per token), sequence i = rows offsets[i] .. + lens[i] -> o [total, heads*64]:
+    the packed self-attention of the CXR-BERT reward batch (no mask inside a sequence)."""
+    lib = _lib.load()
+    total = qkv.shape[0]
+    dt = _lib.CXRM_F32 if qkv.dtype == torch.float32 else _lib.CXRM_BF16
+    o = torch.zeros(total, heads * 64, dtype=qkv.dtype, device=qkv.device)
+    off32, len32 = offsets.to(torch.int32).contiguous(), lens.to(torch.int32).contiguous()
+    rc = lib.cxrm_test_attention_packed(dt, _ptr(qkv), _ptr(o), int(lens.numel()), int(heads), int(lens.max()), _ptr(off32),
+                                        _ptr(len32), int(total), float(scale), _stream())
+    if rc != 0:
+        raise RuntimeError(f"cxrm_test_attention_packed failed ({rc}): {lib.cxrm_last_error(None).decode()}")
+    return o
+
+
 def layernorm_hook(x, gamma, beta, eps: float):
     """x [rows, C] fp32 | bf16 -> LayerNorm(x) like x (the vectorised kernel when rows are 16-byte aligned)."""
     lib = _lib.load()

@@ -110,6 +110,8 @@ SYMBOLS = {
     "cxrm_test_set_gemm_trace": (None, [C.c_void_p]),
     "cxrm_test_attention": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                       C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_void_p]),
+    "cxrm_test_attention_packed": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                             C.c_longlong, C.c_float, C.c_void_p]),
     "cxrm_test_layernorm": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int,
                                       C.c_float, C.c_void_p]),
     "cxrm_test_ln_dwconv": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -355,6 +355,12 @@ CXRM_API void cxrm_test_set_gemm_trace(unsigned long long* dev_buf);
 /* Standalone attention entry used by the kernel tests (q,k,v,o: [batch, L, heads*64] token-major). */
 CXRM_API int cxrm_test_attention(int dtype, const void* q, const void* k, const void* v, void* o, int batch, int heads,
                         int Lq, int Lk, const uint8_t* key_mask, int causal, float scale, void* stream);
+/* The same for a PACKED (ragged) self-attention batch, as the CXR-BERT reward uses it (engine.cu reward_embed): qkv dev
+ * [total, 3 * heads*64] (q | k | v per token), sequence i = rows offsets[i] .. offsets[i] + lens[i] (dev int32 [n_seq],
+ * lens <= Lmax), every key of a sequence visible to every query of it; o dev [total, heads*64]. */
+CXRM_API int cxrm_test_attention_packed(int dtype, const void* qkv, void* o, int n_seq, int heads, int Lmax,
+                                        const int32_t* offsets, const int32_t* lens, long long total, float scale,
+                                        void* stream);
 
 /* Sampling head on caller-provided logits dev fp32 [R, V]: every row is a sample row of a fresh rollout at decode step
  * `step` (< Tmax).  Philox4x32-10 contract of the in-kernel draw (exp_noise == NULL): stream = (seed, subsequence

@@ -147,6 +147,29 @@ def test_attention(dtype, b, h, Lq, Lk, masked, causal):
     assert err < tol, f"attention {dtype} b={b} h={h} {Lq}x{Lk} masked={masked} causal={causal}: max err {err}"
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("lens,heads", [([257, 64, 130, 1, 200, 192, 193], 12), ([100] * 5, 3), ([300, 17], 2)])
+def test_attention_packed(dtype, lens, heads):
+    """packed (ragged) self-attention of the reward batch: bf16 runs on the tcgen05 kernel (sequences of 64+ rows in the
+    longest), rows of one sequence must not see its neighbours' keys"""
+    from cxrmate_b200.engine import attention_packed_hook
+    g = torch.Generator(device="cuda").manual_seed(sum(lens) + heads)
+    C = heads * 64
+    total = sum(lens)
+    qkv = torch.randn(total, 3 * C, device="cuda", generator=g).to(dtype)
+    lens_t = torch.tensor(lens, device="cuda")
+    offs = torch.cumsum(lens_t, 0) - lens_t
+    o = attention_packed_hook(qkv, offs, lens_t, heads, 0.125)
+    torch.cuda.synchronize()
+    ref = torch.empty(total, C, device="cuda")
+    for off, n in zip(offs.tolist(), lens):
+        blk = qkv[off:off + n].float()
+        ref[off:off + n] = _ref_attn(blk[None, :, :C], blk[None, :, C:2 * C], blk[None, :, 2 * C:], heads, None, False, 0.125)[0]
+    err = (o.float() - ref).abs().max().item()
+    tol = 2e-5 if dtype == torch.float32 else 2e-2
+    assert err < tol, f"packed attention {dtype} lens={lens} heads={heads}: max err {err}"
+
+
 # ------------------------------------------------------------------------------ LayerNorm / CvT attention front end
 @pytest.mark.parametrize("rows,C", [(1000, 64), (577, 192), (333, 384), (64, 768), (50, 128), (7, 100)])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
