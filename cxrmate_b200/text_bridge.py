@@ -13,6 +13,7 @@ from __future__ import annotations
 from concurrent.futures import ThreadPoolExecutor
 from typing import List, Sequence, Tuple
 
+import numpy as np
 import torch
 
 
@@ -50,7 +51,13 @@ class TextBridge:
     def reports(self, sequences: torch.Tensor) -> List[str]:
         """f'{findings} {impression}' per row (scst/gen_prompt.py:237,317)"""
         f, i = self.split_ids(sequences)
-        txt = self.dec.batch_decode(f + i, skip_special_tokens=True)
+        backend = getattr(self.dec, "backend_tokenizer", None)
+        if backend is not None and not getattr(self.dec, "clean_up_tokenization_spaces", False):
+            # the Rust tokenizer decodes the whole batch in one call (threads over the rows); `batch_decode` of the
+            # transformers wrapper is a Python loop over `decode` that ends in the same routine
+            txt = backend.decode_batch(f + i, skip_special_tokens=True)
+        else:
+            txt = self.dec.batch_decode(f + i, skip_special_tokens=True)
         n = len(f)
         return [f"{a} {b}" for a, b in zip(txt[:n], txt[n:])]
 
@@ -58,21 +65,42 @@ class TextBridge:
     def encode(self, texts: Sequence[str], key: str = "pred"):
         """(ids int32 [n, L] pinned, lens int32 [n] pinned) exactly as CXRBERTReward tokenises (padding='longest',
         truncation at max_position_embeddings)"""
-        enc = self.rwd(list(texts), add_special_tokens=True, padding="longest", return_tensors="pt", truncation=True,
+        texts = list(texts)
+        backend = getattr(self.rwd, "backend_tokenizer", None)
+        pad_id = getattr(self.rwd, "pad_token_id", None)
+        if backend is not None and pad_id is not None and len(texts) > 0:
+            # straight to the Rust tokenizer: the transformers wrapper spends 4-5x the tokenisation time on building
+            # BatchEncoding objects, Python-side padding and tensor conversion (same ids: tests/test_text_bridge.py)
+            backend.enable_truncation(max_length=self.max_reward_len)
+            backend.no_padding()
+            encs = backend.encode_batch(texts, add_special_tokens=True)
+            lens_np = np.fromiter((len(e.ids) for e in encs), dtype=np.int32, count=len(encs))
+            n, L = len(encs), int(lens_np.max())
+            ids_t, lens_t = self._buffers(key, n, L)
+            ids_np = ids_t.numpy()
+            ids_np.fill(pad_id)
+            for r, e in enumerate(encs):
+                ids_np[r, : lens_np[r]] = e.ids
+            lens_t.numpy()[:] = lens_np
+            return ids_t, lens_t
+        enc = self.rwd(texts, add_special_tokens=True, padding="longest", return_tensors="pt", truncation=True,
                        max_length=self.max_reward_len)
         ids, lens = enc["input_ids"].to(torch.int32), enc["attention_mask"].sum(dim=1).to(torch.int32)
+        out_ids, out_lens = self._buffers(key, ids.shape[0], ids.shape[1])
+        out_ids.copy_(ids)
+        out_lens.copy_(lens)
+        return out_ids, out_lens
+
+    def _buffers(self, key: str, n: int, L: int):
+        """[n, L] int32 ids + [n] int32 lens, views of per-key pinned buffers when a GPU is present"""
+        if not torch.cuda.is_available():
+            return torch.empty(n, L, dtype=torch.int32), torch.empty(n, dtype=torch.int32)
         buf = self._pinned.get(key)
-        if torch.cuda.is_available():
-            if buf is None or buf[0].shape[0] < ids.shape[0] or buf[0].shape[1] < ids.shape[1]:
-                buf = (torch.empty(max(ids.shape[0], 1), self.max_reward_len, dtype=torch.int32).pin_memory(),
-                       torch.empty(max(ids.shape[0], 1), dtype=torch.int32).pin_memory())
-                self._pinned[key] = buf
-            out_ids = buf[0][: ids.shape[0], : ids.shape[1]]
-            out_ids.copy_(ids)
-            out_lens = buf[1][: ids.shape[0]]
-            out_lens.copy_(lens)
-            return out_ids, out_lens
-        return ids, lens
+        if buf is None or buf[0].shape[0] < n or buf[0].shape[1] < L:
+            buf = (torch.empty(max(n, 1), max(self.max_reward_len, L), dtype=torch.int32).pin_memory(),
+                   torch.empty(max(n, 1), dtype=torch.int32).pin_memory())
+            self._pinned[key] = buf
+        return buf[0][:n, :L], buf[1][:n]
 
     def encode_async(self, texts: Sequence[str], key: str = "label"):
         """tokenise on the worker thread (labels, while the GPU is busy with the rollout); .result() -> (ids, lens)"""
