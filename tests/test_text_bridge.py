@@ -63,6 +63,16 @@ def test_bridge_random_ids_truncate_at_512(toks):
     texts, ids, lens = TextBridge(dec, rwd, BOS, SEP, EOS)(seq)
     assert all(len(t) > 100 for t in texts)
     assert ids.shape[1] <= 512 and int(lens.max()) <= 512 and int(ids.max()) < 30522 and int(ids.min()) >= 0
+    # the bridge calls the Rust tokenizers' batch routines directly: same strings and ids as the transformers wrappers the
+    # reference goes through (tokenizer.decode per section, batch_encode_plus with padding='longest' and truncation)
+    br = TextBridge(dec, rwd, BOS, SEP, EOS)
+    f, i = br.split_ids(seq)
+    assert texts == [f"{a} {b}" for a, b in zip(dec.batch_decode(f, skip_special_tokens=True), dec.batch_decode(i, skip_special_tokens=True))]
+    want = rwd(texts, add_special_tokens=True, padding="longest", return_tensors="pt", truncation=True, max_length=512)
+    assert torch.equal(ids.long(), want["input_ids"]) and torch.equal(lens.long(), want["attention_mask"].sum(1))
+    short = TextBridge(dec, rwd, BOS, SEP, EOS, max_reward_len=64)(seq)      # truncation inside the batch call
+    want64 = rwd(texts, add_special_tokens=True, padding="longest", return_tensors="pt", truncation=True, max_length=64)
+    assert torch.equal(short[1].long(), want64["input_ids"]) and int(short[2].max()) == 64
 
 
 def test_tokenize_prompt_and_report_with_bpe(toks):
